@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""Headline benchmark: 7680x4320 frames/s of the fused UYVY -> DXT1 encode (BASELINE.json metric), with the
+HBM roofline of the kernel, the end-to-end number through the C ABI with host buffers, and the CPU baseline.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      CPU arm (rank 0 only)
+
+A "step" = one pass of the hot path over a batch of B distinct 8K frames that are resident in HBM (B x 66 MB is
+far larger than the 126 MB L2, so nothing is served from cache).  Frames are independent units: with N GPUs each
+rank encodes its own B frames per step (weak scaling, no data-path collective); the only collective is the NCCL
+scatter of the int32 frame-index assignment, issued one step ahead on a side stream.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W8K, H8K = 7680, 4320
+ALGO_BYTES_UYVY_DXT1 = W8K * H8K * 2 + W8K * H8K // 2  # 2 + 0.5 B/px, SURVEY.md section 8(d)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=16, help="distinct 8K frames per step per GPU")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary kernels / cpu baseline")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while a timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_fps(seconds=12.0, max_frames=6):
+    """oracle port of the path (oracle/dxt_oracle.c, OpenMP over block rows) on the host cores, bounded sample"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    orc = util.oracle()
+    orc.orc_set_threads(0)
+    cores = orc.orc_get_max_threads()
+    src = util.rng_bytes(W8K * H8K * 2, 4)
+    out = np.zeros(W8K * H8K // 2, dtype=np.uint8)
+    orc.orc_uyvy_to_dxt1(src.ctypes.data, out.ctypes.data, W8K, 256, 0)  # warm the thread pool
+    n, t0 = 0, time.perf_counter()
+    while n < max_frames and (n == 0 or time.perf_counter() - t0 < seconds):
+        orc.orc_uyvy_to_dxt1(src.ctypes.data, out.ctypes.data, W8K, H8K, 0)
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, cores, f"{n} noise frames 7680x4320 UYVY->DXT1, {dt:.1f} s wall"
+
+
+def reference_arm(args, rank):
+    """the reference has no CPU implementation of DXT (only CUDA); the CPU arm is therefore the oracle port of the
+    same path on all host threads.  Rank 0 alone works."""
+    if rank != 0:
+        return
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    orc = util.oracle()
+    orc.orc_set_threads(0)
+    cores = orc.orc_get_max_threads()
+    src = util.rng_bytes(W8K * H8K * 2, 4)
+    out = np.zeros(W8K * H8K // 2, dtype=np.uint8)
+    for _ in range(max(args.warmup, 1)):
+        orc.orc_uyvy_to_dxt1(src.ctypes.data, out.ctypes.data, W8K, H8K // 4, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):  # one step = one 8K frame (bounded sample of the GPU arm's batch)
+        orc.orc_uyvy_to_dxt1(src.ctypes.data, out.ctypes.data, W8K, H8K, 0)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "7680x4320 frames/sec encode (UYVY->DXT1)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "7680x4320 UYVY->DXT1 encode on host cores, 1 noise frame per step",
+                   "note": "UltraGrid has no CPU DXT encoder; this is the CPU port of cuda_dxt's arithmetic (oracle/dxt_oracle.c)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} noise frames 7680x4320, OpenMP over block rows"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ultragrid_b200 import api  # raises if libugb200.so is missing: no fallback
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.frames, args.steps, max(args.warmup, 3)
+    frame_bytes, out_bytes = W8K * H8K * 2, W8K * H8K // 2
+
+    # B distinct noise frames (worst case for DXT: no flat-block shortcut), resident in HBM
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    frames = torch.randint(0, 256, (B, frame_bytes), dtype=torch.uint8, device=dev, generator=g)
+    outs = torch.empty((B, out_bytes), dtype=torch.uint8, device=dev)
+
+    # frame-index assignment: rank 0 owns the queue and scatters int32 indices (the only collective)
+    comm = torch.cuda.Stream(device=dev)
+    assign = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+
+    def scatter_assignment(step):
+        buf = assign[step % 2]
+        with torch.cuda.stream(comm):
+            if world > 1:
+                src = None
+                if rank == 0:
+                    base = torch.arange(world * B, dtype=torch.int32, device=dev).reshape(world, B) + step * world * B
+                    src = [base[r].contiguous() for r in range(world)]
+                dist.scatter(buf, src, src=0)
+            else:
+                buf.copy_(torch.arange(B, dtype=torch.int32, device=dev) + step * B)
+            ready[step % 2].record(comm)
+
+    fr = [frames[f] for f in range(B)]
+    ou = [outs[f] for f in range(B)]
+
+    def run_step(step):
+        scatter_assignment(step + 1)                      # next step's assignment travels while this one encodes
+        torch.cuda.current_stream().wait_event(ready[step % 2])
+        for f in range(B):                               # global frame assign[step%2][f] lives in local slot f
+            api.uyvy_to_dxt(fr[f], W8K, H8K, dxt_type=1, out=ou[f])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    scatter_assignment(0)
+    for s in range(Wm):
+        run_step(s)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(K):
+        run_step(Wm + s)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    fps = world * B * K / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers: pinned frame -> H2D -> kernel -> D2H, 3-deep pipeline
+    depth = 3
+    h_in = [torch.empty(frame_bytes, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+    h_out = [torch.empty(out_bytes, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+    for b in h_in:
+        b.copy_(frames[0].cpu())
+    d_in = [torch.empty(frame_bytes, dtype=torch.uint8, device=dev) for _ in range(depth)]
+    d_out = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(depth)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+
+    def e2e_step():
+        for f in range(B):
+            k = f % depth
+            with torch.cuda.stream(streams[k]):
+                d_in[k].copy_(h_in[k], non_blocking=True)
+                api.uyvy_to_dxt(d_in[k], W8K, H8K, dxt_type=1, out=d_out[k], stream=streams[k])
+                h_out[k].copy_(d_out[k], non_blocking=True)
+        for s_ in streams:
+            s_.synchronize()
+
+    Ke = max(3, min(K, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    cur = torch.cuda.current_stream()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record(cur)
+    for s_ in streams:
+        s_.wait_event(x0)
+    for _ in range(Ke):
+        e2e_step()
+    for s_ in streams:
+        ev = torch.cuda.Event()
+        ev.record(s_)
+        cur.wait_event(ev)
+    x1.record(cur)
+    barrier()
+    e2e_t = torch.tensor([x0.elapsed_time(x1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_fps = world * B * Ke / float(e2e_t.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        per_launch_ms = ms / (B * K)
+        achieved = ALGO_BYTES_UYVY_DXT1 / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("dxt_uyvy_kernel_8k_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": "7680x4320 frames/sec encode (UYVY->DXT1)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "7680x4320 UYVY->DXT1 fused encode (ugb200_uyvy_to_dxt1_async), uniform-noise frames",
+                       "frames_per_step_per_gpu": B, "global_frames_per_step": world * B,
+                       "l2": f"inputs larger than L2: {B} distinct 66 MB frames per GPU", "parallelism": f"frame-sharded x{world}",
+                       "collective": "NCCL scatter of int32 frame indices, one step ahead on a side stream"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "ugb::dxt_uyvy_kernel<1,2,false>", "algorithmic_bytes_per_launch": ALGO_BYTES_UYVY_DXT1,
+                         "us_per_launch": per_launch_ms * 1e3, "peak_source": peak_src},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * out_bytes,
+                    "path": "pinned host frame -> cudaMemcpyAsync -> ugb200_uyvy_to_dxt1_async -> cudaMemcpyAsync, 3 streams"},
+            "gpu_launches": B * K,
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_extra:
+            line["extra"] = extra_kernels(api, torch, dev)
+            v, cores, sample = cpu_port_fps()
+            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+            line["extra"]["cpu_reference_pixfmt"] = cpu_reference_pixfmt()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_kernel(torch, fn, iters, warm=3):
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def extra_kernels(api, torch, dev):
+    """secondary kernels of the path (kernel-only, device-resident, distinct buffers cycled so that L2 does not help)"""
+    from ultragrid_b200 import Codec, vc_get_linesize
+    peak, _ = measured_peaks()
+    res = {}
+
+    def rec(name, secs, nbytes, px):
+        res[name] = {"us": secs * 1e6, "GBps": nbytes / secs / 1e9, "frac_of_peak": nbytes / secs / 1e9 / peak, "fps": 1.0 / secs,
+                     "bytes_per_px": nbytes / px}
+
+    def rnd(n, count):
+        return [torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev) for _ in range(count)]
+
+    # config 2: 3840x2160 UYVY -> DXT1
+    w, h = 3840, 2160
+    src, out = rnd(w * h * 2, 12), torch.empty(w * h // 2, dtype=torch.uint8, device=dev)
+    rec("uyvy_dxt1_4k", time_kernel(torch, lambda i: api.uyvy_to_dxt(src[i % 12], w, h, out=out), 60), w * h * 2.5, w * h)
+    del src
+    # reference-ABI RGB -> DXT1 at 8K (async variant measured through the compat kernel, includes its stream sync)
+    w, h = W8K, H8K
+    src, out = rnd(w * h * 3, 4), torch.empty(w * h // 2, dtype=torch.uint8, device=dev)
+    rec("rgb_dxt1_8k_sync_abi", time_kernel(torch, lambda i: api.compat_to_dxt("cuda_rgb_to_dxt1", src[i % 4], w, h, out=out), 12),
+        w * h * 3.5, w * h)
+    del src
+    # config 4: v210 -> P010 8K
+    ls = vc_get_linesize(w, Codec.v210)
+    src = [torch.randint(0, 1 << 30, (ls // 4 * h,), dtype=torch.int32, device=dev).view(torch.uint8) for _ in range(4)]
+    oy, oc = torch.empty(w * 2 * h, dtype=torch.uint8, device=dev), torch.empty(w * h, dtype=torch.uint8, device=dev)
+    rec("v210_p010_8k", time_kernel(torch, lambda i: api.v210_to_p010le(src[i % 4], w, h, out_y=oy, out_c=oc), 40), ls * h + w * h * 3, w * h)
+    del src
+    # config 1 on GPU + 8K line conversions
+    for name, inc, outc, ww, hh, n in (("uyvy_rgb_1080p", Codec.UYVY, Codec.RGB, 1920, 1080, 64), ("uyvy_rgb_8k", Codec.UYVY, Codec.RGB, w, h, 4),
+                                       ("rgb_uyvy_8k", Codec.RGB, Codec.UYVY, w, h, 4), ("v210_uyvy_8k", Codec.v210, Codec.UYVY, w, h, 4)):
+        src = rnd(vc_get_linesize(ww, inc) * hh, n)
+        dst = torch.empty(vc_get_linesize(ww, outc) * hh, dtype=torch.uint8, device=dev)
+        rec(name, time_kernel(torch, lambda i: api.pixfmt_convert(inc, outc, src[i % n], ww, hh, dst=dst), 40),
+            (vc_get_linesize(ww, inc) + vc_get_linesize(ww, outc)) * hh, ww * hh)
+        del src
+    return res
+
+
+def cpu_reference_pixfmt():
+    """the reference's own CPU pixfmt_conv path (unmodified objects in oracle/_ref) on this host: UYVY->RGB, 1 thread and all
+    cores through parallel_pix_conv (src/utils/parallel_conv.c:64-85)"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    ref = util.ref_cpu()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/libugref.so not present"}
+    src = util.rng_bytes(W8K * H8K * 2, 9)
+    dst = np.zeros(W8K * H8K * 3, dtype=np.uint8)
+    out = {"cores": os.cpu_count(), "flags": "-O3 -msse4.1 (tools/Makefile)"}
+    for label, fn in (("1_thread", lambda: ref.ref_convert(2, 12, dst.ctypes.data, W8K * 3, src.ctypes.data, W8K * 2, W8K * 3, H8K, 0, 8, 16)),
+                      ("all_cores", lambda: ref.ref_convert_parallel(2, 12, dst.ctypes.data, W8K * 3, src.ctypes.data, W8K * 2, H8K, 0))):
+        fn()
+        best = 1e9
+        for _ in range(5):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        out[f"uyvy_rgb_8k_{label}_ms"] = best * 1e3
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+/* TEST INFRASTRUCTURE — CPU restatement of UltraGrid's CUDA DXT encoders (cuda_dxt/cuda_dxt.cu).
+ *
+ * The reference arithmetic is single-precision on the GPU and its result depends on how ptxas contracted
+ * the expressions into FMAs.  That tree was read from the SASS of the reference built with nvcc 12.9 for
+ * sm_100a (default --fmad=true) and is restated here with fmaf(); compile with -ffp-contract=off so that
+ * the C compiler adds no contraction of its own.  Two things a CPU cannot reproduce bit-for-bit:
+ *   - __fdividef(1.0f, x) is MUFU.RCP (approximate, <= 1 ulp); 1.0f / x (correctly rounded) is used here;
+ * so palettes are exact and a very small fraction of DXT1 index words may differ from the GPU.  The
+ * BIT-EXACT oracle for the GPU tests is the unmodified reference kernel, oracle/_ref/libcuda_dxt_ref.so;
+ * this file is pinned against it on the GPU box (tests/test_dxt_gpu.py::test_cpu_oracle_vs_reference) and is
+ * what the CPU-only tests and smoke() use.
+ */
+#include <math.h>
+#include <omp.h>
+#include <stdint.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+
+static const float K255 = 0.00392156862745f; /* cuda_dxt.cu:666 */
+
+static float sat(float v) { return v < 0.f ? 0.f : v > 1.f ? 1.f : (v != v ? 0.f : v); } /* __saturatef */
+
+/* yuv_to_rgb, cuda_dxt.cu:444-451 as contracted: see dxt_device.cuh */
+static void yuv_px(uint8_t Y, uint8_t U, uint8_t V, float *r, float *g, float *b)
+{
+        const float y = fmaf((float) Y, K255, -0.0625f) * 1.1643f;
+        const float u = fmaf((float) U, K255, -0.5f), v = fmaf((float) V, K255, -0.5f);
+        *r = fmaf(v, 1.7926f, y);
+        *g = fmaf(v, -0.5328f, fmaf(u, -0.2132f, y));
+        *b = fmaf(u, 2.1124f, y);
+}
+
+/* encode_endpoint, cuda_dxt.cu:424-431: rintf(saturate(c) * levels) — round half to even */
+static float quant(float v, float levels) { return rintf(sat(v) * levels); }
+
+/* dxt_encode<1>, cuda_dxt.cu:512-617 */
+static void dxt1_block(const float *r, const float *g, const float *b, uint32_t out[2])
+{
+        float mnr = r[0], mng = g[0], mnb = b[0], mxr = r[0], mxg = g[0], mxb = b[0];
+        for (int i = 1; i < 16; ++i) {
+                mnr = fminf(mnr, r[i]), mng = fminf(mng, g[i]), mnb = fminf(mnb, b[i]);
+                mxr = fmaxf(mxr, r[i]), mxg = fmaxf(mxg, g[i]), mxb = fmaxf(mxb, b[i]);
+        }
+        const float dr = mxr - mnr, dg = mxg - mng, db = mxb - mnb;
+        const float lor = fmaf(dr, 0.0625f, mnr), hir = fmaf(dr, -0.0625f, mxr);
+        const float log_ = fmaf(dg, 0.0625f, mng), hig = fmaf(dg, -0.0625f, mxg);
+        const float lob = fmaf(db, 0.0625f, mnb), hib = fmaf(db, -0.0625f, mxb);
+        const float sr = lor + hir, sg = log_ + hig, sb = lob + hib;
+        float covx = 0.f, covy = 0.f;
+        for (int i = 0; i < 16; ++i) {
+                const float er = fmaf(sr, -0.5f, r[i]), eg = fmaf(sg, -0.5f, g[i]), eb = fmaf(sb, -0.5f, b[i]);
+                covx = fmaf(er, eb, covx);
+                covy = fmaf(eg, eb, covy);
+        }
+        const int swr = covx < 0.f, swg = covy < 0.f;
+        const float maxr = swr ? lor : hir, minr = swr ? hir : lor;
+        const float maxg = swg ? log_ : hig, ming = swg ? hig : log_;
+        const float qxr = quant(maxr, 31.f), qxg = quant(maxg, 63.f), qxb = quant(hib, 31.f);
+        const float qnr = quant(minr, 31.f), qng = quant(ming, 63.f), qnb = quant(lob, 31.f);
+        const uint32_t max_code = ((uint32_t) qxr << 11) + ((uint32_t) qxg << 5) + (uint32_t) qxb;
+        const uint32_t min_code = ((uint32_t) qnr << 11) + ((uint32_t) qng << 5) + (uint32_t) qnb;
+        uint32_t indices = 0;
+        if (max_code != min_code) {
+                const float k31 = 0.0322580645161f, k63 = 0.015873015873f;
+                const float ex_r = qxr * k31, ex_g = qxg * k63, ex_b = qxb * k31;
+                const float dir_r = fmaf(qnr, k31, -ex_r), dir_g = fmaf(qng, k63, -ex_g), dir_b = fmaf(qnb, k31, -ex_b);
+                const float len2 = fmaf(dir_b, dir_b, fmaf(dir_r, dir_r, dir_g * dir_g));
+                const float inv = 1.0f / len2; /* GPU: MUFU.RCP */
+                const float tr = dir_r * inv, tg = dir_g * inv, tb = dir_b * inv;
+                const float bias = fmaf(ex_b, tb, fmaf(ex_r, tr, ex_g * tg));
+                for (int i = 0; i < 16; ++i) {
+                        const float t = fmaf(b[i], tb, fmaf(r[i], tr, g[i] * tg));
+                        const float x = fmaf(sat(t - bias), 3.0f, 0.5f);
+                        indices += (uint32_t) x << (2 * i);
+                }
+        }
+        const int swap_end = max_code < min_code;
+        if (swap_end) {
+                indices = ~indices;
+        }
+        const uint32_t lsbs = indices & 0x55555555u, msbs = indices & 0xaaaaaaaau;
+        indices = msbs ^ (2 * lsbs + (msbs >> 1));
+        out[0] = swap_end ? min_code + (max_code << 16) : max_code + (min_code << 16);
+        out[1] = indices;
+}
+
+/* dxt_kernel + dxt_launch, cuda_dxt.cu:622-760: packed 3-byte source, negative size_y = bottom-up */
+static int dxt1_packed3(const uint8_t *src, uint32_t *out, int sx, int sy, int yuv)
+{
+        int mirrored = 0;
+        if (sy < 0) {
+                mirrored = 1, sy = -sy;
+        }
+        if ((sx & 3) || (sy & 3)) {
+                return -1;
+        }
+        for (int by = 0; by < sy / 4; ++by) {
+                for (int bx = 0; bx < sx / 4; ++bx) {
+                        float r[16], g[16], b[16];
+                        for (int y = 0; y < 4; ++y) {
+                                int row = by * 4 + y;
+                                if (mirrored) {
+                                        row = sy - 1 - row;
+                                }
+                                const uint8_t *p = src + ((size_t) row * sx + bx * 4) * 3;
+                                for (int x = 0; x < 4; ++x, p += 3) {
+                                        const int i = 4 * y + x;
+                                        if (yuv) {
+                                                yuv_px(p[0], p[1], p[2], &r[i], &g[i], &b[i]);
+                                        } else {
+                                                r[i] = p[0] * K255, g[i] = p[1] * K255, b[i] = p[2] * K255;
+                                        }
+                                }
+                        }
+                        dxt1_block(r, g, b, out + 2 * ((size_t) by * (sx / 4) + bx));
+                }
+        }
+        return 0;
+}
+API int orc_rgb_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy) { return dxt1_packed3(src, out, sx, sy, 0); }
+API int orc_yuv_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy) { return dxt1_packed3(src, out, sx, sy, 1); }
+
+/* yuv422_to_yuv444_kernel, cuda_dxt.cu:697-732: chroma replication */
+API void orc_yuv422_to_yuv444(const uint8_t *src, uint8_t *out, int pix_count)
+{
+        for (int i = 0; i + 1 < pix_count; i += 2, src += 4, out += 6) {
+                out[0] = src[1], out[1] = src[0], out[2] = src[2];
+                out[3] = src[3], out[4] = src[0], out[5] = src[2];
+        }
+}
+
+/* the pair run by src/video_compress/cuda_dxt.cpp:223-257 for UYVY input: 422->444 then yuv_to_dxt1 */
+API int orc_uyvy_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy, long pitch)
+{
+        int mirrored = 0;
+        if (sy < 0) {
+                mirrored = 1, sy = -sy;
+        }
+        if ((sx & 3) || (sy & 3)) {
+                return -1;
+        }
+        if (pitch == 0) {
+                pitch = (long) sx * 2;
+        }
+#pragma omp parallel for schedule(static)  /* block rows are independent; used by bench.py's cpu_baseline */
+        for (int by = 0; by < sy / 4; ++by) {
+                for (int bx = 0; bx < sx / 4; ++bx) {
+                        float r[16], g[16], b[16];
+                        for (int y = 0; y < 4; ++y) {
+                                int row = by * 4 + y;
+                                if (mirrored) {
+                                        row = sy - 1 - row;
+                                }
+                                const uint8_t *p = src + (size_t) row * pitch + bx * 8;
+                                for (int x = 0; x < 4; ++x) {
+                                        const uint8_t *q = p + (x / 2) * 4;
+                                        yuv_px(q[1 + 2 * (x & 1)], q[0], q[2], &r[4 * y + x], &g[4 * y + x], &b[4 * y + x]);
+                                }
+                        }
+                        dxt1_block(r, g, b, out + 2 * ((size_t) by * (sx / 4) + bx));
+                }
+        }
+        return 0;
+}
+
+/* DXT1 block decoder (S3TC, 4-colour mode) — used only to sanity-check that encoded blocks reproduce the
+ * image (PSNR), never for bit-exact comparisons. */
+API void orc_dxt1_decode(const uint32_t *in, uint8_t *rgb, int sx, int sy)
+{
+        for (int by = 0; by < sy / 4; ++by) {
+                for (int bx = 0; bx < sx / 4; ++bx) {
+                        const uint32_t pal = in[2 * ((size_t) by * (sx / 4) + bx)], idx = in[2 * ((size_t) by * (sx / 4) + bx) + 1];
+                        int c[4][3];
+                        for (int k = 0; k < 2; ++k) {
+                                const uint32_t v = (pal >> (16 * k)) & 0xffff;
+                                const int r5 = v >> 11, g6 = (v >> 5) & 63, b5 = v & 31;
+                                c[k][0] = (r5 << 3) | (r5 >> 2), c[k][1] = (g6 << 2) | (g6 >> 4), c[k][2] = (b5 << 3) | (b5 >> 2);
+                        }
+                        for (int ch = 0; ch < 3; ++ch) {
+                                c[2][ch] = (2 * c[0][ch] + c[1][ch] + 1) / 3;
+                                c[3][ch] = (c[0][ch] + 2 * c[1][ch] + 1) / 3;
+                        }
+                        for (int i = 0; i < 16; ++i) {
+                                const int k = (idx >> (2 * i)) & 3;
+                                uint8_t *p = rgb + (((size_t) by * 4 + i / 4) * sx + bx * 4 + i % 4) * 3;
+                                p[0] = c[k][0], p[1] = c[k][1], p[2] = c[k][2];
+                        }
+                }
+        }
+}
+
+API void orc_set_threads(int n) { omp_set_num_threads(n > 0 ? n : omp_get_num_procs()); }
+API int orc_get_max_threads(void) { return omp_get_max_threads(); }

@@ -1,0 +1,368 @@
+/* TEST INFRASTRUCTURE — CPU restatement of the pixel-format part of the hot path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may call this; the product
+ * (ultragrid_b200/) never links or loads it.  Every function cites the UltraGrid source it restates
+ * (paths relative to /root/reference).  Pinned by tests/test_oracle_pinning.py against
+ *   (1) the unmodified reference objects built into oracle/_ref/libugref.so (in this container),
+ *   (2) the known-answer checksums recorded in SURVEY.md section 6 / BASELINE.md section 2,
+ *   (3) the patterns of the reference's own unit tests (test/codec_conversions_test.cpp),
+ *   (4) the committed golden vectors tests/golden/ (generated from (1) by tests/golden/make_golden.py).
+ * Integer arithmetic only: results must be byte-identical to the reference.
+ */
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+
+/* codec_t values, src/types.h:62-112 */
+enum { C_RGBA = 1, C_UYVY = 2, C_YUYV = 3, C_VUYA = 4, C_R10k = 5, C_R12L = 6, C_v210 = 7, C_DVS10 = 8, C_RGB = 12, C_BGR = 20,
+       C_RG48 = 27, C_I420 = 29, C_Y216 = 30, C_Y416 = 31 };
+
+/* ---- src/color_space.{h,c} ---------------------------------------------------------------------- */
+enum { COMP_BASE = 14 }; /* color_space.h:70 */
+struct coeffs {
+        int y_r, y_g, y_b, cb_r, cb_g, cb_b, cr_r, cr_g, cr_b, y_scale, r_cr, g_cb, g_cr, b_cb;
+};
+
+/* COEFFS(), color_space.c:46-128.  depth 0 = full range. */
+static struct coeffs compute_coeffs(double kr, double kb, int depth)
+{
+        const double kg = 1. - kr - kb;
+        const double D = 2. * (kr + kg), E = 2. * (1. - kr);
+        const double yl = depth == 0 ? 1.0 : (219. * (1 << (depth - 8)) / ((1 << depth) - 1));
+        const double cl = depth == 0 ? 1.0 : (224. * (1 << (depth - 8)) / ((1 << depth) - 1));
+        const double B = 1 << COMP_BASE;
+#define SCALED(x) ((int) (((x) * B) + ((x) > 0 ? 1. : -1.) * 0.5))
+        struct coeffs c;
+        c.y_r = (int) (kr * yl * B + 0.5);
+        c.y_g = (int) (kg * yl * B + 0.5);
+        c.y_b = (int) (kb * yl * B + 0.5);
+        c.cb_r = (int) (-kr / D * cl * B - 0.5);
+        c.cb_g = (int) (-kg / D * cl * B - 0.5);
+        c.cb_b = (int) ((1 - kb) / D * cl * B + 0.5);
+        c.cr_r = (int) ((1 - kr) / E * cl * B - 0.5);
+        c.cr_g = (int) (-kg / E * cl * B - 0.5);
+        c.cr_b = (int) (-kb / E * cl * B + 0.5);
+        c.y_scale = SCALED(1. / yl);
+        c.r_cr = SCALED((2. * (1. - kr)) / cl);
+        c.g_cb = SCALED((-kb * (2. * (kr + kg)) / kg) / cl);
+        c.g_cr = SCALED((-kr * (2. * (1. - kr)) / kg) / cl);
+        c.b_cb = SCALED((2. * (kr + kg)) / cl);
+#undef SCALED
+        return c;
+}
+
+/* get_color_coeffs(CS_DFL|CS_709 -> BT.709, CS_601 -> BT.601), color_space.c:149-183 with the default
+ * colour space (no "color-601" param).  cs: 0 = default, 1 = 601, 2 = 709. */
+API void orc_get_color_coeffs(int cs, int depth, int out[14])
+{
+        const struct coeffs c = cs == 1 ? compute_coeffs(.299, .114, depth) : compute_coeffs(.212639, .072192, depth);
+        memcpy(out, &c, sizeof c);
+}
+static struct coeffs cfs709(int depth) { return compute_coeffs(.212639, .072192, depth); }
+
+/* ---- src/video_codec.c --------------------------------------------------------------------------- */
+/* codec_info[] block_size_bytes / block_size_pixels / h_align, video_codec.c:120-206 */
+static int info(int codec, int *bpx, int *h_align)
+{
+        switch (codec) {
+        case C_RGBA: case C_VUYA: *bpx = 1, *h_align = 1; return 4;
+        case C_UYVY: case C_YUYV: *bpx = 2, *h_align = 2; return 4;
+        case C_R10k: *bpx = 1, *h_align = 64; return 4;
+        case C_R12L: *bpx = 8, *h_align = 8; return 36;
+        case C_v210: case C_DVS10: *bpx = 6, *h_align = 48; return 16;
+        case C_RGB: case C_BGR: *bpx = 1, *h_align = 1; return 3;
+        case C_RG48: *bpx = 1, *h_align = 1; return 6;
+        case C_I420: *bpx = 2, *h_align = 2; return 3;
+        case C_Y216: *bpx = 2, *h_align = 2; return 8;
+        case C_Y416: *bpx = 1, *h_align = 1; return 8;
+        }
+        *bpx = 1, *h_align = 0;
+        return 0;
+}
+/* vc_get_linesize, video_codec.c:507-521 */
+API int orc_vc_get_linesize(unsigned width, int codec)
+{
+        int bpx, ha;
+        const int bytes = info(codec, &bpx, &ha);
+        if (bytes == 0) {
+                return 0;
+        }
+        if (ha) {
+                width = (width + ha - 1) / ha * ha;
+        }
+        return (width + bpx - 1) / bpx * bytes;
+}
+/* vc_get_size, video_codec.c:530-538 */
+API int orc_vc_get_size(unsigned width, int codec)
+{
+        int bpx, ha;
+        const int bytes = info(codec, &bpx, &ha);
+        return bytes == 0 ? 0 : (width + bpx - 1) / bpx * bytes;
+}
+
+/* ---- src/pixfmt_conv.c line converters ----------------------------------------------------------- */
+typedef void line_fn(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs);
+
+static int clamp255(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+static uint32_t rd32(const unsigned char *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static void wr32(unsigned char *p, uint32_t v) { memcpy(p, &v, 4); }
+
+/* vc_copylinev210, pixfmt_conv.c:86-130 */
+static void v210_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+#define A(w) ((((w) >> 0) & 0x3ff) >> 2)
+#define B(w) ((((w) >> 10) & 0x3ff) >> 2)
+#define C(w) ((((w) >> 20) & 0x3ff) >> 2)
+        while (dst_len >= 12) {
+                const uint32_t w0 = rd32(src), w1 = rd32(src + 4), w2 = rd32(src + 8), w3 = rd32(src + 12);
+                wr32(dst, A(w0) | B(w0) << 8 | C(w0) << 16 | A(w1) << 24);
+                wr32(dst + 4, B(w1) | C(w1) << 8 | A(w2) << 16 | B(w2) << 24);
+                wr32(dst + 8, C(w2) | A(w3) << 8 | B(w3) << 16 | C(w3) << 24);
+                src += 16, dst += 12, dst_len -= 12;
+        }
+        if (dst_len >= 4) { /* :118-122 */
+                const uint32_t w0 = rd32(src), w1 = rd32(src + 4);
+                wr32(dst, A(w0) | B(w0) << 8 | C(w0) << 16 | A(w1) << 24);
+        }
+        if (dst_len >= 8) { /* :123-127 */
+                const uint32_t w1 = rd32(src + 4), w2 = rd32(src + 8);
+                wr32(dst + 4, B(w1) | C(w1) << 8 | A(w2) << 16 | B(w2) << 24);
+        }
+#undef A
+#undef B
+#undef C
+}
+
+/* vc_copylineYUYV, pixfmt_conv.c:136-198 (word-wise byte swap; dst_len % 4 == 0 asserted at :156) */
+static void yuyv_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x <= dst_len - 4; x += 4) {
+                dst[x] = src[x + 1], dst[x + 1] = src[x], dst[x + 2] = src[x + 3], dst[x + 3] = src[x + 2];
+        }
+}
+
+/* copylineYUVtoRGB, pixfmt_conv.c:1065-1094 (rgb16 = 0) */
+static void yuv422_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int y1o, int y2o, int uo, int vo)
+{
+        const struct coeffs c = cfs709(8);
+        for (int x = 0; x <= dst_len - 6; x += 6) {
+                const int y1 = c.y_scale * (src[y1o] - 16), y2 = c.y_scale * (src[y2o] - 16);
+                const int u = src[uo] - 128, v = src[vo] - 128;
+                src += 4;
+                *dst++ = clamp255((y1 + v * c.r_cr) >> COMP_BASE);
+                *dst++ = clamp255((y1 + u * c.g_cb + v * c.g_cr) >> COMP_BASE);
+                *dst++ = clamp255((y1 + u * c.b_cb) >> COMP_BASE);
+                *dst++ = clamp255((y2 + v * c.r_cr) >> COMP_BASE);
+                *dst++ = clamp255((y2 + u * c.g_cb + v * c.g_cr) >> COMP_BASE);
+                *dst++ = clamp255((y2 + u * c.b_cb) >> COMP_BASE);
+        }
+}
+/* vc_copylineUYVYtoRGB :1102-1108, vc_copylineYUYVtoRGB :1116-1122 */
+static void uyvy_to_rgb(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; yuv422_to_rgb(d, s, n, 1, 3, 0, 2); }
+static void yuyv_to_rgb(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; yuv422_to_rgb(d, s, n, 0, 2, 1, 3); }
+
+/* vc_copylineUYVYtoRGBA, pixfmt_conv.c:1137-1163: double arithmetic (built with -ffp-contract=off, the
+ * reference build has no FMA target either), truncating int conversion */
+static void uyvy_to_rgba(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        const uint32_t amask = 0xFFFFFFFFU ^ (0xFFU << rs) ^ (0xFFU << gs) ^ (0xFFU << bs);
+        for (int x = 0; x <= dst_len - 8; x += 8) {
+                const int u = src[0], y1 = src[1], v = src[2], y2 = src[3];
+                src += 4;
+                for (int k = 0; k < 2; ++k) {
+                        const int y = k ? y2 : y1;
+                        int r = 1.164 * (y - 16) + 1.793 * (v - 128);
+                        int g = 1.164 * (y - 16) - 0.534 * (v - 128) - 0.213 * (u - 128);
+                        int b = 1.164 * (y - 16) + 2.115 * (u - 128);
+                        r = clamp255(r), g = clamp255(g), b = clamp255(b);
+                        wr32(dst, amask | (uint32_t) r << rs | (uint32_t) g << gs | (uint32_t) b << bs);
+                        dst += 4;
+                }
+        }
+}
+
+/* vc_copylineToUYVY, pixfmt_conv.c:1008-1053 */
+static void to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int roff, int goff, int boff, int pix)
+{
+        const struct coeffs c = cfs709(8);
+        const int count = (dst_len + 3) / 4; /* :1045 */
+        for (int x = 0; x < count; ++x) {
+                int r = src[roff], g = src[goff], b = src[boff];
+                src += pix;
+                const int y1 = ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 16;
+                int u = r * c.cb_r + g * c.cb_g + b * c.cb_b;
+                int v = r * c.cr_r + g * c.cr_g + b * c.cr_b;
+                r = src[roff], g = src[goff], b = src[boff];
+                src += pix;
+                const int y2 = ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 16;
+                u += r * c.cb_r + g * c.cb_g + b * c.cb_b;
+                v += r * c.cr_r + g * c.cr_g + b * c.cr_b;
+                u = ((u / 2) >> COMP_BASE) + 128; /* C division truncates toward zero, then arithmetic shift */
+                v = ((v / 2) >> COMP_BASE) + 128;
+                wr32(dst + 4 * x, ((uint32_t) (y2 & 0xFF) << 24) | ((v & 0xFF) << 16) | ((y1 & 0xFF) << 8) | (u & 0xFF));
+        }
+}
+static void rgb_to_uyvy(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; to_uyvy(d, s, n, 0, 1, 2, 3); }   /* :2061-2068 */
+static void bgr_to_uyvy(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; to_uyvy(d, s, n, 2, 1, 0, 3); }   /* :2271-2278 */
+static void rgba_to_uyvy(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; to_uyvy(d, s, n, 0, 1, 2, 4); }  /* :2309-2316 */
+static void rg48_to_uyvy(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; to_uyvy(d, s, n, 1, 3, 5, 6); }  /* :2336-2343 */
+
+/* vc_copylineRGBtoRGBA, pixfmt_conv.c:944-990 */
+static void rgb_to_rgba(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        const uint32_t amask = 0xFFFFFFFFU ^ (0xFFU << rs) ^ (0xFFU << gs) ^ (0xFFU << bs);
+        for (int x = 0; x <= dst_len - 4; x += 4) {
+                const uint32_t r = src[0], g = src[1], b = src[2];
+                src += 3;
+                wr32(dst + x, amask | r << rs | g << gs | b << bs);
+        }
+}
+/* vc_copylineRGBAtoRGB, pixfmt_conv.c:866-900, SSSE3 build (the reference's tools/Makefile and oracle/_ref use
+ * -msse4.1).  QUIRK kept on purpose: the scalar tail loop at :889-895 never advances `src`, so every pixel after
+ * the pshufb loop (which runs while x <= dst_len - 24) repeats the first tail pixel. */
+static void rgba_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        int x = 0;
+        for (; x <= dst_len - 24; x += 12) { /* :880-887: 4 px per step */
+                for (int k = 0; k < 4; ++k) {
+                        dst[3 * k] = src[4 * k], dst[3 * k + 1] = src[4 * k + 1], dst[3 * k + 2] = src[4 * k + 2];
+                }
+                src += 16, dst += 12;
+        }
+        for (; x <= dst_len - 3; x += 3) { /* :889-895 */
+                const uint32_t in = rd32(src);
+                *dst++ = in & 0xff, *dst++ = (in >> 8) & 0xff, *dst++ = (in >> 16) & 0xff;
+        }
+}
+/* vc_copylineRGBA, pixfmt_conv.c:538-589 */
+static void rgba_to_rgba(unsigned char *dst, const unsigned char *src, int len, int rs, int gs, int bs)
+{
+        if (rs == 0 && gs == 8 && bs == 16) {
+                memcpy(dst, src, len);
+                return;
+        }
+        const uint32_t amask = 0xFFFFFFFFU ^ (0xFFU << rs) ^ (0xFFU << gs) ^ (0xFFU << bs);
+        for (; len >= 4; len -= 4, src += 4, dst += 4) {
+                const uint32_t t = rd32(src);
+                wr32(dst, amask | (t & 0xff) << rs | ((t >> 8) & 0xff) << gs | ((t >> 16) & 0xff) << bs);
+        }
+}
+/* vc_copylineRGB, pixfmt_conv.c:732-753 */
+static void rgb_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        if (rs == 0 && gs == 8 && bs == 16) {
+                memcpy(dst, src, dst_len);
+                return;
+        }
+        for (int x = 0; x <= dst_len - 3; x += 3) {
+                const uint32_t w = (uint32_t) src[0] << rs | (uint32_t) src[1] << gs | (uint32_t) src[2] << bs;
+                src += 3;
+                *dst++ = w & 0xff, *dst++ = (w >> 8) & 0xff, *dst++ = (w >> 16) & 0xff;
+        }
+}
+/* vc_copylineBGRtoRGB, pixfmt_conv.c:2520-2527 */
+static void bgr_to_rgb(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; rgb_to_rgb(d, s, n, 16, 8, 0); }
+/* vc_memcpy, pixfmt_conv.c:2529-2536 */
+static void copy_line(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; memcpy(d, s, n); }
+
+/* get_decoder_from_to, pixfmt_conv.c:3110-3125 (subset of decoders[] :3041-3103 restated so far) */
+static line_fn *decoder_from_to(int in, int out)
+{
+        if (in == out && out != C_RGBA && out != C_RGB) {
+                return copy_line;
+        }
+        switch (in * 256 + out) {
+        case C_v210 * 256 + C_UYVY: return v210_to_uyvy;
+        case C_YUYV * 256 + C_UYVY: case C_UYVY * 256 + C_YUYV: return yuyv_uyvy;
+        case C_UYVY * 256 + C_RGB: return uyvy_to_rgb;
+        case C_YUYV * 256 + C_RGB: return yuyv_to_rgb;
+        case C_UYVY * 256 + C_RGBA: return uyvy_to_rgba;
+        case C_RGB * 256 + C_UYVY: return rgb_to_uyvy;
+        case C_BGR * 256 + C_UYVY: return bgr_to_uyvy;
+        case C_RGBA * 256 + C_UYVY: return rgba_to_uyvy;
+        case C_RG48 * 256 + C_UYVY: return rg48_to_uyvy;
+        case C_RGB * 256 + C_RGBA: return rgb_to_rgba;
+        case C_RGBA * 256 + C_RGB: return rgba_to_rgb;
+        case C_RGBA * 256 + C_RGBA: return rgba_to_rgba;
+        case C_RGB * 256 + C_RGB: return rgb_to_rgb;
+        case C_BGR * 256 + C_RGB: return bgr_to_rgb;
+        }
+        return NULL;
+}
+
+API int orc_has_decoder(int in, int out) { return decoder_from_to(in, out) != NULL; }
+
+/* row loop of tools/convert.cpp:148-152 */
+API int orc_convert(int in_codec, int out_codec, unsigned char *dst, long dst_pitch, const unsigned char *src, long src_pitch,
+                    int dst_len, int height, int rs, int gs, int bs)
+{
+        line_fn *f = decoder_from_to(in_codec, out_codec);
+        if (f == NULL) {
+                return -4;
+        }
+        for (int y = 0; y < height; ++y) {
+                f(dst + y * dst_pitch, src + y * src_pitch, dst_len, rs, gs, bs);
+        }
+        return 0;
+}
+
+/* ---- src/to_planar.c ------------------------------------------------------------------------------ */
+/* v210_to_p010le, to_planar.c:64-155 */
+API void orc_v210_to_p010le(int width, int height, unsigned char *out_y, unsigned ls_y, unsigned char *out_c, unsigned ls_c,
+                            const unsigned char *in)
+{
+        const long in_ls = orc_vc_get_linesize(width, C_v210);
+        void *garbage = NULL;
+        for (int y = 0; y < height; y += 2) {
+                const uint32_t *src = (const uint32_t *) (const void *) (in + y * in_ls);
+                const uint32_t *src2 = (const uint32_t *) (const void *) (in + (y + 1) * in_ls);
+                uint16_t *dst_y = (uint16_t *) (void *) (out_y + (size_t) ls_y * y);
+                uint16_t *dst_y2 = (uint16_t *) (void *) (out_y + (size_t) ls_y * (y + 1));
+                uint16_t *dst_c = (uint16_t *) (void *) (out_c + (size_t) ls_c * y / 2);
+                if (height - y == 1) { /* :84-87 */
+                        dst_y2 = garbage = malloc(ls_y);
+                        src2 = src;
+                }
+                int w = (width + 5) / 6 * 6; /* :89 */
+                if (height - y == 1 || height - y == 2) {
+                        w = width;
+                }
+                for (int x = 0; x < w / 6; ++x) {
+                        const uint32_t a0 = *src++, a1 = *src++, a2 = *src++, a3 = *src++;
+                        const uint32_t b0 = *src2++, b1 = *src2++, b2 = *src2++, b3 = *src2++;
+#define S(w, sh) (((w) >> (sh)) & 0x3ff)
+                        *dst_y++ = S(a0, 10) << 6, *dst_y++ = S(a1, 0) << 6, *dst_y++ = S(a1, 20) << 6;
+                        *dst_y++ = S(a2, 10) << 6, *dst_y++ = S(a3, 0) << 6, *dst_y++ = S(a3, 20) << 6;
+                        *dst_y2++ = S(b0, 10) << 6, *dst_y2++ = S(b1, 0) << 6, *dst_y2++ = S(b1, 20) << 6;
+                        *dst_y2++ = S(b2, 10) << 6, *dst_y2++ = S(b3, 0) << 6, *dst_y2++ = S(b3, 20) << 6;
+                        *dst_c++ = ((S(a0, 0) + S(b0, 0)) / 2) << 6;   /* Cb */
+                        *dst_c++ = ((S(a0, 20) + S(b0, 20)) / 2) << 6; /* Cr */
+                        *dst_c++ = ((S(a1, 10) + S(b1, 10)) / 2) << 6;
+                        *dst_c++ = ((S(a2, 0) + S(b2, 0)) / 2) << 6;
+                        *dst_c++ = ((S(a2, 20) + S(b2, 20)) / 2) << 6;
+                        *dst_c++ = ((S(a3, 10) + S(b3, 10)) / 2) << 6;
+#undef S
+                }
+                /* :141-151 — pointer arithmetic on uint16_t*: "- out_linesize" moves back out_linesize ELEMENTS,
+                 * i.e. two rows.  Where that would read before the buffer (reference UB) nothing is copied. */
+                if ((height - y == 1 || height - y == 2) && width % 6 != 0) {
+                        const size_t pix_cnt = width % 6;
+                        if (y >= 2) {
+                                memcpy(dst_y, dst_y - ls_y, pix_cnt * 2);
+                                if (height - y == 2) {
+                                        memcpy(dst_y2, dst_y - ls_y, pix_cnt * 2);
+                                }
+                        }
+                        if (y / 2 >= 2) {
+                                memcpy(dst_c, dst_c - ls_c, pix_cnt * 2);
+                        }
+                }
+        }
+        free(garbage);
+}

@@ -1,0 +1,81 @@
+/* TEST INFRASTRUCTURE — thin C entry points over the UNMODIFIED reference objects (compiled from
+ * /root/reference where they lie by oracle/Makefile into oracle/_ref/libugref.so).  Nothing in the
+ * product links or loads this.  Used by tests/ and by bench.py's cpu_baseline / --impl reference arms.
+ */
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "color_space.h"
+#include "pixfmt_conv.h"
+#include "to_planar.h"
+#include "utils/parallel_conv.h"
+#include "video_codec.h"
+
+#define API __attribute__((visibility("default")))
+
+/* row loop exactly as tools/convert.cpp:148-152 */
+API int ref_convert(int in_codec, int out_codec, unsigned char *dst, long dst_pitch, const unsigned char *src,
+                    long src_pitch, int dst_len, int height, int rshift, int gshift, int bshift)
+{
+        decoder_t dec = get_decoder_from_to((codec_t) in_codec, (codec_t) out_codec);
+        if (dec == NULL) {
+                return -4;
+        }
+        for (int y = 0; y < height; ++y) {
+                dec(dst + y * dst_pitch, src + y * src_pitch, dst_len, rshift, gshift, bshift);
+        }
+        return 0;
+}
+
+/* all host cores through the reference's own parallel_pix_conv (src/utils/parallel_conv.c:64-85) */
+API int ref_convert_parallel(int in_codec, int out_codec, unsigned char *dst, int dst_pitch, const unsigned char *src,
+                             int src_pitch, int height, int threads)
+{
+        decoder_t dec = get_decoder_from_to((codec_t) in_codec, (codec_t) out_codec);
+        if (dec == NULL) {
+                return -4;
+        }
+        parallel_pix_conv(height, (char *) dst, dst_pitch, (const char *) src, src_pitch, dec, threads);
+        return 0;
+}
+
+API int ref_has_decoder(int in_codec, int out_codec)
+{
+        return get_decoder_from_to((codec_t) in_codec, (codec_t) out_codec) != NULL;
+}
+
+API int ref_vc_get_linesize(unsigned width, int codec) { return vc_get_linesize(width, (codec_t) codec); }
+API int ref_vc_get_size(unsigned width, int codec) { return vc_get_size(width, (codec_t) codec); }
+API const char *ref_get_codec_name(int codec) { return get_codec_name((codec_t) codec); }
+
+API void ref_get_color_coeffs(int cs, int depth, int out[14])
+{
+        const struct color_coeffs *c = get_color_coeffs((enum colorspace) cs, depth);
+        const int v[14] = { c->y_r, c->y_g, c->y_b, c->cb_r, c->cb_g, c->cb_b, c->cr_r, c->cr_g, c->cr_b,
+                            c->y_scale, c->r_cr, c->g_cb, c->g_cr, c->b_cb };
+        memcpy(out, v, sizeof v);
+}
+
+API void ref_v210_to_p010le(int width, int height, unsigned char *out_y, unsigned ls_y, unsigned char *out_c, unsigned ls_c,
+                            const unsigned char *in)
+{
+        struct to_planar_data d = { 0 };
+        d.width = width, d.height = height;
+        d.out_data[0] = out_y, d.out_data[1] = out_c;
+        d.out_linesize[0] = ls_y, d.out_linesize[1] = ls_c;
+        d.in_data = in;
+        v210_to_p010le(d);
+}
+
+/* decode_to_planar_parallel (src/to_planar.c:496-522); threads 0 = all cores */
+API void ref_v210_to_p010le_parallel(int width, int height, unsigned char *out_y, unsigned ls_y, unsigned char *out_c,
+                                     unsigned ls_c, const unsigned char *in, int threads)
+{
+        struct to_planar_data d = { 0 };
+        d.width = width, d.height = height;
+        d.out_data[0] = out_y, d.out_data[1] = out_c;
+        d.out_linesize[0] = ls_y, d.out_linesize[1] = ls_c;
+        d.in_data = in;
+        decode_to_planar_parallel(v210_to_p010le, d, vc_get_linesize(width, v210), threads);
+}

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    import util
+    return util.oracle()
+
+
+@pytest.fixture(scope="session")
+def ref_cpu():
+    import util
+    lib = util.ref_cpu()
+    if lib is None:
+        pytest.skip("oracle/_ref/libugref.so not built (reference tree absent)")
+    return lib

@@ -1,0 +1,31 @@
+"""Small driver for ncu: runs each hot kernel a few times on distinct 8K/4K buffers (no timing here)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ultragrid_b200 import api, Codec, vc_get_linesize
+
+which = sys.argv[1] if len(sys.argv) > 1 else "dxt1"
+dev = torch.device("cuda", 0)
+W, H = 7680, 4320
+if which == "dxt1":
+    src = [torch.randint(0, 256, (W * H * 2,), dtype=torch.uint8, device=dev) for _ in range(3)]
+    out = torch.empty(W * H // 2, dtype=torch.uint8, device=dev)
+    for i in range(6):
+        api.uyvy_to_dxt(src[i % 3], W, H, out=out)
+elif which == "dxt6":
+    src = [torch.randint(0, 256, (W * H * 2,), dtype=torch.uint8, device=dev) for _ in range(3)]
+    out = torch.empty(W * H, dtype=torch.uint8, device=dev)
+    for i in range(6):
+        api.uyvy_to_dxt(src[i % 3], W, H, dxt_type=6, out=out)
+elif which == "p010":
+    ls = vc_get_linesize(W, Codec.v210)
+    src = [torch.randint(0, 1 << 30, (ls // 4 * H,), dtype=torch.int32, device=dev).view(torch.uint8) for _ in range(3)]
+    oy, oc = torch.empty(W * 2 * H, dtype=torch.uint8, device=dev), torch.empty(W * H, dtype=torch.uint8, device=dev)
+    for i in range(6):
+        api.v210_to_p010le(src[i % 3], W, H, out_y=oy, out_c=oc)
+elif which == "uyvy_rgb":
+    src = [torch.randint(0, 256, (W * H * 2,), dtype=torch.uint8, device=dev) for _ in range(3)]
+    dst = torch.empty(W * H * 3, dtype=torch.uint8, device=dev)
+    for i in range(6):
+        api.pixfmt_convert(Codec.UYVY, Codec.RGB, src[i % 3], W, H, dst=dst)
+torch.cuda.synchronize()

@@ -1,0 +1,65 @@
+"""ctypes loader of the in-tree C-ABI library.  Fails loudly when it is missing (no fallback)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libugb200.so")
+
+# every symbol include/*.h declares, with (restype, argtypes); tests check the export list against this
+_vp, _i, _l, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_size_t
+SIGNATURES = {
+    # include/cuda_dxt.h
+    "cuda_rgb_to_dxt1": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cuda_yuv_to_dxt1": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cuda_rgb_to_dxt6": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cuda_yuv_to_dxt6": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cuda_yuv422_to_yuv444": (_i, [_vp, _vp, _i, _vp]),
+    # include/cuda_wrapper.h
+    "cuda_wrapper_free": (_i, [_vp]),
+    "cuda_wrapper_free_host": (_i, [_vp]),
+    "cuda_wrapper_host_alloc": (_i, [ctypes.POINTER(_vp), _sz, ctypes.c_uint]),
+    "cuda_wrapper_malloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "cuda_wrapper_malloc_host": (_i, [ctypes.POINTER(_vp), _sz]),
+    "cuda_wrapper_memcpy": (_i, [_vp, _vp, _sz, _i]),
+    "cuda_wrapper_last_error_string": (ctypes.c_char_p, []),
+    "cuda_wrapper_set_device": (_i, [_i]),
+    "cuda_wrapper_get_last_error": (_i, []),
+    "cuda_wrapper_get_error_string": (ctypes.c_char_p, [_i]),
+    "cuda_wrapper_print_devices_info": (None, [ctypes.c_bool]),
+    "cuda_wrapper_device_reset": (None, []),
+    "cuda_wrapper_get_device_count": (_i, [ctypes.POINTER(_i)]),
+    "cuda_wrapper_stream_create": (_i, [ctypes.POINTER(_vp)]),
+    "cuda_wrapper_stream_destroy": (_i, [_vp]),
+    "cuda_wrapper_stream_synchronize": (_i, [_vp]),
+    "cuda_wrapper_memcpy_async": (_i, [_vp, _vp, _sz, _i, _vp]),
+    # include/ugb200.h
+    "ugb200_rgb_to_dxt1_async": (_i, [_vp, _vp, _i, _i, _vp]),
+    "ugb200_yuv_to_dxt1_async": (_i, [_vp, _vp, _i, _i, _vp]),
+    "ugb200_rgb_to_dxt6_async": (_i, [_vp, _vp, _i, _i, _vp]),
+    "ugb200_yuv_to_dxt6_async": (_i, [_vp, _vp, _i, _i, _vp]),
+    "ugb200_uyvy_to_dxt1_async": (_i, [_vp, _vp, _i, _i, _l, _vp]),
+    "ugb200_uyvy_to_dxt6_async": (_i, [_vp, _vp, _i, _i, _l, _vp]),
+    "ugb200_pixfmt_supported": (_i, [_i, _i]),
+    "ugb200_pixfmt_convert": (_i, [_i, _i, _vp, _l, _vp, _l, _i, _i, _l, _i, _i, _i, _vp]),
+    "ugb200_v210_to_p010le": (_i, [_vp, _l, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libugb200.so and bind the signatures.  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C ultragrid_b200/csrc`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the library is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

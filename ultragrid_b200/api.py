@@ -1,0 +1,96 @@
+"""Thin torch-tensor front end over the C ABI (tests and bench only; plumbing, not the product).
+
+All tensors are ``torch.uint8`` CUDA tensors; results are bit-identical to the reference functions named in
+``include/*.h``.  Every call requires the CUDA library — there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .codec import Codec, vc_get_linesize
+
+_L = _lib.load()
+
+
+def _stream(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with code {rc}")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def dxt_out_bytes(width, height, dxt_type):
+    h = abs(height)
+    return width * h // 2 if dxt_type == 1 else width * h
+
+
+def compat_to_dxt(name, src, width, height, out=None, stream=None):
+    """Synchronous reference-ABI entry points: name in cuda_{rgb,yuv}_to_dxt{1,6}."""
+    dxt_type = 1 if name.endswith("dxt1") else 6
+    if out is None:
+        out = torch.empty(dxt_out_bytes(width, height, dxt_type), dtype=torch.uint8, device=src.device)
+    _check(getattr(_L, name)(_ptr(src), _ptr(out), width, height, _stream(stream)), name)
+    return out
+
+
+def uyvy_to_dxt(src, width, height, dxt_type=1, pitch=0, out=None, stream=None):
+    """Fused UYVY -> DXT1 / DXT5-YCoCg, asynchronous on the stream."""
+    if out is None:
+        out = torch.empty(dxt_out_bytes(width, height, dxt_type), dtype=torch.uint8, device=src.device)
+    fn = _L.ugb200_uyvy_to_dxt1_async if dxt_type == 1 else _L.ugb200_uyvy_to_dxt6_async
+    _check(fn(_ptr(src), _ptr(out), width, height, pitch, _stream(stream)), "ugb200_uyvy_to_dxt")
+    return out
+
+
+def yuv422_to_yuv444(src, pix_count, out=None, stream=None):
+    if out is None:
+        out = torch.empty(pix_count * 3, dtype=torch.uint8, device=src.device)
+    _check(_L.cuda_yuv422_to_yuv444(_ptr(src), _ptr(out), pix_count, _stream(stream)), "cuda_yuv422_to_yuv444")
+    return out
+
+
+def pixfmt_supported(in_codec, out_codec):
+    return bool(_L.ugb200_pixfmt_supported(int(in_codec), int(out_codec)))
+
+
+def pixfmt_convert(in_codec, out_codec, src, width, height, dst=None, dst_len=None, src_pitch=None, dst_pitch=None,
+                   shifts=(0, 8, 16), stream=None):
+    """Device form of the reference row loop (tools/convert.cpp:148-152)."""
+    src_pitch = vc_get_linesize(width, in_codec) if src_pitch is None else src_pitch
+    dst_pitch = vc_get_linesize(width, out_codec) if dst_pitch is None else dst_pitch
+    dst_len = vc_get_linesize(width, out_codec) if dst_len is None else dst_len
+    if dst is None:
+        dst = torch.zeros(dst_pitch * height, dtype=torch.uint8, device=src.device)
+    rc = _L.ugb200_pixfmt_convert(int(in_codec), int(out_codec), _ptr(dst), dst_pitch, _ptr(src), src_pitch, dst_len, height,
+                                  src.numel(), shifts[0], shifts[1], shifts[2], _stream(stream))
+    _check(rc, f"ugb200_pixfmt_convert({Codec(in_codec).name}->{Codec(out_codec).name})")
+    return dst
+
+
+class ToPlanarData(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("out_data", ctypes.c_void_p * 4),
+                ("out_linesize", ctypes.c_uint * 4), ("in_data", ctypes.c_void_p)]
+
+
+def v210_to_p010le(src, width, height, out_y=None, out_c=None, ls_y=None, ls_c=None, stream=None):
+    ls_y = width * 2 if ls_y is None else ls_y
+    ls_c = width * 2 if ls_c is None else ls_c
+    if out_y is None:
+        out_y = torch.zeros(ls_y * height, dtype=torch.uint8, device=src.device)
+    if out_c is None:
+        out_c = torch.zeros(ls_c * ((height + 1) // 2), dtype=torch.uint8, device=src.device)
+    d = ToPlanarData()
+    d.width, d.height = width, height
+    d.out_data[0], d.out_data[1] = out_y.data_ptr(), out_c.data_ptr()
+    d.out_linesize[0], d.out_linesize[1] = ls_y, ls_c
+    d.in_data = src.data_ptr()
+    _check(_L.ugb200_v210_to_p010le(ctypes.byref(d), 0, _stream(stream)), "ugb200_v210_to_p010le")
+    return out_y, out_c

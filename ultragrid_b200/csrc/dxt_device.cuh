@@ -1,0 +1,197 @@
+// DXT1 / DXT5-YCoCg 4x4 block encoders — device side.
+//
+// Arithmetic contract: bit-exact with UltraGrid's cuda_dxt/cuda_dxt.cu *as built by nvcc 12.9 for
+// sm_100a with default flags (--fmad=true)*.  ptxas contracts the reference's float expressions into
+// a specific FMA tree; that tree was read out of the reference cubin's SASS and is restated here with
+// explicit-rounding intrinsics (__fmaf_rn/__fmul_rn/__fadd_rn never re-contract), so the result does
+// not depend on what the optimiser does with *this* file.  Reference source lines are cited per step.
+//
+// What is new here (not in the reference): byte->float through a 2^23 "magic" word folded into the
+// first FMA (no I2F), float->int through magic adds (no F2I/FRND on the slow conversion pipe), a
+// fused UYVY loader (no 4:4:4 intermediate), 128-bit loads/stores, right-sized grids.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ugb {
+
+// ---- constants -------------------------------------------------------------------------------
+// 0.00392156862745f == 0x3B808081 == 8421505 * 2^-31          (cuda_dxt.cu:666-683)
+__device__ constexpr float kInv255 = 0.00392156862745f;
+// 2^23 + b  (b < 256) is exactly representable; fma(2^23 + b, kInv255, -(2^23*kInv255) - k) is
+// the single-rounded value of b*kInv255 - k, i.e. identical to fma(float(b), kInv255, -k).
+// 2^23*kInv255 = 8421505/256 exactly; the three biases below are all exactly representable.
+__device__ constexpr float kBiasRGB = -32896.50390625f;  // k = 0       -> fl(b * kInv255)
+__device__ constexpr float kBiasY   = -32896.56640625f;  // k = 0.0625  -> fma(b, kInv255, -0.0625)
+__device__ constexpr float kBiasC   = -32897.00390625f;  // k = 0.5     -> fma(b, kInv255, -0.5)
+
+__device__ constexpr float kRoundMagic = 12582912.0f;    // 1.5 * 2^23: x + M rounds x to nearest-even int
+__device__ constexpr float kFloorMagic = 8388608.0f;     // 2^23: (x + M) toward -inf == floor(x), x >= 0
+
+__device__ constexpr float kInv31 = 0.0322580645161f;    // cuda_dxt.cu:434
+__device__ constexpr float kInv63 = 0.015873015873f;     // cuda_dxt.cu:435
+
+/// 0x4B0000bb where bb is byte @p sel of @p w, i.e. the float 2^23 + bb.
+__device__ __forceinline__ float magic_byte(uint32_t w, unsigned sel)
+{
+        return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | sel));
+}
+
+/// saturate(a + b) in one instruction, never contracted with neighbours
+__device__ __forceinline__ float add_sat_rn(float a, float b)
+{
+        float d;
+        asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+        return d;
+}
+
+// ---- pixel loaders ---------------------------------------------------------------------------
+
+/// byte (already as 2^23+b magic float) -> unit-range sample, cuda_dxt.cu:666-683
+__device__ __forceinline__ float unit_from_magic(float m)
+{
+        return __fmaf_rn(m, kInv255, kBiasRGB);
+}
+
+/// YCbCr -> RGB of cuda_dxt.cu:444-451 as contracted by ptxas:
+///   Yf = fma(Y, 1/255, -0.0625); y = Yf * 1.1643
+///   u  = fma(U, 1/255, -0.5);    v = fma(V, 1/255, -0.5)
+///   R  = fma(v, 1.7926, y);  G = fma(v, -0.5328, fma(u, -0.2132, y));  B = fma(u, 2.1124, y)
+struct chroma_t {
+        float u, v;
+};
+__device__ __forceinline__ chroma_t chroma_from_magic(float mu, float mv)
+{
+        chroma_t c;
+        c.u = __fmaf_rn(mu, kInv255, kBiasC);
+        c.v = __fmaf_rn(mv, kInv255, kBiasC);
+        return c;
+}
+__device__ __forceinline__ void yuv_px_to_rgb(float my, chroma_t c, float &r, float &g, float &b)
+{
+        const float y = __fmul_rn(__fmaf_rn(my, kInv255, kBiasY), 1.1643f);
+        r = __fmaf_rn(c.v, 1.7926f, y);
+        g = __fmaf_rn(c.v, -0.5328f, __fmaf_rn(c.u, -0.2132f, y));
+        b = __fmaf_rn(c.u, 2.1124f, y);
+}
+
+/// One row (4 px) of a block from packed 3-byte pixels: three 32-bit words p0,p1,p2 (cuda_dxt.cu:661-683).
+template <bool YUV>
+__device__ __forceinline__ void load_row_packed3(uint32_t p0, uint32_t p1, uint32_t p2, float *r, float *g,
+                                                 float *b)
+{
+        const float m[12] = { magic_byte(p0, 0), magic_byte(p0, 1), magic_byte(p0, 2), magic_byte(p0, 3),
+                              magic_byte(p1, 0), magic_byte(p1, 1), magic_byte(p1, 2), magic_byte(p1, 3),
+                              magic_byte(p2, 0), magic_byte(p2, 1), magic_byte(p2, 2), magic_byte(p2, 3) };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+                if (YUV) {
+                        yuv_px_to_rgb(m[3 * i], chroma_from_magic(m[3 * i + 1], m[3 * i + 2]), r[i], g[i], b[i]);
+                } else {
+                        r[i] = unit_from_magic(m[3 * i]);
+                        g[i] = unit_from_magic(m[3 * i + 1]);
+                        b[i] = unit_from_magic(m[3 * i + 2]);
+                }
+        }
+}
+
+/// One row (4 px) of a block straight from UYVY: w0 = U0 Y0 V0 Y1, w1 = U1 Y2 V1 Y3.  Equals
+/// cuda_yuv422_to_yuv444 (chroma replication, cuda_dxt.cu:709-727) followed by the YUV loader above.
+__device__ __forceinline__ void load_row_uyvy(uint32_t w0, uint32_t w1, float *r, float *g, float *b)
+{
+        const chroma_t c0 = chroma_from_magic(magic_byte(w0, 0), magic_byte(w0, 2));
+        const chroma_t c1 = chroma_from_magic(magic_byte(w1, 0), magic_byte(w1, 2));
+        yuv_px_to_rgb(magic_byte(w0, 1), c0, r[0], g[0], b[0]);
+        yuv_px_to_rgb(magic_byte(w0, 3), c0, r[1], g[1], b[1]);
+        yuv_px_to_rgb(magic_byte(w1, 1), c1, r[2], g[2], b[2]);
+        yuv_px_to_rgb(magic_byte(w1, 3), c1, r[3], g[3], b[3]);
+}
+
+// ---- DXT1 --------------------------------------------------------------------------------------
+
+/// 5:6:5 endpoint quantiser of cuda_dxt.cu:424-440.  @returns the magic-biased integer
+/// (float bits 0x4B400000 + q) so that both the integer code and float(q) come out of full-rate adds.
+__device__ __forceinline__ float quant_magic(float v, float levels)
+{
+        return __fadd_rn(__fmul_rn(__saturatef(v), levels), kRoundMagic);
+}
+
+/// dxt_encode<1>, cuda_dxt.cu:512-617.
+__device__ __forceinline__ uint2 dxt1_encode(const float (&r)[16], const float (&g)[16], const float (&b)[16])
+{
+        // bounding box (:516-529) — min/max are order-independent
+        float mnr = r[0], mng = g[0], mnb = b[0], mxr = r[0], mxg = g[0], mxb = b[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+                mnr = fminf(mnr, r[i]);
+                mng = fminf(mng, g[i]);
+                mnb = fminf(mnb, b[i]);
+                mxr = fmaxf(mxr, r[i]);
+                mxg = fmaxf(mxg, g[i]);
+                mxb = fmaxf(mxb, b[i]);
+        }
+        // inset (:532-540): d = max - min; min' = fma(d, 1/16, min); max' = fma(d, -1/16, max)
+        const float dr = __fadd_rn(mxr, -mnr), dg = __fadd_rn(mxg, -mng), db = __fadd_rn(mxb, -mnb);
+        const float lor = __fmaf_rn(dr, 0.0625f, mnr), hir = __fmaf_rn(dr, -0.0625f, mxr);
+        const float log_ = __fmaf_rn(dg, 0.0625f, mng), hig = __fmaf_rn(dg, -0.0625f, mxg);
+        const float lob = __fmaf_rn(db, 0.0625f, mnb), hib = __fmaf_rn(db, -0.0625f, mxb);
+
+        // diagonal select (:543-560): (x - (lo+hi)*0.5) is fma(lo+hi, -0.5, x); cov accumulates
+        // sequentially i = 0..15 from +0 through FMAs
+        const float sr = __fadd_rn(lor, hir), sg = __fadd_rn(log_, hig), sb = __fadd_rn(lob, hib);
+        float covx = 0.0f, covy = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+                const float er = __fmaf_rn(sr, -0.5f, r[i]);
+                const float eg = __fmaf_rn(sg, -0.5f, g[i]);
+                const float eb = __fmaf_rn(sb, -0.5f, b[i]);
+                covx = __fmaf_rn(er, eb, covx);
+                covy = __fmaf_rn(eg, eb, covy);
+        }
+        const bool swr = covx < 0.0f, swg = covy < 0.0f;
+        const float maxr = swr ? lor : hir, minr = swr ? hir : lor;
+        const float maxg = swg ? log_ : hig, ming = swg ? hig : log_;
+
+        // endpoints (:563-572, :424-431)
+        const float qxr = quant_magic(maxr, 31.0f), qxg = quant_magic(maxg, 63.0f), qxb = quant_magic(hib, 31.0f);
+        const float qnr = quant_magic(minr, 31.0f), qng = quant_magic(ming, 63.0f), qnb = quant_magic(lob, 31.0f);
+        constexpr uint32_t kCodeBias = 0x4B400000u * 2081u;  // (1<<11) + (1<<5) + 1, mod 2^32
+        const uint32_t max_code = (__float_as_uint(qxr) << 11) + (__float_as_uint(qxg) << 5) + __float_as_uint(qxb) - kCodeBias;
+        const uint32_t min_code = (__float_as_uint(qnr) << 11) + (__float_as_uint(qng) << 5) + __float_as_uint(qnb) - kCodeBias;
+
+        uint32_t indices = 0;
+        if (max_code != min_code) {  // :576-602
+                // quantised endpoints back in unit range (:434-436); dir = min - max is contracted into
+                // fma(q_min, 1/31, -(q_max * 1/31))
+                const float ex_r = __fmul_rn(__fadd_rn(qxr, -kRoundMagic), kInv31);
+                const float ex_g = __fmul_rn(__fadd_rn(qxg, -kRoundMagic), kInv63);
+                const float ex_b = __fmul_rn(__fadd_rn(qxb, -kRoundMagic), kInv31);
+                const float dir_r = __fmaf_rn(__fadd_rn(qnr, -kRoundMagic), kInv31, -ex_r);
+                const float dir_g = __fmaf_rn(__fadd_rn(qng, -kRoundMagic), kInv63, -ex_g);
+                const float dir_b = __fmaf_rn(__fadd_rn(qnb, -kRoundMagic), kInv31, -ex_b);
+                const float len2 = __fmaf_rn(dir_b, dir_b, __fmaf_rn(dir_r, dir_r, __fmul_rn(dir_g, dir_g)));
+                const float inv = __fdividef(1.0f, len2);  // :584 — MUFU.RCP
+                const float tr = __fmul_rn(dir_r, inv), tg = __fmul_rn(dir_g, inv), tb = __fmul_rn(dir_b, inv);
+                const float nbias = -__fmaf_rn(ex_b, tb, __fmaf_rn(ex_r, tr, __fmul_rn(ex_g, tg)));
+                uint32_t acc = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {  // :591-601
+                        const float t = __fmaf_rn(b[i], tb, __fmaf_rn(r[i], tr, __fmul_rn(g[i], tg)));
+                        const float x = __fmaf_rn(add_sat_rn(t, nbias), 3.0f, 0.5f);
+                        // (u32)x truncates; x is in [0.5, 3.5] so floor == trunc
+                        acc += __float_as_uint(__fadd_rd(x, kFloorMagic)) << (2 * i);
+                }
+                constexpr uint32_t kIdxBias = 0x4B000000u * 0x55555555u;  // sum of (bias << 2i), mod 2^32
+                indices = acc - kIdxBias;
+        }
+        const bool swap_end = max_code < min_code;  // :568-572
+        if (swap_end) {
+                indices = ~indices;  // :605-607
+        }
+        const uint32_t lsbs = indices & 0x55555555u, msbs = indices & 0xaaaaaaaau;  // :611-613
+        indices = msbs ^ (2 * lsbs + (msbs >> 1));
+        const uint32_t palette = swap_end ? min_code + (max_code << 16) : max_code + (min_code << 16);
+        return make_uint2(palette, indices);
+}
+
+}  // namespace ugb

@@ -1,0 +1,440 @@
+// Whole-buffer pixel-format line converters: the device form of UltraGrid's decoder_t line functions
+// (src/pixfmt_conv.c, table :3041-3103) looped over rows as tools/convert.cpp:148-152 does.
+//
+// Every converter is a pure streaming kernel (HBM-bound): a thread owns one "chunk" of a row whose
+// input and output sizes are both multiples of 16 bytes, reads it with 128-bit loads, converts in
+// registers, writes 128-bit stores.  Chunks that straddle the end of a row (or unaligned buffers)
+// take a byte-granular guarded path inside the same kernel, so edge semantics (how many bytes of
+// dst_len each reference loop really writes) are preserved exactly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ugb200.h"
+#include "color_space.h"
+
+namespace ugb {
+
+struct conv_params {
+        int rshift, gshift, bshift;
+        int aux;  // converter-specific, computed on the host from dst_len (see conv_rgba_rgb)
+};
+/// where a chunk sits, for the rare converter whose result depends on more than its own chunk
+struct row_ctx {
+        const uint8_t *src;  // buffer start
+        long row_abs;        // byte offset of this row in src
+        long src_total;      // readable bytes
+        int cx;              // chunk index within the row
+};
+
+// byte k (compile-time) of a packed word array
+template <int K>
+__device__ __forceinline__ uint32_t gb(const uint32_t *a)
+{
+        return (a[K >> 2] >> (8 * (K & 3))) & 0xffu;
+}
+__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3)
+{
+        return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+
+// ---- converters ----------------------------------------------------------------------------------
+// Each declares IN/OUT bytes per chunk, out_len(dst_len) = number of bytes the reference loop writes
+// for a given dst_len, and run().
+
+/// vc_copylinev210, pixfmt_conv.c:86-130: drop the 2 LSBs of each 10-bit sample; 16 B (6 px) -> 12 B
+struct conv_v210_uyvy {
+        static constexpr int IN = 64, OUT = 48;
+        static __host__ int out_len(int dst_len)
+        {
+                const int rem = dst_len % 12;
+                return dst_len - rem + (rem >= 4 ? 4 : 0) + (rem >= 8 ? 4 : 0);  // :118-129
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                        const uint32_t w0 = in[4 * g], w1 = in[4 * g + 1], w2 = in[4 * g + 2], w3 = in[4 * g + 3];
+#define S8(w, sh) (((w) >> ((sh) + 2)) & 0xffu)
+                        out[3 * g + 0] = pack4(S8(w0, 0), S8(w0, 10), S8(w0, 20), S8(w1, 0));
+                        out[3 * g + 1] = pack4(S8(w1, 10), S8(w1, 20), S8(w2, 0), S8(w2, 10));
+                        out[3 * g + 2] = pack4(S8(w2, 20), S8(w3, 0), S8(w3, 10), S8(w3, 20));
+#undef S8
+                }
+        }
+};
+
+/// vc_copylineYUYV, pixfmt_conv.c:136-198 (same byte swap both directions)
+struct conv_yuyv_uyvy {
+        static constexpr int IN = 16, OUT = 16;
+        static __host__ int out_len(int dst_len) { return dst_len / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        out[i] = __byte_perm(in[i], 0, 0x2301);
+                }
+        }
+};
+
+/// copylineYUVtoRGB (pixfmt_conv.c:1065-1094) via vc_copylineUYVYtoRGB (:1102-1108) / YUYVtoRGB (:1116-1122)
+template <int Y1, int Y2, int U, int V>
+struct conv_yuv422_rgb {
+        static constexpr int IN = 32, OUT = 48;
+        static __host__ int out_len(int dst_len) { return dst_len < 6 ? 0 : dst_len / 6 * 6; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(8);
+                uint32_t o[48];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                        const uint32_t w = in[i];
+                        const int y1 = c.y_scale * ((int) ((w >> (8 * Y1)) & 0xff) - 16);
+                        const int y2 = c.y_scale * ((int) ((w >> (8 * Y2)) & 0xff) - 16);
+                        const int u = (int) ((w >> (8 * U)) & 0xff) - 128;
+                        const int v = (int) ((w >> (8 * V)) & 0xff) - 128;
+                        const int rc = v * c.r_cr, gc = u * c.g_cb + v * c.g_cr, bc = u * c.b_cb;
+                        o[6 * i + 0] = clamp255((y1 + rc) >> COMP_BASE);
+                        o[6 * i + 1] = clamp255((y1 + gc) >> COMP_BASE);
+                        o[6 * i + 2] = clamp255((y1 + bc) >> COMP_BASE);
+                        o[6 * i + 3] = clamp255((y2 + rc) >> COMP_BASE);
+                        o[6 * i + 4] = clamp255((y2 + gc) >> COMP_BASE);
+                        o[6 * i + 5] = clamp255((y2 + bc) >> COMP_BASE);
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                        out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+        }
+};
+
+/// vc_copylineUYVYtoRGBA, pixfmt_conv.c:1137-1163 — the one double-precision matrix on the CPU path:
+/// products and sums in IEEE double (no contraction: the reference is built without -mfma), truncation
+/// toward zero, clamp 0..255, packed with runtime shifts + alpha mask.
+struct conv_uyvy_rgba {
+        static constexpr int IN = 16, OUT = 32;
+        static __host__ int out_len(int dst_len) { return dst_len < 8 ? 0 : dst_len / 8 * 8; }
+        static __device__ __forceinline__ uint32_t px(int y, int u, int v, const conv_params &p, uint32_t amask)
+        {
+                const double yy = __dmul_rn(1.164, (double) (y - 16));
+                const double dv = (double) (v - 128), du = (double) (u - 128);
+                const int r = clamp255((int) __dadd_rn(yy, __dmul_rn(1.793, dv)));
+                const int g = clamp255((int) __dadd_rn(__dadd_rn(yy, -__dmul_rn(0.534, dv)), -__dmul_rn(0.213, du)));
+                const int b = clamp255((int) __dadd_rn(yy, __dmul_rn(2.115, du)));
+                return amask | (uint32_t) r << p.rshift | (uint32_t) g << p.gshift | (uint32_t) b << p.bshift;
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+                const uint32_t amask = 0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        const uint32_t w = in[i];
+                        const int u = w & 0xff, y1 = (w >> 8) & 0xff, v = (w >> 16) & 0xff, y2 = w >> 24;
+                        out[2 * i] = px(y1, u, v, p, amask);
+                        out[2 * i + 1] = px(y2, u, v, p, amask);
+                }
+        }
+};
+
+/// vc_copylineToUYVY, pixfmt_conv.c:1008-1053: RGB-like (ROFF/GOFF/BOFF within PIX bytes) -> UYVY.
+/// y = (RGB_TO_Y >> 14) + 16 unclamped; chroma = ((cb0 + cb1) / 2 >> 14) + 128 with C '/' truncation;
+/// bytes stored & 0xFF.  Used by RGB (:2061), BGR (:2271), RGBA (:2316), RG48 (:2343, high bytes).
+template <int ROFF, int GOFF, int BOFF, int PIX>
+struct conv_to_uyvy {
+        static constexpr int NPX = 16 / (PIX == 3 ? 1 : PIX == 4 ? 2 : 2);  // 16, 8 (RGBA), 8 (RG48)
+        static constexpr int IN = NPX * PIX, OUT = NPX * 2;
+        static __host__ int out_len(int dst_len) { return (dst_len + 3) / 4 * 4; }  // count = (dst_len+3)/4 words, :1045
+        template <int K>
+        static __device__ __forceinline__ void pair(const uint32_t *in, uint32_t *out)
+        {
+                constexpr color_coeffs c = coeffs_709(8);
+                constexpr int P0 = 2 * K * PIX, P1 = P0 + PIX;
+                const int r0 = gb<P0 + ROFF>(in), g0 = gb<P0 + GOFF>(in), b0 = gb<P0 + BOFF>(in);
+                const int r1 = gb<P1 + ROFF>(in), g1 = gb<P1 + GOFF>(in), b1 = gb<P1 + BOFF>(in);
+                const int y1 = ((r0 * c.y_r + g0 * c.y_g + b0 * c.y_b) >> COMP_BASE) + 16;
+                const int y2 = ((r1 * c.y_r + g1 * c.y_g + b1 * c.y_b) >> COMP_BASE) + 16;
+                int u = (r0 * c.cb_r + g0 * c.cb_g + b0 * c.cb_b) + (r1 * c.cb_r + g1 * c.cb_g + b1 * c.cb_b);
+                int v = (r0 * c.cr_r + g0 * c.cr_g + b0 * c.cr_b) + (r1 * c.cr_r + g1 * c.cr_g + b1 * c.cr_b);
+                u = ((u / 2) >> COMP_BASE) + 128;
+                v = ((v / 2) >> COMP_BASE) + 128;
+                out[K] = pack4(u & 0xff, y1 & 0xff, v & 0xff, y2 & 0xff);
+        }
+        template <int K>
+        static __device__ __forceinline__ void pairs(const uint32_t *in, uint32_t *out)
+        {
+                if constexpr (K < NPX / 2) {
+                        pair<K>(in, out);
+                        pairs<K + 1>(in, out);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &) { pairs<0>(in, out); }
+};
+
+/// vc_copylineRGBtoRGBA, pixfmt_conv.c:944-990
+struct conv_rgb_rgba {
+        static constexpr int IN = 48, OUT = 64;
+        static __host__ int out_len(int dst_len) { return dst_len < 4 ? 0 : dst_len / 4 * 4; }
+        template <int K>
+        static __device__ __forceinline__ void px(const uint32_t *in, uint32_t *out, const conv_params &p, uint32_t amask)
+        {
+                if constexpr (K < 16) {
+                        out[K] = amask | gb<3 * K>(in) << p.rshift | gb<3 * K + 1>(in) << p.gshift | gb<3 * K + 2>(in) << p.bshift;
+                        px<K + 1>(in, out, p, amask);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+                const uint32_t amask = 0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift);
+                px<0>(in, out, p, amask);
+        }
+};
+
+/// vc_copylineRGBAtoRGB, pixfmt_conv.c:866-900 (SSSE3 build, which is what tools/Makefile and oracle/_ref build).
+/// QUIRK reproduced for bit-exactness: the scalar tail loop (:889-895) never advances `src`, so every pixel from
+/// the end of the pshufb loop (x <= dst_len - 24) on repeats the first tail pixel.  p.aux = first tail pixel.
+struct conv_rgba_rgb {
+        static constexpr int IN = 64, OUT = 48;
+        static __host__ int out_len(int dst_len) { return dst_len < 3 ? 0 : dst_len / 3 * 3; }
+        static __host__ int aux(int dst_len) { return dst_len >= 24 ? ((dst_len - 24) / 12 + 1) * 4 : 0; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &rc)
+        {
+                uint32_t tail = 0;
+                if ((rc.cx + 1) * 16 > p.aux) {  // this chunk reaches into the tail
+                        const long a = rc.row_abs + 4L * p.aux;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                                if (a + k < rc.src_total) {
+                                        tail |= (uint32_t) rc.src[a + k] << (8 * k);
+                                }
+                        }
+                }
+                uint32_t o[48];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                        const uint32_t w = rc.cx * 16 + i >= p.aux ? tail : in[i];
+                        o[3 * i] = w & 0xff;
+                        o[3 * i + 1] = (w >> 8) & 0xff;
+                        o[3 * i + 2] = (w >> 16) & 0xff;
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                        out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+        }
+};
+
+/// vc_copylineRGBA, pixfmt_conv.c:538-589: re-shift an RGBA word, alpha forced to 0xFF in the unused byte.
+/// (With default shifts the reference does a memcpy of `len` bytes; the launcher handles that case.)
+struct conv_rgba_rgba {
+        static constexpr int IN = 16, OUT = 16;
+        static __host__ int out_len(int dst_len) { return dst_len < 4 ? 0 : dst_len / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+                const uint32_t amask = 0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        const uint32_t t = in[i];
+                        out[i] = amask | (t & 0xff) << p.rshift | ((t >> 8) & 0xff) << p.gshift | ((t >> 16) & 0xff) << p.bshift;
+                }
+        }
+};
+
+/// vc_copylineRGB, pixfmt_conv.c:732-753 (colour order change through shifts; default shifts = memcpy)
+/// and vc_copylineBGRtoRGB (rshift 16, gshift 8, bshift 0).
+struct conv_rgb_rgb {
+        static constexpr int IN = 48, OUT = 48;
+        static __host__ int out_len(int dst_len) { return dst_len < 3 ? 0 : dst_len / 3 * 3; }
+        template <int K>
+        static __device__ __forceinline__ void px(const uint32_t *in, uint32_t *o, const conv_params &p)
+        {
+                if constexpr (K < 16) {
+                        const uint32_t w = gb<3 * K>(in) << p.rshift | gb<3 * K + 1>(in) << p.gshift | gb<3 * K + 2>(in) << p.bshift;
+                        o[3 * K] = w & 0xff, o[3 * K + 1] = (w >> 8) & 0xff, o[3 * K + 2] = (w >> 16) & 0xff;
+                        px<K + 1>(in, o, p);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+                uint32_t o[48];
+                px<0>(in, o, p);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                        out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+        }
+};
+
+// ---- generic kernel ------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ dst, long dst_pitch, const uint8_t *__restrict__ src,
+                                                        long src_pitch, int wlen, int height, long src_total, bool vec_ok,
+                                                        conv_params p)
+{
+        constexpr int NI = C::IN / 4, NO = C::OUT / 4;
+        const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+        const long out_off = (long) cx * C::OUT;
+        if (out_off >= wlen) {
+                return;
+        }
+        const long in_off = (long) cx * C::IN;
+        for (int row = blockIdx.y; row < height; row += gridDim.y) {
+                const long in_abs = row * src_pitch + in_off;
+                uint32_t in[NI], out[NO];
+                if (vec_ok && in_abs + C::IN <= src_total) {
+                        const uint4 *s = (const uint4 *) (src + in_abs);
+#pragma unroll
+                        for (int i = 0; i < NI / 4; ++i) {
+                                uint4 v;
+                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                             : "l"(s + i));
+                                in[4 * i] = v.x, in[4 * i + 1] = v.y, in[4 * i + 2] = v.z, in[4 * i + 3] = v.w;
+                        }
+                } else {
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) {
+                                uint32_t w = 0;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                        const long a = in_abs + 4 * i + k;
+                                        if (a < src_total) {
+                                                w |= (uint32_t) src[a] << (8 * k);
+                                        }
+                                }
+                                in[i] = w;
+                        }
+                }
+                const row_ctx rc = { src, row * src_pitch, src_total, cx };
+                C::run(in, out, p, rc);
+                uint8_t *d = dst + row * dst_pitch + out_off;
+                if (vec_ok && out_off + C::OUT <= wlen) {
+#pragma unroll
+                        for (int i = 0; i < NO / 4; ++i) {
+                                ((uint4 *) d)[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                        }
+                } else {
+#pragma unroll
+                        for (int i = 0; i < NO; ++i) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                        if (out_off + 4 * i + k < wlen) {
+                                                d[4 * i + k] = (uint8_t) (out[i] >> (8 * k));
+                                        }
+                                }
+                        }
+                }
+        }
+}
+
+template <class C>
+static int launch_line(void *dst, long dst_pitch, const void *src, long src_pitch, int dst_len, int height, long src_size,
+                       conv_params p, cudaStream_t s)
+{
+        const int wlen = C::out_len(dst_len);
+        if (wlen <= 0 || height <= 0) {
+                return 0;
+        }
+        if (src_size <= 0) {
+                src_size = src_pitch * height;
+        }
+        const bool vec_ok = !(15 & (size_t) dst) && !(15 & (size_t) src) && !(dst_pitch & 15) && !(src_pitch & 15);
+        const int chunks = (wlen + C::OUT - 1) / C::OUT;
+        const int threads = 128;
+        dim3 grid((chunks + threads - 1) / threads, height > 65535 ? 65535 : height);
+        line_conv_kernel<C><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height,
+                                                     src_size, vec_ok, p);
+        return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+static int copy_rows(void *dst, long dst_pitch, const void *src, long src_pitch, int len, int height, cudaStream_t s)
+{
+        if (len <= 0 || height <= 0) {
+                return 0;
+        }
+        return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, len, height, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace ugb
+
+using namespace ugb;
+
+extern "C" UGB_API int ugb200_pixfmt_supported(int in_codec, int out_codec)
+{
+        if (in_codec == out_codec && out_codec != UGB_RGBA && out_codec != UGB_RGB) {
+                return in_codec > UGB_VIDEO_CODEC_NONE && in_codec < UGB_VIDEO_CODEC_COUNT;  // vc_memcpy, pixfmt_conv.c:3111-3114
+        }
+        switch (in_codec * 256 + out_codec) {
+        case UGB_v210 * 256 + UGB_UYVY:
+        case UGB_YUYV * 256 + UGB_UYVY:
+        case UGB_UYVY * 256 + UGB_YUYV:
+        case UGB_UYVY * 256 + UGB_RGB:
+        case UGB_YUYV * 256 + UGB_RGB:
+        case UGB_UYVY * 256 + UGB_RGBA:
+        case UGB_RGB * 256 + UGB_UYVY:
+        case UGB_BGR * 256 + UGB_UYVY:
+        case UGB_RGBA * 256 + UGB_UYVY:
+        case UGB_RG48 * 256 + UGB_UYVY:
+        case UGB_RGB * 256 + UGB_RGBA:
+        case UGB_RGBA * 256 + UGB_RGB:
+        case UGB_RGBA * 256 + UGB_RGBA:
+        case UGB_RGB * 256 + UGB_RGB:
+        case UGB_BGR * 256 + UGB_RGB:
+                return 1;
+        }
+        return 0;
+}
+
+extern "C" UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *dst, long dst_pitch, const void *src, long src_pitch,
+                                     int dst_len, int height, long src_size, int rshift, int gshift, int bshift,
+                                     cuda_wrapper_stream_t stream)
+{
+        cudaStream_t s = (cudaStream_t) stream;
+        const conv_params p = { rshift, gshift, bshift, 0 };
+        if (dst == nullptr || src == nullptr || dst_len < 0 || height < 0) {
+                return -1;
+        }
+        if (in_codec == out_codec && out_codec != UGB_RGBA && out_codec != UGB_RGB) {
+                return copy_rows(dst, dst_pitch, src, src_pitch, dst_len, height, s);  // vc_memcpy (pixfmt_conv.c:2529-2536)
+        }
+        const bool dfl_shift = rshift == 0 && gshift == 8 && bshift == 16;
+        switch (in_codec * 256 + out_codec) {
+        case UGB_v210 * 256 + UGB_UYVY:
+                return launch_line<conv_v210_uyvy>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_YUYV * 256 + UGB_UYVY:
+        case UGB_UYVY * 256 + UGB_YUYV:
+                return launch_line<conv_yuyv_uyvy>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_UYVY * 256 + UGB_RGB:
+                return launch_line<conv_yuv422_rgb<1, 3, 0, 2>>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_YUYV * 256 + UGB_RGB:
+                return launch_line<conv_yuv422_rgb<0, 2, 1, 3>>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_UYVY * 256 + UGB_RGBA:
+                return launch_line<conv_uyvy_rgba>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_RGB * 256 + UGB_UYVY:
+                return launch_line<conv_to_uyvy<0, 1, 2, 3>>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_BGR * 256 + UGB_UYVY:
+                return launch_line<conv_to_uyvy<2, 1, 0, 3>>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_RGBA * 256 + UGB_UYVY:
+                return launch_line<conv_to_uyvy<0, 1, 2, 4>>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_RG48 * 256 + UGB_UYVY:
+                return launch_line<conv_to_uyvy<1, 3, 5, 6>>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_RGB * 256 + UGB_RGBA:
+                return launch_line<conv_rgb_rgba>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_RGBA * 256 + UGB_RGB:
+                return launch_line<conv_rgba_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, conv_params{ 0, 8, 16, conv_rgba_rgb::aux(dst_len) }, s);
+        case UGB_RGBA * 256 + UGB_RGBA:
+                if (dfl_shift) {
+                        return copy_rows(dst, dst_pitch, src, src_pitch, dst_len, height, s);  // pixfmt_conv.c:546-547
+                }
+                return launch_line<conv_rgba_rgba>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_RGB * 256 + UGB_RGB:
+                if (dfl_shift) {
+                        return copy_rows(dst, dst_pitch, src, src_pitch, dst_len, height, s);  // pixfmt_conv.c:740-741
+                }
+                return launch_line<conv_rgb_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_BGR * 256 + UGB_RGB: {
+                const conv_params q = { 16, 8, 0, 0 };  // vc_copylineBGRtoRGB
+                return launch_line<conv_rgb_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, q, s);
+        }
+        }
+        return -4;  // no decoder (get_decoder_from_to() == NULL, pixfmt_conv.c:3122-3124)
+}
