@@ -85,8 +85,106 @@ static void dxt1_block(const float *r, const float *g, const float *b, uint32_t 
         out[1] = indices;
 }
 
+/* dxt_encode<6> (DXT5-YCoCg), cuda_dxt.cu:471-509 with helpers :141-410, as compiled (see dxt6_device.cuh).
+ * Everything here is IEEE single/double with explicit fma, so this restatement is bit-exact with the GPU. */
+static uint32_t roundu(float x) { return (uint32_t) roundf(x); } /* CUDA roundf + (u32): trunc(add.rz(x, .5)), x >= 0 */
+static float satadd(float a, float b) { return sat(a + b); }
+static void dxt6_block(const float *r, const float *g, const float *b, uint32_t out[4])
+{
+        const float off = 0.50196081399917602539f; /* (float)(128.0/255.0), :139 */
+        const double offd = (double) off;
+        float Y[16], Co[16], Cg[16];
+        for (int i = 0; i < 16; ++i) { /* :141-148, double sub-expressions */
+                const double dr = r[i], dg = g[i], db = b[i], g2 = dg + dg;
+                Y[i] = (float) (((dr + g2) + db) * 0.25);
+                Co[i] = (float) fma((dr + dr) - (db + db), 0.25, offd);
+                Cg[i] = (float) fma((-dr + g2) - db, 0.25, offd);
+        }
+        float mnY = Y[0], mxY = Y[0], mnCo = Co[0], mxCo = Co[0], mnCg = Cg[0], mxCg = Cg[0];
+        for (int i = 1; i < 16; ++i) {
+                mnY = fminf(mnY, Y[i]), mxY = fmaxf(mxY, Y[i]);
+                mnCo = fminf(mnCo, Co[i]), mxCo = fmaxf(mxCo, Co[i]);
+                mnCg = fminf(mnCg, Cg[i]), mxCg = fmaxf(mxCg, Cg[i]);
+        }
+        const float sCo = mnCo + mxCo, sCg = mnCg + mxCg; /* :260-270 */
+        float cov = 0.f;
+        for (int i = 0; i < 16; ++i) {
+                cov = fmaf(fmaf(sCo, -0.5f, Co[i]), fmaf(sCg, -0.5f, Cg[i]), cov);
+        }
+        if (cov < 0.f) {
+                const float t = mxCg;
+                mxCg = mnCg, mnCg = t;
+        }
+        const float eXo = mxCo - off, eXg = mxCg - off, eNo = mnCo - off, eNg = mnCg - off; /* :241-258 */
+        const float m = fmaxf(fmaxf(fabsf(eNo), fabsf(eNg)), fmaxf(fabsf(eXo), fabsf(eXg)));
+        uint32_t scale = 1;
+        if (m < (float) (64.0 / 255.0)) {
+                scale = 2;
+        }
+        if (m < (float) (32.0 / 255.0)) {
+                scale = 4;
+        }
+        const float fs = (float) scale, inv_s = 1.0f / fs;
+        const float sXo = fmaf(eXo, fs, off), sXg = fmaf(eXg, fs, off), sNo = fmaf(eNo, fs, off), sNg = fmaf(eNg, fs, off); /* :279-280 */
+        const float kIns = (float) ((8.0 / 255.0) / 16.0); /* :184 */
+        const float insO = fmaf(sXo - sNo, 0.0625f, -kIns), insG = fmaf(sXg - sNg, 0.0625f, -kIns);
+        const float cXo = satadd(sXo, -insO), cXg = satadd(sXg, -insG), cNo = satadd(sNo, insO), cNg = satadd(sNg, insG);
+        const uint32_t qXo = roundu(cXo * 31.f), qXg = roundu(cXg * 63.f), qNo = roundu(cNo * 31.f), qNg = roundu(cNg * 63.f); /* :284-288 */
+        out[2] = ((qXo << 11) | (qXg << 5) | (scale - 1)) | (((qNo << 11) | (qNg << 5) | (scale - 1)) << 16); /* :291-312 */
+        const float k255 = (float) (1.0 / 255.0);
+#define EXPAND(e) fmaf(fmaf((float) (e), k255, -off), inv_s, off) /* :294-304 */
+        const float pXo = EXPAND((qXo << 3) | (qXo >> 2)), pXg = EXPAND((qXg << 2) | (qXg >> 4));
+        const float pNo = EXPAND((qNo << 3) | (qNo >> 2)), pNg = EXPAND((qNg << 2) | (qNg >> 4));
+#undef EXPAND
+        const float q13 = (float) (1.0 / 3.0), q23 = (float) (2.0 / 3.0); /* :321-322 */
+        const float c2o = fmaf(pNo, q13, pXo * (1.0f - q13)), c2g = fmaf(pXg, 1.0f - q13, pNg * q13);
+        const float c3o = fmaf(pXo, 1.0f - q23, pNo * q23), c3g = fmaf(pXg, 1.0f - q23, pNg * q23);
+        uint32_t cidx = 0;
+        for (int i = 0; i < 16; ++i) { /* :326-344 */
+#define DIST(co, cg) fmaf(Co[i] - (co), Co[i] - (co), (Cg[i] - (cg)) * (Cg[i] - (cg)))
+                const float d0 = DIST(pXo, pXg), d1 = DIST(pNo, pNg), d2 = DIST(c2o, c2g), d3 = DIST(c3o, c3g);
+#undef DIST
+                const uint32_t bx = d0 > d3, by = d1 > d2, bz = d0 > d2, bw = d1 > d3, b4 = d2 > d3;
+                cidx |= ((bx & b4) | (((by & bz) | (bx & bw)) << 1)) << (2 * i);
+        }
+        out[3] = cidx;
+        const float insY = (float) fma((double) (mxY - mnY), 1.0 / 32.0, -((16.0 / 255.0) / 32.0)); /* :176-181 */
+        const float nY = satadd(mnY, insY), xY = satadd(mxY, -insY);
+        const uint32_t a0 = roundu(nY * 255.f), a1 = roundu(xY * 255.f); /* :350-357 */
+        const float mid = (xY - nY) / 14.0f;                           /* :364 */
+        const double dX = xY, dN = nY, dM = mid, k7 = 1.0 / 7.0;
+        float ab[7];
+        ab[0] = nY + mid;
+        ab[1] = (float) fma(fma(dX, 6.0, dN), k7, dM);
+        ab[2] = (float) fma(fma(dX, 5.0, dN + dN), k7, dM);
+        ab[3] = (float) fma(fma(dX, 4.0, dN * 3.0), k7, dM);
+        ab[4] = (float) fma(fma(dX, 3.0, dN * 4.0), k7, dM);
+        ab[5] = (float) fma(fma(dX, 2.0, dN * 5.0), k7, dM);
+        ab[6] = (float) fma(fma(dN, 6.0, dX), k7, dM);
+        uint32_t ix = 0, iy = 0;
+        for (int i = 0; i < 16; ++i) { /* :374-407 */
+                uint32_t idx = 1;
+                for (int k = 0; k < 7; ++k) {
+                        idx += Y[i] <= ab[k];
+                }
+                idx &= 7u;
+                idx ^= (2u > idx);
+                if (i < 6) {
+                        ix |= idx << (3 * i + 16);
+                }
+                if (i == 5) {
+                        iy = idx >> 1;
+                }
+                if (i > 5) {
+                        iy |= idx << (3 * i - 16);
+                }
+        }
+        out[0] = (a0 << 8) | a1 | ix;
+        out[1] = iy;
+}
+
 /* dxt_kernel + dxt_launch, cuda_dxt.cu:622-760: packed 3-byte source, negative size_y = bottom-up */
-static int dxt1_packed3(const uint8_t *src, uint32_t *out, int sx, int sy, int yuv)
+static int dxt_packed3(const uint8_t *src, uint32_t *out, int sx, int sy, int yuv, int type)
 {
         int mirrored = 0;
         if (sy < 0) {
@@ -113,13 +211,19 @@ static int dxt1_packed3(const uint8_t *src, uint32_t *out, int sx, int sy, int y
                                         }
                                 }
                         }
-                        dxt1_block(r, g, b, out + 2 * ((size_t) by * (sx / 4) + bx));
+                        if (type == 1) {
+                                dxt1_block(r, g, b, out + 2 * ((size_t) by * (sx / 4) + bx));
+                        } else {
+                                dxt6_block(r, g, b, out + 4 * ((size_t) by * (sx / 4) + bx));
+                        }
                 }
         }
         return 0;
 }
-API int orc_rgb_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy) { return dxt1_packed3(src, out, sx, sy, 0); }
-API int orc_yuv_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy) { return dxt1_packed3(src, out, sx, sy, 1); }
+API int orc_rgb_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy) { return dxt_packed3(src, out, sx, sy, 0, 1); }
+API int orc_yuv_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy) { return dxt_packed3(src, out, sx, sy, 1, 1); }
+API int orc_rgb_to_dxt6(const uint8_t *src, uint32_t *out, int sx, int sy) { return dxt_packed3(src, out, sx, sy, 0, 6); }
+API int orc_yuv_to_dxt6(const uint8_t *src, uint32_t *out, int sx, int sy) { return dxt_packed3(src, out, sx, sy, 1, 6); }
 
 /* yuv422_to_yuv444_kernel, cuda_dxt.cu:697-732: chroma replication */
 API void orc_yuv422_to_yuv444(const uint8_t *src, uint8_t *out, int pix_count)
@@ -131,7 +235,7 @@ API void orc_yuv422_to_yuv444(const uint8_t *src, uint8_t *out, int pix_count)
 }
 
 /* the pair run by src/video_compress/cuda_dxt.cpp:223-257 for UYVY input: 422->444 then yuv_to_dxt1 */
-API int orc_uyvy_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy, long pitch)
+static int uyvy_to_dxt(const uint8_t *src, uint32_t *out, int sx, int sy, long pitch, int type)
 {
         int mirrored = 0;
         if (sy < 0) {
@@ -158,11 +262,17 @@ API int orc_uyvy_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy, long
                                         yuv_px(q[1 + 2 * (x & 1)], q[0], q[2], &r[4 * y + x], &g[4 * y + x], &b[4 * y + x]);
                                 }
                         }
-                        dxt1_block(r, g, b, out + 2 * ((size_t) by * (sx / 4) + bx));
+                        if (type == 1) {
+                                dxt1_block(r, g, b, out + 2 * ((size_t) by * (sx / 4) + bx));
+                        } else {
+                                dxt6_block(r, g, b, out + 4 * ((size_t) by * (sx / 4) + bx));
+                        }
                 }
         }
         return 0;
 }
+API int orc_uyvy_to_dxt1(const uint8_t *src, uint32_t *out, int sx, int sy, long pitch) { return uyvy_to_dxt(src, out, sx, sy, pitch, 1); }
+API int orc_uyvy_to_dxt6(const uint8_t *src, uint32_t *out, int sx, int sy, long pitch) { return uyvy_to_dxt(src, out, sx, sy, pitch, 6); }
 
 /* DXT1 block decoder (S3TC, 4-colour mode) — used only to sanity-check that encoded blocks reproduce the
  * image (PSNR), never for bit-exact comparisons. */

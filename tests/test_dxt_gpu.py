@@ -83,14 +83,50 @@ def make_packed3(kind, w, h, seed=1):
     return special_blocks_rgb(w, h, seed)
 
 
-@pytest.mark.parametrize("name", ["cuda_rgb_to_dxt1", "cuda_yuv_to_dxt1"])
+@pytest.mark.parametrize("name", ["cuda_rgb_to_dxt1", "cuda_yuv_to_dxt1", "cuda_rgb_to_dxt6", "cuda_yuv_to_dxt6"])
 @pytest.mark.parametrize("kind", FRAMES)
 @pytest.mark.parametrize("w,h", [(4, 4), (64, 36), (1920, 1080), (3840, 2160), (1924, -1080), (200, -52)])
 def test_packed3_bit_exact_vs_reference_kernel(api, ref, name, kind, w, h):
     src = dev(make_packed3(kind, w, abs(h), seed=w + abs(h)))
     mine = api.compat_to_dxt(name, src, w, h)
-    theirs = ref_dxt(ref, name, src, w, h)
+    theirs = ref_dxt(ref, name, src, w, h, dxt_type=1 if name.endswith("1") else 6)
+    if not torch.equal(mine, theirs):
+        a, b = mine.cpu().numpy().view(np.uint32), theirs.cpu().numpy().view(np.uint32)
+        nw = 2 if name.endswith("1") else 4
+        bad = np.nonzero((a.reshape(-1, nw) != b.reshape(-1, nw)).any(axis=1))[0]
+        words = (a.reshape(-1, nw) != b.reshape(-1, nw)).sum(axis=0)
+        pytest.fail(f"{len(bad)} of {len(a) // nw} blocks differ; per-word mismatch counts {words.tolist()}; first {bad[:5].tolist()}: "
+                    f"mine {a.reshape(-1, nw)[bad[0]].tolist()} ref {b.reshape(-1, nw)[bad[0]].tolist()}")
+
+
+@pytest.mark.parametrize("kind", FRAMES)
+@pytest.mark.parametrize("w,h", [(8, 4), (36, 20), (1920, 1080), (7680, 4320), (3844, -2160)])
+def test_fused_uyvy_dxt6_equals_reference_pipeline(api, ref, orc, kind, w, h):
+    """config 5: UYVY -> DXT5-YCoCg; reference path = cuda_yuv422_to_yuv444 + cuda_yuv_to_dxt6"""
+    ah = abs(h)
+    if kind == "testcard":
+        uyvy = util.testcard_uyvy(w, ah, orc)
+    elif kind == "noise":
+        uyvy = util.rng_bytes(w * ah * 2, 199 + w)
+    else:
+        uyvy = util.convert_cpu(orc, "orc_convert", 12, 2, special_blocks_rgb(w, ah, 6), w, ah)
+    e = np.zeros(w * ah * 3, dtype=np.uint8)
+    orc.orc_yuv422_to_yuv444(uyvy.ctypes.data, e.ctypes.data, w * ah)
+    theirs = ref_dxt(ref, "cuda_yuv_to_dxt6", dev(e), w, h, dxt_type=6)
+    mine = api.uyvy_to_dxt(dev(uyvy), w, h, dxt_type=6)
     assert torch.equal(mine, theirs)
+
+
+def test_cpu_oracle_dxt6_is_bit_exact(ref, orc):
+    """DXT5-YCoCg has no approximate instruction on its path: oracle/dxt_oracle.c must equal the reference kernel exactly"""
+    w, h = 512, 256
+    for name, fn, kind in (("cuda_rgb_to_dxt6", "orc_rgb_to_dxt6", "noise"), ("cuda_yuv_to_dxt6", "orc_yuv_to_dxt6", "noise"),
+                           ("cuda_rgb_to_dxt6", "orc_rgb_to_dxt6", "special"), ("cuda_rgb_to_dxt6", "orc_rgb_to_dxt6", "testcard")):
+        src = make_packed3(kind, w, h, seed=21)
+        theirs = ref_dxt(ref, name, dev(src), w, h, dxt_type=6).cpu().numpy().view(np.uint32)
+        mine = np.zeros(w * h // 16 * 4, dtype=np.uint32)
+        assert getattr(orc, fn)(src.ctypes.data, mine.ctypes.data, w, h) == 0
+        assert np.array_equal(mine, theirs), (name, kind)
 
 
 @pytest.mark.parametrize("kind", FRAMES)

@@ -116,9 +116,10 @@ def oracle():
     L.orc_get_color_coeffs.argtypes = [_i, _i, _vp]
     L.orc_v210_to_p010le.argtypes = [_i, _i, _vp, _u, _vp, _u, _vp]
     L.orc_v210_to_p010le.restype = None
-    for n in ("orc_rgb_to_dxt1", "orc_yuv_to_dxt1"):
+    for n in ("orc_rgb_to_dxt1", "orc_yuv_to_dxt1", "orc_rgb_to_dxt6", "orc_yuv_to_dxt6"):
         getattr(L, n).argtypes = [_vp, _vp, _i, _i]
     L.orc_uyvy_to_dxt1.argtypes = [_vp, _vp, _i, _i, _l]
+    L.orc_uyvy_to_dxt6.argtypes = [_vp, _vp, _i, _i, _l]
     L.orc_yuv422_to_yuv444.argtypes = [_vp, _vp, _i]
     L.orc_yuv422_to_yuv444.restype = None
     L.orc_dxt1_decode.argtypes = [_vp, _vp, _i, _i]

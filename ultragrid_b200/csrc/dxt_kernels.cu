@@ -67,25 +67,22 @@ __device__ __forceinline__ uint4 encode_block<6>(const float (&r)[16], const flo
 // ------------------------------------------------------------------------------------------------
 template <int DXT_TYPE, int BPT, bool MIRROR>
 __global__ void __launch_bounds__(128) dxt_uyvy_kernel(const uint8_t *__restrict__ src, void *__restrict__ out,
-                                                        int wb /* blocks per row */, int hb, int h, long pitch)
+                                                        int wb /* blocks per row */, int h, long pitch)
 {
         typedef typename block_out<DXT_TYPE>::type out_t;
-        const int groups_per_row = wb / BPT;
-        const long gid = (long) blockIdx.x * blockDim.x + threadIdx.x;
-        if (gid >= (long) groups_per_row * hb) {
+        // grid: x over groups of BPT blocks in a block-row, y = block-row (no division, 32-bit index math)
+        const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+        const int by = blockIdx.y;
+        if (gx >= wb / BPT) {
                 return;
         }
-        const int by = (int) (gid / groups_per_row);
-        const int gx = (int) (gid - (long) by * groups_per_row);
+        const int row0 = MIRROR ? h - 1 - by * 4 : by * 4;  // cuda_dxt.cu:653-655
+        const uint8_t *p = src + (long) row0 * pitch + gx * (8 * BPT);
+        const long step = MIRROR ? -pitch : pitch;
 
         uint32_t w[4][2 * BPT];
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-                int row = by * 4 + y;
-                if (MIRROR) {
-                        row = h - 1 - row;  // cuda_dxt.cu:653-655
-                }
-                const uint8_t *p = src + row * pitch + (long) gx * (8 * BPT);
+        for (int y = 0; y < 4; ++y, p += step) {
                 if (BPT == 2) {
                         const uint4 v = ld_stream_v4(p);
                         w[y][0] = v.x, w[y][1] = v.y, w[y][2] = v.z, w[y][3] = v.w;
@@ -104,7 +101,7 @@ __global__ void __launch_bounds__(128) dxt_uyvy_kernel(const uint8_t *__restrict
                 }
                 res[k] = encode_block<DXT_TYPE>(r, g, b);
         }
-        out_t *o = (out_t *) out + (long) by * wb + (long) gx * BPT;
+        out_t *o = (out_t *) out + ((long) by * wb + gx * BPT);
         if (DXT_TYPE == 1 && BPT == 2) {
                 *(uint4 *) o = make_uint4(((uint2 *) res)[0].x, ((uint2 *) res)[0].y, ((uint2 *) res)[1].x,
                                           ((uint2 *) res)[1].y);
@@ -121,27 +118,24 @@ __global__ void __launch_bounds__(128) dxt_uyvy_kernel(const uint8_t *__restrict
 // ------------------------------------------------------------------------------------------------
 template <bool YUV, bool MIRROR, int DXT_TYPE>
 __global__ void __launch_bounds__(128) dxt_packed3_kernel(const uint32_t *__restrict__ src, void *__restrict__ out,
-                                                           int wb, int hb, int h)
+                                                           int wb, int h)
 {
         typedef typename block_out<DXT_TYPE>::type out_t;
-        const long gid = (long) blockIdx.x * blockDim.x + threadIdx.x;
-        if (gid >= (long) wb * hb) {
+        const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+        const int by = blockIdx.y;
+        if (bx >= wb) {
                 return;
         }
-        const int by = (int) (gid / wb);
-        const int bx = (int) (gid - (long) by * wb);
-        const long stride_w = (long) wb * 3;  // 32-bit words per row (cuda_dxt.cu:646)
+        const int stride_w = wb * 3;  // 32-bit words per row (cuda_dxt.cu:646)
+        const int row0 = MIRROR ? h - 1 - by * 4 : by * 4;
+        const uint32_t *p = src + ((long) stride_w * row0 + bx * 3);
+        const int step = MIRROR ? -stride_w : stride_w;
         float r[16], g[16], b[16];
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-                int row = by * 4 + y;
-                if (MIRROR) {
-                        row = h - 1 - row;
-                }
-                const uint32_t *p = src + stride_w * row + (long) bx * 3;
+        for (int y = 0; y < 4; ++y, p += step) {
                 load_row_packed3<YUV>(__ldg(p), __ldg(p + 1), __ldg(p + 2), r + 4 * y, g + 4 * y, b + 4 * y);
         }
-        ((out_t *) out)[gid] = encode_block<DXT_TYPE>(r, g, b);
+        ((out_t *) out)[(long) by * wb + bx] = encode_block<DXT_TYPE>(r, g, b);
 }
 
 /// UYVY -> packed Y,U,V 4:4:4 with chroma replication (cuda_dxt.cu:697-732). 16 px per thread:
@@ -197,14 +191,16 @@ static int launch_packed3(const void *src, void *out, int sx, int sy, cudaStream
                 return -1;  // cuda_dxt.cu:745-747 (a uint4 store additionally needs 16-B alignment)
         }
         const int wb = sx / 4, hb = sy / 4;
-        const long n = (long) wb * hb;
-        if (n > 0) {
+        if (hb > 65535) {
+                return -1;
+        }
+        if (wb > 0 && hb > 0) {
                 const int threads = 128;
-                const unsigned grid = (unsigned) ((n + threads - 1) / threads);
+                const dim3 grid((wb + threads - 1) / threads, hb);
                 if (mirrored) {
-                        dxt_packed3_kernel<YUV, true, DXT_TYPE><<<grid, threads, 0, str>>>((const uint32_t *) src, out, wb, hb, sy);
+                        dxt_packed3_kernel<YUV, true, DXT_TYPE><<<grid, threads, 0, str>>>((const uint32_t *) src, out, wb, sy);
                 } else {
-                        dxt_packed3_kernel<YUV, false, DXT_TYPE><<<grid, threads, 0, str>>>((const uint32_t *) src, out, wb, hb, sy);
+                        dxt_packed3_kernel<YUV, false, DXT_TYPE><<<grid, threads, 0, str>>>((const uint32_t *) src, out, wb, sy);
                 }
                 if (cudaGetLastError() != cudaSuccess) {
                         return -2;
@@ -237,10 +233,13 @@ static int launch_uyvy(const void *src, void *out, int sx, int sy, long pitch, c
         }
         const int threads = 128;
         const bool pair = !(wb & 1) && !(15 & (size_t) src) && !(pitch & 15) && !(15 & (size_t) out);
-        const long n = (long) (pair ? wb / 2 : wb) * hb;
-        const unsigned grid = (unsigned) ((n + threads - 1) / threads);
+        if (hb > 65535) {
+                return -1;
+        }
+        const int groups = pair ? wb / 2 : wb;
+        const dim3 grid((groups + threads - 1) / threads, hb);
         const uint8_t *s = (const uint8_t *) src;
-#define UGB_LAUNCH(BPT, MIR) dxt_uyvy_kernel<DXT_TYPE, BPT, MIR><<<grid, threads, 0, str>>>(s, out, wb, hb, sy, pitch)
+#define UGB_LAUNCH(BPT, MIR) dxt_uyvy_kernel<DXT_TYPE, BPT, MIR><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch)
         if (pair) {
                 if (mirrored) {
                         UGB_LAUNCH(2, true);
