@@ -1,0 +1,58 @@
+/* Baseline-JPEG encode stage — the C ABI that stands where UltraGrid's GPUJPEG module calls libgpujpeg
+ * (src/video_compress/gpujpeg.cpp: gpujpeg_encoder_create :353, gpujpeg_encoder_input_set_image /
+ * _set_gpu_image :617-622, gpujpeg_encoder_encode :624, gpujpeg_encoder_destroy :639).
+ *
+ * Stream contract (what the reference configures at gpujpeg.cpp:256-369):
+ *   UGB_UYVY input -> YCbCr stored as-is (no colour transform), 4:2:2, ONE interleaved scan (MCU 16x8 = Y0 Y1 Cb Cr)
+ *   UGB_RGB  input -> R,G,B stored as-is, 4:4:4, THREE scans (non-interleaved), Adobe APP14 transform=0
+ *   baseline sequential DCT (SOF0), Annex K Huffman tables, Annex K quantisation tables scaled by IJG quality,
+ *   restart interval `restart_interval` MCUs (0 = default: 4 for UYVY, 8 for RGB — gpujpeg.cpp:351), RSTn markers.
+ * Output capacity is width*height*3 + 4096 bytes like the reference's pool frames (gpujpeg.cpp:355).
+ */
+#ifndef UGB200_JPEG_H
+#define UGB200_JPEG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "cuda_wrapper.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ugb200_jpeg_encoder ugb200_jpeg_encoder;
+
+struct ugb200_jpeg_params {
+        int quality;          /* 1..100; gpujpeg_set_default_parameters() gives 75 */
+        int restart_interval; /* MCUs per restart segment; 0 = default for the input format */
+};
+
+/* gpujpeg_set_default_parameters */
+UGB_API void ugb200_jpeg_default_params(struct ugb200_jpeg_params *p);
+
+/* gpujpeg_encoder_create(stream).  Uses the current CUDA device (cuda_wrapper_set_device first, like
+ * gpujpeg_set_device at gpujpeg.cpp:559).  NULL on failure. */
+UGB_API ugb200_jpeg_encoder *ugb200_jpeg_encoder_create(cuda_wrapper_stream_t stream);
+UGB_API void ugb200_jpeg_encoder_destroy(ugb200_jpeg_encoder *enc);
+
+/* Asynchronous device-side encode: src is a DEVICE pointer (gpujpeg_encoder_input_set_gpu_image), `codec` is UGB_UYVY or
+ * UGB_RGB, pitch 0 = tightly packed.  The stream ends up in an encoder-owned device buffer.  0 ok, -1 bad args,
+ * -2 CUDA failure, -4 unsupported codec. */
+UGB_API int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *enc, const void *src, long pitch, int width, int height, int codec,
+                                      const struct ugb200_jpeg_params *params);
+/* Waits for the encode and returns the device pointer and byte size of the JPEG stream. */
+UGB_API int ugb200_jpeg_result_device(ugb200_jpeg_encoder *enc, const void **dev_ptr, size_t *size);
+
+/* gpujpeg_encoder_encode: synchronous; src is host memory unless src_is_device; *out points to an encoder-owned PINNED host
+ * buffer that stays valid until the next call (the reference memcpy's it into its pool frame, gpujpeg.cpp:629-630). */
+UGB_API int ugb200_jpeg_encode(ugb200_jpeg_encoder *enc, const void *src, int src_is_device, long pitch, int width, int height,
+                               int codec, const struct ugb200_jpeg_params *params, uint8_t **out, size_t *out_size);
+
+/* Stage access for tests: quantised zig-zag coefficients (int16[blocks][64], scan order) of the last encode, device ptr. */
+UGB_API int ugb200_jpeg_debug_coefficients(ugb200_jpeg_encoder *enc, const int16_t **dev_ptr, size_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

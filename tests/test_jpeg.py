@@ -1,0 +1,144 @@
+"""JPEG stage.  CPU part pins the oracle (oracle/jpeg_oracle.c) with an INDEPENDENT decoder (libjpeg through PIL):
+valid baseline stream, PSNR equal to libjpeg's own encoder at the same quality/tables, the reference's flat-grey
+round-trip criterion (test/gpujpeg_test.cpp:68-106).  GPU part: the CUDA encoder emits the oracle's bytes exactly."""
+import ctypes
+import io
+
+import numpy as np
+import pytest
+
+import util
+
+PIL = pytest.importorskip("PIL.Image")
+UYVY, RGB = 2, 12
+
+
+def orc_encode(orc, src, w, h, codec, quality, ri=0, pitch=0):
+    orc.orc_jpeg_encode.restype = ctypes.c_size_t
+    orc.orc_jpeg_encode.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.c_size_t]
+    out = np.zeros(w * h * 4 + 4096, dtype=np.uint8)
+    pitch = pitch or w * (2 if codec == UYVY else 3)
+    n = orc.orc_jpeg_encode(src.ctypes.data, pitch, w, h, 0 if codec == UYVY else 1, quality, ri, out.ctypes.data, out.size)
+    assert n > 0
+    return out[:n].tobytes()
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10 * np.log10(255 ** 2 / mse)
+
+
+def natural_rgb(w, h, seed=1):
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([xx * 255 // max(w - 1, 1), yy * 255 // max(h - 1, 1), (xx + yy) % 256], axis=2).astype(np.int32)
+    img += np.random.default_rng(seed).integers(-6, 7, img.shape)
+    return img.clip(0, 255).astype(np.uint8)
+
+
+def decode_ycc(data, w, h):
+    im = PIL.open(io.BytesIO(data))
+    im.draft("YCbCr", (w, h))
+    im.load()
+    assert im.mode == "YCbCr" and im.size == (w, h)
+    return np.asarray(im)
+
+
+def uyvy_planes(uyvy, w, h):
+    u = uyvy.reshape(h, w // 2, 4)
+    return np.stack([u[:, :, 1], u[:, :, 3]], axis=2).reshape(h, w), u[:, :, 0], u[:, :, 2]
+
+
+@pytest.mark.parametrize("q", [50, 75, 90])
+def test_oracle_uyvy_stream_decodes_and_matches_libjpeg_psnr(orc, q):
+    w, h = 640, 360
+    uyvy = util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h).reshape(-1), w, h)
+    Y, Cb, Cr = uyvy_planes(uyvy, w, h)
+    dec = decode_ycc(orc_encode(orc, uyvy, w, h, UYVY, q), w, h)
+    full = np.stack([Y, np.repeat(Cb, 2, axis=1), np.repeat(Cr, 2, axis=1)], axis=2)
+    b = io.BytesIO()
+    PIL.fromarray(full, mode="YCbCr").save(b, format="JPEG", quality=q, subsampling="4:2:2")
+    lib = decode_ycc(b.getvalue(), w, h)
+    for name, mine, theirs, want in (("Y", dec[:, :, 0], lib[:, :, 0], Y), ("Cb", dec[:, ::2, 1], lib[:, ::2, 1], Cb)):
+        assert abs(psnr(mine, want) - psnr(theirs, want)) < 0.3, (name, psnr(mine, want), psnr(theirs, want))
+    assert psnr(dec[:, :, 0], Y) > 34
+
+
+@pytest.mark.parametrize("w,h", [(16, 8), (48, 24), (100, 52), (130, 37), (1920, 1080)])
+def test_oracle_rgb_stream_is_rgb_and_close(orc, w, h):
+    rgb = natural_rgb(w, h, 3)
+    data = orc_encode(orc, rgb.reshape(-1), w, h, RGB, 90)
+    im = PIL.open(io.BytesIO(data))
+    im.load()
+    assert im.mode == "RGB" and im.size == (w, h)  # Adobe APP14 transform 0: no YCbCr->RGB applied by the decoder
+    assert psnr(np.asarray(im), rgb) > 33
+
+
+def test_flat_grey_roundtrip_like_reference_test(orc):
+    """gpujpeg_test_simple (test/gpujpeg_test.cpp:68-106): 1920x1080 RGB all-127, default quality, max |diff| <= 1"""
+    w, h = 1920, 1080
+    rgb = np.full((h, w, 3), 127, dtype=np.uint8)
+    im = PIL.open(io.BytesIO(orc_encode(orc, rgb.reshape(-1), w, h, RGB, 75)))
+    im.load()
+    assert np.abs(np.asarray(im).astype(int) - 127).max() <= 1
+
+
+def test_restart_markers_and_header_layout(orc):
+    w, h = 64, 32
+    uyvy = util.rng_bytes(w * h * 2, 9)
+    data = orc_encode(orc, uyvy, w, h, UYVY, 90, ri=2)
+    assert data[:2] == b"\xff\xd8" and data[-2:] == b"\xff\xd9"
+    assert data.count(b"\xff\xdb") >= 2 and b"\xff\xc0" in data and data.count(b"\xff\xc4") >= 4 and b"\xff\xdd\x00\x04\x00\x02" in data
+    nm = (w // 16) * (h // 8)
+    body = data[data.index(b"\xff\xda"):]
+    rst = sum(body.count(bytes([0xFF, 0xD0 + k])) for k in range(8))
+    assert rst == (nm + 1) // 2 - 1
+    decode_ycc(data, w, h)
+
+
+# ---- GPU ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("codec,w,h,q,ri", [(UYVY, 16, 8, 90, 0), (UYVY, 64, 32, 75, 2), (UYVY, 100, 52, 90, 0), (UYVY, 1920, 1080, 90, 0),
+                                            (UYVY, 3840, 2160, 90, 0), (RGB, 8, 8, 90, 0), (RGB, 130, 37, 50, 3), (RGB, 1920, 1080, 90, 0)])
+def test_gpu_encoder_equals_oracle_bytes(orc, codec, w, h, q, ri):
+    import torch
+    from ultragrid_b200 import api
+    if codec == UYVY:
+        src = util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h, 5).reshape(-1), w, h)
+        src[: w * 2 * min(h, 8)] = util.rng_bytes(w * 2 * min(h, 8), 1)  # a band of noise: long codes, ZRL, 0xFF stuffing
+    else:
+        src = natural_rgb(w, h, 7).reshape(-1).copy()
+        src[: w * 3 * min(h, 8)] = util.rng_bytes(w * 3 * min(h, 8), 2)
+    want = orc_encode(orc, src, w, h, codec, q, ri)
+    enc = api.JpegEncoder()
+    got = enc.encode(src, w, h, codec, quality=q, restart_interval=ri)  # host buffer in, pinned host buffer out
+    if got != want:
+        fmt = 0 if codec == UYVY else 1
+        nblk = ((w + 15) // 16) * ((h + 7) // 8) * 4 if codec == UYVY else ((w + 7) // 8) * ((h + 7) // 8) * 3
+        ref = np.zeros(nblk * 64, dtype=np.int16)
+        orc.orc_jpeg_coefficients.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        orc.orc_jpeg_coefficients(src.ctypes.data, w * (2 if codec == UYVY else 3), w, h, fmt, q, ref.ctypes.data)
+        co = enc.coefficients()
+        bad = np.nonzero(co != ref)[0]
+        pytest.fail(f"stream differs (len {len(got)} vs {len(want)}); coefficient mismatches: {len(bad)} first {bad[:8].tolist()}")
+    # device-resident input path gives the same bytes
+    enc.encode_device(torch.from_numpy(src).cuda(), w, h, codec, quality=q, restart_interval=ri)
+    assert enc.result() == want
+    enc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_8k_uyvy_jpeg_decodes_with_expected_psnr(orc):
+    """config 3 / metric at full size: size-independent checks (valid stream, PSNR on luma vs source)"""
+    import torch
+    from ultragrid_b200 import api
+    w, h = 7680, 4320
+    uyvy = util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h, 11).reshape(-1), w, h)
+    enc = api.JpegEncoder()
+    enc.encode_device(torch.from_numpy(uyvy).cuda(), w, h, UYVY, quality=90)
+    data = enc.result()
+    PIL.MAX_IMAGE_PIXELS = None
+    dec = decode_ycc(data, w, h)
+    Y, Cb, _ = uyvy_planes(uyvy, w, h)
+    assert psnr(dec[:, :, 0], Y) > 36 and psnr(dec[:, ::2, 1], Cb) > 36
+    enc.close()

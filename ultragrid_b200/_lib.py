@@ -42,6 +42,14 @@ SIGNATURES = {
     "ugb200_pixfmt_supported": (_i, [_i, _i]),
     "ugb200_pixfmt_convert": (_i, [_i, _i, _vp, _l, _vp, _l, _i, _i, _l, _i, _i, _i, _vp]),
     "ugb200_v210_to_p010le": (_i, [_vp, _l, _vp]),
+    # include/ugb200_jpeg.h
+    "ugb200_jpeg_default_params": (None, [_vp]),
+    "ugb200_jpeg_encoder_create": (_vp, [_vp]),
+    "ugb200_jpeg_encoder_destroy": (None, [_vp]),
+    "ugb200_jpeg_encode_device": (_i, [_vp, _vp, _l, _i, _i, _i, _vp]),
+    "ugb200_jpeg_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    "ugb200_jpeg_encode": (_i, [_vp, _vp, _i, _l, _i, _i, _i, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    "ugb200_jpeg_debug_coefficients": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
 }
 
 _lib = None

@@ -94,3 +94,66 @@ def v210_to_p010le(src, width, height, out_y=None, out_c=None, ls_y=None, ls_c=N
     d.in_data = src.data_ptr()
     _check(_L.ugb200_v210_to_p010le(ctypes.byref(d), 0, _stream(stream)), "ugb200_v210_to_p010le")
     return out_y, out_c
+
+
+class JpegParams(ctypes.Structure):
+    _fields_ = [("quality", ctypes.c_int), ("restart_interval", ctypes.c_int)]
+
+
+class JpegEncoder:
+    """ugb200_jpeg_* (include/ugb200_jpeg.h): the stage src/video_compress/gpujpeg.cpp delegates to libgpujpeg."""
+
+    def __init__(self, stream=None):
+        self._stream = stream if stream is not None else torch.cuda.current_stream()
+        self._h = _L.ugb200_jpeg_encoder_create(ctypes.c_void_p(self._stream.cuda_stream))
+        if not self._h:
+            raise RuntimeError("ugb200_jpeg_encoder_create failed")
+
+    def close(self):
+        if self._h:
+            _L.ugb200_jpeg_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _params(self, quality, restart_interval):
+        p = JpegParams()
+        _L.ugb200_jpeg_default_params(ctypes.byref(p))
+        if quality is not None:
+            p.quality = quality
+        p.restart_interval = restart_interval
+        return p
+
+    def encode_device(self, src, width, height, codec, quality=None, restart_interval=0, pitch=0):
+        """asynchronous; returns nothing — call result() for the bytes"""
+        p = self._params(quality, restart_interval)
+        _check(_L.ugb200_jpeg_encode_device(self._h, _ptr(src), pitch, width, height, int(codec), ctypes.byref(p)), "ugb200_jpeg_encode_device")
+
+    def result(self):
+        """waits for the encode; returns the stream as bytes"""
+        ptr, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(_L.ugb200_jpeg_result_device(self._h, ctypes.byref(ptr), ctypes.byref(n)), "ugb200_jpeg_result_device")
+        host = (ctypes.c_uint8 * n.value)()
+        _check(_L.cuda_wrapper_memcpy(host, ptr, n.value, 1), "cuda_wrapper_memcpy")
+        return bytes(host)
+
+    def encode(self, src, width, height, codec, quality=None, restart_interval=0, pitch=0):
+        """gpujpeg_encoder_encode: src is a host numpy array or a CUDA tensor; returns the JPEG bytes"""
+        p = self._params(quality, restart_interval)
+        out, n = ctypes.c_void_p(), ctypes.c_size_t()
+        if isinstance(src, torch.Tensor):
+            sp, is_dev = _ptr(src), 1
+        else:
+            sp, is_dev = ctypes.c_void_p(src.ctypes.data), 0
+        _check(_L.ugb200_jpeg_encode(self._h, sp, is_dev, pitch, width, height, int(codec), ctypes.byref(p), ctypes.byref(out), ctypes.byref(n)),
+               "ugb200_jpeg_encode")
+        return ctypes.string_at(out.value, n.value)
+
+    def coefficients(self):
+        ptr, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(_L.ugb200_jpeg_debug_coefficients(self._h, ctypes.byref(ptr), ctypes.byref(n)), "ugb200_jpeg_debug_coefficients")
+        import numpy as np
+        host = np.empty(n.value, dtype=np.int16)
+        _check(_L.cuda_wrapper_memcpy(ctypes.c_void_p(host.ctypes.data), ptr, n.value * 2, 1), "cuda_wrapper_memcpy")
+        return host

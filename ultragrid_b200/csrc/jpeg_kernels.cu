@@ -1,0 +1,674 @@
+// Baseline JPEG encoder (include/ugb200_jpeg.h): the DCT / quantisation / Huffman stage GPUJPEG performs for
+// UltraGrid's src/video_compress/gpujpeg.cpp, re-designed for sm_100a.
+//
+// Round-1 structure (correct first; fusion of the stages is the next optimisation step):
+//   K1 jpeg_dct_kernel      one thread per 8x8 block: 128-bit row loads straight from UYVY / packed RGB, level
+//                           shift, separable AAN FDCT in registers, quantise (reciprocal multiply + rint),
+//                           zig-zag, one 128-byte store of int16 coefficients          (HBM: 1 B in, 2 B out per sample)
+//   K2 jpeg_huffman_kernel  one thread per restart segment: DC prediction + run-length + Annex K Huffman codes with byte
+//                           stuffing into a private worst-case slot, RSTn appended, byte count recorded
+//   K3 jpeg_scan_kernel     exclusive prefix sum of the segment sizes (single CTA, decoupled from the host)
+//   K4 jpeg_compact_kernel  one warp per segment: slot -> final position; writes SOS headers of scans 2,3 and EOI
+// Arithmetic is float with an explicit operation order so that oracle/jpeg_oracle.c reproduces the bytes exactly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/ugb200.h"
+#include "../../include/ugb200_jpeg.h"
+#include "jpeg_tables.h"
+
+namespace ugb {
+
+enum { FMT_UYVY_422 = 0, FMT_RGB_444 = 1 };
+constexpr int kSlotBytesPerBlock = 416;  // worst case: 1658 bits/block = 208 B, every byte stuffed
+constexpr int kSlotExtra = 8;            // final pad byte + RSTn
+
+struct jpeg_tables_dev {
+        float qmul[2][64];     // [luma|chroma][natural index]
+        uint32_t dc[2][16];    // (len << 16) | code, by category
+        uint32_t ac[2][256];   // (len << 16) | code, by (run << 4 | size)
+};
+__constant__ jpeg_tables_dev c_tab;
+
+struct jpeg_geom {
+        int fmt, w, h;
+        int bw, bh;        // component-0 blocks per row / rows (RGB), or MCUs per row / rows (UYVY)
+        int nblocks;       // total 8x8 blocks (all components)
+        int ri;            // MCUs per restart segment
+        int nseg;          // total restart segments (all scans)
+        int seg_per_scan;  // segments in one scan
+        int mcu_per_scan;  // MCUs in one scan
+        int blocks_per_mcu;
+        int slot;          // bytes reserved per segment
+        int header_len;    // bytes before the first entropy-coded byte (including the first SOS)
+        int sos_len;       // length of one later SOS header (RGB)
+};
+
+// ---- K1 -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fdct8(float &d0, float &d1, float &d2, float &d3, float &d4, float &d5, float &d6, float &d7)
+{
+        const float t0 = __fadd_rn(d0, d7), t7 = __fadd_rn(d0, -d7), t1 = __fadd_rn(d1, d6), t6 = __fadd_rn(d1, -d6);
+        const float t2 = __fadd_rn(d2, d5), t5 = __fadd_rn(d2, -d5), t3 = __fadd_rn(d3, d4), t4 = __fadd_rn(d3, -d4);
+        const float e0 = __fadd_rn(t0, t3), e3 = __fadd_rn(t0, -t3), e1 = __fadd_rn(t1, t2), e2 = __fadd_rn(t1, -t2);
+        d0 = __fadd_rn(e0, e1);
+        d4 = __fadd_rn(e0, -e1);
+        const float z1 = __fmul_rn(__fadd_rn(e2, e3), 0.707106781f);
+        d2 = __fadd_rn(e3, z1);
+        d6 = __fadd_rn(e3, -z1);
+        const float o0 = __fadd_rn(t4, t5), o1 = __fadd_rn(t5, t6), o2 = __fadd_rn(t6, t7);
+        const float z5 = __fmul_rn(__fadd_rn(o0, -o2), 0.382683433f);
+        const float z2 = __fmaf_rn(0.541196100f, o0, z5);
+        const float z4 = __fmaf_rn(1.306562965f, o2, z5);
+        const float z3 = __fmul_rn(o1, 0.707106781f);
+        const float z11 = __fadd_rn(t7, z3), z13 = __fadd_rn(t7, -z3);
+        d5 = __fadd_rn(z13, z2);
+        d3 = __fadd_rn(z13, -z2);
+        d1 = __fadd_rn(z11, z4);
+        d7 = __fadd_rn(z11, -z4);
+}
+
+__device__ __forceinline__ int clampi(int v, int hi) { return min(max(v, 0), hi); }
+
+/// 8 samples of one row of the block into f[0..7] (already level-shifted)
+__device__ __forceinline__ void load_row(const uint8_t *__restrict__ src, long pitch, const jpeg_geom &g, int comp, int bx, int y,
+                                         bool interior, float *f)
+{
+        const uint8_t *row = src + (long) clampi(y, g.h - 1) * pitch;
+        if (g.fmt == FMT_UYVY_422) {
+                if (interior && comp == 0) {  // 8 luma samples = 16 bytes
+                        const uint4 v = __ldg((const uint4 *) (row + (long) bx * 16));
+                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                                f[2 * i] = (float) ((int) ((w[i] >> 8) & 0xff) - 128);
+                                f[2 * i + 1] = (float) ((int) (w[i] >> 24) - 128);
+                        }
+                } else if (interior) {  // 8 chroma samples = 32 bytes
+                        const uint4 a = __ldg((const uint4 *) (row + (long) bx * 32)), b = __ldg((const uint4 *) (row + (long) bx * 32) + 1);
+                        const uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+                        const int sh = comp == 1 ? 0 : 16;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                                f[i] = (float) ((int) ((w[i] >> sh) & 0xff) - 128);
+                        }
+                } else {
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) {
+                                int s;
+                                if (comp == 0) {
+                                        s = row[2 * clampi(bx * 8 + x, g.w - 1) + 1];
+                                } else {
+                                        s = row[4 * clampi(bx * 8 + x, (g.w + 1) / 2 - 1) + (comp == 1 ? 0 : 2)];
+                                }
+                                f[x] = (float) (s - 128);
+                        }
+                }
+        } else {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                        f[x] = (float) ((int) __ldg(row + 3 * clampi(bx * 8 + x, g.w - 1) + comp) - 128);
+                }
+        }
+}
+
+__global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, int16_t *__restrict__ coef,
+                                                       bool vec_ok)
+{
+        const int b = blockIdx.x * blockDim.x + threadIdx.x;
+        if (b >= g.nblocks) {
+                return;
+        }
+        int comp, bx, by;
+        if (g.fmt == FMT_UYVY_422) {
+                const int m = b >> 2, k = b & 3;
+                const int mx = m % g.bw, my = m / g.bw;
+                comp = k < 2 ? 0 : k - 1;
+                bx = comp == 0 ? mx * 2 + k : mx;
+                by = my;
+        } else {
+                const int per = g.bw * g.bh;
+                comp = b / per;
+                const int r = b - comp * per;
+                bx = r % g.bw, by = r / g.bw;
+        }
+        // interior: the whole block lies inside the image (and vector loads are aligned)
+        const int px_w = (g.fmt == FMT_UYVY_422 && comp != 0) ? 16 : 8;
+        const bool interior = vec_ok && (bx + 1) * px_w <= g.w && (by + 1) * 8 <= g.h;
+        float f[64];
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+                load_row(src, pitch, g, comp, bx, by * 8 + y, interior, f + 8 * y);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+                fdct8(f[8 * r], f[8 * r + 1], f[8 * r + 2], f[8 * r + 3], f[8 * r + 4], f[8 * r + 5], f[8 * r + 6], f[8 * r + 7]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+                fdct8(f[c], f[8 + c], f[16 + c], f[24 + c], f[32 + c], f[40 + c], f[48 + c], f[56 + c]);
+        }
+        const float *qm = c_tab.qmul[comp == 0 ? 0 : 1];
+        int q[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+                q[i] = __float2int_rn(__fmul_rn(f[i], qm[i]));
+        }
+        // zig-zag (Figure A.6) + AC clamp to the 10-bit category range, two int16 per word, 8 x 16-byte stores
+        constexpr int zz[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+        uint32_t o[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+                int a = q[zz[2 * k]], c2 = q[zz[2 * k + 1]];
+                if (k > 0) {
+                        a = min(max(a, -1023), 1023);
+                }
+                c2 = min(max(c2, -1023), 1023);
+                o[k] = ((uint32_t) a & 0xffffu) | ((uint32_t) c2 << 16);
+        }
+        uint4 *dst = (uint4 *) (coef + (long) b * 64);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+                dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        }
+}
+
+// ---- K2 -------------------------------------------------------------------------------------------------------------
+struct bit_writer {
+        uint8_t *p;
+        uint64_t acc;
+        int nbits;
+        __device__ __forceinline__ void put(uint32_t code, int len)
+        {
+                acc = (acc << len) | (code & ((1u << len) - 1u));
+                nbits += len;
+                while (nbits >= 8) {
+                        const uint8_t b = (uint8_t) (acc >> (nbits - 8));
+                        *p++ = b;
+                        if (b == 0xFF) {
+                                *p++ = 0;  // T.81 B.1.1.5
+                        }
+                        nbits -= 8;
+                }
+        }
+        __device__ __forceinline__ void flush()
+        {
+                if (nbits > 0) {
+                        put(0x7F, 8 - nbits);  // pad with ones, T.81 F.1.2.3
+                }
+                acc = 0, nbits = 0;
+        }
+};
+
+__device__ __forceinline__ int category(int v) { return 32 - __clz(abs(v)); }
+
+__global__ void __launch_bounds__(128) jpeg_huffman_kernel(const int16_t *__restrict__ coef, jpeg_geom g, uint8_t *__restrict__ slots,
+                                                           uint32_t *__restrict__ sizes)
+{
+        __shared__ uint32_t s_dc[2][16], s_ac[2][256];
+        for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+                s_dc[i >> 4][i & 15] = c_tab.dc[i >> 4][i & 15];
+        }
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+                s_ac[i >> 8][i & 255] = c_tab.ac[i >> 8][i & 255];
+        }
+        __syncthreads();
+        const int s = blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= g.nseg) {
+                return;
+        }
+        const int scan = s / g.seg_per_scan, ls = s - scan * g.seg_per_scan;
+        const int m0 = ls * g.ri, m1 = min(m0 + g.ri, g.mcu_per_scan);
+        bit_writer bw = { slots + (long) s * g.slot, 0, 0 };
+        int pred[3] = { 0, 0, 0 };
+        for (int m = m0; m < m1; ++m) {
+                for (int k = 0; k < g.blocks_per_mcu; ++k) {
+                        int comp;
+                        long blk;
+                        if (g.fmt == FMT_UYVY_422) {
+                                comp = k < 2 ? 0 : k - 1;
+                                blk = (long) m * 4 + k;
+                        } else {
+                                comp = scan;
+                                blk = (long) scan * g.mcu_per_scan + m;
+                        }
+                        const int t = comp == 0 ? 0 : 1;
+                        const int16_t *zz = coef + blk * 64;
+                        const int dcv = zz[0], diff = dcv - pred[comp];
+                        pred[comp] = dcv;
+                        int sz = category(diff);
+                        bw.put(s_dc[t][sz] & 0xffff, s_dc[t][sz] >> 16);
+                        if (sz) {
+                                bw.put((uint32_t) (diff < 0 ? diff - 1 : diff), sz);
+                        }
+                        int run = 0;
+                        for (int i = 1; i < 64; ++i) {
+                                const int v = zz[i];
+                                if (v == 0) {
+                                        ++run;
+                                        continue;
+                                }
+                                while (run > 15) {
+                                        bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);  // ZRL
+                                        run -= 16;
+                                }
+                                sz = category(v);
+                                const uint32_t e = s_ac[t][(run << 4) | sz];
+                                bw.put(e & 0xffff, e >> 16);
+                                bw.put((uint32_t) (v < 0 ? v - 1 : v), sz);
+                                run = 0;
+                        }
+                        if (run > 0) {
+                                bw.put(s_ac[t][0] & 0xffff, s_ac[t][0] >> 16);  // EOB
+                        }
+                }
+        }
+        bw.flush();
+        if (ls != g.seg_per_scan - 1) {  // RSTn between segments of a scan
+                *bw.p++ = 0xFF;
+                *bw.p++ = (uint8_t) (0xD0 + (ls & 7));
+        }
+        sizes[s] = (uint32_t) (bw.p - (slots + (long) s * g.slot));
+}
+
+// ---- K3: exclusive scan of segment sizes (+ later-scan SOS headers) into final offsets ------------------------------------
+__global__ void __launch_bounds__(1024) jpeg_scan_kernel(const uint32_t *__restrict__ sizes, jpeg_geom g, uint32_t *__restrict__ offsets,
+                                                         uint32_t *__restrict__ total)
+{
+        __shared__ uint32_t part[1024];
+        const int t = threadIdx.x, per = (g.nseg + 1023) / 1024;
+        const int i0 = t * per, i1 = min(i0 + per, g.nseg);
+        uint32_t sum = 0;
+        for (int i = i0; i < i1; ++i) {
+                sum += sizes[i] + ((i % g.seg_per_scan == 0 && i > 0) ? g.sos_len : 0);
+        }
+        part[t] = sum;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
+                const uint32_t v = t >= d ? part[t - d] : 0;
+                __syncthreads();
+                part[t] += v;
+                __syncthreads();
+        }
+        uint32_t run = g.header_len + (t ? part[t - 1] : 0);
+        for (int i = i0; i < i1; ++i) {
+                if (i % g.seg_per_scan == 0 && i > 0) {
+                        run += g.sos_len;  // the SOS of this scan sits right before its first segment
+                }
+                offsets[i] = run;
+                run += sizes[i];
+        }
+        if (t == 1023) {
+                *total = g.header_len + part[1023] + 2;  // + EOI
+        }
+}
+
+// ---- K4 -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ sizes,
+                                                           const uint32_t *__restrict__ offsets, jpeg_geom g, uint8_t *__restrict__ out)
+{
+        const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        if (s >= g.nseg) {
+                return;
+        }
+        const uint32_t n = sizes[s], off = offsets[s];
+        const uint8_t *src = slots + (long) s * g.slot;
+        for (uint32_t i = lane; i < n; i += 32) {
+                out[off + i] = src[i];
+        }
+        if (lane == 0 && s > 0 && s % g.seg_per_scan == 0) {  // SOS header of a later scan (RGB: one component per scan)
+                const int c = s / g.seg_per_scan;
+                uint8_t *h = out + off - g.sos_len;
+                const uint8_t sos[10] = { 0xFF, 0xDA, 0, 8, 1, (uint8_t) (c + 1), 0x11, 0, 63, 0 };
+                for (int i = 0; i < 10; ++i) {
+                        h[i] = sos[i];
+                }
+        }
+        if (lane == 0 && s == g.nseg - 1) {
+                out[off + n] = 0xFF, out[off + n + 1] = 0xD9;  // EOI
+        }
+}
+
+}  // namespace ugb
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+using namespace ugb;
+
+struct ugb200_jpeg_encoder {
+        cudaStream_t stream = nullptr;
+        // cached configuration
+        int fmt = -1, w = 0, h = 0, quality = -1, ri = -1;
+        jpeg_geom g{};
+        std::vector<uint8_t> header;
+        // device buffers
+        int16_t *coef = nullptr;
+        uint8_t *slots = nullptr, *out = nullptr, *staging = nullptr;
+        uint32_t *sizes = nullptr, *offsets = nullptr, *total = nullptr;
+        size_t coef_cap = 0, slots_cap = 0, out_cap = 0, seg_cap = 0, staging_cap = 0;
+        // pinned host buffers
+        uint8_t *h_out = nullptr, *h_in = nullptr;
+        uint32_t *h_total = nullptr;
+        size_t h_out_cap = 0, h_in_cap = 0;
+        bool pending = false;
+};
+
+namespace {
+
+template <class T>
+bool grow(T *&ptr, size_t &cap, size_t need)
+{
+        if (need <= cap) {
+                return true;
+        }
+        if (ptr) {
+                cudaFree(ptr);
+        }
+        ptr = nullptr, cap = 0;
+        if (cudaMalloc((void **) &ptr, need * sizeof(T)) != cudaSuccess) {
+                return false;
+        }
+        cap = need;
+        return true;
+}
+bool grow_host(uint8_t *&ptr, size_t &cap, size_t need)
+{
+        if (need <= cap) {
+                return true;
+        }
+        if (ptr) {
+                cudaFreeHost(ptr);
+        }
+        ptr = nullptr, cap = 0;
+        if (cudaMallocHost((void **) &ptr, need) != cudaSuccess) {
+                return false;
+        }
+        cap = need;
+        return true;
+}
+
+void put16(std::vector<uint8_t> &v, unsigned x) { v.push_back((uint8_t) (x >> 8)), v.push_back((uint8_t) x); }
+void put_dht(std::vector<uint8_t> &v, int tc_th, const uint8_t bits[16], const uint8_t *vals, int n)
+{
+        v.push_back(0xFF), v.push_back(0xC4);
+        put16(v, 2 + 1 + 16 + n);
+        v.push_back((uint8_t) tc_th);
+        v.insert(v.end(), bits, bits + 16);
+        v.insert(v.end(), vals, vals + n);
+}
+
+/// header layout as the reference's RFC 2435 writer (src/utils/jpeg_writer.c:215-382): SOI, APPn, DQT x2, SOF0, DHT x4, DRI, SOS
+void build_header(ugb200_jpeg_encoder *e, const uint8_t ql[64], const uint8_t qc[64])
+{
+        std::vector<uint8_t> &v = e->header;
+        v.clear();
+        v.push_back(0xFF), v.push_back(0xD8);
+        if (e->fmt == FMT_RGB_444) {
+                static const uint8_t adobe[] = { 0xFF, 0xEE, 0, 14, 'A', 'd', 'o', 'b', 'e', 0, 100, 0, 0, 0, 0, 0 };
+                v.insert(v.end(), adobe, adobe + sizeof adobe);
+        } else {
+                static const uint8_t jfif[] = { 0xFF, 0xE0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0 };
+                v.insert(v.end(), jfif, jfif + sizeof jfif);
+        }
+        for (int t = 0; t < 2; ++t) {
+                v.push_back(0xFF), v.push_back(0xDB);
+                put16(v, 67);
+                v.push_back((uint8_t) t);
+                for (int k = 0; k < 64; ++k) {
+                        v.push_back((t ? qc : ql)[ugb_jpeg_zigzag[k]]);
+                }
+        }
+        v.push_back(0xFF), v.push_back(0xC0);
+        put16(v, 17);
+        v.push_back(8);
+        put16(v, e->h), put16(v, e->w);
+        v.push_back(3);
+        for (int c = 0; c < 3; ++c) {
+                v.push_back((uint8_t) (c + 1));
+                v.push_back((e->fmt == FMT_UYVY_422 && c == 0) ? 0x21 : 0x11);
+                v.push_back(c == 0 ? 0 : 1);
+        }
+        put_dht(v, 0x00, ugb_jpeg_dc_luma_bits, ugb_jpeg_dc_vals, 12);
+        put_dht(v, 0x10, ugb_jpeg_ac_luma_bits, ugb_jpeg_ac_luma_vals, 162);
+        put_dht(v, 0x01, ugb_jpeg_dc_chroma_bits, ugb_jpeg_dc_vals, 12);
+        put_dht(v, 0x11, ugb_jpeg_ac_chroma_bits, ugb_jpeg_ac_chroma_vals, 162);
+        v.push_back(0xFF), v.push_back(0xDD);
+        put16(v, 4), put16(v, e->ri);
+        const int ncomp = e->fmt == FMT_UYVY_422 ? 3 : 1;
+        v.push_back(0xFF), v.push_back(0xDA);
+        put16(v, 6 + 2 * ncomp);
+        v.push_back((uint8_t) ncomp);
+        for (int c = 0; c < ncomp; ++c) {
+                v.push_back((uint8_t) (c + 1));
+                v.push_back(c == 0 ? 0x00 : 0x11);
+        }
+        v.push_back(0), v.push_back(63), v.push_back(0);
+}
+
+int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri)
+{
+        if (ri <= 0) {
+                ri = fmt == FMT_RGB_444 ? 8 : 4;  // src/video_compress/gpujpeg.cpp:351
+        }
+        if (ri > 65535) {
+                return -1;
+        }
+        quality = quality < 1 ? 1 : quality > 100 ? 100 : quality;
+        const bool same = e->fmt == fmt && e->w == w && e->h == h && e->quality == quality && e->ri == ri;
+        if (same) {
+                return 0;
+        }
+        e->fmt = fmt, e->w = w, e->h = h, e->quality = quality, e->ri = ri;
+        jpeg_geom &g = e->g;
+        g.fmt = fmt, g.w = w, g.h = h, g.ri = ri;
+        if (fmt == FMT_UYVY_422) {
+                g.bw = (w + 15) / 16, g.bh = (h + 7) / 8;
+                g.mcu_per_scan = g.bw * g.bh, g.blocks_per_mcu = 4;
+                g.nblocks = g.mcu_per_scan * 4;
+                g.seg_per_scan = (g.mcu_per_scan + ri - 1) / ri;
+                g.nseg = g.seg_per_scan;
+                g.sos_len = 0;
+        } else {
+                g.bw = (w + 7) / 8, g.bh = (h + 7) / 8;
+                g.mcu_per_scan = g.bw * g.bh, g.blocks_per_mcu = 1;
+                g.nblocks = g.mcu_per_scan * 3;
+                g.seg_per_scan = (g.mcu_per_scan + ri - 1) / ri;
+                g.nseg = g.seg_per_scan * 3;
+                g.sos_len = 10;
+        }
+        g.slot = ri * g.blocks_per_mcu * kSlotBytesPerBlock + kSlotExtra;
+
+        uint8_t ql[64], qc[64];
+        ugb_jpeg_scaled_qtable(ugb_jpeg_q_luma, quality, ql);
+        ugb_jpeg_scaled_qtable(ugb_jpeg_q_chroma, quality, qc);
+        jpeg_tables_dev t;
+        ugb_jpeg_quant_multipliers(ql, t.qmul[0]);
+        ugb_jpeg_quant_multipliers(qc, t.qmul[1]);
+        uint16_t code[256];
+        uint8_t len[256];
+        for (int k = 0; k < 2; ++k) {
+                ugb_jpeg_build_codes(k ? ugb_jpeg_dc_chroma_bits : ugb_jpeg_dc_luma_bits, ugb_jpeg_dc_vals, 12, code, len);
+                for (int i = 0; i < 16; ++i) {
+                        t.dc[k][i] = ((uint32_t) len[i] << 16) | code[i];
+                }
+                ugb_jpeg_build_codes(k ? ugb_jpeg_ac_chroma_bits : ugb_jpeg_ac_luma_bits, k ? ugb_jpeg_ac_chroma_vals : ugb_jpeg_ac_luma_vals,
+                                     162, code, len);
+                for (int i = 0; i < 256; ++i) {
+                        t.ac[k][i] = ((uint32_t) len[i] << 16) | code[i];
+                }
+        }
+        // the constant bank is per-module state; encoders with different quality on one stream order themselves through the stream
+        if (cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+                return -2;
+        }
+        build_header(e, ql, qc);
+        g.header_len = (int) e->header.size();
+
+        const size_t out_need = (size_t) w * h * 3 + 4096;  // gpujpeg.cpp:355
+        if (!grow(e->coef, e->coef_cap, (size_t) g.nblocks * 64) || !grow(e->slots, e->slots_cap, (size_t) g.nseg * g.slot) ||
+            !grow(e->out, e->out_cap, out_need)) {
+                return -2;
+        }
+        size_t cap2 = e->seg_cap;
+        if (!grow(e->sizes, e->seg_cap, (size_t) g.nseg) || !grow(e->offsets, cap2, (size_t) g.nseg)) {
+                return -2;
+        }
+        if (e->total == nullptr && cudaMalloc((void **) &e->total, 4) != cudaSuccess) {
+                return -2;
+        }
+        if (e->h_total == nullptr && cudaMallocHost((void **) &e->h_total, 4) != cudaSuccess) {
+                return -2;
+        }
+        if (cudaMemcpyAsync(e->out, e->header.data(), e->header.size(), cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+                return -2;
+        }
+        cudaStreamSynchronize(e->stream);  // header vector / table struct are host temporaries
+        return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ugb200_jpeg_default_params(struct ugb200_jpeg_params *p)
+{
+        p->quality = 75;  // gpujpeg_set_default_parameters
+        p->restart_interval = 0;
+}
+
+ugb200_jpeg_encoder *ugb200_jpeg_encoder_create(cuda_wrapper_stream_t stream)
+{
+        ugb200_jpeg_encoder *e = new (std::nothrow) ugb200_jpeg_encoder;
+        if (e) {
+                e->stream = (cudaStream_t) stream;
+        }
+        return e;
+}
+
+void ugb200_jpeg_encoder_destroy(ugb200_jpeg_encoder *e)
+{
+        if (!e) {
+                return;
+        }
+        cudaStreamSynchronize(e->stream);
+        cudaFree(e->coef), cudaFree(e->slots), cudaFree(e->out), cudaFree(e->staging);
+        cudaFree(e->sizes), cudaFree(e->offsets), cudaFree(e->total);
+        cudaFreeHost(e->h_out), cudaFreeHost(e->h_in), cudaFreeHost(e->h_total);
+        delete e;
+}
+
+int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitch, int width, int height, int codec,
+                              const struct ugb200_jpeg_params *params)
+{
+        if (!e || !src || width <= 0 || height <= 0 || width > 65535 || height > 65535 || !params) {
+                return -1;
+        }
+        int fmt;
+        if (codec == UGB_UYVY) {
+                fmt = FMT_UYVY_422;
+        } else if (codec == UGB_RGB) {
+                fmt = FMT_RGB_444;
+        } else {
+                return -4;
+        }
+        if (pitch == 0) {
+                pitch = (long) width * (fmt == FMT_UYVY_422 ? 2 : 3);
+        }
+        const int rc = configure(e, fmt, width, height, params->quality, params->restart_interval);
+        if (rc != 0) {
+                return rc;
+        }
+        const jpeg_geom &g = e->g;
+        const bool vec_ok = fmt == FMT_UYVY_422 && !(15 & (size_t) src) && !(pitch & 15);
+        jpeg_dct_kernel<<<(g.nblocks + 127) / 128, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok);
+        jpeg_huffman_kernel<<<(g.nseg + 127) / 128, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes);
+        jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->sizes, g, e->offsets, e->total);
+        jpeg_compact_kernel<<<(int) (((long) g.nseg * 32 + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, g, e->out);
+        if (cudaGetLastError() != cudaSuccess) {
+                return -2;
+        }
+        cudaMemcpyAsync(e->h_total, e->total, 4, cudaMemcpyDeviceToHost, e->stream);
+        e->pending = true;
+        return 0;
+}
+
+int ugb200_jpeg_result_device(ugb200_jpeg_encoder *e, const void **dev_ptr, size_t *size)
+{
+        if (!e || !e->pending) {
+                return -1;
+        }
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+                return -2;
+        }
+        if (dev_ptr) {
+                *dev_ptr = e->out;
+        }
+        if (size) {
+                *size = *e->h_total;
+        }
+        return 0;
+}
+
+int ugb200_jpeg_encode(ugb200_jpeg_encoder *e, const void *src, int src_is_device, long pitch, int width, int height, int codec,
+                       const struct ugb200_jpeg_params *params, uint8_t **out, size_t *out_size)
+{
+        if (!e || !src || !out || !out_size || width <= 0 || height <= 0) {
+                return -1;
+        }
+        const int bpp = codec == UGB_UYVY ? 2 : codec == UGB_RGB ? 3 : 0;
+        if (bpp == 0) {
+                return -4;
+        }
+        const void *dsrc = src;
+        if (!src_is_device) {
+                if (pitch == 0) {
+                        pitch = (long) width * bpp;
+                }
+                const size_t n = (size_t) pitch * height;
+                if (!grow(e->staging, e->staging_cap, n)) {
+                        return -2;
+                }
+                if (cudaMemcpyAsync(e->staging, src, n, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+                        return -2;
+                }
+                dsrc = e->staging;
+        }
+        int rc = ugb200_jpeg_encode_device(e, dsrc, pitch, width, height, codec, params);
+        if (rc != 0) {
+                return rc;
+        }
+        size_t n = 0;
+        rc = ugb200_jpeg_result_device(e, nullptr, &n);
+        if (rc != 0) {
+                return rc;
+        }
+        if (!grow_host(e->h_out, e->h_out_cap, e->out_cap)) {
+                return -2;
+        }
+        if (cudaMemcpyAsync(e->h_out, e->out, n, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess ||
+            cudaStreamSynchronize(e->stream) != cudaSuccess) {
+                return -2;
+        }
+        *out = e->h_out;
+        *out_size = n;
+        return 0;
+}
+
+int ugb200_jpeg_debug_coefficients(ugb200_jpeg_encoder *e, const int16_t **dev_ptr, size_t *count)
+{
+        if (!e || !e->coef) {
+                return -1;
+        }
+        cudaStreamSynchronize(e->stream);
+        *dev_ptr = e->coef;
+        *count = (size_t) e->g.nblocks * 64;
+        return 0;
+}
+
+}  // extern "C"
