@@ -45,38 +45,52 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while a timed region runs"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML every 10 ms while the timed region runs (nvidia-smi as fallback)"""
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, uuid=None, index=0):
+        self.uuid, self.index, self.rows, self.stop_flag, self.thread = uuid, index, [], False, None
+        self.max_mhz = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (f"GPU-{self.uuid}", str(self.uuid)):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), reasons))
+                time.sleep(0.01)
+        except Exception as e:  # noqa: BLE001
+            self.rows.append(("error", str(e)))
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is not None:
-            time.sleep(0.25)
-            self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        good = [r for r in self.rows if r[0] != "error"]
+        sm = sorted(r[0] for r in good)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted({n for r in good for bit, n in names.items() if r[1] & bit})
+        err = [r[1] for r in self.rows if r[0] == "error"]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                **({"error": err[0]} if err else {})}
 
 
 def cpu_port_fps(seconds=12.0, max_frames=6):
@@ -141,7 +155,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from ultragrid_b200 import api  # raises if libugb200.so is missing: no fallback
+    from ultragrid_b200 import api, compress, sharding  # raises if libugb200.so is missing: no fallback
 
     assert torch.cuda.is_available(), "bench.py needs a GPU"
     torch.cuda.set_device(local_rank)
@@ -163,16 +177,8 @@ def main():
     ready = [torch.cuda.Event() for _ in range(2)]
 
     def scatter_assignment(step):
-        buf = assign[step % 2]
         with torch.cuda.stream(comm):
-            if world > 1:
-                src = None
-                if rank == 0:
-                    base = torch.arange(world * B, dtype=torch.int32, device=dev).reshape(world, B) + step * world * B
-                    src = [base[r].contiguous() for r in range(world)]
-                dist.scatter(buf, src, src=0)
-            else:
-                buf.copy_(torch.arange(B, dtype=torch.int32, device=dev) + step * B)
+            sharding.scatter_assignment(step, B, assign[step % 2])  # NCCL scatter from rank 0 (a copy when world == 1)
             ready[step % 2].record(comm)
 
     fr = [frames[f] for f in range(B)]
@@ -193,7 +199,11 @@ def main():
     for s in range(Wm):
         run_step(s)
     barrier()
-    clocks = ClockSampler(local_rank)
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    clocks = ClockSampler(uuid, local_rank)
     if rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -210,47 +220,36 @@ def main():
     ms_max = float(t.item())
     fps = world * B * K / (ms_max * 1e-3)
 
-    # ---- end to end through the C ABI with HOST buffers: pinned frame -> H2D -> kernel -> D2H, 3-deep pipeline
-    depth = 3
-    h_in = [torch.empty(frame_bytes, dtype=torch.uint8).pin_memory() for _ in range(depth)]
-    h_out = [torch.empty(out_bytes, dtype=torch.uint8).pin_memory() for _ in range(depth)]
-    for b in h_in:
-        b.copy_(frames[0].cpu())
-    d_in = [torch.empty(frame_bytes, dtype=torch.uint8, device=dev) for _ in range(depth)]
-    d_out = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(depth)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+    # ---- end to end through the reference-facing plugin: compress_init("cuda_dxt:DXT1") / compress_frame / compress_pop with HOST
+    # frames (pinned, like UltraGrid's capture buffers can be); H2D + kernel + D2H are inside the timed region, every frame
+    compress.set_cuda_devices([local_rank])
+    nhost = 4
+    h_in = [torch.empty(frame_bytes, dtype=torch.uint8).pin_memory() for _ in range(nhost)]
+    for i, b in enumerate(h_in):
+        b.copy_(frames[i % B].cpu())
+    h_np = [b.numpy() for b in h_in]
+    h_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory().numpy()
+    plugin = compress.Compress("cuda_dxt:DXT1")
 
     def e2e_step():
         for f in range(B):
-            k = f % depth
-            with torch.cuda.stream(streams[k]):
-                d_in[k].copy_(h_in[k], non_blocking=True)
-                api.uyvy_to_dxt(d_in[k], W8K, H8K, dxt_type=1, out=d_out[k], stream=streams[k])
-                h_out[k].copy_(d_out[k], non_blocking=True)
-        for s_ in streams:
-            s_.synchronize()
+            plugin.push(h_np[f % nhost], W8K, H8K, 2)  # codec_t UYVY
+            got = plugin.pop_into(h_out)
+            assert got is not None and got[0] == out_bytes
 
     Ke = max(3, min(K, 10))
     for _ in range(2):
         e2e_step()
     barrier()
-    cur = torch.cuda.current_stream()
-    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    x0.record(cur)
-    for s_ in streams:
-        s_.wait_event(x0)
+    t0 = time.perf_counter()  # the module synchronises its own stream per frame: host wall clock brackets whole frames
     for _ in range(Ke):
         e2e_step()
-    for s_ in streams:
-        ev = torch.cuda.Event()
-        ev.record(s_)
-        cur.wait_event(ev)
-    x1.record(cur)
-    barrier()
-    e2e_t = torch.tensor([x0.elapsed_time(x1) * 1e-3], dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_fps = world * B * Ke / float(e2e_t.item())
+    plugin.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -274,12 +273,14 @@ def main():
                          "kernel": "ugb::dxt_uyvy_kernel<1,2,false>", "algorithmic_bytes_per_launch": ALGO_BYTES_UYVY_DXT1,
                          "us_per_launch": per_launch_ms * 1e3, "peak_source": peak_src},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * out_bytes,
-                    "path": "pinned host frame -> cudaMemcpyAsync -> ugb200_uyvy_to_dxt1_async -> cudaMemcpyAsync, 3 streams"},
+                    "path": "compress_init('cuda_dxt:DXT1'): pinned host UYVY frame -> compress_frame (H2D, fused kernel, D2H into a pooled "
+                            "pinned frame) -> compress_pop -> host copy; one frame in flight (synchronous tile API like the reference module)"},
             "gpu_launches": B * K,
             "clocks": clk,
         }
         if world == 1 and not args.no_extra:
             line["extra"] = extra_kernels(api, torch, dev)
+            line["extra"]["jpeg"] = extra_jpeg(api, compress, torch, dev)
             v, cores, sample = cpu_port_fps()
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
             line["extra"]["cpu_reference_pixfmt"] = cpu_reference_pixfmt()
@@ -339,6 +340,50 @@ def extra_kernels(api, torch, dev):
         rec(name, time_kernel(torch, lambda i: api.pixfmt_convert(inc, outc, src[i % n], ww, hh, dst=dst), 40),
             (vc_get_linesize(ww, inc) + vc_get_linesize(ww, outc)) * hh, ww * hh)
         del src
+    return res
+
+
+def extra_jpeg(api, compress, torch, dev):
+    """second half of the metric: 7680x4320 UYVY -> JPEG (q=90), kernel-only (device-resident) and through the GPUJPEG module"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    res = {}
+    orc = util.oracle()
+    yy, xx = np.mgrid[0:H8K, 0:W8K]
+    rgb = np.stack([xx * 255 // (W8K - 1), yy * 255 // (H8K - 1), (xx + yy) % 256], axis=2).astype(np.uint8)
+    rgb = (rgb.astype(np.int16) + np.random.default_rng(1).integers(-6, 7, rgb.shape, dtype=np.int16)).clip(0, 255).astype(np.uint8)
+    natural = util.convert_cpu(orc, "orc_convert", 12, 2, rgb.reshape(-1), W8K, H8K)
+    del rgb
+    inputs = {"natural": torch.from_numpy(natural).cuda(), "testcard": torch.from_numpy(util.testcard_uyvy(W8K, H8K, orc)).cuda(),
+              "noise": torch.randint(0, 256, (W8K * H8K * 2,), dtype=torch.uint8, device=dev)}
+    enc = api.JpegEncoder()
+    for name, src in inputs.items():
+        enc.encode_device(src, W8K, H8K, 2, quality=90)
+        nbytes = len(enc.result())
+        n = 6
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            enc.encode_device(src, W8K, H8K, 2, quality=90)
+        e1.record()
+        enc.result()
+        secs = e0.elapsed_time(e1) / n * 1e-3
+        res[name] = {"us": secs * 1e6, "fps": 1 / secs, "stream_bytes": nbytes, "algorithmic_GBps": (W8K * H8K * 2 + nbytes) / secs / 1e9}
+    enc.close()
+    # through the module with a host frame
+    host = torch.from_numpy(natural).pin_memory().numpy()
+    out = np.empty(W8K * H8K * 3, dtype=np.uint8)
+    c = compress.Compress("GPUJPEG:q=90")
+    c.push(host, W8K, H8K, 2)
+    c.pop_into(out)
+    t0 = time.perf_counter()
+    n = 5
+    for _ in range(n):
+        c.push(host, W8K, H8K, 2)
+        c.pop_into(out)
+    res["natural_e2e_module_fps"] = n / (time.perf_counter() - t0)
+    c.close()
     return res
 
 

@@ -1,0 +1,44 @@
+/* Plain-C driver of the C++ video_compress module layer (ultragrid_b200/csrc/host/video_compress.h), for tests,
+ * bench.py and non-C++ hosts.  It stands where UltraGrid's sender calls compress_init / compress_frame / compress_pop
+ * (src/video_compress.h:95-107, call sites src/rxtx.cpp:183-194,260-289).
+ */
+#ifndef UGB200_VCOMPRESS_H
+#define UGB200_VCOMPRESS_H
+
+#include <stddef.h>
+
+#include "cuda_wrapper.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ugb200_compress ugb200_compress;
+
+/* -D/--cuda-device a,b,... (src/main.cpp:402-431 -> cuda_devices[], src/host.cpp:177-179); up to 8 devices */
+UGB_API int ugb200_set_cuda_devices(const int *devices, int count);
+
+/* compress_init(parent, config): "cuda_dxt[:DXT1|:DXT5]" (src/video_compress/cuda_dxt.cpp:108-119) or
+ * "GPUJPEG[:q=<1-100>][:restart=<n>]" (src/video_compress/gpujpeg.cpp:371-424).  NULL on error. */
+UGB_API ugb200_compress *ugb200_compress_init(const char *config);
+
+/* compress_frame(): hand one frame to the compressor.  data is a host pointer (mem_location 0 = CPU_MEM) or a device
+ * pointer (1 = CUDA_MEM, src/types.h:295-298); it must stay valid until the frame has been popped (the reference holds the input shared_ptr the same way).  data == NULL passes the
+ * poison pill that ends the stream (src/video_compress.h:143-147).  0 ok, <0 error. */
+UGB_API int ugb200_compress_push(ugb200_compress *s, const void *data, int mem_location, int width, int height, int codec,
+                                 double fps);
+
+/* compress_pop(): blocks for the next compressed frame, in submission order.  Copies it to out (capacity cap).
+ * 0 ok; 1 end of stream (poison pill came through); -1 error / buffer too small. */
+UGB_API int ugb200_compress_pop(ugb200_compress *s, void *out, size_t cap, size_t *out_len, int *out_codec, unsigned *seq);
+
+UGB_API void ugb200_compress_done(ugb200_compress *s);
+
+/* get_best_decoder_from(in, candidates, &out) (src/pixfmt_conv.c:3148-3172): the codec_t a module converts `in` to when it
+ * natively accepts `candidates`; 0 (VIDEO_CODEC_NONE) if no conversion exists. */
+UGB_API int ugb200_get_best_decoder_from(int in_codec, const int *candidates, int count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -79,3 +79,15 @@ API void ref_v210_to_p010le_parallel(int width, int height, unsigned char *out_y
         d.in_data = in;
         decode_to_planar_parallel(v210_to_p010le, d, vc_get_linesize(width, v210), threads);
 }
+
+API int ref_get_best_decoder_from(int in_codec, const int *candidates, int count)
+{
+        codec_t cand[VIDEO_CODEC_END + 1];
+        int n = 0;
+        for (; n < count && n < VIDEO_CODEC_END; ++n) {
+                cand[n] = (codec_t) candidates[n];
+        }
+        cand[n] = VIDEO_CODEC_NONE;
+        codec_t out = VIDEO_CODEC_NONE;
+        return get_best_decoder_from((codec_t) in_codec, cand, &out) != NULL ? (int) out : 0;
+}

@@ -50,6 +50,13 @@ SIGNATURES = {
     "ugb200_jpeg_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ugb200_jpeg_encode": (_i, [_vp, _vp, _i, _l, _i, _i, _i, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ugb200_jpeg_debug_coefficients": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    # include/ugb200_vcompress.h
+    "ugb200_set_cuda_devices": (_i, [ctypes.POINTER(_i), _i]),
+    "ugb200_compress_init": (_vp, [ctypes.c_char_p]),
+    "ugb200_compress_push": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.c_double]),
+    "ugb200_compress_pop": (_i, [_vp, _vp, _sz, ctypes.POINTER(_sz), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_uint)]),
+    "ugb200_compress_done": (None, [_vp]),
+    "ugb200_get_best_decoder_from": (_i, [_i, ctypes.POINTER(_i), _i]),
 }
 
 _lib = None

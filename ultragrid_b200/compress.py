@@ -1,0 +1,68 @@
+"""Python driver of the C++ video_compress module layer (include/ugb200_vcompress.h) — the call a user of the
+reference makes: compress_init("cuda_dxt:DXT1") / compress_frame / compress_pop (src/video_compress.h:95-107)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_L = _lib.load()
+
+
+def set_cuda_devices(devices):
+    """-D/--cuda-device (src/main.cpp:402-431)"""
+    arr = (ctypes.c_int * len(devices))(*devices)
+    if _L.ugb200_set_cuda_devices(arr, len(devices)) != 0:
+        raise ValueError("bad device list")
+
+
+def get_best_decoder_from(in_codec, candidates):
+    arr = (ctypes.c_int * len(candidates))(*[int(c) for c in candidates])
+    return _L.ugb200_get_best_decoder_from(int(in_codec), arr, len(candidates))
+
+
+class Compress:
+    def __init__(self, config):
+        self._h = _L.ugb200_compress_init(config.encode())
+        if not self._h:
+            raise RuntimeError(f"compress_init({config!r}) failed")
+        self._keep = []
+
+    def push(self, frame, width, height, codec, fps=60.0):
+        """frame: host numpy uint8 array, a CUDA torch tensor (CUDA_MEM), or None (poison pill)"""
+        if frame is None:
+            rc = _L.ugb200_compress_push(self._h, None, 0, 0, 0, 0, 0.0)
+        elif isinstance(frame, np.ndarray):
+            self._keep.append(frame)
+            rc = _L.ugb200_compress_push(self._h, ctypes.c_void_p(frame.ctypes.data), 0, width, height, int(codec), fps)
+        else:
+            self._keep.append(frame)
+            rc = _L.ugb200_compress_push(self._h, ctypes.c_void_p(frame.data_ptr()), 1, width, height, int(codec), fps)
+        if rc != 0:
+            raise RuntimeError(f"compress_frame failed ({rc})")
+
+    def pop_into(self, out):
+        """pops the next frame into the numpy buffer `out`; returns (nbytes, codec, seq) or None at end of stream"""
+        n, codec, seq = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_uint()
+        rc = _L.ugb200_compress_pop(self._h, ctypes.c_void_p(out.ctypes.data), out.size, ctypes.byref(n), ctypes.byref(codec), ctypes.byref(seq))
+        if rc == 1:
+            return None
+        if rc != 0:
+            raise RuntimeError(f"compress_pop failed ({rc}), frame len {n.value}")
+        if self._keep:
+            self._keep.pop(0)
+        return n.value, codec.value, seq.value
+
+    def pop(self, capacity):
+        """returns (bytes array, codec, seq) or None at end of stream"""
+        out = np.empty(capacity, dtype=np.uint8)
+        r = self.pop_into(out)
+        return None if r is None else (out[:r[0]], r[1], r[2])
+
+    def close(self):
+        if self._h:
+            _L.ugb200_compress_done(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
