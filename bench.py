@@ -31,7 +31,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=16, help="distinct 8K frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=48, help="distinct 8K frames per step per GPU")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary kernels / cpu baseline")
     return ap.parse_args()
 
@@ -49,7 +49,7 @@ class ClockSampler:
 
     def __init__(self, uuid=None, index=0):
         self.uuid, self.index, self.rows, self.stop_flag, self.thread = uuid, index, [], False, None
-        self.max_mhz = None
+        self.max_mhz, self.t0, self.t1 = None, None, None
 
     def _run(self):
         try:
@@ -71,8 +71,8 @@ class ClockSampler:
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), reasons))
-                time.sleep(0.01)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), reasons, time.perf_counter()))
+                time.sleep(0.001)
         except Exception as e:  # noqa: BLE001
             self.rows.append(("error", str(e)))
 
@@ -80,11 +80,17 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
+    def window_begin(self):
+        self.t0 = time.perf_counter()
+
+    def window_end(self):
+        self.t1 = time.perf_counter()
+
     def stop(self):
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=2)
-        good = [r for r in self.rows if r[0] != "error"]
+        good = [r for r in self.rows if r[0] != "error" and (self.t0 is None or self.t0 <= r[2] <= (self.t1 or 1e30))]
         sm = sorted(r[0] for r in good)
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         reasons = sorted({n for r in good for bit, n in names.items() if r[1] & bit})
@@ -195,23 +201,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    scatter_assignment(0)
-    for s in range(Wm):
-        run_step(s)
-    barrier()
     try:
         uuid = str(torch.cuda.get_device_properties(dev).uuid)
     except Exception:
         uuid = None
     clocks = ClockSampler(uuid, local_rank)
     if rank == 0:
-        clocks.start()
+        clocks.start()  # NVML initialises while the warm-up runs; only samples inside the timed window are kept
+    scatter_assignment(0)
+    for s in range(Wm):
+        run_step(s)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.window_begin()
     e0.record()
     for s in range(K):
         run_step(Wm + s)
     e1.record()
     barrier()
+    clocks.window_end()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)

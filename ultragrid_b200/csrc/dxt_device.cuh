@@ -195,3 +195,110 @@ __device__ __forceinline__ uint2 dxt1_encode(const float (&r)[16], const float (
 }
 
 }  // namespace ugb
+
+// ================================================================================================
+// Packed (f32x2) formulation of the fused UYVY -> DXT1 block encode.
+//
+// Same operation tree, hence the same bits, as load_row_uyvy() + dxt1_encode(); only the ISSUE width changes:
+// sm_100 executes fma/mul/add .f32x2 on two lanes of a 64-bit register pair in one issue slot (measured: no extra
+// FMA throughput, half the issue slots — profiles/r01_ubench_instruction_throughput.txt), which lets the ~150
+// ALU-pipe instructions of a block (PRMT, FMNMX3, LEA …) overlap the ~340 FMA-pipe lane-operations.
+// Pairing: pixels x and x+2 of a row share an instruction, because their chroma (U0,U1)/(V0,V1) is itself a natural
+// pair; element [2y + (x&1)].{x,y}[x>>1] of an array holds pixel (x, y).
+// ================================================================================================
+namespace ugb {
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float px(const float2 (&v)[8], int i) { return ((i & 3) >> 1) ? v[2 * (i >> 2) + (i & 1)].y : v[2 * (i >> 2) + (i & 1)].x; }
+
+__device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][2])
+{
+        float2 R[8], G[8], B[8];
+        const float2 c2 = dup(kInv255), ky2 = dup(kBiasY), kc2 = dup(kBiasC);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+                const uint32_t w0 = w[y][0], w1 = w[y][1];
+                const float2 u = __ffma2_rn(f2(magic_byte(w0, 0), magic_byte(w1, 0)), c2, kc2);
+                const float2 v = __ffma2_rn(f2(magic_byte(w0, 2), magic_byte(w1, 2)), c2, kc2);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {  // k = 0: pixels x = 0, 2;  k = 1: pixels x = 1, 3
+                        const float2 yy = __fmul2_rn(__ffma2_rn(f2(magic_byte(w0, 1 + 2 * k), magic_byte(w1, 1 + 2 * k)), c2, ky2), dup(1.1643f));
+                        R[2 * y + k] = __ffma2_rn(v, dup(1.7926f), yy);
+                        G[2 * y + k] = __ffma2_rn(v, dup(-0.5328f), __ffma2_rn(u, dup(-0.2132f), yy));
+                        B[2 * y + k] = __ffma2_rn(u, dup(2.1124f), yy);
+                }
+        }
+        // bounding box
+        float mnr = R[0].x, mng = G[0].x, mnb = B[0].x, mxr = mnr, mxg = mng, mxb = mnb;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+                mnr = fminf(mnr, fminf(R[j].x, R[j].y)), mxr = fmaxf(mxr, fmaxf(R[j].x, R[j].y));
+                mng = fminf(mng, fminf(G[j].x, G[j].y)), mxg = fmaxf(mxg, fmaxf(G[j].x, G[j].y));
+                mnb = fminf(mnb, fminf(B[j].x, B[j].y)), mxb = fmaxf(mxb, fmaxf(B[j].x, B[j].y));
+        }
+        const float dr = __fadd_rn(mxr, -mnr), dg = __fadd_rn(mxg, -mng), db = __fadd_rn(mxb, -mnb);
+        const float lor = __fmaf_rn(dr, 0.0625f, mnr), hir = __fmaf_rn(dr, -0.0625f, mxr);
+        const float log_ = __fmaf_rn(dg, 0.0625f, mng), hig = __fmaf_rn(dg, -0.0625f, mxg);
+        const float lob = __fmaf_rn(db, 0.0625f, mnb), hib = __fmaf_rn(db, -0.0625f, mxb);
+        // deviations from the box centre, packed; covariance chains stay scalar and sequential (i = 0..15)
+        const float2 sr2 = dup(__fadd_rn(lor, hir)), sg2 = dup(__fadd_rn(log_, hig)), sb2 = dup(__fadd_rn(lob, hib)), mh = dup(-0.5f);
+        float2 ER[8], EG[8], EB[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+                ER[j] = __ffma2_rn(sr2, mh, R[j]);
+                EG[j] = __ffma2_rn(sg2, mh, G[j]);
+                EB[j] = __ffma2_rn(sb2, mh, B[j]);
+        }
+        float covx = 0.0f, covy = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+                covx = __fmaf_rn(px(ER, i), px(EB, i), covx);
+                covy = __fmaf_rn(px(EG, i), px(EB, i), covy);
+        }
+        const bool swr = covx < 0.0f, swg = covy < 0.0f;
+        const float maxr = swr ? lor : hir, minr = swr ? hir : lor;
+        const float maxg = swg ? log_ : hig, ming = swg ? hig : log_;
+        const float qxr = quant_magic(maxr, 31.0f), qxg = quant_magic(maxg, 63.0f), qxb = quant_magic(hib, 31.0f);
+        const float qnr = quant_magic(minr, 31.0f), qng = quant_magic(ming, 63.0f), qnb = quant_magic(lob, 31.0f);
+        constexpr uint32_t kCodeBias = 0x4B400000u * 2081u;
+        const uint32_t max_code = (__float_as_uint(qxr) << 11) + (__float_as_uint(qxg) << 5) + __float_as_uint(qxb) - kCodeBias;
+        const uint32_t min_code = (__float_as_uint(qnr) << 11) + (__float_as_uint(qng) << 5) + __float_as_uint(qnb) - kCodeBias;
+
+        uint32_t indices = 0;
+        if (max_code != min_code) {
+                const float ex_r = __fmul_rn(__fadd_rn(qxr, -kRoundMagic), kInv31);
+                const float ex_g = __fmul_rn(__fadd_rn(qxg, -kRoundMagic), kInv63);
+                const float ex_b = __fmul_rn(__fadd_rn(qxb, -kRoundMagic), kInv31);
+                const float dir_r = __fmaf_rn(__fadd_rn(qnr, -kRoundMagic), kInv31, -ex_r);
+                const float dir_g = __fmaf_rn(__fadd_rn(qng, -kRoundMagic), kInv63, -ex_g);
+                const float dir_b = __fmaf_rn(__fadd_rn(qnb, -kRoundMagic), kInv31, -ex_b);
+                const float len2 = __fmaf_rn(dir_b, dir_b, __fmaf_rn(dir_r, dir_r, __fmul_rn(dir_g, dir_g)));
+                const float inv = __fdividef(1.0f, len2);
+                const float tr = __fmul_rn(dir_r, inv), tg = __fmul_rn(dir_g, inv), tb = __fmul_rn(dir_b, inv);
+                const float nbias = -__fmaf_rn(ex_b, tb, __fmaf_rn(ex_r, tr, __fmul_rn(ex_g, tg)));
+                const float2 tr2 = dup(tr), tg2 = dup(tg), tb2 = dup(tb);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                        const float2 t = __ffma2_rn(B[j], tb2, __ffma2_rn(R[j], tr2, __fmul2_rn(G[j], tg2)));
+                        const float2 x = __ffma2_rn(f2(add_sat_rn(t.x, nbias), add_sat_rn(t.y, nbias)), dup(3.0f), dup(0.5f));
+                        const float2 m = __fadd2_rd(x, dup(kFloorMagic));
+                        const int i0 = 4 * (j >> 1) + (j & 1);  // pixel of .x; .y is pixel i0 + 2
+                        acc += __float_as_uint(m.x) << (2 * i0);
+                        acc += __float_as_uint(m.y) << (2 * (i0 + 2));
+                }
+                constexpr uint32_t kIdxBias = 0x4B000000u * 0x55555555u;
+                indices = acc - kIdxBias;
+        }
+        const bool swap_end = max_code < min_code;
+        if (swap_end) {
+                indices = ~indices;
+        }
+        const uint32_t lsbs = indices & 0x55555555u, msbs = indices & 0xaaaaaaaau;
+        indices = msbs ^ (2 * lsbs + (msbs >> 1));
+        const uint32_t palette = swap_end ? min_code + (max_code << 16) : max_code + (min_code << 16);
+        return make_uint2(palette, indices);
+}
+
+}  // namespace ugb

@@ -94,12 +94,18 @@ __global__ void __launch_bounds__(128) dxt_uyvy_kernel(const uint8_t *__restrict
         out_t res[BPT];
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
-                float r[16], g[16], b[16];
+                if constexpr (DXT_TYPE == 1) {  // packed f32x2 formulation (same operation tree)
+                        const uint32_t wk[4][2] = { { w[0][2 * k], w[0][2 * k + 1] }, { w[1][2 * k], w[1][2 * k + 1] },
+                                                    { w[2][2 * k], w[2][2 * k + 1] }, { w[3][2 * k], w[3][2 * k + 1] } };
+                        res[k] = dxt1_encode_uyvy_packed(wk);
+                } else {
+                        float r[16], g[16], b[16];
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                        load_row_uyvy(w[y][2 * k], w[y][2 * k + 1], r + 4 * y, g + 4 * y, b + 4 * y);
+                        for (int y = 0; y < 4; ++y) {
+                                load_row_uyvy(w[y][2 * k], w[y][2 * k + 1], r + 4 * y, g + 4 * y, b + 4 * y);
+                        }
+                        res[k] = encode_block<DXT_TYPE>(r, g, b);
                 }
-                res[k] = encode_block<DXT_TYPE>(r, g, b);
         }
         out_t *o = (out_t *) out + ((long) by * wb + gx * BPT);
         if (DXT_TYPE == 1 && BPT == 2) {
