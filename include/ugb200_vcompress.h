@@ -18,7 +18,8 @@ typedef struct ugb200_compress ugb200_compress;
 /* -D/--cuda-device a,b,... (src/main.cpp:402-431 -> cuda_devices[], src/host.cpp:177-179); up to 8 devices */
 UGB_API int ugb200_set_cuda_devices(const int *devices, int count);
 
-/* compress_init(parent, config): "cuda_dxt[:DXT1|:DXT5]" (src/video_compress/cuda_dxt.cpp:108-119) or
+/* compress_init(parent, config): "cuda_dxt[:DXT1|:DXT5]" (src/video_compress/cuda_dxt.cpp:108-119; asynchronous, 3 frames in
+ * flight; "cuda_dxt_sync" is the same module behind the reference's synchronous tile API) or
  * "GPUJPEG[:q=<1-100>][:restart=<n>]" (src/video_compress/gpujpeg.cpp:371-424).  NULL on error. */
 UGB_API ugb200_compress *ugb200_compress_init(const char *config);
 
@@ -31,6 +32,10 @@ UGB_API int ugb200_compress_push(ugb200_compress *s, const void *data, int mem_l
 /* compress_pop(): blocks for the next compressed frame, in submission order.  Copies it to out (capacity cap).
  * 0 ok; 1 end of stream (poison pill came through); -1 error / buffer too small. */
 UGB_API int ugb200_compress_pop(ugb200_compress *s, void *out, size_t cap, size_t *out_len, int *out_codec, unsigned *seq);
+
+/* Same as ugb200_compress_pop without the copy: *data points into the pooled (pinned) output frame and stays valid until the
+ * next pop / done on this handle — what UltraGrid's sender gets as shared_ptr<video_frame>. */
+UGB_API int ugb200_compress_pop_ref(ugb200_compress *s, const void **data, size_t *len, int *out_codec, unsigned *seq);
 
 UGB_API void ugb200_compress_done(ugb200_compress *s);
 

@@ -271,6 +271,86 @@ static void bgr_to_rgb(unsigned char *d, const unsigned char *s, int n, int rs, 
 /* vc_memcpy, pixfmt_conv.c:2529-2536 */
 static void copy_line(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; memcpy(d, s, n); }
 
+/* ---- v210 family ---------------------------------------------------------------------------------------- */
+#define S10(w, sh) (((w) >> (sh)) & 0x3ffu)
+/* vc_copylineUYVYtoV210, pixfmt_conv.c:2581-2607 */
+static void uyvy_to_v210(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (; dst_len >= 4; dst_len -= 4, dst += 4, src += 3) {
+                wr32(dst, (uint32_t) src[0] << 2 | (uint32_t) src[1] << 12 | (uint32_t) src[2] << 22);
+        }
+}
+/* vc_copylineY216toV210, pixfmt_conv.c:2761-2790 */
+static void y216_to_v210(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x < (dst_len + 15) / 16; ++x) {
+                uint16_t s[12];
+                memcpy(s, src + x * 24, 24);
+                unsigned char *d = dst + x * 16;
+                wr32(d, (uint32_t) (s[1] >> 6) | (uint32_t) (s[0] >> 6) << 10 | (uint32_t) (s[3] >> 6) << 20);
+                wr32(d + 4, (uint32_t) (s[2] >> 6) | (uint32_t) (s[5] >> 6) << 10 | (uint32_t) (s[4] >> 6) << 20);
+                wr32(d + 8, (uint32_t) (s[7] >> 6) | (uint32_t) (s[6] >> 6) << 10 | (uint32_t) (s[9] >> 6) << 20);
+                wr32(d + 12, (uint32_t) (s[8] >> 6) | (uint32_t) (s[11] >> 6) << 10 | (uint32_t) (s[10] >> 6) << 20);
+        }
+}
+static void v210_group(const unsigned char *src, unsigned y[6], unsigned u[3], unsigned v[3])
+{
+        const uint32_t w0 = rd32(src), w1 = rd32(src + 4), w2 = rd32(src + 8), w3 = rd32(src + 12);
+        y[0] = S10(w0, 10), y[1] = S10(w1, 0), y[2] = S10(w1, 20), y[3] = S10(w2, 10), y[4] = S10(w3, 0), y[5] = S10(w3, 20);
+        u[0] = S10(w0, 0), u[1] = S10(w1, 10), u[2] = S10(w2, 20);
+        v[0] = S10(w0, 20), v[1] = S10(w2, 0), v[2] = S10(w3, 10);
+}
+/* vc_copylineV210toY216, pixfmt_conv.c:2792-2832 */
+static void v210_to_y216(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x < dst_len / 24; ++x) {
+                unsigned y[6], u[3], v[3];
+                v210_group(src + x * 16, y, u, v);
+                uint16_t d[12];
+                for (int i = 0; i < 3; ++i) {
+                        d[4 * i] = y[2 * i] << 6, d[4 * i + 1] = u[i] << 6, d[4 * i + 2] = y[2 * i + 1] << 6, d[4 * i + 3] = v[i] << 6;
+                }
+                memcpy(dst + x * 24, d, 24);
+        }
+}
+/* vc_copylineV210toY416, pixfmt_conv.c:2834-2882 */
+static void v210_to_y416(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x < dst_len / 48; ++x) {
+                unsigned y[6], u[3], v[3];
+                v210_group(src + x * 16, y, u, v);
+                uint16_t d[24];
+                for (int i = 0; i < 6; ++i) {
+                        d[4 * i] = u[i / 2] << 6, d[4 * i + 1] = y[i] << 6, d[4 * i + 2] = v[i / 2] << 6, d[4 * i + 3] = 0xFFFFU;
+                }
+                memcpy(dst + x * 48, d, 48);
+        }
+}
+/* vc_copylineV210toRGB, pixfmt_conv.c:2884-2940 */
+static void v210_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(8);
+        for (int x = 0; x < dst_len; x += 18, src += 16) {
+                unsigned y[6], u[3], v[3];
+                v210_group(src, y, u, v);
+                for (int i = 0; i < 6; ++i) {
+                        const int ys = c.y_scale * ((int) (y[i] >> 2) - 16), uu = (int) (u[i / 2] >> 2) - 128, vv = (int) (v[i / 2] >> 2) - 128;
+                        int val = (ys + vv * c.r_cr) >> COMP_BASE;
+                        *dst++ = val < 1 ? 1 : val > 254 ? 254 : val; /* CLAMP_FULL, color_space.h:96-98 */
+                        val = (ys + uu * c.g_cb + vv * c.g_cr) >> COMP_BASE;
+                        *dst++ = val < 1 ? 1 : val > 254 ? 254 : val;
+                        val = (ys + uu * c.b_cb) >> COMP_BASE;
+                        *dst++ = val < 1 ? 1 : val > 254 ? 254 : val;
+                }
+        }
+}
+#undef S10
+
 /* get_decoder_from_to, pixfmt_conv.c:3110-3125 (subset of decoders[] :3041-3103 restated so far) */
 static line_fn *decoder_from_to(int in, int out)
 {
@@ -292,6 +372,11 @@ static line_fn *decoder_from_to(int in, int out)
         case C_RGBA * 256 + C_RGBA: return rgba_to_rgba;
         case C_RGB * 256 + C_RGB: return rgb_to_rgb;
         case C_BGR * 256 + C_RGB: return bgr_to_rgb;
+        case C_UYVY * 256 + C_v210: return uyvy_to_v210;
+        case C_Y216 * 256 + C_v210: return y216_to_v210;
+        case C_v210 * 256 + C_Y216: return v210_to_y216;
+        case C_v210 * 256 + C_Y416: return v210_to_y416;
+        case C_v210 * 256 + C_RGB: return v210_to_rgb;
         }
         return NULL;
 }

@@ -12,10 +12,11 @@ import pytest
 
 import util
 
-UYVY, YUYV, RGBA, RGB, BGR, RG48, V210 = 2, 3, 1, 12, 20, 27, 7
+UYVY, YUYV, RGBA, RGB, BGR, RG48, V210, Y216, Y416 = 2, 3, 1, 12, 20, 27, 7, 30, 31
 
 PAIRS = [(V210, UYVY), (YUYV, UYVY), (UYVY, YUYV), (UYVY, RGB), (YUYV, RGB), (UYVY, RGBA), (RGB, UYVY), (BGR, UYVY), (RGBA, UYVY),
-         (RG48, UYVY), (RGB, RGBA), (RGBA, RGB), (RGBA, RGBA), (RGB, RGB), (BGR, RGB), (UYVY, UYVY)]
+         (RG48, UYVY), (RGB, RGBA), (RGBA, RGB), (RGBA, RGBA), (RGB, RGB), (BGR, RGB), (UYVY, UYVY),
+         (UYVY, V210), (Y216, V210), (V210, Y216), (V210, Y416), (V210, RGB)]
 
 
 def test_known_answer_checksums(orc):

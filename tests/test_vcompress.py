@@ -68,6 +68,23 @@ def test_cuda_dxt_module_equals_kernel_path(orc, cfg, inc):
     c.push(d, w, h, inc)  # device-resident input (mem_location == CUDA_MEM)
     got, _, _ = c.pop(w * h)
     assert np.array_equal(got, want)
+    # pipelined use of the asynchronous shape: five frames pushed back to back (3 in flight), popped in order, zero-copy
+    frames = [src.copy() for _ in range(5)]
+    frames[2][:] = 0
+    for f in frames:
+        c.push(f, w, h, inc)
+    c.push(None, 0, 0, 0)
+    for i in range(5):
+        view, codec, seq = c.pop_ref()
+        assert seq == 4 + i
+        assert np.array_equal(view, want) == (i != 2)
+    assert c.pop_ref() is None
+    c.close()
+    # the same module behind the reference's synchronous tile API
+    c = compress.Compress(cfg.replace("cuda_dxt", "cuda_dxt_sync"))
+    c.push(src, w, h, inc)
+    got, _, _ = c.pop(w * h)
+    assert np.array_equal(got, want)
     c.close()
 
 

@@ -167,7 +167,7 @@ def convert_cpu(lib, fn, in_c, out_c, src, width, height, dst_len=None, src_pitc
     src_pitch = ls(width, in_c) if src_pitch is None else src_pitch
     dst_pitch = ls(width, out_c) if dst_pitch is None else dst_pitch
     dst_len = ls(width, out_c) if dst_len is None else dst_len
-    srcp = np.concatenate([src, np.zeros(64, dtype=np.uint8)])  # MAX_PADDING slack, video_codec.h:61
+    srcp = np.concatenate([src, np.zeros(4096, dtype=np.uint8)])  # zero slack (>= MAX_PADDING, video_codec.h:61): over-reads see zeros, like the GPU path
     dst = np.zeros(dst_pitch * height + 64, dtype=np.uint8)
     rc = getattr(lib, fn)(in_c, out_c, dst.ctypes.data, dst_pitch, srcp.ctypes.data, src_pitch, dst_len, height, *shifts)
     assert rc == 0, rc

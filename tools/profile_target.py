@@ -28,4 +28,17 @@ elif which == "uyvy_rgb":
     dst = torch.empty(W * H * 3, dtype=torch.uint8, device=dev)
     for i in range(6):
         api.pixfmt_convert(Codec.UYVY, Codec.RGB, src[i % 3], W, H, dst=dst)
+elif which == "jpeg":
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import util
+    orc = util.oracle()
+    yy, xx = np.mgrid[0:H, 0:W]
+    rgb = np.stack([xx * 255 // (W - 1), yy * 255 // (H - 1), (xx + yy) % 256], axis=2).astype(np.uint8)
+    rgb = (rgb.astype(np.int16) + np.random.default_rng(1).integers(-6, 7, rgb.shape, dtype=np.int16)).clip(0, 255).astype(np.uint8)
+    src = torch.from_numpy(util.convert_cpu(orc, "orc_convert", 12, 2, rgb.reshape(-1), W, H)).cuda()
+    enc = api.JpegEncoder()
+    for i in range(3):
+        enc.encode_device(src, W, H, 2, quality=90)
+    print("jpeg bytes", len(enc.result()))
 torch.cuda.synchronize()

@@ -55,6 +55,7 @@ SIGNATURES = {
     "ugb200_compress_init": (_vp, [ctypes.c_char_p]),
     "ugb200_compress_push": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.c_double]),
     "ugb200_compress_pop": (_i, [_vp, _vp, _sz, ctypes.POINTER(_sz), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_uint)]),
+    "ugb200_compress_pop_ref": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_uint)]),
     "ugb200_compress_done": (None, [_vp]),
     "ugb200_get_best_decoder_from": (_i, [_i, ctypes.POINTER(_i), _i]),
 }

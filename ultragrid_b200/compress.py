@@ -53,6 +53,19 @@ class Compress:
             self._keep.pop(0)
         return n.value, codec.value, seq.value
 
+    def pop_ref(self):
+        """zero-copy pop: (numpy view into the pooled pinned frame — valid until the next pop, codec, seq) or None at end"""
+        ptr, n, codec, seq = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int(), ctypes.c_uint()
+        rc = _L.ugb200_compress_pop_ref(self._h, ctypes.byref(ptr), ctypes.byref(n), ctypes.byref(codec), ctypes.byref(seq))
+        if rc == 1:
+            return None
+        if rc != 0:
+            raise RuntimeError(f"compress_pop failed ({rc})")
+        if self._keep:
+            self._keep.pop(0)
+        view = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(n.value,))
+        return view, codec.value, seq.value
+
     def pop(self, capacity):
         """returns (bytes array, codec, seq) or None at end of stream"""
         out = np.empty(capacity, dtype=np.uint8)

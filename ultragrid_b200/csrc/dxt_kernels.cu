@@ -14,6 +14,7 @@
 //   yuv422_to_yuv444_kernel  ABI-compat only; the fused kernels never materialise 4:4:4
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/cuda_dxt.h"
 #include "../../include/ugb200.h"
@@ -65,8 +66,8 @@ __device__ __forceinline__ uint4 encode_block<6>(const float (&r)[16], const flo
 // ------------------------------------------------------------------------------------------------
 // fused UYVY -> DXT.  One thread = BPT horizontally adjacent blocks.
 // ------------------------------------------------------------------------------------------------
-template <int DXT_TYPE, int BPT, bool MIRROR>
-__global__ void __launch_bounds__(128) dxt_uyvy_kernel(const uint8_t *__restrict__ src, void *__restrict__ out,
+template <int DXT_TYPE, int BPT, bool MIRROR, int MINB = 6>
+__global__ void __launch_bounds__(128, MINB) dxt_uyvy_kernel(const uint8_t *__restrict__ src, void *__restrict__ out,
                                                         int wb /* blocks per row */, int h, long pitch)
 {
         typedef typename block_out<DXT_TYPE>::type out_t;
@@ -246,7 +247,16 @@ static int launch_uyvy(const void *src, void *out, int sx, int sy, long pitch, c
         const dim3 grid((groups + threads - 1) / threads, hb);
         const uint8_t *s = (const uint8_t *) src;
 #define UGB_LAUNCH(BPT, MIR) dxt_uyvy_kernel<DXT_TYPE, BPT, MIR><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch)
-        if (pair) {
+        static const int tune_minb = getenv("UGB200_DXT_MINB") ? atoi(getenv("UGB200_DXT_MINB")) : 0;  // occupancy experiment knob
+        if (DXT_TYPE == 1 && pair && !mirrored && (tune_minb == 1 || tune_minb >= 7)) {
+                if (tune_minb == 1) {
+                        dxt_uyvy_kernel<DXT_TYPE, 2, false, 1><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch);
+                } else if (tune_minb == 7) {
+                        dxt_uyvy_kernel<DXT_TYPE, 2, false, 7><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch);
+                } else {
+                        dxt_uyvy_kernel<DXT_TYPE, 2, false, 8><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch);
+                }
+        } else if (pair) {
                 if (mirrored) {
                         UGB_LAUNCH(2, true);
                 } else {

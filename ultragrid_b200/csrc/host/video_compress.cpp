@@ -121,15 +121,28 @@ namespace {
                 }                                                                                                                          \
         } while (0)
 
-struct state_video_compress_cuda_dxt {
-        struct video_desc saved_desc {};
+/// one in-flight frame: own stream and buffers, so that the H2D of frame n+1 overlaps the kernel + D2H of frame n
+struct dxt_slot {
+        cuda_wrapper_stream_t stream = nullptr;
         char *cuda_src_buffer = nullptr;  ///< frame as captured, device memory
         char *cuda_in_buffer = nullptr;   ///< frame converted to in_codec (only when a conversion is needed)
         char *cuda_out_buffer = nullptr;
+        std::shared_ptr<video_frame> in, out;
+        bool busy = false;
+};
+
+struct state_video_compress_cuda_dxt {
+        enum { DEPTH = 3 };
+        struct video_desc saved_desc {};
+        dxt_slot slots[DEPTH];
         codec_t in_codec = VIDEO_CODEC_NONE, out_codec = DXT1;
         decoder_t decoder{ VIDEO_CODEC_NONE, VIDEO_CODEC_NONE };
-        cuda_wrapper_stream_t stream = nullptr;
         size_t out_len = 0;
+        unsigned head = 0, tail = 0;  ///< next slot to fill / oldest slot in flight
+        std::deque<std::shared_ptr<video_frame>> ready;
+        bool ended = false;
+        std::mutex m;
+        std::condition_variable cv;
 };
 
 void *cuda_dxt_compress_init(struct module *, const char *fmt)
@@ -151,10 +164,12 @@ void *cuda_dxt_compress_init(struct module *, const char *fmt)
 
 void cleanup(state_video_compress_cuda_dxt *s)
 {
-        for (char **p : { &s->cuda_src_buffer, &s->cuda_in_buffer, &s->cuda_out_buffer }) {
-                if (*p) {
-                        cuda_wrapper_free(*p);
-                        *p = nullptr;
+        for (dxt_slot &sl : s->slots) {
+                for (char **p : { &sl.cuda_src_buffer, &sl.cuda_in_buffer, &sl.cuda_out_buffer }) {
+                        if (*p) {
+                                cuda_wrapper_free(*p);
+                                *p = nullptr;
+                        }
                 }
         }
 }
@@ -172,93 +187,182 @@ bool configure_with(state_video_compress_cuda_dxt *s, struct video_desc desc)
                 fprintf(stderr, "[CUDA DXT] Unsupported codec: %s\n", get_codec_name(desc.color_spec));
                 return false;
         }
-        if (!s->stream) {
-                CHECK_CUDA(cuda_wrapper_stream_create(&s->stream), "Could not create stream", return false);
-        }
-        CHECK_CUDA(cuda_wrapper_malloc((void **) &s->cuda_src_buffer, vc_get_datalen(desc.width, desc.height, desc.color_spec) + 64),
-                   "Could not allocate CUDA input buffer", return false);
-        if (desc.color_spec != s->in_codec) {
-                CHECK_CUDA(cuda_wrapper_malloc((void **) &s->cuda_in_buffer, vc_get_datalen(desc.width, desc.height, s->in_codec)),
-                           "Could not allocate CUDA conversion buffer", return false);
-        }
         s->out_len = (size_t) desc.width * desc.height / (s->out_codec == DXT1 ? 2 : 1);  // cuda_dxt.cpp:176
-        CHECK_CUDA(cuda_wrapper_malloc((void **) &s->cuda_out_buffer, s->out_len), "Could not allocate CUDA output buffer", return false);
+        for (dxt_slot &sl : s->slots) {
+                if (!sl.stream) {
+                        CHECK_CUDA(cuda_wrapper_stream_create(&sl.stream), "Could not create stream", return false);
+                }
+                CHECK_CUDA(cuda_wrapper_malloc((void **) &sl.cuda_src_buffer, vc_get_datalen(desc.width, desc.height, desc.color_spec) + 64),
+                           "Could not allocate CUDA input buffer", return false);
+                if (desc.color_spec != s->in_codec) {
+                        CHECK_CUDA(cuda_wrapper_malloc((void **) &sl.cuda_in_buffer, vc_get_datalen(desc.width, desc.height, s->in_codec)),
+                                   "Could not allocate CUDA conversion buffer", return false);
+                }
+                CHECK_CUDA(cuda_wrapper_malloc((void **) &sl.cuda_out_buffer, s->out_len), "Could not allocate CUDA output buffer", return false);
+        }
         return true;
 }
 
+/// enqueue H2D -> (convert) -> encode -> D2H for one frame on the slot's stream; nothing here waits for the GPU
+bool enqueue(state_video_compress_cuda_dxt *s, dxt_slot &sl, const std::shared_ptr<video_frame> &tx)
+{
+        const struct video_desc desc = video_desc_from_frame(tx.get());
+        const unsigned w = desc.width, h = desc.height;
+        const char *in = tx->tiles[0].data;
+        if (tx->mem_location == CPU_MEM) {  // H2D of the frame as captured; conversion (if any) happens on the device
+                CHECK_CUDA(cuda_wrapper_memcpy_async(sl.cuda_src_buffer, in, vc_get_datalen(w, h, tx->color_spec),
+                                                     CUDA_WRAPPER_MEMCPY_HOST_TO_DEVICE, sl.stream),
+                           "Memcpy failed", return false);
+                in = sl.cuda_src_buffer;
+        }
+        if (tx->color_spec != s->in_codec) {  // replaces the per-row CPU decoder loop of cuda_dxt.cpp:207-220
+                const int rc = ugb200_pixfmt_convert(tx->color_spec, s->in_codec, sl.cuda_in_buffer, vc_get_linesize(w, s->in_codec), in,
+                                                     vc_get_linesize(w, tx->color_spec), vc_get_linesize(w, s->in_codec), (int) h,
+                                                     (long) vc_get_datalen(w, h, tx->color_spec), 0, 8, 16, sl.stream);
+                if (rc != 0) {
+                        fprintf(stderr, "[CUDA DXT] conversion kernel failed (%d)\n", rc);
+                        return false;
+                }
+                in = sl.cuda_in_buffer;
+        }
+        int rc;
+        if (s->in_codec == UYVY) {  // fused: no 4:4:4 intermediate (reference: cuda_yuv422_to_yuv444 + cuda_yuv_to_dxt*)
+                rc = s->out_codec == DXT1 ? ugb200_uyvy_to_dxt1_async(in, sl.cuda_out_buffer, (int) w, (int) h, 0, sl.stream)
+                                          : ugb200_uyvy_to_dxt6_async(in, sl.cuda_out_buffer, (int) w, (int) h, 0, sl.stream);
+        } else {
+                rc = s->out_codec == DXT1 ? ugb200_rgb_to_dxt1_async(in, sl.cuda_out_buffer, (int) w, (int) h, sl.stream)
+                                          : ugb200_rgb_to_dxt6_async(in, sl.cuda_out_buffer, (int) w, (int) h, sl.stream);
+        }
+        if (rc != 0) {
+                fprintf(stderr, "[CUDA DXT] Encoding failed (%d)\n", rc);
+                return false;
+        }
+        sl.out = pinned_pool_get(s->out_len);
+        if (!sl.out) {
+                return false;
+        }
+        sl.out->color_spec = s->out_codec, sl.out->fps = tx->fps, sl.out->interlacing = tx->interlacing, sl.out->seq = tx->seq;
+        sl.out->tiles[0].width = w, sl.out->tiles[0].height = h, sl.out->tiles[0].data_len = (unsigned) s->out_len;
+        CHECK_CUDA(cuda_wrapper_memcpy_async(sl.out->tiles[0].data, sl.cuda_out_buffer, s->out_len, CUDA_WRAPPER_MEMCPY_DEVICE_TO_HOST,
+                                             sl.stream),
+                   "Memcpy failed", return false);
+        return true;
+}
+
+/// wait for the oldest frame in flight and move it to the ready queue (lock held)
+void retire_oldest(state_video_compress_cuda_dxt *s)
+{
+        dxt_slot &sl = s->slots[s->tail % state_video_compress_cuda_dxt::DEPTH];
+        if (cuda_wrapper_stream_synchronize(sl.stream) != CUDA_WRAPPER_SUCCESS) {
+                fprintf(stderr, "[CUDA DXT] Synchronize failed: %s\n", cuda_wrapper_last_error_string());
+                sl.out->tiles[0].data_len = 0;  // error marker: skipped by the consumer
+        }
+        sl.out->compress_end = now_ns();
+        s->ready.push_back(std::move(sl.out));
+        sl.in.reset();
+        sl.busy = false;
+        s->tail++;
+}
+
+/// async API, push side.  Up to DEPTH frames are in flight; the input frame is held until its result has been produced.
+void cuda_dxt_compress_push(void *state, std::shared_ptr<video_frame> tx)
+{
+        auto *s = (state_video_compress_cuda_dxt *) state;
+        std::unique_lock<std::mutex> lk(s->m);
+        if (!tx) {  // poison pill
+                s->ended = true;
+                lk.unlock();
+                s->cv.notify_all();
+                return;
+        }
+        cuda_wrapper_set_device((int) cuda_devices[0]);  // cuda_dxt.cpp:194
+        const struct video_desc desc = video_desc_from_frame(tx.get());
+        if (!video_desc_eq(desc, s->saved_desc)) {
+                while (s->tail != s->head) {
+                        retire_oldest(s);
+                }
+                if (configure_with(s, desc)) {
+                        s->saved_desc = desc;
+                } else {
+                        fprintf(stderr, "[CUDA DXT] Reconfiguration failed!\n");
+                        return;
+                }
+        }
+        dxt_slot &sl = s->slots[s->head % state_video_compress_cuda_dxt::DEPTH];
+        if (sl.busy) {
+                retire_oldest(s);
+        }
+        if (!enqueue(s, sl, tx)) {  // failed frame: empty marker keeps the sequence complete (video_compress.cpp:396-398)
+                std::shared_ptr<video_frame> bad(new video_frame());
+                bad->seq = tx->seq;
+                while (s->tail != s->head) {
+                        retire_oldest(s);
+                }
+                s->ready.push_back(bad);
+        } else {
+                sl.in = std::move(tx);
+                sl.busy = true;
+                s->head++;
+        }
+        lk.unlock();
+        s->cv.notify_all();
+}
+
+std::shared_ptr<video_frame> cuda_dxt_compress_pop(void *state)
+{
+        auto *s = (state_video_compress_cuda_dxt *) state;
+        std::unique_lock<std::mutex> lk(s->m);
+        s->cv.wait(lk, [s] { return !s->ready.empty() || s->tail != s->head || s->ended; });
+        if (s->ready.empty() && s->tail != s->head) {
+                cuda_wrapper_set_device((int) cuda_devices[0]);
+                retire_oldest(s);
+        }
+        if (s->ready.empty()) {
+                return {};  // ended
+        }
+        std::shared_ptr<video_frame> f = std::move(s->ready.front());
+        s->ready.pop_front();
+        return f;
+}
+
+/// synchronous tile API of the reference module (cuda_dxt.cpp:186-266) = push + pop
 std::shared_ptr<video_frame> cuda_dxt_compress_tile(void *state, std::shared_ptr<video_frame> tx)
 {
         if (!tx) {
                 return {};
         }
-        auto *s = (state_video_compress_cuda_dxt *) state;
-        cuda_wrapper_set_device((int) cuda_devices[0]);  // cuda_dxt.cpp:194
-
-        const struct video_desc desc = video_desc_from_frame(tx.get());
-        if (!video_desc_eq(desc, s->saved_desc)) {
-                if (configure_with(s, desc)) {
-                        s->saved_desc = desc;
-                } else {
-                        fprintf(stderr, "[CUDA DXT] Reconfiguration failed!\n");
-                        return {};
-                }
-        }
-        const unsigned w = desc.width, h = desc.height;
-        const char *in = tx->tiles[0].data;
-        if (tx->mem_location == CPU_MEM) {  // H2D of the frame as captured; conversion (if any) happens on the device
-                CHECK_CUDA(cuda_wrapper_memcpy_async(s->cuda_src_buffer, in, vc_get_datalen(w, h, tx->color_spec),
-                                                     CUDA_WRAPPER_MEMCPY_HOST_TO_DEVICE, s->stream),
-                           "Memcpy failed", return {});
-                in = s->cuda_src_buffer;
-        }
-        if (tx->color_spec != s->in_codec) {  // replaces the per-row CPU decoder loop of cuda_dxt.cpp:207-220
-                const int rc = ugb200_pixfmt_convert(tx->color_spec, s->in_codec, s->cuda_in_buffer, vc_get_linesize(w, s->in_codec), in,
-                                                     vc_get_linesize(w, tx->color_spec), vc_get_linesize(w, s->in_codec), (int) h,
-                                                     (long) vc_get_datalen(w, h, tx->color_spec), 0, 8, 16, s->stream);
-                if (rc != 0) {
-                        fprintf(stderr, "[CUDA DXT] conversion kernel failed (%d)\n", rc);
-                        return {};
-                }
-                in = s->cuda_in_buffer;
-        }
-        int rc;
-        if (s->in_codec == UYVY) {  // fused: no 4:4:4 intermediate (reference: cuda_yuv422_to_yuv444 + cuda_yuv_to_dxt*)
-                rc = s->out_codec == DXT1 ? ugb200_uyvy_to_dxt1_async(in, s->cuda_out_buffer, (int) w, (int) h, 0, s->stream)
-                                          : ugb200_uyvy_to_dxt6_async(in, s->cuda_out_buffer, (int) w, (int) h, 0, s->stream);
-        } else {
-                rc = s->out_codec == DXT1 ? ugb200_rgb_to_dxt1_async(in, s->cuda_out_buffer, (int) w, (int) h, s->stream)
-                                          : ugb200_rgb_to_dxt6_async(in, s->cuda_out_buffer, (int) w, (int) h, s->stream);
-        }
-        if (rc != 0) {
-                fprintf(stderr, "[CUDA DXT] Encoding failed (%d)\n", rc);
-                return {};
-        }
-        std::shared_ptr<video_frame> out = pinned_pool_get(s->out_len);
-        if (!out) {
-                return {};
-        }
-        out->color_spec = s->out_codec, out->fps = tx->fps, out->interlacing = tx->interlacing, out->seq = tx->seq;
-        out->tiles[0].width = w, out->tiles[0].height = h, out->tiles[0].data_len = (unsigned) s->out_len;
-        CHECK_CUDA(cuda_wrapper_memcpy_async(out->tiles[0].data, s->cuda_out_buffer, s->out_len, CUDA_WRAPPER_MEMCPY_DEVICE_TO_HOST, s->stream),
-                   "Memcpy failed", return {});
-        CHECK_CUDA(cuda_wrapper_stream_synchronize(s->stream), "Synchronize failed", return {});
-        return out;
+        cuda_dxt_compress_push(state, std::move(tx));
+        std::shared_ptr<video_frame> out = cuda_dxt_compress_pop(state);
+        return out && out->tiles[0].data_len ? out : std::shared_ptr<video_frame>();
 }
 
 void cuda_dxt_compress_done(void *state)
 {
         auto *s = (state_video_compress_cuda_dxt *) state;
+        {
+                std::lock_guard<std::mutex> lk(s->m);
+                while (s->tail != s->head) {
+                        retire_oldest(s);
+                }
+        }
         cleanup(s);
-        if (s->stream) {
-                cuda_wrapper_stream_destroy(s->stream);
+        for (dxt_slot &sl : s->slots) {
+                if (sl.stream) {
+                        cuda_wrapper_stream_destroy(sl.stream);
+                }
         }
         delete s;
 }
 
-const struct video_compress_info cuda_dxt_info = { cuda_dxt_compress_init, cuda_dxt_compress_done, nullptr, cuda_dxt_compress_tile,
-                                                   nullptr,                nullptr,                nullptr, nullptr,
+// B200 build: asynchronous shape (frames of a stream overlap on the PCIe link); "cuda_dxt_sync" keeps the reference's tile API
+const struct video_compress_info cuda_dxt_info = { cuda_dxt_compress_init, cuda_dxt_compress_done, nullptr, nullptr,
+                                                   cuda_dxt_compress_push, cuda_dxt_compress_pop,  nullptr, nullptr,
                                                    nullptr };
 REGISTER_MODULE(cuda_dxt, &cuda_dxt_info, LIBRARY_CLASS_VIDEO_COMPRESS, VIDEO_COMPRESS_ABI_VERSION);
+const struct video_compress_info cuda_dxt_sync_info = { cuda_dxt_compress_init, cuda_dxt_compress_done, nullptr, cuda_dxt_compress_tile,
+                                                        nullptr,                nullptr,                nullptr, nullptr,
+                                                        nullptr };
+REGISTER_MODULE(cuda_dxt_sync, &cuda_dxt_sync_info, LIBRARY_CLASS_VIDEO_COMPRESS, VIDEO_COMPRESS_ABI_VERSION);
 
 // =====================================================================================================================
 // module: GPUJPEG
@@ -658,6 +762,7 @@ void compress_done(struct compress_state *s)
 struct ugb200_compress {
         compress_state *cs = nullptr;
         uint32_t seq = 0;
+        std::shared_ptr<video_frame> last;  // keeps the frame handed out by ugb200_compress_pop_ref alive
 };
 
 extern "C" {
@@ -739,6 +844,26 @@ int ugb200_get_best_decoder_from(int in_codec, const int *candidates, int count)
         cand[n] = VIDEO_CODEC_NONE;
         codec_t out = VIDEO_CODEC_NONE;
         return get_best_decoder_from((codec_t) in_codec, cand, &out) ? (int) out : 0;
+}
+
+int ugb200_compress_pop_ref(ugb200_compress *s, const void **data, size_t *len, int *out_codec, unsigned *seq)
+{
+        if (!s || !data || !len) {
+                return -1;
+        }
+        s->last = compress_pop(s->cs);
+        if (!s->last) {
+                return 1;
+        }
+        *data = s->last->tiles[0].data;
+        *len = s->last->tiles[0].data_len;
+        if (out_codec) {
+                *out_codec = s->last->color_spec;
+        }
+        if (seq) {
+                *seq = s->last->seq;
+        }
+        return s->last->tiles[0].data_len ? 0 : -1;
 }
 
 void ugb200_compress_done(ugb200_compress *s)

@@ -264,6 +264,120 @@ struct conv_rgb_rgb {
         }
 };
 
+// ---- v210 family (A8) ---------------------------------------------------------------------------------------------
+#define UGB_S10(w, sh) (((w) >> (sh)) & 0x3ffu)
+
+/// vc_copylineUYVYtoV210, pixfmt_conv.c:2581-2607: every 3 consecutive source BYTES (u, y, v in the loop's naming) become one
+/// v210 word with each byte << 2; one word per 4 bytes of dst_len
+struct conv_uyvy_v210 {
+        static constexpr int IN = 48, OUT = 64;
+        static __host__ int out_len(int dst_len) { return dst_len < 4 ? 0 : dst_len / 4 * 4; }
+        template <int K>
+        static __device__ __forceinline__ void word(const uint32_t *in, uint32_t *out)
+        {
+                if constexpr (K < 16) {
+                        out[K] = (gb<3 * K>(in) << 2) | (gb<3 * K + 1>(in) << 12) | (gb<3 * K + 2>(in) << 22);
+                        word<K + 1>(in, out);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &) { word<0>(in, out); }
+};
+
+/// vc_copylineY216toV210, pixfmt_conv.c:2761-2790: 12 16-bit samples (Y U Y V ...) >> 6 into four v210 words; ceil(dst_len/16) groups
+struct conv_y216_v210 {
+        static constexpr int IN = 48, OUT = 32;
+        static __host__ int out_len(int dst_len) { return (dst_len + 15) / 16 * 16; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                        uint32_t s[12];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                                s[2 * i] = (in[6 * g + i] & 0xffffu) >> 6, s[2 * i + 1] = in[6 * g + i] >> 22;
+                        }
+                        // s = y1 u y2 v | y1 u y2 v | y1 u y2 v
+                        out[4 * g + 0] = s[1] | s[0] << 10 | s[3] << 20;
+                        out[4 * g + 1] = s[2] | s[5] << 10 | s[4] << 20;
+                        out[4 * g + 2] = s[7] | s[6] << 10 | s[9] << 20;
+                        out[4 * g + 3] = s[8] | s[11] << 10 | s[10] << 20;
+                }
+        }
+};
+
+/// vc_copylineV210toY216, pixfmt_conv.c:2792-2832: 10-bit samples << 6 into Y U Y V 16-bit words; floor(dst_len/24) groups
+struct conv_v210_y216 {
+        static constexpr int IN = 32, OUT = 48;
+        static __host__ int out_len(int dst_len) { return dst_len / 24 * 24; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                        const uint32_t w0 = in[4 * g], w1 = in[4 * g + 1], w2 = in[4 * g + 2], w3 = in[4 * g + 3];
+#define UGB_P(a, b) ((a) << 6 | (b) << 22)
+                        out[6 * g + 0] = UGB_P(UGB_S10(w0, 10), UGB_S10(w0, 0));   // Y0 U0
+                        out[6 * g + 1] = UGB_P(UGB_S10(w1, 0), UGB_S10(w0, 20));   // Y1 V0
+                        out[6 * g + 2] = UGB_P(UGB_S10(w1, 20), UGB_S10(w1, 10));  // Y2 U1
+                        out[6 * g + 3] = UGB_P(UGB_S10(w2, 10), UGB_S10(w2, 0));   // Y3 V1
+                        out[6 * g + 4] = UGB_P(UGB_S10(w3, 0), UGB_S10(w2, 20));   // Y4 U2
+                        out[6 * g + 5] = UGB_P(UGB_S10(w3, 20), UGB_S10(w3, 10));  // Y5 V2
+#undef UGB_P
+                }
+        }
+};
+
+/// vc_copylineV210toY416, pixfmt_conv.c:2834-2882: U Y V A per pixel (chroma replicated, alpha 0xFFFF); floor(dst_len/48) groups
+struct conv_v210_y416 {
+        static constexpr int IN = 16, OUT = 48;
+        static __host__ int out_len(int dst_len) { return dst_len / 48 * 48; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                const uint32_t w0 = in[0], w1 = in[1], w2 = in[2], w3 = in[3];
+                const uint32_t y[6] = { UGB_S10(w0, 10), UGB_S10(w1, 0), UGB_S10(w1, 20), UGB_S10(w2, 10), UGB_S10(w3, 0), UGB_S10(w3, 20) };
+                const uint32_t u[3] = { UGB_S10(w0, 0), UGB_S10(w1, 10), UGB_S10(w2, 20) };
+                const uint32_t v[3] = { UGB_S10(w0, 20), UGB_S10(w2, 0), UGB_S10(w3, 10) };
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                        out[2 * i] = u[i / 2] << 6 | y[i] << 22;
+                        out[2 * i + 1] = v[i / 2] << 6 | 0xFFFF0000u;
+                }
+        }
+};
+
+/// vc_copylineV210toRGB, pixfmt_conv.c:2884-2940: top 8 bits of each sample, depth-8 coefficients, CLAMP_FULL (1..254);
+/// the loop runs while x < dst_len in steps of 18 bytes, i.e. it may write past dst_len up to the end of the last group
+struct conv_v210_rgb {
+        static constexpr int IN = 128, OUT = 144;
+        static __host__ int out_len(int dst_len) { return (dst_len + 17) / 18 * 18; }
+        static __device__ __forceinline__ int cf(int v) { return min(max(v, 1), 254); }  // CLAMP_FULL, color_space.h:96-98
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(8);
+                uint32_t o[144];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                        const uint32_t w0 = in[4 * g], w1 = in[4 * g + 1], w2 = in[4 * g + 2], w3 = in[4 * g + 3];
+#define UGB_S8(w, sh) ((int) (((w) >> ((sh) + 2)) & 0xffu))
+                        const int y[6] = { UGB_S8(w0, 10), UGB_S8(w1, 0), UGB_S8(w1, 20), UGB_S8(w2, 10), UGB_S8(w3, 0), UGB_S8(w3, 20) };
+                        const int u[3] = { UGB_S8(w0, 0) - 128, UGB_S8(w1, 10) - 128, UGB_S8(w2, 20) - 128 };
+                        const int v[3] = { UGB_S8(w0, 20) - 128, UGB_S8(w2, 0) - 128, UGB_S8(w3, 10) - 128 };
+#undef UGB_S8
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                                const int ys = c.y_scale * (y[i] - 16), uu = u[i / 2], vv = v[i / 2];
+                                o[18 * g + 3 * i + 0] = cf((ys + vv * c.r_cr) >> COMP_BASE);
+                                o[18 * g + 3 * i + 1] = cf((ys + uu * c.g_cb + vv * c.g_cr) >> COMP_BASE);
+                                o[18 * g + 3 * i + 2] = cf((ys + uu * c.b_cb) >> COMP_BASE);
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < 36; ++i) {
+                        out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+        }
+};
+#undef UGB_S10
+
 // ---- generic kernel ------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ dst, long dst_pitch, const uint8_t *__restrict__ src,
@@ -379,6 +493,11 @@ extern "C" UGB_API int ugb200_pixfmt_supported(int in_codec, int out_codec)
         case UGB_RGBA * 256 + UGB_RGBA:
         case UGB_RGB * 256 + UGB_RGB:
         case UGB_BGR * 256 + UGB_RGB:
+        case UGB_UYVY * 256 + UGB_v210:
+        case UGB_Y216 * 256 + UGB_v210:
+        case UGB_v210 * 256 + UGB_Y216:
+        case UGB_v210 * 256 + UGB_Y416:
+        case UGB_v210 * 256 + UGB_RGB:
                 return 1;
         }
         return 0;
@@ -431,6 +550,16 @@ extern "C" UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *
                         return copy_rows(dst, dst_pitch, src, src_pitch, dst_len, height, s);  // pixfmt_conv.c:740-741
                 }
                 return launch_line<conv_rgb_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_UYVY * 256 + UGB_v210:
+                return launch_line<conv_uyvy_v210>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_Y216 * 256 + UGB_v210:
+                return launch_line<conv_y216_v210>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_v210 * 256 + UGB_Y216:
+                return launch_line<conv_v210_y216>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_v210 * 256 + UGB_Y416:
+                return launch_line<conv_v210_y416>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+        case UGB_v210 * 256 + UGB_RGB:
+                return launch_line<conv_v210_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
         case UGB_BGR * 256 + UGB_RGB: {
                 const conv_params q = { 16, 8, 0, 0 };  // vc_copylineBGRtoRGB
                 return launch_line<conv_rgb_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, q, s);
