@@ -351,6 +351,171 @@ static void v210_to_rgb(unsigned char *dst, const unsigned char *src, int dst_le
 }
 #undef S10
 
+/* ---- RG48 / Y216 / Y416 / VUYA / R10k byte and bit repackers ----------------------------------------------------- */
+#define UNUSED3 (void) rs, (void) gs, (void) bs
+/* vc_copylineRG48toRGB, pixfmt_conv.c:2030-2042 */
+static void rg48_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (int x = 0; x <= dst_len - 3; x += 3, src += 6) {
+                *dst++ = src[1], *dst++ = src[3], *dst++ = src[5];
+        }
+}
+/* vc_copylineRG48toRGBA, :2044-2055 */
+static void rg48_to_rgba(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        const uint32_t amask = 0xFFFFFFFFU ^ (0xFFU << rs) ^ (0xFFU << gs) ^ (0xFFU << bs);
+        for (int x = 0; x <= dst_len - 4; x += 4, src += 6) {
+                wr32(dst + x, amask | (uint32_t) src[1] << rs | (uint32_t) src[3] << gs | (uint32_t) src[5] << bs);
+        }
+}
+/* vc_copylineRG48toR10k, :2008-2028 */
+static void rg48_to_r10k(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (int x = 0; x <= dst_len - 4; x += 4, src += 6) {
+                uint16_t in[3];
+                memcpy(in, src, 6);
+                const unsigned r = in[0] >> 6, g = in[1] >> 6, b = in[2] >> 6;
+                wr32(dst + x, (b & 0x3FU) << 26U | 0x3000000U | (g & 0xFU) << 20U | (b >> 6U) << 16U | (r & 0x3U) << 14U | (g >> 4U) << 8U | r >> 2U);
+        }
+}
+/* vc_copylineRGBAtoRG48, :1336-1351 */
+static void rgba_to_rg48(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (int x = 0; x <= dst_len - 6; x += 6, src += 4) {
+                *dst++ = 0, *dst++ = src[0], *dst++ = 0, *dst++ = src[1], *dst++ = 0, *dst++ = src[2];
+        }
+}
+/* vc_copylineRGBtoRG48, :1353-1363 */
+static void rgb_to_rg48(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (int x = 0; x <= dst_len - 2; x += 2) {
+                *dst++ = 0, *dst++ = *src++;
+        }
+}
+/* vc_copylineUYVYtoY216, :2609-2627 */
+static void uyvy_to_y216(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (; dst_len >= 8; dst_len -= 8, src += 4) {
+                *dst++ = 0, *dst++ = src[1], *dst++ = 0, *dst++ = src[0], *dst++ = 0, *dst++ = src[3], *dst++ = 0, *dst++ = src[2];
+        }
+}
+/* vc_copylineUYVYtoY416, :2629-2665 — the loop tests >= 12 but consumes 16 (kept) */
+static void uyvy_to_y416(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        while (dst_len >= 12) {
+                *dst++ = 0, *dst++ = src[0], *dst++ = 0, *dst++ = src[1], *dst++ = 0, *dst++ = src[2], *dst++ = 0xFF, *dst++ = 0xFF;
+                *dst++ = 0, *dst++ = src[0], *dst++ = 0, *dst++ = src[3], *dst++ = 0, *dst++ = src[2], *dst++ = 0xFF, *dst++ = 0xFF;
+                src += 4;
+                dst_len -= 16;
+        }
+        if (dst_len >= 8) {
+                *dst++ = 0, *dst++ = src[0], *dst++ = 0, *dst++ = src[1], *dst++ = 0, *dst++ = src[2], *dst++ = 0xFF, *dst++ = 0xFF;
+        }
+}
+/* vc_copylineY216toUYVY, :2728-2743 */
+static void y216_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (; dst_len >= 4; dst_len -= 4, src += 8) {
+                *dst++ = src[3], *dst++ = src[1], *dst++ = src[7], *dst++ = src[5];
+        }
+}
+/* vc_copylineY416toUYVY, :2745-2759 */
+static void y416_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (; dst_len >= 4; dst_len -= 4, src += 16) {
+                *dst++ = (src[1] + src[9]) / 2, *dst++ = src[3], *dst++ = (src[5] + src[13]) / 2, *dst++ = src[11];
+        }
+}
+/* vc_copylineVUYAtoY416, :2667-2686 */
+static void vuya_to_y416(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (; dst_len > 7; dst_len -= 8, src += 4) {
+                *dst++ = 0, *dst++ = src[1], *dst++ = 0, *dst++ = src[2], *dst++ = 0, *dst++ = src[0], *dst++ = 0, *dst++ = src[3];
+        }
+}
+/* vc_copylineVUYAtoUYVY, :2688-2703 — src[7] (alpha of the 2nd pixel) is what the reference stores as Y1 (kept) */
+static void vuya_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (; dst_len > 3; dst_len -= 4, src += 8) {
+                *dst++ = (src[1] + src[5]) / 2, *dst++ = src[2], *dst++ = (src[0] + src[4]) / 2, *dst++ = src[7];
+        }
+}
+/* vc_copylineVUYAtoRGB, :2705-2726 */
+static void vuya_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        const struct coeffs c = cfs709(8);
+        for (int x = 0; x < dst_len; x += 3, src += 4) {
+                const int v = src[0] - 128, u = src[1] - 128, y = c.y_scale * (src[2] - 16);
+                int val = (y + v * c.r_cr) >> COMP_BASE;
+                *dst++ = val < 1 ? 1 : val > 254 ? 254 : val;
+                val = (y + u * c.g_cb + v * c.g_cr) >> COMP_BASE;
+                *dst++ = val < 1 ? 1 : val > 254 ? 254 : val;
+                val = (y + u * c.b_cb) >> COMP_BASE;
+                *dst++ = val < 1 ? 1 : val > 254 ? 254 : val;
+        }
+}
+/* vc_copylineRGBAtoVUYA, :2280-2302 */
+static void rgba_to_vuya(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        const struct coeffs c = cfs709(8);
+        for (; dst_len > 3; dst_len -= 4, src += 4) {
+                const int r = src[0], g = src[1], b = src[2];
+                *dst++ = ((r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE) + 128;
+                *dst++ = ((r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE) + 128;
+                *dst++ = ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 16;
+                *dst++ = src[3];
+        }
+}
+/* vc_copyliner10k, :211-272 */
+static void r10k_to_rgba(unsigned char *dst, const unsigned char *src, int len, int rs, int gs, int bs)
+{
+        const uint32_t amask = 0xFFFFFFFFU ^ (0xFFU << rs) ^ (0xFFU << gs) ^ (0xFFU << bs);
+        for (; len >= 4; len -= 4, src += 4, dst += 4) {
+                const uint32_t r = src[0], g = (src[1] & 0x3FU) << 2 | src[2] >> 6, b = (src[2] & 0xFU) << 4 | src[3] >> 4;
+                wr32(dst, amask | r << rs | g << gs | b << bs);
+        }
+}
+/* vc_copyliner10ktoRGB, :331-340 */
+static void r10k_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (int x = 0; x < dst_len; x += 3, src += 4) {
+                *dst++ = src[0], *dst++ = src[1] << 2 | src[2] >> 6, *dst++ = src[2] << 4 | src[3] >> 4;
+        }
+}
+/* vc_copyliner10ktoRG48, :274-292 */
+static void r10k_to_rg48(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (; dst_len > 0; dst_len -= 6, dst += 6, src += 4) {
+                const unsigned b2 = src[1], b3 = src[2], b4 = src[3];
+                dst[1] = src[0], dst[0] = b2 & 0xC0U, dst[3] = b2 << 2U | b3 >> 6U, dst[2] = (b3 & 0x30U) << 2U;
+                dst[5] = (b3 & 0xFU) << 4U | b4 >> 4U, dst[4] = (b4 & 0xCU) << 4U;
+        }
+}
+/* vc_copylineRGBAtoR10k, :2538-2577 */
+static void rgba_to_r10k(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        UNUSED3;
+        for (; dst_len >= 4; dst_len -= 4, src += 4, dst += 4) {
+                const unsigned r = src[0], g = src[1], b = src[2];
+                dst[0] = r, dst[1] = g >> 2, dst[2] = (b >> 4) | (g & 3) << 6, dst[3] = 0x3 | (b & 0xF) << 4;
+        }
+}
+#undef UNUSED3
+
 /* get_decoder_from_to, pixfmt_conv.c:3110-3125 (subset of decoders[] :3041-3103 restated so far) */
 static line_fn *decoder_from_to(int in, int out)
 {
@@ -377,6 +542,23 @@ static line_fn *decoder_from_to(int in, int out)
         case C_v210 * 256 + C_Y216: return v210_to_y216;
         case C_v210 * 256 + C_Y416: return v210_to_y416;
         case C_v210 * 256 + C_RGB: return v210_to_rgb;
+        case C_RG48 * 256 + C_RGB: return rg48_to_rgb;
+        case C_RG48 * 256 + C_RGBA: return rg48_to_rgba;
+        case C_RG48 * 256 + C_R10k: return rg48_to_r10k;
+        case C_RGBA * 256 + C_RG48: return rgba_to_rg48;
+        case C_RGB * 256 + C_RG48: return rgb_to_rg48;
+        case C_UYVY * 256 + C_Y216: return uyvy_to_y216;
+        case C_UYVY * 256 + C_Y416: return uyvy_to_y416;
+        case C_Y216 * 256 + C_UYVY: return y216_to_uyvy;
+        case C_Y416 * 256 + C_UYVY: return y416_to_uyvy;
+        case C_VUYA * 256 + C_Y416: return vuya_to_y416;
+        case C_VUYA * 256 + C_UYVY: return vuya_to_uyvy;
+        case C_VUYA * 256 + C_RGB: return vuya_to_rgb;
+        case C_RGBA * 256 + C_VUYA: return rgba_to_vuya;
+        case C_R10k * 256 + C_RGBA: return r10k_to_rgba;
+        case C_R10k * 256 + C_RGB: return r10k_to_rgb;
+        case C_R10k * 256 + C_RG48: return r10k_to_rg48;
+        case C_RGBA * 256 + C_R10k: return rgba_to_r10k;
         }
         return NULL;
 }

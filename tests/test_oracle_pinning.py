@@ -12,11 +12,13 @@ import pytest
 
 import util
 
-UYVY, YUYV, RGBA, RGB, BGR, RG48, V210, Y216, Y416 = 2, 3, 1, 12, 20, 27, 7, 30, 31
+UYVY, YUYV, RGBA, RGB, BGR, RG48, V210, Y216, Y416, VUYA, R10K = 2, 3, 1, 12, 20, 27, 7, 30, 31, 4, 5
 
 PAIRS = [(V210, UYVY), (YUYV, UYVY), (UYVY, YUYV), (UYVY, RGB), (YUYV, RGB), (UYVY, RGBA), (RGB, UYVY), (BGR, UYVY), (RGBA, UYVY),
          (RG48, UYVY), (RGB, RGBA), (RGBA, RGB), (RGBA, RGBA), (RGB, RGB), (BGR, RGB), (UYVY, UYVY),
-         (UYVY, V210), (Y216, V210), (V210, Y216), (V210, Y416), (V210, RGB)]
+         (UYVY, V210), (Y216, V210), (V210, Y216), (V210, Y416), (V210, RGB),
+         (RG48, RGB), (RG48, RGBA), (RG48, R10K), (RGBA, RG48), (RGB, RG48), (UYVY, Y216), (UYVY, Y416), (Y216, UYVY), (Y416, UYVY),
+         (VUYA, Y416), (VUYA, UYVY), (VUYA, RGB), (RGBA, VUYA), (R10K, RGBA), (R10K, RGB), (R10K, RG48), (RGBA, R10K)]
 
 
 def test_known_answer_checksums(orc):

@@ -110,9 +110,9 @@ class JpegEncoder:
             raise RuntimeError("ugb200_jpeg_encoder_create failed")
 
     def close(self):
-        if self._h:
+        if self._h and _L is not None:
             _L.ugb200_jpeg_encoder_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.close()

@@ -73,9 +73,9 @@ class Compress:
         return None if r is None else (out[:r[0]], r[1], r[2])
 
     def close(self):
-        if self._h:
+        if self._h and _L is not None:
             _L.ugb200_compress_done(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.close()

@@ -5,9 +5,9 @@
 //   K1 jpeg_dct_kernel      one thread per 8x8 block: 128-bit row loads straight from UYVY / packed RGB, level
 //                           shift, separable AAN FDCT in registers, quantise (reciprocal multiply + rint),
 //                           zig-zag, one 128-byte store of int16 coefficients          (HBM: 1 B in, 2 B out per sample)
-//   K2 jpeg_huffman_kernel  one thread per restart segment: DC prediction + run-length + Annex K Huffman codes with byte
-//                           stuffing into a private worst-case slot, RSTn appended, byte count recorded
-//   K3 jpeg_scan_kernel     exclusive prefix sum of the segment sizes (single CTA, decoupled from the host)
+//   K2 jpeg_huffman_kernel  one thread per restart segment: non-zero map per block, one loop turn per NON-ZERO coefficient,
+//                           Annex K codes + byte stuffing into a private worst-case slot (32-bit stores), RSTn, byte count
+//   K3 jpeg_scan_kernel     second level of the stream-offset prefix sum (first level: inside K2's CTAs); no host round trip
 //   K4 jpeg_compact_kernel  one warp per segment: slot -> final position; writes SOS headers of scans 2,3 and EOI
 // Arithmetic is float with an explicit operation order so that oracle/jpeg_oracle.c reproduces the bytes exactly.
 #include <cuda_runtime.h>
@@ -179,38 +179,62 @@ __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict
 }
 
 // ---- K2 -------------------------------------------------------------------------------------------------------------
+/// MSB-first bit writer with byte stuffing; bytes are gathered into aligned 32-bit words before they go to memory
 struct bit_writer {
-        uint8_t *p;
+        uint32_t *p;     // next aligned word of the slot
+        uint32_t word;   // bytes gathered so far (little endian in memory)
+        int nbytes;      // 0..3 bytes in `word`
         uint64_t acc;
         int nbits;
+        __device__ __forceinline__ void emit_byte(uint32_t b)
+        {
+                word |= b << (8 * nbytes);
+                if (++nbytes == 4) {
+                        *p++ = word;
+                        word = 0, nbytes = 0;
+                }
+        }
         __device__ __forceinline__ void put(uint32_t code, int len)
         {
                 acc = (acc << len) | (code & ((1u << len) - 1u));
                 nbits += len;
                 while (nbits >= 8) {
-                        const uint8_t b = (uint8_t) (acc >> (nbits - 8));
-                        *p++ = b;
+                        const uint32_t b = (uint32_t) (acc >> (nbits - 8)) & 0xffu;
+                        emit_byte(b);
                         if (b == 0xFF) {
-                                *p++ = 0;  // T.81 B.1.1.5
+                                emit_byte(0);  // T.81 B.1.1.5
                         }
                         nbits -= 8;
                 }
         }
-        __device__ __forceinline__ void flush()
+        __device__ __forceinline__ void flush_bits()
         {
                 if (nbits > 0) {
                         put(0x7F, 8 - nbits);  // pad with ones, T.81 F.1.2.3
                 }
                 acc = 0, nbits = 0;
         }
+        /// @returns total bytes written to the slot starting at `base`
+        __device__ __forceinline__ uint32_t finish(uint32_t *base)
+        {
+                const uint32_t n = (uint32_t) (p - base) * 4 + nbytes;
+                if (nbytes) {
+                        *p = word;
+                }
+                return n;
+        }
 };
 
 __device__ __forceinline__ int category(int v) { return 32 - __clz(abs(v)); }
 
+/// One thread per restart segment.  Per block: 8 x LDG.128 build a 64-bit non-zero map (uniform work), then the loop runs once
+/// per NON-ZERO coefficient (ffs over the map) instead of once per coefficient — far less divergence inside a warp.
+/// The CTA also produces the exclusive prefix of its 128 segment sizes and its total (first level of the stream scan).
 __global__ void __launch_bounds__(128) jpeg_huffman_kernel(const int16_t *__restrict__ coef, jpeg_geom g, uint8_t *__restrict__ slots,
-                                                           uint32_t *__restrict__ sizes)
+                                                           uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
+                                                           uint32_t *__restrict__ cta_total)
 {
-        __shared__ uint32_t s_dc[2][16], s_ac[2][256];
+        __shared__ uint32_t s_dc[2][16], s_ac[2][256], s_warp[4];
         for (int i = threadIdx.x; i < 32; i += blockDim.x) {
                 s_dc[i >> 4][i & 15] = c_tab.dc[i >> 4][i & 15];
         }
@@ -219,112 +243,178 @@ __global__ void __launch_bounds__(128) jpeg_huffman_kernel(const int16_t *__rest
         }
         __syncthreads();
         const int s = blockIdx.x * blockDim.x + threadIdx.x;
-        if (s >= g.nseg) {
-                return;
-        }
-        const int scan = s / g.seg_per_scan, ls = s - scan * g.seg_per_scan;
-        const int m0 = ls * g.ri, m1 = min(m0 + g.ri, g.mcu_per_scan);
-        bit_writer bw = { slots + (long) s * g.slot, 0, 0 };
-        int pred[3] = { 0, 0, 0 };
-        for (int m = m0; m < m1; ++m) {
-                for (int k = 0; k < g.blocks_per_mcu; ++k) {
-                        int comp;
-                        long blk;
-                        if (g.fmt == FMT_UYVY_422) {
-                                comp = k < 2 ? 0 : k - 1;
-                                blk = (long) m * 4 + k;
-                        } else {
-                                comp = scan;
-                                blk = (long) scan * g.mcu_per_scan + m;
-                        }
-                        const int t = comp == 0 ? 0 : 1;
-                        const int16_t *zz = coef + blk * 64;
-                        const int dcv = zz[0], diff = dcv - pred[comp];
-                        pred[comp] = dcv;
-                        int sz = category(diff);
-                        bw.put(s_dc[t][sz] & 0xffff, s_dc[t][sz] >> 16);
-                        if (sz) {
-                                bw.put((uint32_t) (diff < 0 ? diff - 1 : diff), sz);
-                        }
-                        int run = 0;
-                        for (int i = 1; i < 64; ++i) {
-                                const int v = zz[i];
-                                if (v == 0) {
-                                        ++run;
-                                        continue;
+        uint32_t nbytes = 0;
+        if (s < g.nseg) {
+                const int scan = s / g.seg_per_scan, ls = s - scan * g.seg_per_scan;
+                const int m0 = ls * g.ri, m1 = min(m0 + g.ri, g.mcu_per_scan);
+                uint32_t *base = (uint32_t *) (slots + (long) s * g.slot);
+                bit_writer bw = { base, 0, 0, 0, 0 };
+                int pred[3] = { 0, 0, 0 };
+                for (int m = m0; m < m1; ++m) {
+                        for (int k = 0; k < g.blocks_per_mcu; ++k) {
+                                int comp;
+                                long blk;
+                                if (g.fmt == FMT_UYVY_422) {
+                                        comp = k < 2 ? 0 : k - 1;
+                                        blk = (long) m * 4 + k;
+                                } else {
+                                        comp = scan;
+                                        blk = (long) scan * g.mcu_per_scan + m;
                                 }
-                                while (run > 15) {
-                                        bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);  // ZRL
-                                        run -= 16;
+                                const int t = comp == 0 ? 0 : 1;
+                                const int16_t *zz = coef + blk * 64;
+                                // non-zero map of the block
+                                uint64_t nz = 0;
+                                int dcv = 0;
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                        const uint4 v = __ldg((const uint4 *) zz + q);
+                                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+                                        if (q == 0) {
+                                                dcv = (int) (short) (v.x & 0xffff);
+                                        }
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                                const uint64_t lo = (w[j] & 0xffffu) != 0, hi = (w[j] >> 16) != 0;
+                                                nz |= (lo | hi << 1) << (8 * q + 2 * j);
+                                        }
                                 }
-                                sz = category(v);
-                                const uint32_t e = s_ac[t][(run << 4) | sz];
-                                bw.put(e & 0xffff, e >> 16);
-                                bw.put((uint32_t) (v < 0 ? v - 1 : v), sz);
-                                run = 0;
-                        }
-                        if (run > 0) {
-                                bw.put(s_ac[t][0] & 0xffff, s_ac[t][0] >> 16);  // EOB
+                                nz &= ~1ull;
+                                // DC difference (T.81 F.1.2.1)
+                                const int diff = dcv - pred[comp];
+                                pred[comp] = dcv;
+                                int sz = category(diff);
+                                bw.put(s_dc[t][sz] & 0xffff, s_dc[t][sz] >> 16);
+                                if (sz) {
+                                        bw.put((uint32_t) (diff < 0 ? diff - 1 : diff), sz);
+                                }
+                                // AC run-lengths (F.1.2.2): one turn per non-zero coefficient
+                                int prev = 0;
+                                while (nz) {
+                                        const int i = __ffsll((long long) nz) - 1;
+                                        nz &= nz - 1;
+                                        int run = i - prev - 1;
+                                        prev = i;
+                                        while (run > 15) {
+                                                bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);  // ZRL
+                                                run -= 16;
+                                        }
+                                        const int v = zz[i];  // L1 hit: the line was just read for the map
+                                        sz = category(v);
+                                        const uint32_t e = s_ac[t][(run << 4) | sz];
+                                        // code and value bits in one put (<= 16 + 10 bits)
+                                        bw.put(((e & 0xffff) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), (int) (e >> 16) + sz);
+                                }
+                                if (prev != 63) {
+                                        bw.put(s_ac[t][0] & 0xffff, s_ac[t][0] >> 16);  // EOB
+                                }
                         }
                 }
+                bw.flush_bits();
+                if (ls != g.seg_per_scan - 1) {  // RSTn between segments of a scan
+                        bw.emit_byte(0xFF);
+                        bw.emit_byte(0xD0 + (ls & 7));
+                }
+                nbytes = bw.finish(base);
+                sizes[s] = nbytes;
         }
-        bw.flush();
-        if (ls != g.seg_per_scan - 1) {  // RSTn between segments of a scan
-                *bw.p++ = 0xFF;
-                *bw.p++ = (uint8_t) (0xD0 + (ls & 7));
+        // exclusive prefix of the CTA's 128 sizes
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t incl = nbytes;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) {
+                        incl += o;
+                }
         }
-        sizes[s] = (uint32_t) (bw.p - (slots + (long) s * g.slot));
+        if (lane == 31) {
+                s_warp[warp] = incl;
+        }
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < warp; ++w) {
+                before += s_warp[w];
+        }
+        if (s < g.nseg) {
+                local_off[s] = before + incl - nbytes;
+        }
+        if (threadIdx.x == blockDim.x - 1) {
+                cta_total[blockIdx.x] = before + incl;
+        }
 }
 
-// ---- K3: exclusive scan of segment sizes (+ later-scan SOS headers) into final offsets ------------------------------------
-__global__ void __launch_bounds__(1024) jpeg_scan_kernel(const uint32_t *__restrict__ sizes, jpeg_geom g, uint32_t *__restrict__ offsets,
-                                                         uint32_t *__restrict__ total)
+// ---- K3: exclusive scan of the per-CTA totals (second level; a frame has a few hundred of them) --------------------------------
+__global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *__restrict__ cta_total, int n, jpeg_geom g, uint32_t *__restrict__ total)
 {
-        __shared__ uint32_t part[1024];
-        const int t = threadIdx.x, per = (g.nseg + 1023) / 1024;
-        const int i0 = t * per, i1 = min(i0 + per, g.nseg);
-        uint32_t sum = 0;
-        for (int i = i0; i < i1; ++i) {
-                sum += sizes[i] + ((i % g.seg_per_scan == 0 && i > 0) ? g.sos_len : 0);
+        __shared__ uint32_t s_warp[32];
+        __shared__ uint32_t s_carry;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (threadIdx.x == 0) {
+                s_carry = 0;
         }
-        part[t] = sum;
         __syncthreads();
-        for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
-                const uint32_t v = t >= d ? part[t - d] : 0;
-                __syncthreads();
-                part[t] += v;
-                __syncthreads();
-        }
-        uint32_t run = g.header_len + (t ? part[t - 1] : 0);
-        for (int i = i0; i < i1; ++i) {
-                if (i % g.seg_per_scan == 0 && i > 0) {
-                        run += g.sos_len;  // the SOS of this scan sits right before its first segment
+        for (int base = 0; base < n; base += 1024) {
+                const int i = base + threadIdx.x;
+                const uint32_t v = i < n ? cta_total[i] : 0;
+                uint32_t incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) {
+                                incl += o;
+                        }
                 }
-                offsets[i] = run;
-                run += sizes[i];
+                if (lane == 31) {
+                        s_warp[warp] = incl;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                        uint32_t w = s_warp[lane];
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                                const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
+                                if (lane >= d) {
+                                        w += o;
+                                }
+                        }
+                        s_warp[lane] = w;  // inclusive over warps
+                }
+                __syncthreads();
+                const uint32_t before = s_carry + (warp ? s_warp[warp - 1] : 0);
+                if (i < n) {
+                        cta_total[i] = before + incl - v;  // exclusive prefix in place
+                }
+                __syncthreads();
+                if (threadIdx.x == 1023) {
+                        s_carry = before + incl;
+                }
+                __syncthreads();
         }
-        if (t == 1023) {
-                *total = g.header_len + part[1023] + 2;  // + EOI
+        if (threadIdx.x == 0) {
+                const int nscans = g.nseg / g.seg_per_scan;
+                *total = g.header_len + s_carry + g.sos_len * (nscans - 1) + 2;  // + later SOS headers + EOI
         }
 }
 
 // ---- K4 -------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ sizes,
-                                                           const uint32_t *__restrict__ offsets, jpeg_geom g, uint8_t *__restrict__ out)
+                                                           const uint32_t *__restrict__ local_off, const uint32_t *__restrict__ cta_base,
+                                                           jpeg_geom g, uint8_t *__restrict__ out)
 {
         const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
         if (s >= g.nseg) {
                 return;
         }
-        const uint32_t n = sizes[s], off = offsets[s];
+        const int scan = s / g.seg_per_scan;
+        const uint32_t n = sizes[s], off = g.header_len + cta_base[s >> 7] + local_off[s] + g.sos_len * scan;
         const uint8_t *src = slots + (long) s * g.slot;
         for (uint32_t i = lane; i < n; i += 32) {
                 out[off + i] = src[i];
         }
         if (lane == 0 && s > 0 && s % g.seg_per_scan == 0) {  // SOS header of a later scan (RGB: one component per scan)
-                const int c = s / g.seg_per_scan;
                 uint8_t *h = out + off - g.sos_len;
-                const uint8_t sos[10] = { 0xFF, 0xDA, 0, 8, 1, (uint8_t) (c + 1), 0x11, 0, 63, 0 };
+                const uint8_t sos[10] = { 0xFF, 0xDA, 0, 8, 1, (uint8_t) (scan + 1), 0x11, 0, 63, 0 };
                 for (int i = 0; i < 10; ++i) {
                         h[i] = sos[i];
                 }
@@ -350,8 +440,8 @@ struct ugb200_jpeg_encoder {
         // device buffers
         int16_t *coef = nullptr;
         uint8_t *slots = nullptr, *out = nullptr, *staging = nullptr;
-        uint32_t *sizes = nullptr, *offsets = nullptr, *total = nullptr;
-        size_t coef_cap = 0, slots_cap = 0, out_cap = 0, seg_cap = 0, staging_cap = 0;
+        uint32_t *sizes = nullptr, *offsets = nullptr, *cta_total = nullptr, *total = nullptr;
+        size_t coef_cap = 0, slots_cap = 0, out_cap = 0, seg_cap = 0, staging_cap = 0, cta_cap = 0;
         // pinned host buffers
         uint8_t *h_out = nullptr, *h_in = nullptr;
         uint32_t *h_total = nullptr;
@@ -516,7 +606,8 @@ int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri
                 return -2;
         }
         size_t cap2 = e->seg_cap;
-        if (!grow(e->sizes, e->seg_cap, (size_t) g.nseg) || !grow(e->offsets, cap2, (size_t) g.nseg)) {
+        if (!grow(e->sizes, e->seg_cap, (size_t) g.nseg) || !grow(e->offsets, cap2, (size_t) g.nseg) ||
+            !grow(e->cta_total, e->cta_cap, (size_t) (g.nseg + 127) / 128)) {
                 return -2;
         }
         if (e->total == nullptr && cudaMalloc((void **) &e->total, 4) != cudaSuccess) {
@@ -558,7 +649,7 @@ void ugb200_jpeg_encoder_destroy(ugb200_jpeg_encoder *e)
         }
         cudaStreamSynchronize(e->stream);
         cudaFree(e->coef), cudaFree(e->slots), cudaFree(e->out), cudaFree(e->staging);
-        cudaFree(e->sizes), cudaFree(e->offsets), cudaFree(e->total);
+        cudaFree(e->sizes), cudaFree(e->offsets), cudaFree(e->cta_total), cudaFree(e->total);
         cudaFreeHost(e->h_out), cudaFreeHost(e->h_in), cudaFreeHost(e->h_total);
         delete e;
 }
@@ -587,9 +678,11 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         const jpeg_geom &g = e->g;
         const bool vec_ok = fmt == FMT_UYVY_422 && !(15 & (size_t) src) && !(pitch & 15);
         jpeg_dct_kernel<<<(g.nblocks + 127) / 128, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok);
-        jpeg_huffman_kernel<<<(g.nseg + 127) / 128, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes);
-        jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->sizes, g, e->offsets, e->total);
-        jpeg_compact_kernel<<<(int) (((long) g.nseg * 32 + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, g, e->out);
+        const int nctas = (g.nseg + 127) / 128;
+        jpeg_huffman_kernel<<<nctas, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes, e->offsets, e->cta_total);
+        jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
+        jpeg_compact_kernel<<<(int) (((long) g.nseg * 32 + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
+                                                                                           e->out);
         if (cudaGetLastError() != cudaSuccess) {
                 return -2;
         }

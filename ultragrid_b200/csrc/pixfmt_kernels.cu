@@ -378,6 +378,251 @@ struct conv_v210_rgb {
 };
 #undef UGB_S10
 
+// ---- pure byte-permutation converters (A9): out byte j = in byte M::src(j), or 0x00 (-1) / 0xFF (-2) -------------------
+template <class M>
+struct conv_bytemap {
+        static constexpr int IN = M::IN, OUT = M::OUT;
+        static __host__ int out_len(int dst_len) { return M::out_len(dst_len); }
+        template <int J>
+        static __device__ __forceinline__ uint32_t byte(const uint32_t *in)
+        {
+                constexpr int sidx = M::src(J);
+                if constexpr (sidx == -1) {
+                        return 0u;
+                } else if constexpr (sidx == -2) {
+                        return 0xffu;
+                } else {
+                        return gb<sidx>(in);
+                }
+        }
+        template <int W>
+        static __device__ __forceinline__ void word(const uint32_t *in, uint32_t *out)
+        {
+                if constexpr (W < OUT / 4) {
+                        out[W] = byte<4 * W>(in) | byte<4 * W + 1>(in) << 8 | byte<4 * W + 2>(in) << 16 | byte<4 * W + 3>(in) << 24;
+                        word<W + 1>(in, out);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &) { word<0>(in, out); }
+};
+struct map_rg48_rgb {  // vc_copylineRG48toRGB, pixfmt_conv.c:2030-2042: the high byte of each 16-bit sample
+        static constexpr int IN = 96, OUT = 48;
+        static __host__ int out_len(int n) { return n < 3 ? 0 : n / 3 * 3; }
+        static constexpr int src(int j) { return 6 * (j / 3) + 2 * (j % 3) + 1; }
+};
+struct map_rgba_rg48 {  // vc_copylineRGBAtoRG48, :1336-1351
+        static constexpr int IN = 32, OUT = 48;
+        static __host__ int out_len(int n) { return n < 6 ? 0 : n / 6 * 6; }
+        static constexpr int src(int j) { return (j % 2) ? 4 * (j / 6) + (j % 6) / 2 : -1; }
+};
+struct map_rgb_rg48 {  // vc_copylineRGBtoRG48, :1353-1363
+        static constexpr int IN = 16, OUT = 32;
+        static __host__ int out_len(int n) { return n < 2 ? 0 : n / 2 * 2; }
+        static constexpr int src(int j) { return (j % 2) ? j / 2 : -1; }
+};
+struct map_uyvy_y216 {  // vc_copylineUYVYtoY216, :2609-2627: Y0 U Y1 V, value in the high byte
+        static constexpr int IN = 16, OUT = 32;
+        static __host__ int out_len(int n) { return n / 8 * 8; }
+        static constexpr int src(int j)
+        {
+                const int k = j % 8, g = j / 8;
+                return k == 1 ? 4 * g + 1 : k == 3 ? 4 * g : k == 5 ? 4 * g + 3 : k == 7 ? 4 * g + 2 : -1;
+        }
+};
+struct map_uyvy_y416 {  // vc_copylineUYVYtoY416, :2629-2665.  QUIRK: the loop tests dst_len >= 12 but consumes 16 per turn
+        static constexpr int IN = 16, OUT = 64;
+        static __host__ int out_len(int n)
+        {
+                if (n < 8) {
+                        return 0;
+                }
+                const int turns = (n + 4) / 16, rem = n - 16 * turns;
+                return 16 * turns + (rem >= 8 ? 8 : 0);
+        }
+        static constexpr int src(int j)
+        {
+                const int k = j % 16, g = j / 16;
+                return k == 1 || k == 9 ? 4 * g : k == 3 ? 4 * g + 1 : k == 11 ? 4 * g + 3 : k == 5 || k == 13 ? 4 * g + 2 : k == 6 || k == 7 || k == 14 || k == 15 ? -2 : -1;
+        }
+};
+struct map_y216_uyvy {  // vc_copylineY216toUYVY, :2728-2743
+        static constexpr int IN = 32, OUT = 16;
+        static __host__ int out_len(int n) { return n / 4 * 4; }
+        static constexpr int src(int j)
+        {
+                const int k = j % 4, g = j / 4;
+                return 8 * g + (k == 0 ? 3 : k == 1 ? 1 : k == 2 ? 7 : 5);
+        }
+};
+struct map_vuya_y416 {  // vc_copylineVUYAtoY416, :2667-2686
+        static constexpr int IN = 16, OUT = 32;
+        static __host__ int out_len(int n) { return n / 8 * 8; }
+        static constexpr int src(int j)
+        {
+                const int k = j % 8, g = j / 8;
+                return k == 1 ? 4 * g + 1 : k == 3 ? 4 * g + 2 : k == 5 ? 4 * g : k == 7 ? 4 * g + 3 : -1;
+        }
+};
+
+// ---- R10k (10-bit RGB, 4 B/px: R9..2 | R1..0 G9..4 | G3..0 B9..6 | B5..0 xx) --------------------------------------------
+/// vc_copyliner10k, pixfmt_conv.c:211-272: top 8 bits of each component into an RGBA word with runtime shifts
+struct conv_r10k_rgba {
+        static constexpr int IN = 16, OUT = 16;
+        static __host__ int out_len(int n) { return n / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+                const uint32_t amask = 0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        const uint32_t w = in[i];
+                        const uint32_t r = w & 0xff, g = ((w >> 8) & 0x3f) << 2 | ((w >> 22) & 3), b = ((w >> 16) & 0xf) << 4 | (w >> 28);
+                        out[i] = amask | r << p.rshift | g << p.gshift | b << p.bshift;
+                }
+        }
+};
+/// vc_copyliner10ktoRGB, :331-340 (runs while x < dstlen in steps of 3)
+struct conv_r10k_rgb {
+        static constexpr int IN = 64, OUT = 48;
+        static __host__ int out_len(int n) { return (n + 2) / 3 * 3; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                uint32_t o[48];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                        const uint32_t b0 = in[i] & 0xff, b1 = (in[i] >> 8) & 0xff, b2 = (in[i] >> 16) & 0xff, b3 = in[i] >> 24;
+                        o[3 * i] = b0, o[3 * i + 1] = (b1 << 2 | b2 >> 6) & 0xff, o[3 * i + 2] = (b2 << 4 | b3 >> 4) & 0xff;
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                        out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+        }
+};
+/// vc_copyliner10ktoRG48, :274-292 (runs while dstlen > 0 in steps of 6)
+struct conv_r10k_rg48 {
+        static constexpr int IN = 32, OUT = 48;
+        static __host__ int out_len(int n) { return (n + 5) / 6 * 6; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                uint32_t h[24];  // 16-bit samples
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                        const uint32_t b1 = in[i] & 0xff, b2 = (in[i] >> 8) & 0xff, b3 = (in[i] >> 16) & 0xff, b4 = in[i] >> 24;
+                        h[3 * i] = b1 << 8 | (b2 & 0xC0);
+                        h[3 * i + 1] = ((b2 << 2 | b3 >> 6) & 0xff) << 8 | ((b3 & 0x30) << 2);
+                        h[3 * i + 2] = (((b3 & 0xf) << 4 | b4 >> 4) & 0xff) << 8 | ((b4 & 0xC) << 4);
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                        out[i] = h[2 * i] | h[2 * i + 1] << 16;
+                }
+        }
+};
+/// vc_copylineRGBAtoR10k, :2538-2577
+struct conv_rgba_r10k {
+        static constexpr int IN = 16, OUT = 16;
+        static __host__ int out_len(int n) { return n / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        const uint32_t r = in[i] & 0xff, g = (in[i] >> 8) & 0xff, b = (in[i] >> 16) & 0xff;
+                        out[i] = r | (g >> 2) << 8 | (b >> 4) << 16 | (g & 3) << 22 | 3u << 24 | (b & 0xf) << 28;
+                }
+        }
+};
+/// vc_copylineRG48toR10k, :2008-2028
+struct conv_rg48_r10k {
+        static constexpr int IN = 48, OUT = 32;
+        static __host__ int out_len(int n) { return n < 4 ? 0 : n / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                        const uint32_t s0 = 3 * i, s1 = 3 * i + 1, s2 = 3 * i + 2;
+                        const uint32_t r = ((in[s0 / 2] >> (16 * (s0 & 1))) & 0xffff) >> 6, g = ((in[s1 / 2] >> (16 * (s1 & 1))) & 0xffff) >> 6,
+                                       b = ((in[s2 / 2] >> (16 * (s2 & 1))) & 0xffff) >> 6;
+                        out[i] = (b & 0x3F) << 26 | 0x3000000u | (g & 0xF) << 20 | (b >> 6) << 16 | (r & 0x3) << 14 | (g >> 4) << 8 | r >> 2;
+                }
+        }
+};
+/// vc_copylineRG48toRGBA, :2044-2055
+struct conv_rg48_rgba {
+        static constexpr int IN = 48, OUT = 32;
+        static __host__ int out_len(int n) { return n < 4 ? 0 : n / 4 * 4; }
+        template <int K>
+        static __device__ __forceinline__ void px(const uint32_t *in, uint32_t *out, const conv_params &p, uint32_t amask)
+        {
+                if constexpr (K < 8) {
+                        out[K] = amask | gb<6 * K + 1>(in) << p.rshift | gb<6 * K + 3>(in) << p.gshift | gb<6 * K + 5>(in) << p.bshift;
+                        px<K + 1>(in, out, p, amask);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+                px<0>(in, out, p, 0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift));
+        }
+};
+
+// ---- 4:4:4 <-> 4:2:2 with chroma averaging, VUYA colour conversions ----------------------------------------------------
+/// vc_copylineVUYAtoUYVY (:2688-2703) and vc_copylineY416toUYVY (:2745-2759): chroma = (c0 + c1) / 2, luma copied.
+/// OFF_Y1 is relative to the start of the pixel PAIR.  QUIRK kept: VUYAtoUYVY takes src[7] — the second pixel's ALPHA — as Y1.
+template <int PIX, int OFF_U, int OFF_Y, int OFF_V, int OFF_Y1>
+struct conv_444_uyvy {
+        static constexpr int IN = 8 * PIX, OUT = 16;
+        static __host__ int out_len(int n) { return n / 4 * 4; }
+        template <int K>
+        static __device__ __forceinline__ void pair(const uint32_t *in, uint32_t *out)
+        {
+                if constexpr (K < 4) {
+                        constexpr int A = 2 * K * PIX, B = A + PIX;
+                        out[K] = pack4((gb<A + OFF_U>(in) + gb<B + OFF_U>(in)) / 2, gb<A + OFF_Y>(in), (gb<A + OFF_V>(in) + gb<B + OFF_V>(in)) / 2,
+                                       gb<A + OFF_Y1>(in));
+                        pair<K + 1>(in, out);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &) { pair<0>(in, out); }
+};
+using conv_vuya_uyvy = conv_444_uyvy<4, 1, 2, 0, 7>;
+using conv_y416_uyvy = conv_444_uyvy<8, 1, 3, 5, 11>;
+/// vc_copylineVUYAtoRGB, :2705-2726 (depth-8 coefficients, CLAMP_FULL 1..254, runs while x < dst_len in steps of 3)
+struct conv_vuya_rgb {
+        static constexpr int IN = 64, OUT = 48;
+        static __host__ int out_len(int n) { return (n + 2) / 3 * 3; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(8);
+                uint32_t o[48];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                        const int v = (int) (in[i] & 0xff) - 128, u = (int) ((in[i] >> 8) & 0xff) - 128, y = c.y_scale * ((int) ((in[i] >> 16) & 0xff) - 16);
+                        o[3 * i] = min(max((y + v * c.r_cr) >> COMP_BASE, 1), 254);
+                        o[3 * i + 1] = min(max((y + u * c.g_cb + v * c.g_cr) >> COMP_BASE, 1), 254);
+                        o[3 * i + 2] = min(max((y + u * c.b_cb) >> COMP_BASE, 1), 254);
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                        out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+        }
+};
+/// vc_copylineRGBAtoVUYA, :2280-2302 (V U Y A; no clamp, bytes wrap)
+struct conv_rgba_vuya {
+        static constexpr int IN = 16, OUT = 16;
+        static __host__ int out_len(int n) { return n / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(8);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        const int r = in[i] & 0xff, g = (in[i] >> 8) & 0xff, b = (in[i] >> 16) & 0xff;
+                        const int v = ((r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE) + 128, u = ((r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE) + 128;
+                        const int y = ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 16;
+                        out[i] = pack4(v & 0xff, u & 0xff, y & 0xff, in[i] >> 24);
+                }
+        }
+};
+
 // ---- generic kernel ------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ dst, long dst_pitch, const uint8_t *__restrict__ src,
@@ -391,7 +636,14 @@ __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ ds
                 return;
         }
         const long in_off = (long) cx * C::IN;
+        // Some reference loops write a whole pixel group past dst_len.  In the CPU row loop the next row then overwrites the
+        // spill; rows run concurrently here, so every row but the last stops at the pitch (same final bytes, no race).
+        const int wlen_last = wlen;
         for (int row = blockIdx.y; row < height; row += gridDim.y) {
+                const int wlen = (row == height - 1 || wlen_last <= dst_pitch) ? wlen_last : (int) dst_pitch;
+                if (out_off >= wlen) {
+                        continue;
+                }
                 const long in_abs = row * src_pitch + in_off;
                 uint32_t in[NI], out[NO];
                 if (vec_ok && in_abs + C::IN <= src_total) {
@@ -498,6 +750,23 @@ extern "C" UGB_API int ugb200_pixfmt_supported(int in_codec, int out_codec)
         case UGB_v210 * 256 + UGB_Y216:
         case UGB_v210 * 256 + UGB_Y416:
         case UGB_v210 * 256 + UGB_RGB:
+        case UGB_RG48 * 256 + UGB_RGB:
+        case UGB_RGBA * 256 + UGB_RG48:
+        case UGB_RGB * 256 + UGB_RG48:
+        case UGB_UYVY * 256 + UGB_Y216:
+        case UGB_UYVY * 256 + UGB_Y416:
+        case UGB_Y216 * 256 + UGB_UYVY:
+        case UGB_VUYA * 256 + UGB_Y416:
+        case UGB_R10k * 256 + UGB_RGBA:
+        case UGB_R10k * 256 + UGB_RGB:
+        case UGB_R10k * 256 + UGB_RG48:
+        case UGB_RGBA * 256 + UGB_R10k:
+        case UGB_RG48 * 256 + UGB_R10k:
+        case UGB_RG48 * 256 + UGB_RGBA:
+        case UGB_VUYA * 256 + UGB_UYVY:
+        case UGB_Y416 * 256 + UGB_UYVY:
+        case UGB_VUYA * 256 + UGB_RGB:
+        case UGB_RGBA * 256 + UGB_VUYA:
                 return 1;
         }
         return 0;
@@ -560,6 +829,27 @@ extern "C" UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *
                 return launch_line<conv_v210_y416>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
         case UGB_v210 * 256 + UGB_RGB:
                 return launch_line<conv_v210_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+#define UGB_CASE(IN_C, OUT_C, CONV)                                                                                                         \
+        case IN_C * 256 + OUT_C:                                                                                                            \
+                return launch_line<CONV>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, p, s);
+                UGB_CASE(UGB_RG48, UGB_RGB, conv_bytemap<map_rg48_rgb>)
+                UGB_CASE(UGB_RGBA, UGB_RG48, conv_bytemap<map_rgba_rg48>)
+                UGB_CASE(UGB_RGB, UGB_RG48, conv_bytemap<map_rgb_rg48>)
+                UGB_CASE(UGB_UYVY, UGB_Y216, conv_bytemap<map_uyvy_y216>)
+                UGB_CASE(UGB_UYVY, UGB_Y416, conv_bytemap<map_uyvy_y416>)
+                UGB_CASE(UGB_Y216, UGB_UYVY, conv_bytemap<map_y216_uyvy>)
+                UGB_CASE(UGB_VUYA, UGB_Y416, conv_bytemap<map_vuya_y416>)
+                UGB_CASE(UGB_R10k, UGB_RGBA, conv_r10k_rgba)
+                UGB_CASE(UGB_R10k, UGB_RGB, conv_r10k_rgb)
+                UGB_CASE(UGB_R10k, UGB_RG48, conv_r10k_rg48)
+                UGB_CASE(UGB_RGBA, UGB_R10k, conv_rgba_r10k)
+                UGB_CASE(UGB_RG48, UGB_R10k, conv_rg48_r10k)
+                UGB_CASE(UGB_RG48, UGB_RGBA, conv_rg48_rgba)
+                UGB_CASE(UGB_VUYA, UGB_UYVY, conv_vuya_uyvy)
+                UGB_CASE(UGB_Y416, UGB_UYVY, conv_y416_uyvy)
+                UGB_CASE(UGB_VUYA, UGB_RGB, conv_vuya_rgb)
+                UGB_CASE(UGB_RGBA, UGB_VUYA, conv_rgba_vuya)
+#undef UGB_CASE
         case UGB_BGR * 256 + UGB_RGB: {
                 const conv_params q = { 16, 8, 0, 0 };  // vc_copylineBGRtoRGB
                 return launch_line<conv_rgb_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, q, s);
