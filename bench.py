@@ -335,6 +335,11 @@ def extra_kernels(api, torch, dev):
     src, out = rnd(w * h * 2, 12), torch.empty(w * h // 2, dtype=torch.uint8, device=dev)
     rec("uyvy_dxt1_4k", time_kernel(torch, lambda i: api.uyvy_to_dxt(src[i % 12], w, h, out=out), 60), w * h * 2.5, w * h)
     del src
+    # config 5: 7680x4320 UYVY -> DXT5-YCoCg (fused)
+    w, h = W8K, H8K
+    src, out = rnd(w * h * 2, 4), torch.empty(w * h, dtype=torch.uint8, device=dev)
+    rec("uyvy_dxt5ycocg_8k", time_kernel(torch, lambda i: api.uyvy_to_dxt(src[i % 4], w, h, dxt_type=6, out=out), 12), w * h * 3.0, w * h)
+    del src
     # reference-ABI RGB -> DXT1 at 8K (async variant measured through the compat kernel, includes its stream sync)
     w, h = W8K, H8K
     src, out = rnd(w * h * 3, 4), torch.empty(w * h // 2, dtype=torch.uint8, device=dev)

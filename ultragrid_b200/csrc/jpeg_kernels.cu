@@ -73,6 +73,12 @@ __device__ __forceinline__ void fdct8(float &d0, float &d1, float &d2, float &d3
 
 __device__ __forceinline__ int clampi(int v, int hi) { return min(max(v, 0), hi); }
 
+/// level-shifted sample as float without the slow I2F pipe: as_float(0x4B000000 | b) = 2^23 + b, minus (2^23 + 128) is exact
+__device__ __forceinline__ float shifted(uint32_t word, unsigned byte_sel)
+{
+        return __fadd_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | byte_sel)), -8388736.0f);
+}
+
 /// 8 samples of one row of the block into f[0..7] (already level-shifted)
 __device__ __forceinline__ void load_row(const uint8_t *__restrict__ src, long pitch, const jpeg_geom &g, int comp, int bx, int y,
                                          bool interior, float *f)
@@ -84,16 +90,16 @@ __device__ __forceinline__ void load_row(const uint8_t *__restrict__ src, long p
                         const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                                f[2 * i] = (float) ((int) ((w[i] >> 8) & 0xff) - 128);
-                                f[2 * i + 1] = (float) ((int) (w[i] >> 24) - 128);
+                                f[2 * i] = shifted(w[i], 1);
+                                f[2 * i + 1] = shifted(w[i], 3);
                         }
                 } else if (interior) {  // 8 chroma samples = 32 bytes
                         const uint4 a = __ldg((const uint4 *) (row + (long) bx * 32)), b = __ldg((const uint4 *) (row + (long) bx * 32) + 1);
                         const uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-                        const int sh = comp == 1 ? 0 : 16;
+                        const unsigned sel = comp == 1 ? 0 : 2;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                                f[i] = (float) ((int) ((w[i] >> sh) & 0xff) - 128);
+                                f[i] = shifted(w[i], sel);
                         }
                 } else {
 #pragma unroll
@@ -104,13 +110,13 @@ __device__ __forceinline__ void load_row(const uint8_t *__restrict__ src, long p
                                 } else {
                                         s = row[4 * clampi(bx * 8 + x, (g.w + 1) / 2 - 1) + (comp == 1 ? 0 : 2)];
                                 }
-                                f[x] = (float) (s - 128);
+                                f[x] = shifted((uint32_t) s, 0);
                         }
                 }
         } else {
 #pragma unroll
                 for (int x = 0; x < 8; ++x) {
-                        f[x] = (float) ((int) __ldg(row + 3 * clampi(bx * 8 + x, g.w - 1) + comp) - 128);
+                        f[x] = shifted((uint32_t) __ldg(row + 3 * clampi(bx * 8 + x, g.w - 1) + comp), 0);
                 }
         }
 }
@@ -118,18 +124,24 @@ __device__ __forceinline__ void load_row(const uint8_t *__restrict__ src, long p
 __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, int16_t *__restrict__ coef,
                                                        bool vec_ok)
 {
-        const int b = blockIdx.x * blockDim.x + threadIdx.x;
-        if (b >= g.nblocks) {
-                return;
-        }
+        int b = blockIdx.x * blockDim.x + threadIdx.x;
         int comp, bx, by;
         if (g.fmt == FMT_UYVY_422) {
-                const int m = b >> 2, k = b & 3;
+                // a CTA of 4 warps owns 32 MCUs; warp k encodes block k (Y0, Y1, Cb, Cr) of each, so that a warp is
+                // component-uniform: no luma/chroma divergence, uniform constant-bank reads of the quantiser table
+                const int k = threadIdx.x >> 5, m = blockIdx.x * 32 + (threadIdx.x & 31);
+                if (m >= g.mcu_per_scan) {
+                        return;
+                }
+                b = m * 4 + k;
                 const int mx = m % g.bw, my = m / g.bw;
                 comp = k < 2 ? 0 : k - 1;
                 bx = comp == 0 ? mx * 2 + k : mx;
                 by = my;
         } else {
+                if (b >= g.nblocks) {
+                        return;
+                }
                 const int per = g.bw * g.bh;
                 comp = b / per;
                 const int r = b - comp * per;
@@ -155,7 +167,7 @@ __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict
         int q[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
-                q[i] = __float2int_rn(__fmul_rn(f[i], qm[i]));
+                q[i] = (int) __float_as_uint(__fadd_rn(__fmul_rn(f[i], qm[i]), 12582912.0f)) - 0x4B400000;  // rint without F2I
         }
         // zig-zag (Figure A.6) + AC clamp to the 10-bit category range, two int16 per word, 8 x 16-byte stores
         constexpr int zz[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
@@ -677,7 +689,8 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         }
         const jpeg_geom &g = e->g;
         const bool vec_ok = fmt == FMT_UYVY_422 && !(15 & (size_t) src) && !(pitch & 15);
-        jpeg_dct_kernel<<<(g.nblocks + 127) / 128, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok);
+        const int dct_ctas = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
+        jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok);
         const int nctas = (g.nseg + 127) / 128;
         jpeg_huffman_kernel<<<nctas, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes, e->offsets, e->cta_total);
         jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
