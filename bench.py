@@ -299,6 +299,7 @@ def main():
             v, cores, sample = cpu_port_fps()
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
             line["extra"]["cpu_reference_pixfmt"] = cpu_reference_pixfmt()
+            line["extra"]["reference_gpu_kernels"] = reference_gpu_kernels(torch, dev)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -404,6 +405,38 @@ def extra_jpeg(api, compress, torch, dev):
         c.pop_into(out)
     res["natural_e2e_module_fps"] = n / (time.perf_counter() - t0)
     c.close()
+    return res
+
+
+def reference_gpu_kernels(torch, dev):
+    """for the DXT configs the reference beside the product is its own CUDA path — the UNMODIFIED cuda_dxt.cu built for
+    sm_100a (oracle/_ref/libcuda_dxt_ref.so), i.e. cuda_yuv422_to_yuv444 + cuda_yuv_to_dxt{1,6} as src/video_compress/cuda_dxt.cpp
+    :229,257 runs them (each call synchronises its stream, cuda_dxt.cu:759).  Baseline only; never part of `value`."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    ref = util.ref_gpu()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/libcuda_dxt_ref.so not present"}
+    w, h = W8K, H8K
+    srcs = [torch.randint(0, 256, (w * h * 2,), dtype=torch.uint8, device=dev) for _ in range(3)]
+    mid = torch.empty(w * h * 3, dtype=torch.uint8, device=dev)
+    out = torch.empty(w * h, dtype=torch.uint8, device=dev)
+    res = {}
+    for name, fn in (("uyvy_dxt1_8k", ref.cuda_yuv_to_dxt1), ("uyvy_dxt5ycocg_8k", ref.cuda_yuv_to_dxt6)):
+        def step(i):
+            ref.cuda_yuv422_to_yuv444(ctypes.c_void_p(srcs[i % 3].data_ptr()), ctypes.c_void_p(mid.data_ptr()), w * h, None)
+            fn(ctypes.c_void_p(mid.data_ptr()), ctypes.c_void_p(out.data_ptr()), w, h, None)
+        for i in range(2):
+            step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 6
+        for i in range(n):
+            step(i)
+        torch.cuda.synchronize()
+        secs = (time.perf_counter() - t0) / n
+        res[name] = {"us": secs * 1e6, "fps": 1 / secs}
     return res
 
 

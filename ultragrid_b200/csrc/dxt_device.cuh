@@ -278,18 +278,18 @@ __device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][
                 const float tr = __fmul_rn(dir_r, inv), tg = __fmul_rn(dir_g, inv), tb = __fmul_rn(dir_b, inv);
                 const float nbias = -__fmaf_rn(ex_b, tb, __fmaf_rn(ex_r, tr, __fmul_rn(ex_g, tg)));
                 const float2 tr2 = dup(tr), tg2 = dup(tg), tb2 = dup(tb);
-                uint32_t acc = 0;
+                uint32_t acc0 = 0, acc1 = 0;  // two independent chains; integer adds are associative, the bits are the same
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                         const float2 t = __ffma2_rn(B[j], tb2, __ffma2_rn(R[j], tr2, __fmul2_rn(G[j], tg2)));
                         const float2 x = __ffma2_rn(f2(add_sat_rn(t.x, nbias), add_sat_rn(t.y, nbias)), dup(3.0f), dup(0.5f));
                         const float2 m = __fadd2_rd(x, dup(kFloorMagic));
                         const int i0 = 4 * (j >> 1) + (j & 1);  // pixel of .x; .y is pixel i0 + 2
-                        acc += __float_as_uint(m.x) << (2 * i0);
-                        acc += __float_as_uint(m.y) << (2 * (i0 + 2));
+                        acc0 += __float_as_uint(m.x) << (2 * i0);
+                        acc1 += __float_as_uint(m.y) << (2 * (i0 + 2));
                 }
                 constexpr uint32_t kIdxBias = 0x4B000000u * 0x55555555u;
-                indices = acc - kIdxBias;
+                indices = acc0 + acc1 - kIdxBias;
         }
         const bool swap_end = max_code < min_code;
         if (swap_end) {

@@ -239,7 +239,8 @@ static int launch_uyvy(const void *src, void *out, int sx, int sy, long pitch, c
                 return 0;
         }
         const int threads = 128;
-        const bool pair = !(wb & 1) && !(15 & (size_t) src) && !(pitch & 15) && !(15 & (size_t) out);
+        static const bool tune_bpt1 = getenv("UGB200_DXT_BPT1") != nullptr;  // experiment knob: one block per thread
+        const bool pair = !tune_bpt1 && !(wb & 1) && !(15 & (size_t) src) && !(pitch & 15) && !(15 & (size_t) out);
         if (hb > 65535) {
                 return -1;
         }
