@@ -516,6 +516,174 @@ static void rgba_to_r10k(unsigned char *dst, const unsigned char *src, int dst_l
 }
 #undef UNUSED3
 
+/* ---- 16-bit colour-space converters ----------------------------------------------------------------------------- */
+static int clampr(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+static void y416_px(const unsigned char *src, int shift, int lo, int hi, int *r, int *g, int *b)
+{
+        const struct coeffs c = cfs709(16);
+        uint16_t in[4];
+        memcpy(in, src, 8);
+        const int u = in[0] - 32768, y = c.y_scale * (in[1] - 4096), v = in[2] - 32768;
+        *r = clampr((y + v * c.r_cr) >> shift, lo, hi);
+        *g = clampr((y + u * c.g_cb + v * c.g_cr) >> shift, lo, hi);
+        *b = clampr((y + u * c.b_cb) >> shift, lo, hi);
+}
+/* vc_copylineY416toRG48, pixfmt_conv.c:2485-2514 */
+static void y416_to_rg48(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x < dst_len; x += 6, src += 8, dst += 6) {
+                int r, g, b;
+                y416_px(src, COMP_BASE, 256, 65279, &r, &g, &b);
+                const uint16_t o[3] = { r, g, b };
+                memcpy(dst, o, 6);
+        }
+}
+/* vc_copylineY416toRGB, :1948-1976 */
+static void y416_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x < dst_len; x += 3, src += 8) {
+                int r, g, b;
+                y416_px(src, COMP_BASE + 8, 1, 254, &r, &g, &b);
+                *dst++ = r, *dst++ = g, *dst++ = b;
+        }
+}
+/* vc_copylineY416toRGBA, :1978-2006 */
+static void y416_to_rgba(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        const uint32_t amask = 0xFFFFFFFFU ^ (0xFFU << rs) ^ (0xFFU << gs) ^ (0xFFU << bs);
+        for (int x = 0; x < dst_len; x += 4, src += 8) {
+                int r, g, b;
+                y416_px(src, COMP_BASE + 8, 1, 254, &r, &g, &b);
+                wr32(dst + x, amask | (uint32_t) r << rs | (uint32_t) g << gs | (uint32_t) b << bs);
+        }
+}
+/* vc_copylineY416toR10k, :1917-1946 */
+static void y416_to_r10k(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x < dst_len; x += 4, src += 8) {
+                int r, g, b;
+                y416_px(src, COMP_BASE + 6, 4, 1019, &r, &g, &b);
+                *dst++ = r >> 2, *dst++ = (r & 0x3) << 6 | g >> 4, *dst++ = (g & 0xF) << 4 | b >> 6, *dst++ = (b & 0x3F) << 2;
+        }
+}
+/* vc_copylineY416toV210, :3004-3033 */
+static void y416_to_v210(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x < dst_len / 16; ++x) {
+                uint16_t s[24];
+                memcpy(s, src + x * 48, 48);
+                unsigned char *d = dst + x * 16;
+#define AVG(a, b) ((uint32_t) (uint16_t) ((s[a] + s[b]) / 2) >> 6)
+#define YY(a) ((uint32_t) s[a] >> 6)
+                wr32(d, AVG(0, 4) | YY(1) << 10 | AVG(2, 6) << 20);
+                wr32(d + 4, YY(5) | AVG(8, 12) << 10 | YY(9) << 20);
+                wr32(d + 8, AVG(10, 14) | YY(13) << 10 | AVG(16, 20) << 20);
+                wr32(d + 12, YY(17) | AVG(18, 22) << 10 | YY(21) << 20);
+#undef AVG
+#undef YY
+        }
+}
+/* vc_copylineRG48toY416, :2451-2483 */
+static void rg48_to_y416(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(16);
+        for (int x = 0; x < dst_len; x += 8, src += 6, dst += 8) {
+                uint16_t in[3];
+                memcpy(in, src, 6);
+                const int r = in[0], g = in[1], b = in[2];
+                const uint16_t o[4] = { ((r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE) + 32768, ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 4096,
+                                        ((r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE) + 32768, 0xFFFFU };
+                memcpy(dst, o, 8);
+        }
+}
+/* vc_copylineRG48toY216, :2410-2449 */
+static void rg48_to_y216(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(16);
+        for (int x = 0; x < dst_len; x += 8, src += 12, dst += 8) {
+                uint16_t in[6];
+                memcpy(in, src, 12);
+                int r = in[0], g = in[1], b = in[2];
+                const int y0 = ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 4096;
+                int u = (r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE, v = (r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE;
+                r = in[3], g = in[4], b = in[5];
+                u = ((u + ((r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE)) / 2) + 32768;
+                const int y1 = ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 4096;
+                v = ((v + ((r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE)) / 2) + 32768;
+                const uint16_t o[4] = { y0, u, y1, v };
+                memcpy(dst, o, 8);
+        }
+}
+/* vc_copylineRG48toV210, :2354-2407 */
+static void rg48_to_v210(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(10);
+        enum { OFF = COMP_BASE + 6 };
+        for (int x = 0; x <= dst_len - 16; x += 16, dst += 16) {
+                uint32_t y[6], u[3], v[3];
+                for (int p = 0; p < 3; ++p, src += 12) {
+                        uint16_t in[6];
+                        memcpy(in, src, 12);
+                        int r = in[0], g = in[1], b = in[2];
+                        y[2 * p] = ((r * c.y_r + g * c.y_g + b * c.y_b) >> OFF) + 64;
+                        int uu = (r * c.cb_r + g * c.cb_g + b * c.cb_b) >> OFF, vv = (r * c.cr_r + g * c.cr_g + b * c.cr_b) >> OFF;
+                        r = in[3], g = in[4], b = in[5];
+                        y[2 * p + 1] = ((r * c.y_r + g * c.y_g + b * c.y_b) >> OFF) + 64;
+                        uu += (r * c.cb_r + g * c.cb_g + b * c.cb_b) >> OFF, vv += (r * c.cr_r + g * c.cr_g + b * c.cr_b) >> OFF;
+                        u[p] = uu / 2 + 512, v[p] = vv / 2 + 512;
+                }
+                wr32(dst, u[0] | y[0] << 10 | v[0] << 20);
+                wr32(dst + 4, y[1] | u[1] << 10 | y[2] << 20);
+                wr32(dst + 8, v[1] | y[3] << 10 | u[2] << 20);
+                wr32(dst + 12, y[4] | v[2] << 10 | y[5] << 20);
+        }
+}
+/* vc_copylineUYVYtoRG48, :1124-1130: copylineYUVtoRGB (:1065-1094) with rgb16 = 1 */
+static void uyvy_to_rg48(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(8);
+        for (int x = 0; x <= dst_len - 12; x += 12, src += 4) {
+                const int y1 = c.y_scale * (src[1] - 16), y2 = c.y_scale * (src[3] - 16), u = src[0] - 128, v = src[2] - 128;
+                const int vals[6] = { (y1 + v * c.r_cr) >> COMP_BASE, (y1 + u * c.g_cb + v * c.g_cr) >> COMP_BASE, (y1 + u * c.b_cb) >> COMP_BASE,
+                                      (y2 + v * c.r_cr) >> COMP_BASE, (y2 + u * c.g_cb + v * c.g_cr) >> COMP_BASE, (y2 + u * c.b_cb) >> COMP_BASE };
+                for (int k = 0; k < 6; ++k) {
+                        *dst++ = 0, *dst++ = clamp255(vals[k]);
+                }
+        }
+}
+/* vc_copyliner10ktoY416, :294-329 */
+static void r10k_to_y416(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(16);
+        for (int x = 0; x < dst_len; x += 8, src += 4, dst += 8) {
+                const int r = src[0] << 8 | (src[1] & 0xC0), g = (src[1] & 0x3F) << 10 | (src[2] & 0xF0) << 2, b = (src[2] & 0xF) << 12 | (src[3] & 0xFC) << 4;
+                const uint16_t o[4] = { ((r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE) + 32768, ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 4096,
+                                        ((r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE) + 32768, 0xFFFFU };
+                memcpy(dst, o, 8);
+        }
+}
+/* vc_copylineR10ktoUYVY, :2318-2334 */
+static void r10k_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (const unsigned char *end = dst + dst_len; dst < end; dst += 4, src += 8) {
+                unsigned char rgb[6];
+                for (int k = 0; k < 2; ++k) {
+                        rgb[3 * k] = src[4 * k], rgb[3 * k + 1] = src[4 * k + 1] << 2 | src[4 * k + 2] >> 6, rgb[3 * k + 2] = src[4 * k + 2] << 4 | src[4 * k + 3] >> 4;
+                }
+                rgb_to_uyvy(dst, rgb, 4, 0, 8, 16);
+        }
+}
+
 /* get_decoder_from_to, pixfmt_conv.c:3110-3125 (subset of decoders[] :3041-3103 restated so far) */
 static line_fn *decoder_from_to(int in, int out)
 {
@@ -559,6 +727,17 @@ static line_fn *decoder_from_to(int in, int out)
         case C_R10k * 256 + C_RGB: return r10k_to_rgb;
         case C_R10k * 256 + C_RG48: return r10k_to_rg48;
         case C_RGBA * 256 + C_R10k: return rgba_to_r10k;
+        case C_Y416 * 256 + C_RG48: return y416_to_rg48;
+        case C_Y416 * 256 + C_RGB: return y416_to_rgb;
+        case C_Y416 * 256 + C_RGBA: return y416_to_rgba;
+        case C_Y416 * 256 + C_R10k: return y416_to_r10k;
+        case C_Y416 * 256 + C_v210: return y416_to_v210;
+        case C_RG48 * 256 + C_Y416: return rg48_to_y416;
+        case C_RG48 * 256 + C_Y216: return rg48_to_y216;
+        case C_RG48 * 256 + C_v210: return rg48_to_v210;
+        case C_UYVY * 256 + C_RG48: return uyvy_to_rg48;
+        case C_R10k * 256 + C_Y416: return r10k_to_y416;
+        case C_R10k * 256 + C_UYVY: return r10k_to_uyvy;
         }
         return NULL;
 }

@@ -18,7 +18,9 @@ PAIRS = [(V210, UYVY), (YUYV, UYVY), (UYVY, YUYV), (UYVY, RGB), (YUYV, RGB), (UY
          (RG48, UYVY), (RGB, RGBA), (RGBA, RGB), (RGBA, RGBA), (RGB, RGB), (BGR, RGB), (UYVY, UYVY),
          (UYVY, V210), (Y216, V210), (V210, Y216), (V210, Y416), (V210, RGB),
          (RG48, RGB), (RG48, RGBA), (RG48, R10K), (RGBA, RG48), (RGB, RG48), (UYVY, Y216), (UYVY, Y416), (Y216, UYVY), (Y416, UYVY),
-         (VUYA, Y416), (VUYA, UYVY), (VUYA, RGB), (RGBA, VUYA), (R10K, RGBA), (R10K, RGB), (R10K, RG48), (RGBA, R10K)]
+         (VUYA, Y416), (VUYA, UYVY), (VUYA, RGB), (RGBA, VUYA), (R10K, RGBA), (R10K, RGB), (R10K, RG48), (RGBA, R10K),
+         (Y416, RG48), (Y416, RGB), (Y416, RGBA), (Y416, R10K), (Y416, V210), (RG48, Y416), (RG48, Y216), (RG48, V210), (UYVY, RG48),
+         (R10K, Y416), (R10K, UYVY)]
 
 
 def test_known_answer_checksums(orc):

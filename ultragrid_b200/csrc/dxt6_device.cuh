@@ -91,15 +91,33 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
         const float c2g = __fmaf_rn(pXg, 0.66666662693023681641f, __fmul_rn(pNg, 0.3333333432674407959f));
         const float c3o = __fmaf_rn(pXo, 0.3333333134651184082f, __fmul_rn(pNo, 0.6666666865348815918f));
         const float c3g = __fmaf_rn(pXg, 0.3333333134651184082f, __fmul_rn(pNg, 0.6666666865348815918f));
+        // colorDistance = fma(dCo, dCo, dCg*dCg) for the four palette entries; pixels i and i+1 share packed (f32x2) instructions —
+        // same operations, half the issue slots
         uint32_t cidx = 0;
+        const float2 nXo = dup(-pXo), nXg = dup(-pXg), nNo = dup(-pNo), nNg = dup(-pNg), n2o = dup(-c2o), n2g = dup(-c2g), n3o = dup(-c3o),
+                     n3g = dup(-c3g);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-                // colorDistance = fma(dCo, dCo, dCg*dCg)
-#define UGB_DIST(co, cg) __fmaf_rn(__fadd_rn(Co[i], -(co)), __fadd_rn(Co[i], -(co)), __fmul_rn(__fadd_rn(Cg[i], -(cg)), __fadd_rn(Cg[i], -(cg))))
-                const float d0 = UGB_DIST(pXo, pXg), d1 = UGB_DIST(pNo, pNg), d2 = UGB_DIST(c2o, c2g), d3 = UGB_DIST(c3o, c3g);
-#undef UGB_DIST
-                const uint32_t bx = d0 > d3, by = d1 > d2, bz = d0 > d2, bw = d1 > d3, b4 = d2 > d3;
-                cidx |= ((bx & b4) | (((by & bz) | (bx & bw)) << 1)) << (2 * i);
+        for (int i = 0; i < 16; i += 2) {
+                const float2 co = f2(Co[i], Co[i + 1]), cg = f2(Cg[i], Cg[i + 1]);
+#define UGB_DIST2(no, ng, d)                                                                                                               \
+        {                                                                                                                                  \
+                const float2 eo = __fadd2_rn(co, no), eg = __fadd2_rn(cg, ng);                                                             \
+                d = __ffma2_rn(eo, eo, __fmul2_rn(eg, eg));                                                                                \
+        }
+                float2 d0, d1, d2, d3;
+                UGB_DIST2(nXo, nXg, d0)
+                UGB_DIST2(nNo, nNg, d1)
+                UGB_DIST2(n2o, n2g, d2)
+                UGB_DIST2(n3o, n3g, d3)
+#undef UGB_DIST2
+                {
+                        const uint32_t bx = d0.x > d3.x, by = d1.x > d2.x, bz = d0.x > d2.x, bw = d1.x > d3.x, b4 = d2.x > d3.x;
+                        cidx |= ((bx & b4) | (((by & bz) | (bx & bw)) << 1)) << (2 * i);
+                }
+                {
+                        const uint32_t bx = d0.y > d3.y, by = d1.y > d2.y, bz = d0.y > d2.y, bw = d1.y > d3.y, b4 = d2.y > d3.y;
+                        cidx |= ((bx & b4) | (((by & bz) | (bx & bw)) << 1)) << (2 * i + 2);
+                }
         }
         outp.w = cidx;
 
@@ -120,16 +138,19 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
         ab[4] = __double2float_rn(__fma_rn(__fma_rn(dX, 3.0, __dmul_rn(dN, 4.0)), k7, dM));
         ab[5] = __double2float_rn(__fma_rn(__fma_rn(dX, 2.0, __dmul_rn(dN, 5.0)), k7, dM));
         ab[6] = __double2float_rn(__fma_rn(__fma_rn(dN, 6.0, dX), k7, dM));
+        // index = 1 + #{k : Y <= ab_k}, & 7, ^ (2 > index)  (:376-388).  The thresholds are ordered ab2 >= ab3 >= ... >= ab7 >= ab1
+        // (rounding is monotone and max >= min), so the count is a 3-step binary search instead of 7 compares, and the
+        // "& 7, ^ (2 > idx)" fix-up is the nibble table 0,2,3,4,5,6,7,1 indexed by the count.
+        const float T0 = ab[1], T1 = ab[2], T2 = ab[3], T3 = ab[4], T4 = ab[5], T5 = ab[6], T6 = ab[0];
         uint32_t ix = 0, iy = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-                uint32_t idx = 1u;
-#pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                        idx += (Y[i] <= ab[k]) ? 1u : 0u;
-                }
-                idx &= 7u;
-                idx ^= (2u > idx) ? 1u : 0u;
+                const float a = Y[i];
+                const bool p1 = a <= T3;
+                const bool p2 = a <= (p1 ? T5 : T1);
+                const bool p3 = a <= (p1 ? (p2 ? T6 : T4) : (p2 ? T2 : T0));
+                const uint32_t cnt = (p1 ? 4u : 0u) + (p2 ? 2u : 0u) + (p3 ? 1u : 0u);
+                const uint32_t idx = (0x17654320u >> (4u * cnt)) & 7u;
                 if (i < 6) {
                         ix |= idx << (3 * i + 16);  // pixel 5 keeps only its bit 0 here (:389) ...
                 }

@@ -240,7 +240,9 @@ static int launch_uyvy(const void *src, void *out, int sx, int sy, long pitch, c
         }
         const int threads = 128;
         static const bool tune_bpt1 = getenv("UGB200_DXT_BPT1") != nullptr;  // experiment knob: one block per thread
-        const bool pair = !tune_bpt1 && !(wb & 1) && !(15 & (size_t) src) && !(pitch & 15) && !(15 & (size_t) out);
+        // DXT5-YCoCg: one block per thread — two unrolled blocks (~50 KB of SASS) overflow the instruction cache (ncu: the top stall
+        // was no_instruction); DXT1: two blocks per thread for 128-bit loads/stores
+        const bool pair = DXT_TYPE == 1 && !tune_bpt1 && !(wb & 1) && !(15 & (size_t) src) && !(pitch & 15) && !(15 & (size_t) out);
         if (hb > 65535) {
                 return -1;
         }

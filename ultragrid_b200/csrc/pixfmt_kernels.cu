@@ -623,6 +623,220 @@ struct conv_rgba_vuya {
         }
 };
 
+// ---- 16-bit colour-space converters (Y416 / RG48 / R10k), depth-10/16 coefficients ------------------------------------------
+// 16-bit sample K of a packed word array
+template <int K>
+__device__ __forceinline__ int gh(const uint32_t *a)
+{
+        return (int) ((a[K >> 1] >> (16 * (K & 1))) & 0xffffu);
+}
+__device__ __forceinline__ int clampr(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+/// Y416 (U Y V A, 16 bit) -> RGB-like.  MODE 0: RG48 (vc_copylineY416toRG48, pixfmt_conv.c:2485-2514), 1: RGB (:1948-1976),
+/// 2: RGBA (:1978-2006), 3: R10k (:1917-1946).  int32 arithmetic wraps exactly like the reference's comp_type_t.
+template <int MODE>
+struct conv_y416_rgbx {
+        static constexpr int NPX = MODE == 0 ? 8 : MODE == 1 ? 16 : 4;
+        static constexpr int IN = NPX * 8, OUT = NPX * (MODE == 0 ? 6 : MODE == 1 ? 3 : 4);
+        static __host__ int out_len(int n) { return MODE == 0 ? (n + 5) / 6 * 6 : MODE == 1 ? (n + 2) / 3 * 3 : (n + 3) / 4 * 4; }
+        template <int K>
+        static __device__ __forceinline__ void px(const uint32_t *in, uint32_t *o, const conv_params &p)
+        {
+                if constexpr (K < NPX) {
+                        constexpr color_coeffs c = coeffs_709(16);
+                        constexpr int SH = COMP_BASE + (MODE == 0 ? 0 : MODE == 3 ? 6 : 8);
+                        constexpr int LO = MODE == 0 ? 256 : MODE == 3 ? 4 : 1, HI = MODE == 0 ? 65279 : MODE == 3 ? 1019 : 254;  // CLAMP_FULL
+                        const int u = gh<4 * K>(in) - 32768, y = c.y_scale * (gh<4 * K + 1>(in) - 4096), v = gh<4 * K + 2>(in) - 32768;
+                        const uint32_t r = clampr((y + v * c.r_cr) >> SH, LO, HI), g = clampr((y + u * c.g_cb + v * c.g_cr) >> SH, LO, HI),
+                                       b = clampr((y + u * c.b_cb) >> SH, LO, HI);
+                        if constexpr (MODE == 0 || MODE == 1) {
+                                o[3 * K] = r, o[3 * K + 1] = g, o[3 * K + 2] = b;
+                        } else if constexpr (MODE == 2) {
+                                o[K] = (0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift)) | r << p.rshift | g << p.gshift |
+                                       b << p.bshift;
+                        } else {
+                                o[K] = (r >> 2) | (((r & 3) << 6 | g >> 4) & 0xff) << 8 | (((g & 0xf) << 4 | b >> 6) & 0xff) << 16 | ((b & 0x3f) << 2) << 24;
+                        }
+                        px<K + 1>(in, o, p);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+                if constexpr (MODE == 0) {
+                        uint32_t o[24];
+                        px<0>(in, o, p);
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) {
+                                out[i] = o[2 * i] | o[2 * i + 1] << 16;
+                        }
+                } else if constexpr (MODE == 1) {
+                        uint32_t o[48];
+                        px<0>(in, o, p);
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) {
+                                out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                        }
+                } else {
+                        px<0>(in, out, p);
+                }
+        }
+};
+
+/// vc_copylineY416toV210, pixfmt_conv.c:3004-3033: chroma of a pixel pair averaged as uint16, every sample >> 6
+struct conv_y416_v210 {
+        static constexpr int IN = 96, OUT = 32;
+        static __host__ int out_len(int n) { return n / 16 * 16; }
+        template <int G>
+        static __device__ __forceinline__ void group(const uint32_t *in, uint32_t *out)
+        {
+                if constexpr (G < 2) {
+                        constexpr int S = 24 * G;  // 16-bit sample index of the group's first pixel (U Y V A per pixel)
+#define UGB_AVG(a, b) ((uint32_t) ((gh<S + (a)>(in) + gh<S + (b)>(in)) / 2) >> 6)
+#define UGB_Y(a) ((uint32_t) gh<S + (a)>(in) >> 6)
+                        out[4 * G + 0] = UGB_AVG(0, 4) | UGB_Y(1) << 10 | UGB_AVG(2, 6) << 20;
+                        out[4 * G + 1] = UGB_Y(5) | UGB_AVG(8, 12) << 10 | UGB_Y(9) << 20;
+                        out[4 * G + 2] = UGB_AVG(10, 14) | UGB_Y(13) << 10 | UGB_AVG(16, 20) << 20;
+                        out[4 * G + 3] = UGB_Y(17) | UGB_AVG(18, 22) << 10 | UGB_Y(21) << 20;
+#undef UGB_AVG
+#undef UGB_Y
+                        group<G + 1>(in, out);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &) { group<0>(in, out); }
+};
+
+/// RG48 -> Y416 (vc_copylineRG48toY416, :2451-2483) / Y216 (:2410-2449) with depth-16 coefficients; results stored as uint16 (wrap)
+struct conv_rg48_y416 {
+        static constexpr int IN = 48, OUT = 64;
+        static __host__ int out_len(int n) { return (n + 7) / 8 * 8; }
+        template <int K>
+        static __device__ __forceinline__ void px(const uint32_t *in, uint32_t *out)
+        {
+                if constexpr (K < 8) {
+                        constexpr color_coeffs c = coeffs_709(16);
+                        const int r = gh<3 * K>(in), g = gh<3 * K + 1>(in), b = gh<3 * K + 2>(in);
+                        const uint32_t u = ((r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE) + 32768, y = ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 4096,
+                                       v = ((r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE) + 32768;
+                        out[2 * K] = (u & 0xffff) | (y & 0xffff) << 16;
+                        out[2 * K + 1] = (v & 0xffff) | 0xFFFF0000u;
+                        px<K + 1>(in, out);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &) { px<0>(in, out); }
+};
+struct conv_rg48_y216 {
+        static constexpr int IN = 48, OUT = 32;
+        static __host__ int out_len(int n) { return (n + 7) / 8 * 8; }
+        template <int K>
+        static __device__ __forceinline__ void pair(const uint32_t *in, uint32_t *out)
+        {
+                if constexpr (K < 4) {
+                        constexpr color_coeffs c = coeffs_709(16);
+                        const int r0 = gh<6 * K>(in), g0 = gh<6 * K + 1>(in), b0 = gh<6 * K + 2>(in), r1 = gh<6 * K + 3>(in), g1 = gh<6 * K + 4>(in),
+                                  b1 = gh<6 * K + 5>(in);
+                        const int y0 = ((r0 * c.y_r + g0 * c.y_g + b0 * c.y_b) >> COMP_BASE) + 4096, y1 = ((r1 * c.y_r + g1 * c.y_g + b1 * c.y_b) >> COMP_BASE) + 4096;
+                        const int u = (((r0 * c.cb_r + g0 * c.cb_g + b0 * c.cb_b) >> COMP_BASE) + ((r1 * c.cb_r + g1 * c.cb_g + b1 * c.cb_b) >> COMP_BASE)) / 2 + 32768;
+                        const int v = (((r0 * c.cr_r + g0 * c.cr_g + b0 * c.cr_b) >> COMP_BASE) + ((r1 * c.cr_r + g1 * c.cr_g + b1 * c.cr_b) >> COMP_BASE)) / 2 + 32768;
+                        out[2 * K] = ((uint32_t) y0 & 0xffff) | ((uint32_t) u & 0xffff) << 16;
+                        out[2 * K + 1] = ((uint32_t) y1 & 0xffff) | ((uint32_t) v & 0xffff) << 16;
+                        pair<K + 1>(in, out);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &) { pair<0>(in, out); }
+};
+/// vc_copylineRG48toV210, :2354-2407: depth-10 coefficients, shift COMP_BASE + 6; chroma shifted per pixel, summed, C '/ 2'
+struct conv_rg48_v210 {
+        static constexpr int IN = 144, OUT = 64;
+        static __host__ int out_len(int n) { return n < 16 ? 0 : n / 16 * 16; }
+        template <int P>  // pixel pair P of the chunk (12 pairs): y1, y2, u, v
+        static __device__ __forceinline__ void fetch(const uint32_t *in, uint32_t &y1, uint32_t &y2, uint32_t &u, uint32_t &v)
+        {
+                constexpr color_coeffs c = coeffs_709(10);
+                constexpr int OFF = COMP_BASE + 6;
+                const int r0 = gh<6 * P>(in), g0 = gh<6 * P + 1>(in), b0 = gh<6 * P + 2>(in), r1 = gh<6 * P + 3>(in), g1 = gh<6 * P + 4>(in), b1 = gh<6 * P + 5>(in);
+                y1 = (uint32_t) (((r0 * c.y_r + g0 * c.y_g + b0 * c.y_b) >> OFF) + 64);
+                y2 = (uint32_t) (((r1 * c.y_r + g1 * c.y_g + b1 * c.y_b) >> OFF) + 64);
+                u = (uint32_t) ((((r0 * c.cb_r + g0 * c.cb_g + b0 * c.cb_b) >> OFF) + ((r1 * c.cb_r + g1 * c.cb_g + b1 * c.cb_b) >> OFF)) / 2 + 512);
+                v = (uint32_t) ((((r0 * c.cr_r + g0 * c.cr_g + b0 * c.cr_b) >> OFF) + ((r1 * c.cr_r + g1 * c.cr_g + b1 * c.cr_b) >> OFF)) / 2 + 512);
+        }
+        template <int G>
+        static __device__ __forceinline__ void group(const uint32_t *in, uint32_t *out)
+        {
+                if constexpr (G < 4) {
+                        uint32_t ya, yb, u0, v0, yc, yd, u1, v1, ye, yf, u2, v2;
+                        fetch<3 * G>(in, ya, yb, u0, v0);
+                        fetch<3 * G + 1>(in, yc, yd, u1, v1);
+                        fetch<3 * G + 2>(in, ye, yf, u2, v2);
+                        out[4 * G + 0] = u0 | ya << 10 | v0 << 20;
+                        out[4 * G + 1] = yb | u1 << 10 | yc << 20;
+                        out[4 * G + 2] = v1 | yd << 10 | u2 << 20;
+                        out[4 * G + 3] = ye | v2 << 10 | yf << 20;
+                        group<G + 1>(in, out);
+                }
+        }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &) { group<0>(in, out); }
+};
+/// vc_copylineUYVYtoRG48, :1124-1130 = copylineYUVtoRGB with rgb16: each 8-bit result in the HIGH byte of a 16-bit sample
+struct conv_uyvy_rg48 {
+        static constexpr int IN = 16, OUT = 48;
+        static __host__ int out_len(int n) { return n < 12 ? 0 : n / 12 * 12; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(8);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        const uint32_t w = in[i];
+                        const int y1 = c.y_scale * ((int) ((w >> 8) & 0xff) - 16), y2 = c.y_scale * ((int) (w >> 24) - 16);
+                        const int u = (int) (w & 0xff) - 128, v = (int) ((w >> 16) & 0xff) - 128;
+                        const int rc = v * c.r_cr, gc = u * c.g_cb + v * c.g_cr, bc = u * c.b_cb;
+                        const uint32_t r1 = clamp255((y1 + rc) >> COMP_BASE), g1 = clamp255((y1 + gc) >> COMP_BASE), b1 = clamp255((y1 + bc) >> COMP_BASE);
+                        const uint32_t r2 = clamp255((y2 + rc) >> COMP_BASE), g2 = clamp255((y2 + gc) >> COMP_BASE), b2 = clamp255((y2 + bc) >> COMP_BASE);
+                        out[3 * i] = r1 << 8 | g1 << 24, out[3 * i + 1] = b1 << 8 | r2 << 24, out[3 * i + 2] = g2 << 8 | b2 << 24;
+                }
+        }
+};
+/// vc_copyliner10ktoY416, :294-329 (components widened to 16 bit, depth-16 coefficients) and vc_copylineR10ktoUYVY, :2318-2334
+/// (8-bit truncation, then the RGB -> UYVY body)
+struct conv_r10k_y416 {
+        static constexpr int IN = 32, OUT = 64;
+        static __host__ int out_len(int n) { return (n + 7) / 8 * 8; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(16);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                        const int b1 = in[i] & 0xff, b2 = (in[i] >> 8) & 0xff, b3 = (in[i] >> 16) & 0xff, b4 = in[i] >> 24;
+                        const int r = b1 << 8 | (b2 & 0xC0), g = (b2 & 0x3F) << 10 | (b3 & 0xF0) << 2, b = (b3 & 0xF) << 12 | (b4 & 0xFC) << 4;
+                        const uint32_t u = ((r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE) + 32768, y = ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 4096,
+                                       v = ((r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE) + 32768;
+                        out[2 * i] = (u & 0xffff) | (y & 0xffff) << 16;
+                        out[2 * i + 1] = (v & 0xffff) | 0xFFFF0000u;
+                }
+        }
+};
+struct conv_r10k_uyvy {
+        static constexpr int IN = 32, OUT = 16;
+        static __host__ int out_len(int n) { return (n + 3) / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(8);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        int r[2], g[2], b[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                                const uint32_t w = in[2 * i + k];
+                                r[k] = w & 0xff, g[k] = (((w >> 8) & 0xff) << 2 | ((w >> 16) & 0xff) >> 6) & 0xff, b[k] = (((w >> 16) & 0xff) << 4 | (w >> 24) >> 4) & 0xff;
+                        }
+                        const int y1 = ((r[0] * c.y_r + g[0] * c.y_g + b[0] * c.y_b) >> COMP_BASE) + 16, y2 = ((r[1] * c.y_r + g[1] * c.y_g + b[1] * c.y_b) >> COMP_BASE) + 16;
+                        int u = (r[0] * c.cb_r + g[0] * c.cb_g + b[0] * c.cb_b) + (r[1] * c.cb_r + g[1] * c.cb_g + b[1] * c.cb_b);
+                        int v = (r[0] * c.cr_r + g[0] * c.cr_g + b[0] * c.cr_b) + (r[1] * c.cr_r + g[1] * c.cr_g + b[1] * c.cr_b);
+                        u = ((u / 2) >> COMP_BASE) + 128, v = ((v / 2) >> COMP_BASE) + 128;
+                        out[i] = pack4(u & 0xff, y1 & 0xff, v & 0xff, y2 & 0xff);
+                }
+        }
+};
+
 // ---- generic kernel ------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ dst, long dst_pitch, const uint8_t *__restrict__ src,
@@ -767,6 +981,17 @@ extern "C" UGB_API int ugb200_pixfmt_supported(int in_codec, int out_codec)
         case UGB_Y416 * 256 + UGB_UYVY:
         case UGB_VUYA * 256 + UGB_RGB:
         case UGB_RGBA * 256 + UGB_VUYA:
+        case UGB_Y416 * 256 + UGB_RG48:
+        case UGB_Y416 * 256 + UGB_RGB:
+        case UGB_Y416 * 256 + UGB_RGBA:
+        case UGB_Y416 * 256 + UGB_R10k:
+        case UGB_Y416 * 256 + UGB_v210:
+        case UGB_RG48 * 256 + UGB_Y416:
+        case UGB_RG48 * 256 + UGB_Y216:
+        case UGB_RG48 * 256 + UGB_v210:
+        case UGB_UYVY * 256 + UGB_RG48:
+        case UGB_R10k * 256 + UGB_Y416:
+        case UGB_R10k * 256 + UGB_UYVY:
                 return 1;
         }
         return 0;
@@ -849,6 +1074,17 @@ extern "C" UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *
                 UGB_CASE(UGB_Y416, UGB_UYVY, conv_y416_uyvy)
                 UGB_CASE(UGB_VUYA, UGB_RGB, conv_vuya_rgb)
                 UGB_CASE(UGB_RGBA, UGB_VUYA, conv_rgba_vuya)
+                UGB_CASE(UGB_Y416, UGB_RG48, conv_y416_rgbx<0>)
+                UGB_CASE(UGB_Y416, UGB_RGB, conv_y416_rgbx<1>)
+                UGB_CASE(UGB_Y416, UGB_RGBA, conv_y416_rgbx<2>)
+                UGB_CASE(UGB_Y416, UGB_R10k, conv_y416_rgbx<3>)
+                UGB_CASE(UGB_Y416, UGB_v210, conv_y416_v210)
+                UGB_CASE(UGB_RG48, UGB_Y416, conv_rg48_y416)
+                UGB_CASE(UGB_RG48, UGB_Y216, conv_rg48_y216)
+                UGB_CASE(UGB_RG48, UGB_v210, conv_rg48_v210)
+                UGB_CASE(UGB_UYVY, UGB_RG48, conv_uyvy_rg48)
+                UGB_CASE(UGB_R10k, UGB_Y416, conv_r10k_y416)
+                UGB_CASE(UGB_R10k, UGB_UYVY, conv_r10k_uyvy)
 #undef UGB_CASE
         case UGB_BGR * 256 + UGB_RGB: {
                 const conv_params q = { 16, 8, 0, 0 };  // vc_copylineBGRtoRGB
