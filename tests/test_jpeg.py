@@ -99,7 +99,9 @@ def test_restart_markers_and_header_layout(orc):
 # ---- GPU ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("codec,w,h,q,ri", [(UYVY, 16, 8, 90, 0), (UYVY, 64, 32, 75, 2), (UYVY, 100, 52, 90, 0), (UYVY, 1920, 1080, 90, 0),
-                                            (UYVY, 3840, 2160, 90, 0), (RGB, 8, 8, 90, 0), (RGB, 130, 37, 50, 3), (RGB, 1920, 1080, 90, 0)])
+                                            (UYVY, 3840, 2160, 90, 0), (RGB, 8, 8, 90, 0), (RGB, 130, 37, 50, 3), (RGB, 1920, 1080, 90, 0),
+                                            (UYVY, 100, 52, 90, 5), (UYVY, 1920, 1080, 75, 8), (UYVY, 640, 360, 90, 1), (RGB, 200, 120, 90, 32),
+                                            (RGB, 64, 64, 100, 4), (UYVY, 48, 24, 100, 16)])
 def test_gpu_encoder_equals_oracle_bytes(orc, codec, w, h, q, ri):
     import torch
     from ultragrid_b200 import api

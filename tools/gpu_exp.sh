@@ -1,5 +1,18 @@
 #!/bin/bash
-for v in "" "UGB200_DXT_BPT1=1"; do
-  echo "== $v"
-  env $v timeout 300 python bench.py --steps 10 --warmup 3 --no-extra 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['us_per_launch'], d['roofline']['frac'], d['e2e']['value'])"
-done
+python - <<'PY'
+import sys, torch, time
+sys.path.insert(0, '.')
+from ultragrid_b200 import api
+W,H=7680,4320
+dev=torch.device('cuda',0)
+src=[torch.randint(0,256,(W*H*2,),dtype=torch.uint8,device=dev) for _ in range(4)]
+out=torch.empty(W*H,dtype=torch.uint8,device=dev)
+for t in (6,1):
+    for i in range(3): api.uyvy_to_dxt(src[i%4],W,H,dxt_type=t,out=out)
+    torch.cuda.synchronize()
+    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20): api.uyvy_to_dxt(src[i%4],W,H,dxt_type=t,out=out)
+    e1.record(); torch.cuda.synchronize()
+    print("dxt type",t,"us/frame",e0.elapsed_time(e1)/20*1e3)
+PY

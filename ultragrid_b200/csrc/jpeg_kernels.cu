@@ -12,6 +12,7 @@
 // Arithmetic is float with an explicit operation order so that oracle/jpeg_oracle.c reproduces the bytes exactly.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -190,6 +191,260 @@ __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict
         }
 }
 
+// ---- fused path: DCT + quantise + per-block entropy coding + restart-segment assembly in ONE kernel ----------------------------
+// No int16 coefficient round trip through HBM (2 B/sample written + read by the split path), and the unit of serial work is one
+// 8x8 block instead of one restart segment.  CTA = 128 threads = 128 blocks in scan order:
+//   1. every thread loads its block straight from the frame, DCT + quantise in registers, zig-zag coefficients to shared memory
+//   2. DC prediction through shared memory, Huffman-codes its block into a private (shared-memory) bit string
+//   3. threads are re-mapped to blocks in scan order; the blocks of a restart segment (4..32 threads) prefix-sum their bit lengths
+//      and OR their bit strings into the segment buffer
+//   4. the same threads byte-stuff the segment cooperatively (ballot of 0xFF bytes) into its slot, append RSTn, record the size
+//   5. CTA-level prefix of its segment sizes (first level of the stream-offset scan, as in the split path)
+constexpr int kBlkWords = 52;  // 1658 bits worst case per block
+
+__device__ __forceinline__ int category(int v) { return 32 - __clz(abs(v)); }
+
+struct block_bits {  // MSB-first bit string of one block in shared memory, word w of block p at base[w * 128 + p]
+        uint32_t *base;
+        uint64_t acc;
+        int nbits, nwords;
+        __device__ __forceinline__ void put(uint32_t code, int len)
+        {
+                acc = (acc << len) | (code & ((1u << len) - 1u));
+                nbits += len;
+                if (nbits >= 32) {
+                        base[nwords * 128] = (uint32_t) (acc >> (nbits - 32));
+                        ++nwords;
+                        nbits -= 32;
+                }
+        }
+        __device__ __forceinline__ uint32_t finish()
+        {
+                if (nbits > 0) {
+                        base[nwords * 128] = (uint32_t) ((acc & ((1ull << nbits) - 1ull)) << (32 - nbits));
+                }
+                return (uint32_t) (nwords * 32 + nbits);
+        }
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
+                                                         uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
+                                                         uint32_t *__restrict__ cta_total, bool vec_ok)
+{
+        extern __shared__ uint32_t smem[];
+        uint32_t *s_coef = smem;                      // [32][128] zig-zag coefficients, two int16 per word
+        uint32_t *s_bits = s_coef + 32 * 128;         // [kBlkWords][128]
+        uint32_t *s_seg = s_bits + kBlkWords * 128;   // [segments of the CTA][bps * kBlkWords]
+        __shared__ uint32_t s_dctab[2][16], s_ac[2][256], s_len[128], s_warp[4];
+        __shared__ int s_dc[128];
+        const int tid = threadIdx.x;
+        for (int i = tid; i < 32; i += 128) {
+                s_dctab[i >> 4][i & 15] = c_tab.dc[i >> 4][i & 15];
+        }
+        for (int i = tid; i < 512; i += 128) {
+                s_ac[i >> 8][i & 255] = c_tab.ac[i >> 8][i & 255];
+        }
+        for (int i = tid; i < kBlkWords * 128; i += 128) {
+                s_seg[i] = 0;
+        }
+        // ---- which block is mine -------------------------------------------------------------------------------------------
+        const int bps = g.ri * g.blocks_per_mcu;  // blocks per restart segment: 4, 8, 16 or 32 (checked by the host)
+        int comp, bx, by, p;                      // p = position of my block in the CTA's scan order
+        bool valid;
+        int first_mcu;                            // scan-local index of the CTA's first MCU
+        if (FMT == FMT_UYVY_422) {
+                const int k = tid >> 5, lane = tid & 31;
+                first_mcu = blockIdx.x * 32;
+                const int m = first_mcu + lane;
+                valid = m < g.mcu_per_scan;
+                comp = k < 2 ? 0 : k - 1;
+                const int mx = m % g.bw;
+                bx = comp == 0 ? mx * 2 + k : mx, by = m / g.bw;
+                p = lane * 4 + k;
+        } else {
+                first_mcu = blockIdx.x * 128;
+                const int b = first_mcu + tid;
+                valid = b < g.mcu_per_scan;
+                comp = blockIdx.y;
+                bx = b % g.bw, by = b / g.bw;
+                p = tid;
+        }
+        // ---- 1. DCT + quantise -------------------------------------------------------------------------------------------------
+        int q[64];
+        {
+                const int px_w = (FMT == FMT_UYVY_422 && comp != 0) ? 16 : 8;
+                const bool interior = vec_ok && valid && (bx + 1) * px_w <= g.w && (by + 1) * 8 <= g.h;
+                float f[64];
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                        load_row(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + y : 0, interior, f + 8 * y);
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                        fdct8(f[8 * r], f[8 * r + 1], f[8 * r + 2], f[8 * r + 3], f[8 * r + 4], f[8 * r + 5], f[8 * r + 6], f[8 * r + 7]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                        fdct8(f[c], f[8 + c], f[16 + c], f[24 + c], f[32 + c], f[40 + c], f[48 + c], f[56 + c]);
+                }
+                const float *qm = c_tab.qmul[comp == 0 ? 0 : 1];
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                        q[i] = (int) __float_as_uint(__fadd_rn(__fmul_rn(f[i], qm[i]), 12582912.0f)) - 0x4B400000;
+                }
+        }
+        constexpr int zz[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+        uint64_t nz = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+                int a = q[zz[2 * k]], c2 = q[zz[2 * k + 1]];
+                if (k > 0) {
+                        a = min(max(a, -1023), 1023);
+                }
+                c2 = min(max(c2, -1023), 1023);
+                s_coef[k * 128 + p] = ((uint32_t) a & 0xffffu) | ((uint32_t) c2 << 16);
+                nz |= ((uint64_t) (a != 0) | (uint64_t) (c2 != 0) << 1) << (2 * k);
+        }
+        nz &= ~1ull;
+        const int dcv = q[0];
+        s_dc[p] = dcv;
+        __syncthreads();
+        // ---- 2. entropy-code my block --------------------------------------------------------------------------------------------
+        uint32_t bits = 0;
+        if (valid) {
+                const int t = comp == 0 ? 0 : 1;
+                int pred;
+                if (FMT == FMT_UYVY_422) {  // MCU = Y0 Y1 Cb Cr; a segment starts every ri MCUs (ri divides the CTA's 32 MCUs)
+                        const int k = tid >> 5;
+                        const bool first = (p % bps) < 4;
+                        pred = k == 1 ? s_dc[p - 1] : first ? 0 : k == 0 ? s_dc[p - 3] : s_dc[p - 4];
+                } else {
+                        pred = (p % bps) == 0 ? 0 : s_dc[p - 1];
+                }
+                block_bits bw = { s_bits + p, 0, 0, 0 };
+                const int diff = dcv - pred;
+                int sz = category(diff);
+                bw.put(s_dctab[t][sz] & 0xffff, s_dctab[t][sz] >> 16);
+                if (sz) {
+                        bw.put((uint32_t) (diff < 0 ? diff - 1 : diff), sz);
+                }
+                int prev = 0;
+                while (nz) {
+                        const int i = __ffsll((long long) nz) - 1;
+                        nz &= nz - 1;
+                        int run = i - prev - 1;
+                        prev = i;
+                        while (run > 15) {
+                                bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);  // ZRL
+                                run -= 16;
+                        }
+                        const int v = (int) (short) (s_coef[(i >> 1) * 128 + p] >> (16 * (i & 1)));
+                        sz = category(v);
+                        const uint32_t e = s_ac[t][(run << 4) | sz];
+                        bw.put(((e & 0xffff) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), (int) (e >> 16) + sz);
+                }
+                if (prev != 63) {
+                        bw.put(s_ac[t][0] & 0xffff, s_ac[t][0] >> 16);  // EOB
+                }
+                bits = bw.finish();
+        }
+        s_len[p] = bits;
+        __syncthreads();
+        // ---- 3. assemble restart segments: thread tid now owns scan-order block tid ---------------------------------------------------
+        const int sg = tid / bps, gl = tid % bps;          // segment within the CTA, my lane within the segment's group
+        const unsigned lane32 = tid & 31;
+        const unsigned gmask = bps == 32 ? 0xffffffffu : (((1u << bps) - 1u) << (lane32 - gl));
+        const uint32_t L = s_len[tid];
+        uint32_t incl = L;
+        for (int d = 1; d < bps; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(gmask, incl, d, bps);
+                if (gl >= d) {
+                        incl += o;
+                }
+        }
+        const uint32_t T = __shfl_sync(gmask, incl, bps - 1, bps);  // bits of the whole segment
+        uint32_t *seg = s_seg + sg * bps * kBlkWords;
+        {
+                const uint32_t off = incl - L, sh = off & 31;
+                uint32_t *d = seg + (off >> 5);
+                for (uint32_t w = 0; w * 32 < L; ++w) {
+                        const uint32_t v = s_bits[w * 128 + tid];
+                        atomicOr(d + w, v >> sh);
+                        if (sh) {
+                                atomicOr(d + w + 1, v << (32 - sh));
+                        }
+                }
+                if (gl == 0 && (T & 7)) {  // pad the last byte with ones (T.81 F.1.2.3)
+                        const uint32_t pad = 8 - (T & 7);
+                        atomicOr(seg + (T >> 5), ((1u << pad) - 1u) << (32 - (T & 31) - pad));
+                }
+        }
+        __syncthreads();
+        // ---- 4. byte stuffing into the slot ------------------------------------------------------------------------------------------
+        int seg_global, ls;  // global segment index, index within its scan
+        if (FMT == FMT_UYVY_422) {
+                ls = first_mcu / g.ri + sg;
+                seg_global = ls;
+        } else {
+                ls = first_mcu / g.ri + sg;
+                seg_global = blockIdx.y * g.seg_per_scan + ls;
+        }
+        const bool seg_valid = ls < g.seg_per_scan && (long) ls * g.ri < g.mcu_per_scan;
+        uint32_t written = 0;
+        if (seg_valid) {
+                uint8_t *slot = slots + (long) seg_global * g.slot;
+                const uint32_t n = (T + 7) >> 3;
+                for (uint32_t base = 0; base < n; base += bps) {
+                        const uint32_t i = base + gl;
+                        const uint32_t b = i < n ? (seg[i >> 2] >> (24 - 8 * (i & 3))) & 0xffu : 0u;
+                        const unsigned ff = __ballot_sync(gmask, b == 0xFF) & gmask;
+                        const uint32_t before = __popc(ff & ((1u << lane32) - 1u));
+                        if (i < n) {
+                                slot[written + gl + before] = (uint8_t) b;
+                                if (b == 0xFF) {
+                                        slot[written + gl + before + 1] = 0;
+                                }
+                        }
+                        written += min((uint32_t) bps, n - base) + __popc(ff);
+                }
+                if (gl == 0) {
+                        if (ls != g.seg_per_scan - 1) {
+                                slot[written] = 0xFF, slot[written + 1] = (uint8_t) (0xD0 + (ls & 7));
+                                written += 2;
+                        }
+                        sizes[seg_global] = written;
+                }
+        }
+        // ---- 5. CTA prefix of the segment sizes ----------------------------------------------------------------------------------------
+        const uint32_t mine = (gl == 0 && seg_valid) ? (written) : 0;  // one value per segment, carried by its first thread
+        uint32_t inc2 = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc2, d);
+                if (lane32 >= (unsigned) d) {
+                        inc2 += o;
+                }
+        }
+        if (lane32 == 31) {
+                s_warp[tid >> 5] = inc2;
+        }
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < (tid >> 5); ++w) {
+                before += s_warp[w];
+        }
+        if (gl == 0 && seg_valid) {
+                local_off[seg_global] = before + inc2 - mine;
+        }
+        if (tid == 127) {
+                const int cta = FMT == FMT_UYVY_422 ? blockIdx.x : blockIdx.y * gridDim.x + blockIdx.x;
+                cta_total[cta] = before + inc2;
+        }
+}
+
 // ---- K2 -------------------------------------------------------------------------------------------------------------
 /// MSB-first bit writer with byte stuffing; bytes are gathered into aligned 32-bit words before they go to memory
 struct bit_writer {
@@ -237,7 +492,6 @@ struct bit_writer {
         }
 };
 
-__device__ __forceinline__ int category(int v) { return 32 - __clz(abs(v)); }
 
 /// One thread per restart segment.  Per block: 8 x LDG.128 build a 64-bit non-zero map (uniform work), then the loop runs once
 /// per NON-ZERO coefficient (ffs over the map) instead of once per coefficient — far less divergence inside a warp.
@@ -412,14 +666,16 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *__restrict__ 
 // ---- K4 -------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ sizes,
                                                            const uint32_t *__restrict__ local_off, const uint32_t *__restrict__ cta_base,
-                                                           jpeg_geom g, uint8_t *__restrict__ out)
+                                                           jpeg_geom g, int segs_per_cta, int ctas_per_scan, uint8_t *__restrict__ out)
 {
         const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
         if (s >= g.nseg) {
                 return;
         }
         const int scan = s / g.seg_per_scan;
-        const uint32_t n = sizes[s], off = g.header_len + cta_base[s >> 7] + local_off[s] + g.sos_len * scan;
+        // which CTA of the entropy kernel produced this segment: split path = 128 consecutive segments; fused path = per scan
+        const int cta = ctas_per_scan ? scan * ctas_per_scan + (s - scan * g.seg_per_scan) / segs_per_cta : s / segs_per_cta;
+        const uint32_t n = sizes[s], off = g.header_len + cta_base[cta] + local_off[s] + g.sos_len * scan;
         const uint8_t *src = slots + (long) s * g.slot;
         for (uint32_t i = lane; i < n; i += 32) {
                 out[off + i] = src[i];
@@ -459,6 +715,9 @@ struct ugb200_jpeg_encoder {
         uint32_t *h_total = nullptr;
         size_t h_out_cap = 0, h_in_cap = 0;
         bool pending = false;
+        const void *last_src = nullptr;  // for ugb200_jpeg_debug_coefficients (the fused path keeps coefficients on chip)
+        long last_pitch = 0;
+        bool last_vec_ok = false;
 };
 
 namespace {
@@ -619,7 +878,7 @@ int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri
         }
         size_t cap2 = e->seg_cap;
         if (!grow(e->sizes, e->seg_cap, (size_t) g.nseg) || !grow(e->offsets, cap2, (size_t) g.nseg) ||
-            !grow(e->cta_total, e->cta_cap, (size_t) (g.nseg + 127) / 128)) {
+            !grow(e->cta_total, e->cta_cap, (size_t) g.nseg + 8)) {
                 return -2;
         }
         if (e->total == nullptr && cudaMalloc((void **) &e->total, 4) != cudaSuccess) {
@@ -689,13 +948,44 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         }
         const jpeg_geom &g = e->g;
         const bool vec_ok = fmt == FMT_UYVY_422 && !(15 & (size_t) src) && !(pitch & 15);
-        const int dct_ctas = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
-        jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok);
-        const int nctas = (g.nseg + 127) / 128;
-        jpeg_huffman_kernel<<<nctas, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes, e->offsets, e->cta_total);
+        e->last_src = src, e->last_pitch = pitch, e->last_vec_ok = vec_ok;
+        const int bps = g.ri * g.blocks_per_mcu;
+        static const bool force_split = getenv("UGB200_JPEG_SPLIT") != nullptr;
+        const bool fused = !force_split && (bps == 4 || bps == 8 || bps == 16 || bps == 32);
+        int nctas, segs_per_cta, ctas_per_scan;
+        if (fused) {  // one kernel: DCT + entropy coding + segment assembly
+                const size_t smem = (size_t) (32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t);
+                segs_per_cta = 128 / bps;
+                if (fmt == FMT_UYVY_422) {
+                        ctas_per_scan = (g.mcu_per_scan + 31) / 32;
+                        nctas = ctas_per_scan;
+                        static bool attr_set = false;
+                        if (!attr_set) {
+                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_UYVY_422>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+                                attr_set = true;
+                        }
+                        jpeg_fused_kernel<FMT_UYVY_422><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
+                                                                                       e->cta_total, vec_ok);
+                } else {
+                        ctas_per_scan = (g.mcu_per_scan + 127) / 128;
+                        nctas = ctas_per_scan * 3;
+                        static bool attr_set = false;
+                        if (!attr_set) {
+                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+                                attr_set = true;
+                        }
+                        jpeg_fused_kernel<FMT_RGB_444><<<dim3(ctas_per_scan, 3), 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes,
+                                                                                                       e->offsets, e->cta_total, vec_ok);
+                }
+        } else {  // split path: any restart interval
+                const int dct_ctas = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
+                jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok);
+                nctas = (g.nseg + 127) / 128, segs_per_cta = 128, ctas_per_scan = 0;
+                jpeg_huffman_kernel<<<nctas, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes, e->offsets, e->cta_total);
+        }
         jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
         jpeg_compact_kernel<<<(int) (((long) g.nseg * 32 + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
-                                                                                           e->out);
+                                                                                           segs_per_cta, ctas_per_scan, e->out);
         if (cudaGetLastError() != cudaSuccess) {
                 return -2;
         }
@@ -768,8 +1058,13 @@ int ugb200_jpeg_encode(ugb200_jpeg_encoder *e, const void *src, int src_is_devic
 
 int ugb200_jpeg_debug_coefficients(ugb200_jpeg_encoder *e, const int16_t **dev_ptr, size_t *count)
 {
-        if (!e || !e->coef) {
+        if (!e || !e->coef || !e->last_src) {
                 return -1;
+        }
+        {  // recompute them with the stand-alone DCT kernel from the last source frame (which must still be alive)
+                const jpeg_geom &g = e->g;
+                const int dct_ctas = g.fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
+                jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) e->last_src, e->last_pitch, g, e->coef, e->last_vec_ok);
         }
         cudaStreamSynchronize(e->stream);
         *dev_ptr = e->coef;
