@@ -684,6 +684,157 @@ static void r10k_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_l
         }
 }
 
+/* ---- R12L: 8 px x 3 x 12 bit = 36 bytes, component k of a group at bit 12k (little endian) -------------------------------- */
+static unsigned r12_get(const unsigned char *blk, int k)
+{
+        const int off = 12 * k;
+        const uint32_t v = blk[off >> 3] | (uint32_t) blk[(off >> 3) + 1] << 8;
+        return (v >> (off & 7)) & 0xfff;
+}
+static void r12_put(unsigned char *blk, int k, unsigned v)
+{
+        const int off = 12 * k;
+        if (off & 7) {
+                blk[off >> 3] |= (v & 0xf) << 4, blk[(off >> 3) + 1] = v >> 4;
+        } else {
+                blk[off >> 3] = v & 0xff, blk[(off >> 3) + 1] = (blk[(off >> 3) + 1] & 0xf0) | v >> 8;
+        }
+}
+/* vc_copylineR12LtoRGB, pixfmt_conv.c:353-430 */
+static void r12l_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x <= dst_len - 24; x += 24, src += 36) {
+                for (int k = 0; k < 24; ++k) {
+                        *dst++ = r12_get(src, k) >> 4;
+                }
+        }
+}
+/* vc_copylineR12L, :438-523 (the last, possibly partial group goes through a temporary: exactly dst_len bytes are written) */
+static void r12l_to_rgba(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        const uint32_t amask = 0xFFFFFFFFU ^ (0xFFU << rs) ^ (0xFFU << gs) ^ (0xFFU << bs);
+        for (int x = 0; x < dst_len; x += 32, src += 36) {
+                unsigned char tmp[32];
+                for (int i = 0; i < 8; ++i) {
+                        wr32(tmp + 4 * i, amask | (r12_get(src, 3 * i) >> 4) << rs | (r12_get(src, 3 * i + 1) >> 4) << gs | (r12_get(src, 3 * i + 2) >> 4) << bs);
+                }
+                memcpy(dst + x, tmp, dst_len - x < 32 ? dst_len - x : 32);
+        }
+}
+/* vc_copylineR12LtoRG48, :1371-1476 (partial last group through a temporary, like R12L -> RGBA) */
+static void r12l_to_rg48(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x < dst_len; x += 48, src += 36) {
+                unsigned char tmp[48];
+                for (int k = 0; k < 24; ++k) {
+                        const uint16_t v = r12_get(src, k) << 4;
+                        memcpy(tmp + 2 * k, &v, 2);
+                }
+                memcpy(dst + x, tmp, dst_len - x < 48 ? dst_len - x : 48);
+        }
+}
+/* vc_copylineR12LtoR10k, :1640-1699.  Not a clean R10k: the 4th byte keeps all of B[7:0] (so the two padding bits carry B[1:0]), and for
+ * pixel 1 of each group its low nibble is R[3:0] instead of B[3:0] (:1661 reads src[4] where src[7] holds B) */
+static void r12l_to_r10k(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x <= dst_len - 32; x += 32, src += 36) {
+                for (int i = 0; i < 8; ++i) {
+                        const unsigned r = r12_get(src, 3 * i), g = r12_get(src, 3 * i + 1), b = r12_get(src, 3 * i + 2);
+                        *dst++ = r >> 4, *dst++ = (r & 0xC) << 4 | g >> 6, *dst++ = ((g >> 2) & 0xF) << 4 | b >> 8;
+                        *dst++ = i == 1 ? (b & 0xF0) | (r & 0xF) : b & 0xFF;
+                }
+        }
+}
+/* vc_copylineR12LtoY416, :1478-1542 */
+static void r12l_to_y416(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(16);
+        for (int x = 0; x < dst_len; x += 64, src += 36) {
+                for (int i = 0; i < 8; ++i, dst += 8) {
+                        const int r = r12_get(src, 3 * i) << 4, g = r12_get(src, 3 * i + 1) << 4, b = r12_get(src, 3 * i + 2) << 4;
+                        const uint16_t o[4] = { ((r * c.cb_r + g * c.cb_g + b * c.cb_b) >> COMP_BASE) + 32768, ((r * c.y_r + g * c.y_g + b * c.y_b) >> COMP_BASE) + 4096,
+                                                ((r * c.cr_r + g * c.cr_g + b * c.cr_b) >> COMP_BASE) + 32768, 0xFFFFU };
+                        memcpy(dst, o, 8);
+                }
+        }
+}
+/* vc_copylineR12LtoUYVY, :1544-1638 */
+static void r12l_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(8);
+        for (int x = 0; x < dst_len; x += 16, src += 36) {
+                for (int i = 0; i < 4; ++i) {
+                        int r[2], g[2], b[2];
+                        for (int k = 0; k < 2; ++k) {
+                                r[k] = r12_get(src, 6 * i + 3 * k) << 4, g[k] = r12_get(src, 6 * i + 3 * k + 1) << 4, b[k] = r12_get(src, 6 * i + 3 * k + 2) << 4;
+                        }
+                        *dst++ = (((r[0] * c.cb_r + g[0] * c.cb_g + b[0] * c.cb_b) + (r[1] * c.cb_r + g[1] * c.cb_g + b[1] * c.cb_b)) >> (COMP_BASE + 9)) + 128;
+                        *dst++ = ((r[0] * c.y_r + g[0] * c.y_g + b[0] * c.y_b) >> (COMP_BASE + 8)) + 16;
+                        *dst++ = (((r[0] * c.cr_r + g[0] * c.cr_g + b[0] * c.cr_b) + (r[1] * c.cr_r + g[1] * c.cr_g + b[1] * c.cr_b)) >> (COMP_BASE + 9)) + 128;
+                        *dst++ = ((r[1] * c.y_r + g[1] * c.y_g + b[1] * c.y_b) >> (COMP_BASE + 8)) + 16;
+                }
+        }
+}
+/* vc_copylineRGB_AtoR12L, :1258-1334 (pix = 3: RGB :1324, pix = 4: RGBA :1330); vc_copylineRG48toR12L, :1701-1826; vc_copylineY416toR12L, :1828-1915 */
+static void x_to_r12l(unsigned char *dst, const unsigned char *src, int dst_len, int kind)
+{
+        const struct coeffs c = cfs709(16);
+        for (int x = 0; kind == 3 ? x < dst_len : x <= dst_len - 36; x += 36, dst += 36) {
+                memset(dst, 0, 36);
+                for (int i = 0; i < 8; ++i) {
+                        unsigned r, g, b;
+                        if (kind == 0 || kind == 1) {
+                                r = src[0] << 4, g = src[1] << 4, b = src[2] << 4;
+                                src += kind == 0 ? 3 : 4;
+                        } else if (kind == 2) {
+                                uint16_t in[3];
+                                memcpy(in, src, 6);
+                                r = in[0] >> 4, g = in[1] >> 4, b = in[2] >> 4;
+                                src += 6;
+                        } else {
+                                uint16_t in[4];
+                                memcpy(in, src, 8);
+                                const int u = in[0] - 32768, y = c.y_scale * (in[1] - 4096), v = in[2] - 32768;
+                                r = clampr((y + v * c.r_cr) >> (COMP_BASE + 4), 16, 4079);
+                                g = clampr((y + u * c.g_cb + v * c.g_cr) >> (COMP_BASE + 4), 16, 4079);
+                                b = clampr((y + u * c.b_cb) >> (COMP_BASE + 4), 16, 4079);
+                                src += 8;
+                        }
+                        r12_put(dst, 3 * i, r), r12_put(dst, 3 * i + 1, g), r12_put(dst, 3 * i + 2, b);
+                }
+        }
+}
+static void rgb_to_r12l(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; x_to_r12l(d, s, n, 0); }
+static void rgba_to_r12l(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; x_to_r12l(d, s, n, 1); }
+static void rg48_to_r12l(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; x_to_r12l(d, s, n, 2); }
+static void y416_to_r12l(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; x_to_r12l(d, s, n, 3); }
+
+/* vc_copylineDVS10 (the C variant that is compiled, pixfmt_conv.c:690-720): keeps bytes 0..2 of every 32-bit word */
+static void dvs10_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const int src_len = dst_len / 1.5;
+        for (int x = 0; x <= src_len - 16; x += 16, src += 32) {
+                for (int k = 0; k < 8; ++k) {
+                        *dst++ = src[4 * k], *dst++ = src[4 * k + 1], *dst++ = src[4 * k + 2];
+                }
+        }
+}
+/* vc_copylineDVS10toV210, :595-618 */
+static void dvs10_to_v210(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        for (int x = 0; x <= dst_len - 4; x += 4) {
+                const uint32_t a = rd32(src + x);
+                wr32(dst + x, (((a >> 24) * 0x00010101U) & 0x00300c03U) | ((a << 2) & (0xffU << 2)) | ((a << 4) & (0xff00U << 4)) | ((a << 6) & (0xff0000U << 6)));
+        }
+}
+
 /* get_decoder_from_to, pixfmt_conv.c:3110-3125 (subset of decoders[] :3041-3103 restated so far) */
 static line_fn *decoder_from_to(int in, int out)
 {
@@ -738,6 +889,18 @@ static line_fn *decoder_from_to(int in, int out)
         case C_UYVY * 256 + C_RG48: return uyvy_to_rg48;
         case C_R10k * 256 + C_Y416: return r10k_to_y416;
         case C_R10k * 256 + C_UYVY: return r10k_to_uyvy;
+        case C_DVS10 * 256 + C_UYVY: return dvs10_to_uyvy;
+        case C_DVS10 * 256 + C_v210: return dvs10_to_v210;
+        case C_R12L * 256 + C_RGB: return r12l_to_rgb;
+        case C_R12L * 256 + C_RGBA: return r12l_to_rgba;
+        case C_R12L * 256 + C_RG48: return r12l_to_rg48;
+        case C_R12L * 256 + C_R10k: return r12l_to_r10k;
+        case C_R12L * 256 + C_Y416: return r12l_to_y416;
+        case C_R12L * 256 + C_UYVY: return r12l_to_uyvy;
+        case C_RGB * 256 + C_R12L: return rgb_to_r12l;
+        case C_RGBA * 256 + C_R12L: return rgba_to_r12l;
+        case C_RG48 * 256 + C_R12L: return rg48_to_r12l;
+        case C_Y416 * 256 + C_R12L: return y416_to_r12l;
         }
         return NULL;
 }

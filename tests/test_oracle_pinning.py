@@ -12,7 +12,7 @@ import pytest
 
 import util
 
-UYVY, YUYV, RGBA, RGB, BGR, RG48, V210, Y216, Y416, VUYA, R10K = 2, 3, 1, 12, 20, 27, 7, 30, 31, 4, 5
+UYVY, YUYV, RGBA, RGB, BGR, RG48, V210, Y216, Y416, VUYA, R10K, R12L, DVS10 = 2, 3, 1, 12, 20, 27, 7, 30, 31, 4, 5, 6, 8
 
 PAIRS = [(V210, UYVY), (YUYV, UYVY), (UYVY, YUYV), (UYVY, RGB), (YUYV, RGB), (UYVY, RGBA), (RGB, UYVY), (BGR, UYVY), (RGBA, UYVY),
          (RG48, UYVY), (RGB, RGBA), (RGBA, RGB), (RGBA, RGBA), (RGB, RGB), (BGR, RGB), (UYVY, UYVY),
@@ -20,7 +20,9 @@ PAIRS = [(V210, UYVY), (YUYV, UYVY), (UYVY, YUYV), (UYVY, RGB), (YUYV, RGB), (UY
          (RG48, RGB), (RG48, RGBA), (RG48, R10K), (RGBA, RG48), (RGB, RG48), (UYVY, Y216), (UYVY, Y416), (Y216, UYVY), (Y416, UYVY),
          (VUYA, Y416), (VUYA, UYVY), (VUYA, RGB), (RGBA, VUYA), (R10K, RGBA), (R10K, RGB), (R10K, RG48), (RGBA, R10K),
          (Y416, RG48), (Y416, RGB), (Y416, RGBA), (Y416, R10K), (Y416, V210), (RG48, Y416), (RG48, Y216), (RG48, V210), (UYVY, RG48),
-         (R10K, Y416), (R10K, UYVY)]
+         (R10K, Y416), (R10K, UYVY),
+         (R12L, RGB), (R12L, RGBA), (R12L, RG48), (R12L, R10K), (R12L, Y416), (R12L, UYVY), (RGB, R12L), (RGBA, R12L), (RG48, R12L),
+         (Y416, R12L), (DVS10, UYVY), (DVS10, V210)]
 
 
 def test_known_answer_checksums(orc):

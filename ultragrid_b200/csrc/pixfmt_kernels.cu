@@ -410,6 +410,11 @@ struct map_rg48_rgb {  // vc_copylineRG48toRGB, pixfmt_conv.c:2030-2042: the hig
         static __host__ int out_len(int n) { return n < 3 ? 0 : n / 3 * 3; }
         static constexpr int src(int j) { return 6 * (j / 3) + 2 * (j % 3) + 1; }
 };
+struct map_dvs10_uyvy {  // vc_copylineDVS10 (C variant, pixfmt_conv.c:690-720): bytes 0..2 of every 32-bit word; src_len = dst_len / 1.5
+        static constexpr int IN = 64, OUT = 48;
+        static __host__ int out_len(int n) { return (int) (2 * (long long) n / 3) / 16 * 24; }
+        static constexpr int src(int j) { return 4 * (j / 3) + j % 3; }
+};
 struct map_rgba_rg48 {  // vc_copylineRGBAtoRG48, :1336-1351
         static constexpr int IN = 32, OUT = 48;
         static __host__ int out_len(int n) { return n < 6 ? 0 : n / 6 * 6; }
@@ -837,6 +842,161 @@ struct conv_r10k_uyvy {
         }
 };
 
+// ---- R12L: 8 pixels x 3 components x 12 bits = 36 bytes, component k of a group at bit 12k (little endian) --------------------
+__device__ __forceinline__ uint32_t r12_get(const uint32_t *w, int k)  // k folds to a constant once the loops are unrolled
+{
+        const int off = 12 * k, wi = off >> 5, sh = off & 31;
+        return sh <= 20 ? (w[wi] >> sh) & 0xfffu : ((w[wi] >> sh) | (w[wi + 1] << (32 - sh))) & 0xfffu;
+}
+__device__ __forceinline__ void r12_put(uint32_t *w, int k, uint32_t v)
+{
+        const int off = 12 * k, wi = off >> 5, sh = off & 31;
+        w[wi] |= v << sh;
+        if (sh > 20) {
+                w[wi + 1] |= v >> (32 - sh);
+        }
+}
+
+/// R12L -> 8/10/16-bit RGB layouts.  MODE 0: RGB (vc_copylineR12LtoRGB, pixfmt_conv.c:353-430), 1: RGBA (vc_copylineR12L, :438-523),
+/// 2: RG48 (:1371-1476), 3: R10k (:1640-1699)
+template <int MODE>
+struct conv_r12l_rgbx {
+        static constexpr int IN = 144, OUT = MODE == 0 ? 96 : MODE == 2 ? 192 : 128;
+        static __host__ int out_len(int n) { return MODE == 0 ? n / 24 * 24 : MODE == 3 ? n / 32 * 32 : n; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+                const uint32_t amask = 0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift);
+                uint32_t o8[MODE == 0 ? 96 : 1];
+                uint32_t o16[MODE == 2 ? 96 : 1];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                                const uint32_t r = r12_get(in + 9 * g, 3 * i), gg = r12_get(in + 9 * g, 3 * i + 1), b = r12_get(in + 9 * g, 3 * i + 2);
+                                const int px = 8 * g + i;
+                                if (MODE == 0) {
+                                        o8[3 * px] = r >> 4, o8[3 * px + 1] = gg >> 4, o8[3 * px + 2] = b >> 4;
+                                } else if (MODE == 1) {
+                                        out[px] = amask | (r >> 4) << p.rshift | (gg >> 4) << p.gshift | (b >> 4) << p.bshift;
+                                } else if (MODE == 2) {
+                                        o16[3 * px] = r << 4, o16[3 * px + 1] = gg << 4, o16[3 * px + 2] = b << 4;
+                                } else {  // not a clean R10k: byte 3 keeps B[7:0]; pixel 1 of a group gets R[3:0] in its low nibble (pixfmt_conv.c:1661)
+                                        out[px] = (r >> 4) | ((r & 0xC) << 4 | gg >> 6) << 8 | (((gg >> 2) & 0xF) << 4 | b >> 8) << 16 |
+                                                  (i == 1 ? (b & 0xF0) | (r & 0xF) : b & 0xFF) << 24;
+                                }
+                        }
+                }
+                if (MODE == 0) {
+#pragma unroll
+                        for (int i = 0; i < 24; ++i) {
+                                out[i] = pack4(o8[4 * i], o8[4 * i + 1], o8[4 * i + 2], o8[4 * i + 3]);
+                        }
+                }
+                if (MODE == 2) {
+#pragma unroll
+                        for (int i = 0; i < 48; ++i) {
+                                out[i] = o16[2 * i] | o16[2 * i + 1] << 16;
+                        }
+                }
+        }
+};
+
+/// R12L -> Y416 (vc_copylineR12LtoY416, :1478-1542; components << 4, depth-16 coefficients) and
+/// R12L -> UYVY (vc_copylineR12LtoUYVY, :1544-1638; depth-8 coefficients on 16-bit components, one shift of COMP_BASE + 8 (+1 for chroma))
+struct conv_r12l_y416 {
+        static constexpr int IN = 144, OUT = 256;
+        static __host__ int out_len(int n) { return (n + 63) / 64 * 64; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(16);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                                const int r = r12_get(in + 9 * g, 3 * i) << 4, gg = r12_get(in + 9 * g, 3 * i + 1) << 4, b = r12_get(in + 9 * g, 3 * i + 2) << 4;
+                                const uint32_t u = ((r * c.cb_r + gg * c.cb_g + b * c.cb_b) >> COMP_BASE) + 32768, y = ((r * c.y_r + gg * c.y_g + b * c.y_b) >> COMP_BASE) + 4096,
+                                               v = ((r * c.cr_r + gg * c.cr_g + b * c.cr_b) >> COMP_BASE) + 32768;
+                                out[2 * (8 * g + i)] = (u & 0xffff) | (y & 0xffff) << 16;
+                                out[2 * (8 * g + i) + 1] = (v & 0xffff) | 0xFFFF0000u;
+                        }
+                }
+        }
+};
+struct conv_r12l_uyvy {
+        static constexpr int IN = 144, OUT = 64;
+        static __host__ int out_len(int n) { return (n + 15) / 16 * 16; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(8);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                                int r[2], gg[2], b[2];
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                        r[k] = r12_get(in + 9 * g, 6 * i + 3 * k) << 4, gg[k] = r12_get(in + 9 * g, 6 * i + 3 * k + 1) << 4,
+                                        b[k] = r12_get(in + 9 * g, 6 * i + 3 * k + 2) << 4;
+                                }
+                                const int u = (((r[0] * c.cb_r + gg[0] * c.cb_g + b[0] * c.cb_b) + (r[1] * c.cb_r + gg[1] * c.cb_g + b[1] * c.cb_b)) >> (COMP_BASE + 9)) + 128;
+                                const int v = (((r[0] * c.cr_r + gg[0] * c.cr_g + b[0] * c.cr_b) + (r[1] * c.cr_r + gg[1] * c.cr_g + b[1] * c.cr_b)) >> (COMP_BASE + 9)) + 128;
+                                const int y0 = ((r[0] * c.y_r + gg[0] * c.y_g + b[0] * c.y_b) >> (COMP_BASE + 8)) + 16;
+                                const int y1 = ((r[1] * c.y_r + gg[1] * c.y_g + b[1] * c.y_b) >> (COMP_BASE + 8)) + 16;
+                                out[4 * g + i] = pack4(u & 0xff, y0 & 0xff, v & 0xff, y1 & 0xff);
+                        }
+                }
+        }
+};
+
+/// X -> R12L.  SRC 0: RGB, 1: RGBA (vc_copylineRGB_AtoR12L, :1258-1334: 8-bit << 4), 2: RG48 (vc_copylineRG48toR12L, :1701-1826: 16-bit >> 4),
+/// 3: Y416 (vc_copylineY416toR12L, :1828-1915: depth-16 coefficients, >> COMP_BASE + 4, CLAMP_FULL 12 bit)
+template <int SRC>
+struct conv_x_r12l {
+        static constexpr int IN = SRC == 0 ? 96 : SRC == 1 ? 128 : SRC == 2 ? 192 : 256, OUT = 144;
+        static __host__ int out_len(int n) { return SRC == 3 ? (n + 35) / 36 * 36 : n / 36 * 36; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+#pragma unroll
+                for (int i = 0; i < 36; ++i) {
+                        out[i] = 0;
+                }
+#pragma unroll
+                for (int px = 0; px < 32; ++px) {
+                        uint32_t r, g, b;
+                        if (SRC == 0 || SRC == 1) {
+                                const int o = px * (SRC == 0 ? 3 : 4);
+                                r = ((in[o >> 2] >> (8 * (o & 3))) & 0xff) << 4, g = ((in[(o + 1) >> 2] >> (8 * ((o + 1) & 3))) & 0xff) << 4,
+                                b = ((in[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 0xff) << 4;
+                        } else if (SRC == 2) {
+                                const int o = 3 * px;
+                                r = ((in[o >> 1] >> (16 * (o & 1))) & 0xffff) >> 4, g = ((in[(o + 1) >> 1] >> (16 * ((o + 1) & 1))) & 0xffff) >> 4,
+                                b = ((in[(o + 2) >> 1] >> (16 * ((o + 2) & 1))) & 0xffff) >> 4;
+                        } else {
+                                constexpr color_coeffs c = coeffs_709(16);
+                                const int u = (int) (in[2 * px] & 0xffff) - 32768, y = c.y_scale * ((int) (in[2 * px] >> 16) - 4096), v = (int) (in[2 * px + 1] & 0xffff) - 32768;
+                                r = clampr((y + v * c.r_cr) >> (COMP_BASE + 4), 16, 4079), g = clampr((y + u * c.g_cb + v * c.g_cr) >> (COMP_BASE + 4), 16, 4079),
+                                b = clampr((y + u * c.b_cb) >> (COMP_BASE + 4), 16, 4079);
+                        }
+                        uint32_t *w = out + 9 * (px >> 3);
+                        r12_put(w, 3 * (px & 7), r), r12_put(w, 3 * (px & 7) + 1, g), r12_put(w, 3 * (px & 7) + 2, b);
+                }
+        }
+};
+
+/// DVS10 -> v210 (vc_copylineDVS10toV210, pixfmt_conv.c:595-618): the 2 LSBs of the three samples live in byte 3 of each word
+struct conv_dvs10_v210 {
+        static constexpr int IN = 16, OUT = 16;
+        static __host__ int out_len(int n) { return n / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        const uint32_t a = in[i];
+                        out[i] = (((a >> 24) * 0x00010101u) & 0x00300c03u) | ((a << 2) & (0xffu << 2)) | ((a << 4) & (0xff00u << 4)) | ((a << 6) & (0xff0000u << 6));
+                }
+        }
+};
+
 // ---- generic kernel ------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ dst, long dst_pitch, const uint8_t *__restrict__ src,
@@ -992,6 +1152,18 @@ extern "C" UGB_API int ugb200_pixfmt_supported(int in_codec, int out_codec)
         case UGB_UYVY * 256 + UGB_RG48:
         case UGB_R10k * 256 + UGB_Y416:
         case UGB_R10k * 256 + UGB_UYVY:
+        case UGB_DVS10 * 256 + UGB_UYVY:
+        case UGB_DVS10 * 256 + UGB_v210:
+        case UGB_R12L * 256 + UGB_RGB:
+        case UGB_R12L * 256 + UGB_RGBA:
+        case UGB_R12L * 256 + UGB_RG48:
+        case UGB_R12L * 256 + UGB_R10k:
+        case UGB_R12L * 256 + UGB_Y416:
+        case UGB_R12L * 256 + UGB_UYVY:
+        case UGB_RGB * 256 + UGB_R12L:
+        case UGB_RGBA * 256 + UGB_R12L:
+        case UGB_RG48 * 256 + UGB_R12L:
+        case UGB_Y416 * 256 + UGB_R12L:
                 return 1;
         }
         return 0;
@@ -1085,6 +1257,18 @@ extern "C" UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *
                 UGB_CASE(UGB_UYVY, UGB_RG48, conv_uyvy_rg48)
                 UGB_CASE(UGB_R10k, UGB_Y416, conv_r10k_y416)
                 UGB_CASE(UGB_R10k, UGB_UYVY, conv_r10k_uyvy)
+                UGB_CASE(UGB_DVS10, UGB_UYVY, conv_bytemap<map_dvs10_uyvy>)
+                UGB_CASE(UGB_DVS10, UGB_v210, conv_dvs10_v210)
+                UGB_CASE(UGB_R12L, UGB_RGB, conv_r12l_rgbx<0>)
+                UGB_CASE(UGB_R12L, UGB_RGBA, conv_r12l_rgbx<1>)
+                UGB_CASE(UGB_R12L, UGB_RG48, conv_r12l_rgbx<2>)
+                UGB_CASE(UGB_R12L, UGB_R10k, conv_r12l_rgbx<3>)
+                UGB_CASE(UGB_R12L, UGB_Y416, conv_r12l_y416)
+                UGB_CASE(UGB_R12L, UGB_UYVY, conv_r12l_uyvy)
+                UGB_CASE(UGB_RGB, UGB_R12L, conv_x_r12l<0>)
+                UGB_CASE(UGB_RGBA, UGB_R12L, conv_x_r12l<1>)
+                UGB_CASE(UGB_RG48, UGB_R12L, conv_x_r12l<2>)
+                UGB_CASE(UGB_Y416, UGB_R12L, conv_x_r12l<3>)
 #undef UGB_CASE
         case UGB_BGR * 256 + UGB_RGB: {
                 const conv_params q = { 16, 8, 0, 0 };  // vc_copylineBGRtoRGB
