@@ -814,6 +814,25 @@ static void rgba_to_r12l(unsigned char *d, const unsigned char *s, int n, int rs
 static void rg48_to_r12l(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; x_to_r12l(d, s, n, 2); }
 static void y416_to_r12l(unsigned char *d, const unsigned char *s, int n, int rs, int gs, int bs) { (void) rs, (void) gs, (void) bs; x_to_r12l(d, s, n, 3); }
 
+/* vc_copylineV210toRG48, pixfmt_conv.c:2942-3002 */
+static void v210_to_rg48(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
+{
+        (void) rs, (void) gs, (void) bs;
+        const struct coeffs c = cfs709(10);
+        for (int x = 0; x < dst_len; x += 36, src += 16) {
+                const uint32_t w0 = rd32(src), w1 = rd32(src + 4), w2 = rd32(src + 8), w3 = rd32(src + 12);
+                const int y[6] = { (w0 >> 10) & 0x3ff, w1 & 0x3ff, (w1 >> 20) & 0x3ff, (w2 >> 10) & 0x3ff, w3 & 0x3ff, (w3 >> 20) & 0x3ff };
+                const int u[3] = { (int) (w0 & 0x3ff) - 512, (int) ((w1 >> 10) & 0x3ff) - 512, (int) ((w2 >> 20) & 0x3ff) - 512 };
+                const int v[3] = { (int) ((w0 >> 20) & 0x3ff) - 512, (int) (w2 & 0x3ff) - 512, (int) ((w3 >> 10) & 0x3ff) - 512 };
+                for (int i = 0; i < 6; ++i, dst += 6) {
+                        const int ys = c.y_scale * (y[i] - 64);
+                        const uint16_t o[3] = { clampr((ys + v[i / 2] * c.r_cr) >> (COMP_BASE - 6), 256, 65279),
+                                                clampr((ys + u[i / 2] * c.g_cb + v[i / 2] * c.g_cr) >> (COMP_BASE - 6), 256, 65279),
+                                                clampr((ys + u[i / 2] * c.b_cb) >> (COMP_BASE - 6), 256, 65279) };
+                        memcpy(dst, o, 6);
+                }
+        }
+}
 /* vc_copylineDVS10 (the C variant that is compiled, pixfmt_conv.c:690-720): keeps bytes 0..2 of every 32-bit word */
 static void dvs10_to_uyvy(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs)
 {
@@ -889,6 +908,7 @@ static line_fn *decoder_from_to(int in, int out)
         case C_UYVY * 256 + C_RG48: return uyvy_to_rg48;
         case C_R10k * 256 + C_Y416: return r10k_to_y416;
         case C_R10k * 256 + C_UYVY: return r10k_to_uyvy;
+        case C_v210 * 256 + C_RG48: return v210_to_rg48;
         case C_DVS10 * 256 + C_UYVY: return dvs10_to_uyvy;
         case C_DVS10 * 256 + C_v210: return dvs10_to_v210;
         case C_R12L * 256 + C_RGB: return r12l_to_rgb;

@@ -22,7 +22,7 @@ PAIRS = [(V210, UYVY), (YUYV, UYVY), (UYVY, YUYV), (UYVY, RGB), (YUYV, RGB), (UY
          (Y416, RG48), (Y416, RGB), (Y416, RGBA), (Y416, R10K), (Y416, V210), (RG48, Y416), (RG48, Y216), (RG48, V210), (UYVY, RG48),
          (R10K, Y416), (R10K, UYVY),
          (R12L, RGB), (R12L, RGBA), (R12L, RG48), (R12L, R10K), (R12L, Y416), (R12L, UYVY), (RGB, R12L), (RGBA, R12L), (RG48, R12L),
-         (Y416, R12L), (DVS10, UYVY), (DVS10, V210)]
+         (Y416, R12L), (DVS10, UYVY), (DVS10, V210), (V210, RG48)]
 
 
 def test_known_answer_checksums(orc):

@@ -77,33 +77,45 @@ struct conv_yuyv_uyvy {
         }
 };
 
-/// copylineYUVtoRGB (pixfmt_conv.c:1065-1094) via vc_copylineUYVYtoRGB (:1102-1108) / YUYVtoRGB (:1116-1122)
+/// copylineYUVtoRGB (pixfmt_conv.c:1065-1094) via vc_copylineUYVYtoRGB (:1102-1108) / YUYVtoRGB (:1116-1122).
+/// The reference computes (y_scale * (Y - 16) + c * (C - 128)) >> 14 in int32.  Every intermediate is an integer below 2^24, so the
+/// same values are formed exactly in fp32 (FFMA2 issues two lanes per slot where the integer pipe is half rate); the arithmetic
+/// shift is a round-down FMA onto the 1.5 * 2^23 magic (mantissa = floor(x / 2^14)), the clamp one VIMNMX.S16x2.RELU per two values.
 template <int Y1, int Y2, int U, int V>
 struct conv_yuv422_rgb {
         static constexpr int IN = 32, OUT = 48;
         static __host__ int out_len(int dst_len) { return dst_len < 6 ? 0 : dst_len / 6 * 6; }
+        static __device__ __forceinline__ float2 magic2(uint32_t w0, uint32_t w1, int byte)
+        {
+                return make_float2(__uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7540u | byte)), __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7540u | byte)));
+        }
+        static __device__ __forceinline__ uint32_t floor_clamp2(float2 x)  // {clamp(x.x >> 14), clamp(x.y >> 14)} as two 16-bit lanes
+        {
+                const float2 f = __ffma2_rd(x, make_float2(0x1p-14f, 0x1p-14f), make_float2(12582912.0f, 12582912.0f));
+                return __vimin_s16x2_relu(__byte_perm(__float_as_uint(f.x), __float_as_uint(f.y), 0x5410), 0x00ff00ffu);
+        }
         static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
         {
                 constexpr color_coeffs c = coeffs_709(8);
-                uint32_t o[48];
+                static_assert(239L * c.y_scale + 128L * c.b_cb < (1L << 24) && 239L * c.y_scale + 128L * c.r_cr < (1L << 24), "fp32 must hold the sums exactly");
+                const float2 ys = make_float2((float) c.y_scale, (float) c.y_scale);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                        const uint32_t w = in[i];
-                        const int y1 = c.y_scale * ((int) ((w >> (8 * Y1)) & 0xff) - 16);
-                        const int y2 = c.y_scale * ((int) ((w >> (8 * Y2)) & 0xff) - 16);
-                        const int u = (int) ((w >> (8 * U)) & 0xff) - 128;
-                        const int v = (int) ((w >> (8 * V)) & 0xff) - 128;
-                        const int rc = v * c.r_cr, gc = u * c.g_cb + v * c.g_cr, bc = u * c.b_cb;
-                        o[6 * i + 0] = clamp255((y1 + rc) >> COMP_BASE);
-                        o[6 * i + 1] = clamp255((y1 + gc) >> COMP_BASE);
-                        o[6 * i + 2] = clamp255((y1 + bc) >> COMP_BASE);
-                        o[6 * i + 3] = clamp255((y2 + rc) >> COMP_BASE);
-                        o[6 * i + 4] = clamp255((y2 + gc) >> COMP_BASE);
-                        o[6 * i + 5] = clamp255((y2 + bc) >> COMP_BASE);
-                }
-#pragma unroll
-                for (int i = 0; i < 12; ++i) {
-                        out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                for (int i = 0; i < 8; i += 2) {  // lanes = the same sample of words i and i + 1 (four pixels)
+                        const float2 ya = __fadd2_rn(magic2(in[i], in[i + 1], Y1), make_float2(-8388624.0f, -8388624.0f));  // Y - 16
+                        const float2 yb = __fadd2_rn(magic2(in[i], in[i + 1], Y2), make_float2(-8388624.0f, -8388624.0f));
+                        const float2 u = __fadd2_rn(magic2(in[i], in[i + 1], U), make_float2(-8388736.0f, -8388736.0f));    // Cb - 128
+                        const float2 v = __fadd2_rn(magic2(in[i], in[i + 1], V), make_float2(-8388736.0f, -8388736.0f));
+                        const float2 rc = __fmul2_rn(v, make_float2((float) c.r_cr, (float) c.r_cr));
+                        const float2 gc = __ffma2_rn(u, make_float2((float) c.g_cb, (float) c.g_cb), __fmul2_rn(v, make_float2((float) c.g_cr, (float) c.g_cr)));
+                        const float2 bc = __fmul2_rn(u, make_float2((float) c.b_cb, (float) c.b_cb));
+                        // lanes of each: {word i, word i + 1}
+                        const uint32_t r1 = floor_clamp2(__ffma2_rn(ya, ys, rc)), g1 = floor_clamp2(__ffma2_rn(ya, ys, gc)), b1 = floor_clamp2(__ffma2_rn(ya, ys, bc));
+                        const uint32_t r2 = floor_clamp2(__ffma2_rn(yb, ys, rc)), g2 = floor_clamp2(__ffma2_rn(yb, ys, gc)), b2 = floor_clamp2(__ffma2_rn(yb, ys, bc));
+                        // bytes of the 12 output bytes: word i -> r1 g1 b1 r2 g2 b2 (low lanes), word i + 1 -> the high lanes
+                        const uint32_t rg1 = __byte_perm(r1, g1, 0x6240), br = __byte_perm(b1, r2, 0x6240), gb2 = __byte_perm(g2, b2, 0x6240);  // {lo.a, lo.b, hi.a, hi.b}
+                        out[3 * (i / 2) + 0] = __byte_perm(rg1, br, 0x5410);   // r1 g1 b1 r2   (word i)
+                        out[3 * (i / 2) + 1] = __byte_perm(gb2, rg1, 0x7610);  // g2 b2 | r1' g1' (word i + 1)
+                        out[3 * (i / 2) + 2] = __byte_perm(br, gb2, 0x7632);   // b1' r2' g2' b2'
                 }
         }
 };
@@ -376,7 +388,37 @@ struct conv_v210_rgb {
                 }
         }
 };
-#undef UGB_S10
+/// vc_copylineV210toRG48, pixfmt_conv.c:2942-3002: all 10 bits, depth-10 coefficients, >> (COMP_BASE - 6), CLAMP_FULL at 16 bit
+struct conv_v210_rg48 {
+        static constexpr int IN = 64, OUT = 144;
+        static __host__ int out_len(int dst_len) { return (dst_len + 35) / 36 * 36; }
+        static __device__ __forceinline__ uint32_t cf(int v) { return (uint32_t) min(max(v, 256), 65279); }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
+        {
+                constexpr color_coeffs c = coeffs_709(10);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                        const uint32_t w0 = in[4 * g], w1 = in[4 * g + 1], w2 = in[4 * g + 2], w3 = in[4 * g + 3];
+#define UGB_T10(w, sh) ((int) (((w) >> (sh)) & 0x3ffu))
+                        const int y[6] = { UGB_T10(w0, 10), UGB_T10(w1, 0), UGB_T10(w1, 20), UGB_T10(w2, 10), UGB_T10(w3, 0), UGB_T10(w3, 20) };
+                        const int u[3] = { UGB_T10(w0, 0) - 512, UGB_T10(w1, 10) - 512, UGB_T10(w2, 20) - 512 };
+                        const int v[3] = { UGB_T10(w0, 20) - 512, UGB_T10(w2, 0) - 512, UGB_T10(w3, 10) - 512 };
+#undef UGB_T10
+                        uint32_t o[18];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                                const int ys = c.y_scale * (y[i] - 64), uu = u[i / 2], vv = v[i / 2];
+                                o[3 * i + 0] = cf((ys + vv * c.r_cr) >> (COMP_BASE - 6));
+                                o[3 * i + 1] = cf((ys + uu * c.g_cb + vv * c.g_cr) >> (COMP_BASE - 6));
+                                o[3 * i + 2] = cf((ys + uu * c.b_cb) >> (COMP_BASE - 6));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) {
+                                out[9 * g + i] = o[2 * i] | o[2 * i + 1] << 16;
+                        }
+                }
+        }
+};
 
 // ---- pure byte-permutation converters (A9): out byte j = in byte M::src(j), or 0x00 (-1) / 0xFF (-2) -------------------
 template <class M>
@@ -1124,6 +1166,7 @@ extern "C" UGB_API int ugb200_pixfmt_supported(int in_codec, int out_codec)
         case UGB_v210 * 256 + UGB_Y216:
         case UGB_v210 * 256 + UGB_Y416:
         case UGB_v210 * 256 + UGB_RGB:
+        case UGB_v210 * 256 + UGB_RG48:
         case UGB_RG48 * 256 + UGB_RGB:
         case UGB_RGBA * 256 + UGB_RG48:
         case UGB_RGB * 256 + UGB_RG48:
@@ -1257,6 +1300,7 @@ extern "C" UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *
                 UGB_CASE(UGB_UYVY, UGB_RG48, conv_uyvy_rg48)
                 UGB_CASE(UGB_R10k, UGB_Y416, conv_r10k_y416)
                 UGB_CASE(UGB_R10k, UGB_UYVY, conv_r10k_uyvy)
+                UGB_CASE(UGB_v210, UGB_RG48, conv_v210_rg48)
                 UGB_CASE(UGB_DVS10, UGB_UYVY, conv_bytemap<map_dvs10_uyvy>)
                 UGB_CASE(UGB_DVS10, UGB_v210, conv_dvs10_v210)
                 UGB_CASE(UGB_R12L, UGB_RGB, conv_r12l_rgbx<0>)
