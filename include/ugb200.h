@@ -63,6 +63,58 @@ struct ugb200_to_planar_data { /* same fields as struct to_planar_data; pointers
 };
 /* v210_to_p010le (src/to_planar.c:64-155). in_linesize 0 = vc_get_linesize(width, v210). */
 UGB_API int ugb200_v210_to_p010le(const struct ugb200_to_planar_data *d, long in_linesize, cuda_wrapper_stream_t stream);
+/* The other decode_buffer_func_t of src/to_planar.h:65-74, same names.  Input rows are vc_get_linesize(width, <in codec>) apart
+ * (uyvy_to_nv12: width * 2, as to_planar.c:215).  Asynchronous on `stream`; 0 ok, -1 bad arguments, -2 launch failure. */
+UGB_API int ugb200_y216_to_p010le(const struct ugb200_to_planar_data *d, cuda_wrapper_stream_t stream);   /* to_planar.c:164-200 */
+UGB_API int ugb200_uyvy_to_nv12(const struct ugb200_to_planar_data *d, cuda_wrapper_stream_t stream);     /* :207-302 */
+UGB_API int ugb200_rgba_to_bgra(const struct ugb200_to_planar_data *d, cuda_wrapper_stream_t stream);     /* :304-319 */
+UGB_API int ugb200_vuya_to_i444(const struct ugb200_to_planar_data *d, cuda_wrapper_stream_t stream);     /* :321-337 */
+UGB_API int ugb200_uyvy_to_i420(const struct ugb200_to_planar_data *d, cuda_wrapper_stream_t stream);     /* :343-378 */
+UGB_API int ugb200_r12l_to_gbrp12le(const struct ugb200_to_planar_data *d, cuda_wrapper_stream_t stream); /* :381-481 */
+UGB_API int ugb200_r12l_to_gbrp16le(const struct ugb200_to_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_r12l_to_rgbp12le(const struct ugb200_to_planar_data *d, cuda_wrapper_stream_t stream);
+
+/* ---- planar -> packed (src/from_planar.h:58-70) ---------------------------------------------------- */
+struct ugb200_from_planar_data { /* same fields as struct from_planar_data; pointers are DEVICE pointers */
+        int            width;
+        int            height;
+        unsigned char *out_data;
+        unsigned       out_pitch;
+        const unsigned char *in_data[4];
+        unsigned       in_linesize[4];
+        int            in_depth;       /* the XX (generic) conversions */
+        int            log2_chroma_h;  /* unused on the device (only decode_planar_parallel's row split needs it) */
+        int            rgb_shift[3];   /* RGBA output only */
+};
+/* decode_planar_func_t of src/from_planar.h:88-115, same names.  Asynchronous on `stream`; 0 ok, -1 bad arguments, -2 launch failure. */
+UGB_API int ugb200_gbrap_to_rgb(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* from_planar.c:335-366 (8-bit planes G, B, R, A) */
+UGB_API int ugb200_gbrap_to_rgba(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp10le_to_rgb(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :465-484, :521-563 (XX: in_depth; 8 = byte planes) */
+UGB_API int ugb200_gbrp12le_to_rgb(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp16le_to_rgb(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_rgbpXX_to_rgb(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp10le_to_rgba(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :486-517 (rgb_shift[]) */
+UGB_API int ugb200_gbrp12le_to_rgba(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp16le_to_rgba(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp10le_to_rg48(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :157-201 */
+UGB_API int ugb200_gbrp12le_to_rg48(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp16le_to_rg48(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_rgbpXXle_to_rg48(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp10le_to_r10k(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :203-250 */
+UGB_API int ugb200_gbrp12le_to_r10k(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp16le_to_r10k(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_rgbpXXle_to_r10k(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_gbrp12le_to_r12l(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :61-155 */
+UGB_API int ugb200_gbrp16le_to_r12l(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_rgbpXXle_to_r12l(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_yuv444p_to_vuya(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :565-580 */
+UGB_API int ugb200_yuv420p_to_uyvy(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :582-683 */
+UGB_API int ugb200_yuv420_to_i420(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :368-390 (out = contiguous I420, out_pitch ignored) */
+UGB_API int ugb200_yuv422p_to_uyvy(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :392-463 */
+UGB_API int ugb200_yuv422p_to_yuyv(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_yuv422pXX_to_uyvy(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_yuv422p10le_to_uyvy(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_yuv422p10le_to_v210(const struct ugb200_from_planar_data *d, cuda_wrapper_stream_t stream);  /* :295-333 (whole 6-pixel groups) */
 
 #ifdef __cplusplus
 }

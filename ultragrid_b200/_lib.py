@@ -42,6 +42,43 @@ SIGNATURES = {
     "ugb200_pixfmt_supported": (_i, [_i, _i]),
     "ugb200_pixfmt_convert": (_i, [_i, _i, _vp, _l, _vp, _l, _i, _i, _l, _i, _i, _i, _vp]),
     "ugb200_v210_to_p010le": (_i, [_vp, _l, _vp]),
+    # the other to_planar.h / from_planar.h functions: (struct *, stream)
+    "ugb200_y216_to_p010le": (_i, [_vp, _vp]),
+    "ugb200_uyvy_to_nv12": (_i, [_vp, _vp]),
+    "ugb200_rgba_to_bgra": (_i, [_vp, _vp]),
+    "ugb200_vuya_to_i444": (_i, [_vp, _vp]),
+    "ugb200_uyvy_to_i420": (_i, [_vp, _vp]),
+    "ugb200_r12l_to_gbrp12le": (_i, [_vp, _vp]),
+    "ugb200_r12l_to_gbrp16le": (_i, [_vp, _vp]),
+    "ugb200_r12l_to_rgbp12le": (_i, [_vp, _vp]),
+    "ugb200_gbrap_to_rgb": (_i, [_vp, _vp]),
+    "ugb200_gbrap_to_rgba": (_i, [_vp, _vp]),
+    "ugb200_gbrp10le_to_rgb": (_i, [_vp, _vp]),
+    "ugb200_gbrp12le_to_rgb": (_i, [_vp, _vp]),
+    "ugb200_gbrp16le_to_rgb": (_i, [_vp, _vp]),
+    "ugb200_rgbpXX_to_rgb": (_i, [_vp, _vp]),
+    "ugb200_gbrp10le_to_rgba": (_i, [_vp, _vp]),
+    "ugb200_gbrp12le_to_rgba": (_i, [_vp, _vp]),
+    "ugb200_gbrp16le_to_rgba": (_i, [_vp, _vp]),
+    "ugb200_gbrp10le_to_rg48": (_i, [_vp, _vp]),
+    "ugb200_gbrp12le_to_rg48": (_i, [_vp, _vp]),
+    "ugb200_gbrp16le_to_rg48": (_i, [_vp, _vp]),
+    "ugb200_rgbpXXle_to_rg48": (_i, [_vp, _vp]),
+    "ugb200_gbrp10le_to_r10k": (_i, [_vp, _vp]),
+    "ugb200_gbrp12le_to_r10k": (_i, [_vp, _vp]),
+    "ugb200_gbrp16le_to_r10k": (_i, [_vp, _vp]),
+    "ugb200_rgbpXXle_to_r10k": (_i, [_vp, _vp]),
+    "ugb200_gbrp12le_to_r12l": (_i, [_vp, _vp]),
+    "ugb200_gbrp16le_to_r12l": (_i, [_vp, _vp]),
+    "ugb200_rgbpXXle_to_r12l": (_i, [_vp, _vp]),
+    "ugb200_yuv444p_to_vuya": (_i, [_vp, _vp]),
+    "ugb200_yuv420p_to_uyvy": (_i, [_vp, _vp]),
+    "ugb200_yuv420_to_i420": (_i, [_vp, _vp]),
+    "ugb200_yuv422p_to_uyvy": (_i, [_vp, _vp]),
+    "ugb200_yuv422p_to_yuyv": (_i, [_vp, _vp]),
+    "ugb200_yuv422pXX_to_uyvy": (_i, [_vp, _vp]),
+    "ugb200_yuv422p10le_to_uyvy": (_i, [_vp, _vp]),
+    "ugb200_yuv422p10le_to_v210": (_i, [_vp, _vp]),
     # include/ugb200_jpeg.h
     "ugb200_jpeg_default_params": (None, [_vp]),
     "ugb200_jpeg_encoder_create": (_vp, [_vp]),

@@ -96,6 +96,34 @@ def v210_to_p010le(src, width, height, out_y=None, out_c=None, ls_y=None, ls_c=N
     return out_y, out_c
 
 
+class FromPlanarData(ctypes.Structure):
+    """struct from_planar_data (src/from_planar.h:58-70) with device pointers"""
+    _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("out_data", ctypes.c_void_p), ("out_pitch", ctypes.c_uint),
+                ("in_data", ctypes.c_void_p * 4), ("in_linesize", ctypes.c_uint * 4), ("in_depth", ctypes.c_int),
+                ("log2_chroma_h", ctypes.c_int), ("rgb_shift", ctypes.c_int * 3)]
+
+
+def to_planar(name, src, width, height, planes, linesizes, stream=None):
+    """decode_buffer_func_t `name` of src/to_planar.h:65-74 (e.g. "uyvy_to_nv12") on device tensors"""
+    d = ToPlanarData()
+    d.width, d.height, d.in_data = width, height, src.data_ptr()
+    for i, (t, ls) in enumerate(zip(planes, linesizes)):
+        d.out_data[i], d.out_linesize[i] = t.data_ptr(), ls
+    _check(getattr(_L, "ugb200_" + name)(ctypes.byref(d), _stream(stream)), "ugb200_" + name)
+    return planes
+
+
+def from_planar(name, planes, linesizes, width, height, out, out_pitch, in_depth=0, rgb_shift=(0, 8, 16), stream=None):
+    """decode_planar_func_t `name` of src/from_planar.h:88-115 (e.g. "gbrp10le_to_rgb") on device tensors"""
+    d = FromPlanarData()
+    d.width, d.height, d.out_data, d.out_pitch, d.in_depth = width, height, out.data_ptr(), out_pitch, in_depth
+    for i, (t, ls) in enumerate(zip(planes, linesizes)):
+        d.in_data[i], d.in_linesize[i] = t.data_ptr(), ls
+    d.rgb_shift[0], d.rgb_shift[1], d.rgb_shift[2] = rgb_shift
+    _check(getattr(_L, "ugb200_" + name)(ctypes.byref(d), _stream(stream)), "ugb200_" + name)
+    return out
+
+
 class JpegParams(ctypes.Structure):
     _fields_ = [("quality", ctypes.c_int), ("restart_interval", ctypes.c_int)]
 
