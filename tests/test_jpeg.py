@@ -130,6 +130,24 @@ def test_gpu_encoder_equals_oracle_bytes(orc, codec, w, h, q, ri):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("codec,q", [(UYVY, 100), (UYVY, 85), (RGB, 100)])
+def test_gpu_noise_takes_serial_route_then_adapts(orc, codec, q):
+    """Pure noise overflows the capped per-block bit buffers of the fused kernel: the first frame goes through the serial route of the
+    overflowing CTAs, the following ones through a larger cap chosen from the first frame's statistics; calm content shrinks it again."""
+    import torch
+    from ultragrid_b200 import api
+    w, h = 320, 96
+    noise = util.rng_bytes(w * h * (2 if codec == UYVY else 3), 9)
+    calm = np.full_like(noise, 100)
+    enc = api.JpegEncoder()
+    for src in (noise, noise, noise, calm, calm, noise):
+        want = orc_encode(orc, src, w, h, codec, q, 0)
+        enc.encode_device(torch.from_numpy(src).cuda(), w, h, codec, quality=q)
+        assert enc.result() == want
+    enc.close()
+
+
+@pytest.mark.gpu
 def test_gpu_8k_uyvy_jpeg_decodes_with_expected_psnr(orc):
     """config 3 / metric at full size: size-independent checks (valid stream, PSNR on luma vs source)"""
     import torch

@@ -200,27 +200,83 @@ __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict
 //      and OR their bit strings into the segment buffer
 //   4. the same threads byte-stuff the segment cooperatively (ballot of 0xFF bytes) into its slot, append RSTn, record the size
 //   5. CTA-level prefix of its segment sizes (first level of the stream-offset scan, as in the split path)
+//
+// Shared memory is what bounds the occupancy of this kernel, and a block's worst case is 1658 bits (52 words) although a
+// typical one needs well below 200.  The per-block bit strings are therefore CAPPED at `cap` words (16 by default = 35 KB per
+// CTA, six CTAs per SM).  A CTA in which any block exceeds the cap (noise at high quality) takes the serial route instead:
+// one thread per restart segment codes its blocks from the shared coefficients straight into the slot, exactly like the split
+// path's jpeg_huffman_kernel.  The largest block seen is reported so that the host can raise the cap for the next frame.
 constexpr int kBlkWords = 52;  // 1658 bits worst case per block
+constexpr int kCapDefault = 16;
 
 __device__ __forceinline__ int category(int v) { return 32 - __clz(abs(v)); }
+
+/// MSB-first bit writer with byte stuffing; bytes are gathered into aligned 32-bit words before they go to memory
+struct bit_writer {
+        uint32_t *p;     // next aligned word of the slot
+        uint32_t word;   // bytes gathered so far (little endian in memory)
+        int nbytes;      // 0..3 bytes in `word`
+        uint64_t acc;
+        int nbits;
+        __device__ __forceinline__ void emit_byte(uint32_t b)
+        {
+                word |= b << (8 * nbytes);
+                if (++nbytes == 4) {
+                        *p++ = word;
+                        word = 0, nbytes = 0;
+                }
+        }
+        __device__ __forceinline__ void put(uint32_t code, int len)
+        {
+                acc = (acc << len) | (code & ((1u << len) - 1u));
+                nbits += len;
+                while (nbits >= 8) {
+                        const uint32_t b = (uint32_t) (acc >> (nbits - 8)) & 0xffu;
+                        emit_byte(b);
+                        if (b == 0xFF) {
+                                emit_byte(0);  // T.81 B.1.1.5
+                        }
+                        nbits -= 8;
+                }
+        }
+        __device__ __forceinline__ void flush_bits()
+        {
+                if (nbits > 0) {
+                        put(0x7F, 8 - nbits);  // pad with ones, T.81 F.1.2.3
+                }
+                acc = 0, nbits = 0;
+        }
+        /// @returns total bytes written to the slot starting at `base`
+        __device__ __forceinline__ uint32_t finish(uint32_t *base)
+        {
+                const uint32_t n = (uint32_t) (p - base) * 4 + nbytes;
+                if (nbytes) {
+                        *p = word;
+                }
+                return n;
+        }
+};
+
 
 struct block_bits {  // MSB-first bit string of one block in shared memory, word w of block p at base[w * 128 + p]
         uint32_t *base;
         uint64_t acc;
-        int nbits, nwords;
+        int nbits, nwords, cap;  // words beyond `cap` are counted but not stored
         __device__ __forceinline__ void put(uint32_t code, int len)
         {
                 acc = (acc << len) | (code & ((1u << len) - 1u));
                 nbits += len;
                 if (nbits >= 32) {
-                        base[nwords * 128] = (uint32_t) (acc >> (nbits - 32));
+                        if (nwords < cap) {
+                                base[nwords * 128] = (uint32_t) (acc >> (nbits - 32));
+                        }
                         ++nwords;
                         nbits -= 32;
                 }
         }
         __device__ __forceinline__ uint32_t finish()
         {
-                if (nbits > 0) {
+                if (nbits > 0 && nwords < cap) {
                         base[nwords * 128] = (uint32_t) ((acc & ((1ull << nbits) - 1ull)) << (32 - nbits));
                 }
                 return (uint32_t) (nwords * 32 + nbits);
@@ -230,13 +286,13 @@ struct block_bits {  // MSB-first bit string of one block in shared memory, word
 template <int FMT>
 __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
                                                          uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
-                                                         uint32_t *__restrict__ cta_total, bool vec_ok)
+                                                         uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats)
 {
         extern __shared__ uint32_t smem[];
-        uint32_t *s_coef = smem;                      // [32][128] zig-zag coefficients, two int16 per word
-        uint32_t *s_bits = s_coef + 32 * 128;         // [kBlkWords][128]
-        uint32_t *s_seg = s_bits + kBlkWords * 128;   // [segments of the CTA][bps * kBlkWords]
-        __shared__ uint32_t s_dctab[2][16], s_ac[2][256], s_len[128], s_warp[4];
+        uint32_t *s_coef = smem;                // [32][128] zig-zag coefficients, two int16 per word
+        uint32_t *s_bits = s_coef + 32 * 128;   // [cap][128]
+        uint32_t *s_seg = s_bits + cap * 128;   // [segments of the CTA][bps * cap]
+        __shared__ uint32_t s_dctab[2][16], s_ac[2][256], s_len[128], s_warp[4], s_max[4];
         __shared__ int s_dc[128];
         const int tid = threadIdx.x;
         for (int i = tid; i < 32; i += 128) {
@@ -245,7 +301,7 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
         for (int i = tid; i < 512; i += 128) {
                 s_ac[i >> 8][i & 255] = c_tab.ac[i >> 8][i & 255];
         }
-        for (int i = tid; i < kBlkWords * 128; i += 128) {
+        for (int i = tid; i < cap * 128; i += 128) {
                 s_seg[i] = 0;
         }
         // ---- which block is mine -------------------------------------------------------------------------------------------
@@ -324,7 +380,7 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
                 } else {
                         pred = (p % bps) == 0 ? 0 : s_dc[p - 1];
                 }
-                block_bits bw = { s_bits + p, 0, 0, 0 };
+                block_bits bw = { s_bits + p, 0, 0, 0, cap };
                 const int diff = dcv - pred;
                 int sz = category(diff);
                 bw.put(s_dctab[t][sz] & 0xffff, s_dctab[t][sz] >> 16);
@@ -352,70 +408,129 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
                 bits = bw.finish();
         }
         s_len[p] = bits;
-        __syncthreads();
-        // ---- 3. assemble restart segments: thread tid now owns scan-order block tid ---------------------------------------------------
+        const bool overflow = __syncthreads_or(bits > (uint32_t) cap * 32u) != 0;
+        {  // largest block of the CTA (reported at the end: the host sizes the next frame's cap from the frame maximum)
+                uint32_t mx = bits;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+                }
+                if ((tid & 31) == 0) {
+                        s_max[tid >> 5] = mx;
+                }
+        }
         const int sg = tid / bps, gl = tid % bps;          // segment within the CTA, my lane within the segment's group
         const unsigned lane32 = tid & 31;
-        const unsigned gmask = bps == 32 ? 0xffffffffu : (((1u << bps) - 1u) << (lane32 - gl));
-        const uint32_t L = s_len[tid];
-        uint32_t incl = L;
-        for (int d = 1; d < bps; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(gmask, incl, d, bps);
-                if (gl >= d) {
-                        incl += o;
-                }
-        }
-        const uint32_t T = __shfl_sync(gmask, incl, bps - 1, bps);  // bits of the whole segment
-        uint32_t *seg = s_seg + sg * bps * kBlkWords;
-        {
-                const uint32_t off = incl - L, sh = off & 31;
-                uint32_t *d = seg + (off >> 5);
-                for (uint32_t w = 0; w * 32 < L; ++w) {
-                        const uint32_t v = s_bits[w * 128 + tid];
-                        atomicOr(d + w, v >> sh);
-                        if (sh) {
-                                atomicOr(d + w + 1, v << (32 - sh));
-                        }
-                }
-                if (gl == 0 && (T & 7)) {  // pad the last byte with ones (T.81 F.1.2.3)
-                        const uint32_t pad = 8 - (T & 7);
-                        atomicOr(seg + (T >> 5), ((1u << pad) - 1u) << (32 - (T & 31) - pad));
-                }
-        }
-        __syncthreads();
-        // ---- 4. byte stuffing into the slot ------------------------------------------------------------------------------------------
-        int seg_global, ls;  // global segment index, index within its scan
-        if (FMT == FMT_UYVY_422) {
-                ls = first_mcu / g.ri + sg;
-                seg_global = ls;
-        } else {
-                ls = first_mcu / g.ri + sg;
-                seg_global = blockIdx.y * g.seg_per_scan + ls;
-        }
+        const int ls = first_mcu / g.ri + sg;              // index of the segment within its scan
+        const int seg_global = FMT == FMT_UYVY_422 ? ls : blockIdx.y * g.seg_per_scan + ls;
         const bool seg_valid = ls < g.seg_per_scan && (long) ls * g.ri < g.mcu_per_scan;
         uint32_t written = 0;
-        if (seg_valid) {
-                uint8_t *slot = slots + (long) seg_global * g.slot;
-                const uint32_t n = (T + 7) >> 3;
-                for (uint32_t base = 0; base < n; base += bps) {
-                        const uint32_t i = base + gl;
-                        const uint32_t b = i < n ? (seg[i >> 2] >> (24 - 8 * (i & 3))) & 0xffu : 0u;
-                        const unsigned ff = __ballot_sync(gmask, b == 0xFF) & gmask;
-                        const uint32_t before = __popc(ff & ((1u << lane32) - 1u));
-                        if (i < n) {
-                                slot[written + gl + before] = (uint8_t) b;
-                                if (b == 0xFF) {
-                                        slot[written + gl + before + 1] = 0;
+        if (overflow) {
+                // ---- serial route: the segment's first thread codes all its blocks into the slot --------------------------------------
+                if (gl == 0 && seg_valid) {
+                        uint32_t *base = (uint32_t *) (slots + (long) seg_global * g.slot);
+                        bit_writer bw = { base, 0, 0, 0, 0 };
+                        int pred[3] = { 0, 0, 0 };
+                        for (int q = tid; q < tid + bps; ++q) {
+                                const int m = first_mcu + (FMT == FMT_UYVY_422 ? q >> 2 : q);
+                                if (m >= g.mcu_per_scan) {
+                                        break;
+                                }
+                                const int comp = FMT == FMT_UYVY_422 ? ((q & 3) < 2 ? 0 : (q & 3) - 1) : (int) blockIdx.y;
+                                const int t = comp == 0 ? 0 : 1;
+                                uint64_t map = 0;
+                                for (int k = 0; k < 32; ++k) {
+                                        const uint32_t w = s_coef[k * 128 + q];
+                                        map |= ((uint64_t) ((w & 0xffffu) != 0) | (uint64_t) ((w >> 16) != 0) << 1) << (2 * k);
+                                }
+                                map &= ~1ull;
+                                const int dc = s_dc[q], diff = dc - pred[FMT == FMT_UYVY_422 ? comp : 0];
+                                pred[FMT == FMT_UYVY_422 ? comp : 0] = dc;
+                                int sz = category(diff);
+                                bw.put(s_dctab[t][sz] & 0xffff, s_dctab[t][sz] >> 16);
+                                if (sz) {
+                                        bw.put((uint32_t) (diff < 0 ? diff - 1 : diff), sz);
+                                }
+                                int prev = 0;
+                                while (map) {
+                                        const int i = __ffsll((long long) map) - 1;
+                                        map &= map - 1;
+                                        int run = i - prev - 1;
+                                        prev = i;
+                                        while (run > 15) {
+                                                bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);
+                                                run -= 16;
+                                        }
+                                        const int v = (int) (short) (s_coef[(i >> 1) * 128 + q] >> (16 * (i & 1)));
+                                        sz = category(v);
+                                        const uint32_t e = s_ac[t][(run << 4) | sz];
+                                        bw.put(((e & 0xffff) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), (int) (e >> 16) + sz);
+                                }
+                                if (prev != 63) {
+                                        bw.put(s_ac[t][0] & 0xffff, s_ac[t][0] >> 16);
                                 }
                         }
-                        written += min((uint32_t) bps, n - base) + __popc(ff);
-                }
-                if (gl == 0) {
+                        bw.flush_bits();
                         if (ls != g.seg_per_scan - 1) {
-                                slot[written] = 0xFF, slot[written + 1] = (uint8_t) (0xD0 + (ls & 7));
-                                written += 2;
+                                bw.emit_byte(0xFF);
+                                bw.emit_byte(0xD0 + (ls & 7));
                         }
+                        written = bw.finish(base);
                         sizes[seg_global] = written;
+                }
+        } else {
+                // ---- 3. assemble restart segments: thread tid now owns scan-order block tid ---------------------------------------------
+                const unsigned gmask = bps == 32 ? 0xffffffffu : (((1u << bps) - 1u) << (lane32 - gl));
+                const uint32_t L = s_len[tid];
+                uint32_t incl = L;
+                for (int d = 1; d < bps; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(gmask, incl, d, bps);
+                        if (gl >= d) {
+                                incl += o;
+                        }
+                }
+                const uint32_t T = __shfl_sync(gmask, incl, bps - 1, bps);  // bits of the whole segment
+                uint32_t *seg = s_seg + sg * bps * cap;
+                {
+                        const uint32_t off = incl - L, sh = off & 31;
+                        uint32_t *d = seg + (off >> 5);
+                        for (uint32_t w = 0; w * 32 < L; ++w) {
+                                const uint32_t v = s_bits[w * 128 + tid];
+                                atomicOr(d + w, v >> sh);
+                                if (sh && (v << (32 - sh))) {
+                                        atomicOr(d + w + 1, v << (32 - sh));
+                                }
+                        }
+                        if (gl == 0 && (T & 7)) {  // pad the last byte with ones (T.81 F.1.2.3)
+                                const uint32_t pad = 8 - (T & 7);
+                                atomicOr(seg + (T >> 5), ((1u << pad) - 1u) << (32 - (T & 31) - pad));
+                        }
+                }
+                __syncthreads();
+                // ---- 4. byte stuffing into the slot ----------------------------------------------------------------------------------
+                if (seg_valid) {
+                        uint8_t *slot = slots + (long) seg_global * g.slot;
+                        const uint32_t n = (T + 7) >> 3;
+                        for (uint32_t base = 0; base < n; base += bps) {
+                                const uint32_t i = base + gl;
+                                const uint32_t b = i < n ? (seg[i >> 2] >> (24 - 8 * (i & 3))) & 0xffu : 0u;
+                                const unsigned ff = __ballot_sync(gmask, b == 0xFF) & gmask;
+                                const uint32_t before = __popc(ff & ((1u << lane32) - 1u));
+                                if (i < n) {
+                                        slot[written + gl + before] = (uint8_t) b;
+                                        if (b == 0xFF) {
+                                                slot[written + gl + before + 1] = 0;
+                                        }
+                                }
+                                written += min((uint32_t) bps, n - base) + __popc(ff);
+                        }
+                        if (gl == 0) {
+                                if (ls != g.seg_per_scan - 1) {
+                                        slot[written] = 0xFF, slot[written + 1] = (uint8_t) (0xD0 + (ls & 7));
+                                        written += 2;
+                                }
+                                sizes[seg_global] = written;
+                        }
                 }
         }
         // ---- 5. CTA prefix of the segment sizes ----------------------------------------------------------------------------------------
@@ -442,57 +557,14 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
         if (tid == 127) {
                 const int cta = FMT == FMT_UYVY_422 ? blockIdx.x : blockIdx.y * gridDim.x + blockIdx.x;
                 cta_total[cta] = before + inc2;
+                atomicMax(stats, max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3])));
+                if (overflow) {
+                        atomicAdd(stats + 1, 1u);
+                }
         }
 }
 
 // ---- K2 -------------------------------------------------------------------------------------------------------------
-/// MSB-first bit writer with byte stuffing; bytes are gathered into aligned 32-bit words before they go to memory
-struct bit_writer {
-        uint32_t *p;     // next aligned word of the slot
-        uint32_t word;   // bytes gathered so far (little endian in memory)
-        int nbytes;      // 0..3 bytes in `word`
-        uint64_t acc;
-        int nbits;
-        __device__ __forceinline__ void emit_byte(uint32_t b)
-        {
-                word |= b << (8 * nbytes);
-                if (++nbytes == 4) {
-                        *p++ = word;
-                        word = 0, nbytes = 0;
-                }
-        }
-        __device__ __forceinline__ void put(uint32_t code, int len)
-        {
-                acc = (acc << len) | (code & ((1u << len) - 1u));
-                nbits += len;
-                while (nbits >= 8) {
-                        const uint32_t b = (uint32_t) (acc >> (nbits - 8)) & 0xffu;
-                        emit_byte(b);
-                        if (b == 0xFF) {
-                                emit_byte(0);  // T.81 B.1.1.5
-                        }
-                        nbits -= 8;
-                }
-        }
-        __device__ __forceinline__ void flush_bits()
-        {
-                if (nbits > 0) {
-                        put(0x7F, 8 - nbits);  // pad with ones, T.81 F.1.2.3
-                }
-                acc = 0, nbits = 0;
-        }
-        /// @returns total bytes written to the slot starting at `base`
-        __device__ __forceinline__ uint32_t finish(uint32_t *base)
-        {
-                const uint32_t n = (uint32_t) (p - base) * 4 + nbytes;
-                if (nbytes) {
-                        *p = word;
-                }
-                return n;
-        }
-};
-
-
 /// One thread per restart segment.  Per block: 8 x LDG.128 build a 64-bit non-zero map (uniform work), then the loop runs once
 /// per NON-ZERO coefficient (ffs over the map) instead of once per coefficient — far less divergence inside a warp.
 /// The CTA also produces the exclusive prefix of its 128 segment sizes and its total (first level of the stream scan).
@@ -712,12 +784,13 @@ struct ugb200_jpeg_encoder {
         size_t coef_cap = 0, slots_cap = 0, out_cap = 0, seg_cap = 0, staging_cap = 0, cta_cap = 0;
         // pinned host buffers
         uint8_t *h_out = nullptr, *h_in = nullptr;
-        uint32_t *h_total = nullptr;
+        uint32_t *h_total = nullptr;  // [0] stream bytes, [1] largest block (bits) if above half the cap, [2] CTAs on the serial route
+        int cap_words = kCapDefault;  // shared-memory words per block of the fused kernel (adapted from the previous frame)
         size_t h_out_cap = 0, h_in_cap = 0;
         bool pending = false;
         const void *last_src = nullptr;  // for ugb200_jpeg_debug_coefficients (the fused path keeps coefficients on chip)
         long last_pitch = 0;
-        bool last_vec_ok = false;
+        bool last_vec_ok = false, last_fused = false;
 };
 
 namespace {
@@ -881,10 +954,10 @@ int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri
             !grow(e->cta_total, e->cta_cap, (size_t) g.nseg + 8)) {
                 return -2;
         }
-        if (e->total == nullptr && cudaMalloc((void **) &e->total, 4) != cudaSuccess) {
+        if (e->total == nullptr && cudaMalloc((void **) &e->total, 16) != cudaSuccess) {
                 return -2;
         }
-        if (e->h_total == nullptr && cudaMallocHost((void **) &e->h_total, 4) != cudaSuccess) {
+        if (e->h_total == nullptr && cudaMallocHost((void **) &e->h_total, 16) != cudaSuccess) {
                 return -2;
         }
         if (cudaMemcpyAsync(e->out, e->header.data(), e->header.size(), cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
@@ -952,30 +1025,36 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         const int bps = g.ri * g.blocks_per_mcu;
         static const bool force_split = getenv("UGB200_JPEG_SPLIT") != nullptr;
         const bool fused = !force_split && (bps == 4 || bps == 8 || bps == 16 || bps == 32);
+        e->last_fused = fused;
         int nctas, segs_per_cta, ctas_per_scan;
         if (fused) {  // one kernel: DCT + entropy coding + segment assembly
-                const size_t smem = (size_t) (32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t);
+                static const char *cap_env = getenv("UGB200_JPEG_CAP");
+                const int cap = cap_env ? atoi(cap_env) : e->cap_words;
+                const size_t smem = (size_t) (32 * 128 + 2 * cap * 128) * sizeof(uint32_t);
                 segs_per_cta = 128 / bps;
+                cudaMemsetAsync(e->total + 1, 0, 8, e->stream);
                 if (fmt == FMT_UYVY_422) {
                         ctas_per_scan = (g.mcu_per_scan + 31) / 32;
                         nctas = ctas_per_scan;
                         static bool attr_set = false;
                         if (!attr_set) {
-                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_UYVY_422>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_UYVY_422>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t)));
                                 attr_set = true;
                         }
                         jpeg_fused_kernel<FMT_UYVY_422><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
-                                                                                       e->cta_total, vec_ok);
+                                                                                       e->cta_total, vec_ok, cap, e->total + 1);
                 } else {
                         ctas_per_scan = (g.mcu_per_scan + 127) / 128;
                         nctas = ctas_per_scan * 3;
                         static bool attr_set = false;
                         if (!attr_set) {
-                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t)));
                                 attr_set = true;
                         }
                         jpeg_fused_kernel<FMT_RGB_444><<<dim3(ctas_per_scan, 3), 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes,
-                                                                                                       e->offsets, e->cta_total, vec_ok);
+                                                                                                       e->offsets, e->cta_total, vec_ok, cap, e->total + 1);
                 }
         } else {  // split path: any restart interval
                 const int dct_ctas = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
@@ -989,7 +1068,7 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         if (cudaGetLastError() != cudaSuccess) {
                 return -2;
         }
-        cudaMemcpyAsync(e->h_total, e->total, 4, cudaMemcpyDeviceToHost, e->stream);
+        cudaMemcpyAsync(e->h_total, e->total, 12, cudaMemcpyDeviceToHost, e->stream);
         e->pending = true;
         return 0;
 }
@@ -1004,6 +1083,10 @@ int ugb200_jpeg_result_device(ugb200_jpeg_encoder *e, const void **dev_ptr, size
         }
         if (dev_ptr) {
                 *dev_ptr = e->out;
+        }
+        if (e->last_fused) {  // size the fused kernel's per-block bit buffer for the next frame: this frame's largest block + 25 %
+                const int want = (int) ((e->h_total[1] + e->h_total[1] / 4 + 31) / 32);
+                e->cap_words = want <= 16 ? 16 : want <= 24 ? 24 : want <= 32 ? 32 : kBlkWords;
         }
         if (size) {
                 *size = *e->h_total;
