@@ -38,7 +38,8 @@ UGB_API void ugb200_jpeg_encoder_destroy(ugb200_jpeg_encoder *enc);
 
 /* Asynchronous device-side encode: src is a DEVICE pointer (gpujpeg_encoder_input_set_gpu_image), `codec` is UGB_UYVY or
  * UGB_RGB, pitch 0 = tightly packed.  The stream ends up in an encoder-owned device buffer.  0 ok, -1 bad args,
- * -2 CUDA failure, -4 unsupported codec. */
+ * -2 CUDA failure, -4 unsupported codec, -5 (from the result call) the stream is larger than the w * h * 3 + 4096 byte output
+ * buffer, the capacity the reference gives libgpujpeg at gpujpeg.cpp:355 (noise at quality ~100 only). */
 UGB_API int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *enc, const void *src, long pitch, int width, int height, int codec,
                                       const struct ugb200_jpeg_params *params);
 /* Waits for the encode and returns the device pointer and byte size of the JPEG stream. */

@@ -237,7 +237,9 @@ API int orc_jpeg_default_restart_interval(int fmt) { return fmt == FMT_RGB_444 ?
 /* @returns number of bytes written (0 on error) */
 API size_t orc_jpeg_encode(const uint8_t *src, long pitch, int w, int h, int fmt, int quality, int ri, uint8_t *out, size_t cap)
 {
-        if (w <= 0 || h <= 0 || cap < 1024 + (size_t) w * h * 4) {
+        /* worst case: 1658 bits per block, every byte stuffed (416 B), + RSTn per segment + headers */
+        const size_t nblk = fmt == FMT_UYVY_422 ? (size_t) ((w + 15) / 16) * ((h + 7) / 8) * 4 : (size_t) ((w + 7) / 8) * ((h + 7) / 8) * 3;
+        if (w <= 0 || h <= 0 || cap < 2048 + nblk * 418) {
                 return 0;
         }
         if (ri <= 0) {

@@ -17,7 +17,7 @@ def orc_encode(orc, src, w, h, codec, quality, ri=0, pitch=0):
     orc.orc_jpeg_encode.restype = ctypes.c_size_t
     orc.orc_jpeg_encode.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_void_p, ctypes.c_size_t]
-    out = np.zeros(w * h * 4 + 4096, dtype=np.uint8)
+    out = np.zeros(((w + 15) // 16 * 16) * ((h + 7) // 8 * 8) * 3 // 64 * 418 + 4096, dtype=np.uint8)  # worst case, see orc_jpeg_encode
     pitch = pitch or w * (2 if codec == UYVY else 3)
     n = orc.orc_jpeg_encode(src.ctypes.data, pitch, w, h, 0 if codec == UYVY else 1, quality, ri, out.ctypes.data, out.size)
     assert n > 0
@@ -130,7 +130,7 @@ def test_gpu_encoder_equals_oracle_bytes(orc, codec, w, h, q, ri):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("codec,q", [(UYVY, 100), (UYVY, 85), (RGB, 100)])
+@pytest.mark.parametrize("codec,q", [(UYVY, 100), (UYVY, 85), (RGB, 90)])
 def test_gpu_noise_takes_serial_route_then_adapts(orc, codec, q):
     """Pure noise overflows the capped per-block bit buffers of the fused kernel: the first frame goes through the serial route of the
     overflowing CTAs, the following ones through a larger cap chosen from the first frame's statistics; calm content shrinks it again."""
@@ -144,6 +144,21 @@ def test_gpu_noise_takes_serial_route_then_adapts(orc, codec, q):
         want = orc_encode(orc, src, w, h, codec, q, 0)
         enc.encode_device(torch.from_numpy(src).cuda(), w, h, codec, quality=q)
         assert enc.result() == want
+    enc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_stream_larger_than_output_buffer_is_an_error(orc):
+    """RGB noise at quality 100 codes to more than w * h * 3 bytes (the capacity the reference hands libgpujpeg, gpujpeg.cpp:355)"""
+    import torch
+    from ultragrid_b200 import api
+    w, h = 320, 96
+    enc = api.JpegEncoder()
+    enc.encode_device(torch.from_numpy(util.rng_bytes(w * h * 3, 3)).cuda(), w, h, RGB, quality=100)
+    with pytest.raises(RuntimeError):
+        enc.result()
+    enc.encode_device(torch.from_numpy(np.full(w * h * 3, 90, np.uint8)).cuda(), w, h, RGB, quality=100)  # the encoder stays usable
+    assert len(enc.result()) > 600
     enc.close()
 
 

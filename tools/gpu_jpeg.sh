@@ -1,7 +1,7 @@
 #!/bin/bash
 # JPEG experiment: event timing of the fused and the split path on three 8K contents + one full ncu capture of the fused kernel
 mkdir -p gpurun_out
-python - <<'PY' 2>&1 | tee gpurun_out/jpeg_timing.log
+timeout 300 python - <<'PY' 2>&1 | tee gpurun_out/jpeg_timing.log
 import os, sys, subprocess
 code = r'''
 import sys, os, numpy as np, torch

@@ -738,10 +738,11 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *__restrict__ 
 // ---- K4 -------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ sizes,
                                                            const uint32_t *__restrict__ local_off, const uint32_t *__restrict__ cta_base,
-                                                           jpeg_geom g, int segs_per_cta, int ctas_per_scan, uint8_t *__restrict__ out)
+                                                           jpeg_geom g, int segs_per_cta, int ctas_per_scan, uint8_t *__restrict__ out,
+                                                           const uint32_t *__restrict__ total, uint32_t out_cap)
 {
         const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-        if (s >= g.nseg) {
+        if (s >= g.nseg || *total > out_cap) {  // a stream larger than the output buffer is reported by the host, never written
                 return;
         }
         const int scan = s / g.seg_per_scan;
@@ -791,6 +792,8 @@ struct ugb200_jpeg_encoder {
         const void *last_src = nullptr;  // for ugb200_jpeg_debug_coefficients (the fused path keeps coefficients on chip)
         long last_pitch = 0;
         bool last_vec_ok = false, last_fused = false;
+        cudaEvent_t stats_ev = nullptr;  // recorded behind the copy of h_total: lets an asynchronous caller adapt the cap too
+        bool stats_pending = false;
 };
 
 namespace {
@@ -995,7 +998,20 @@ void ugb200_jpeg_encoder_destroy(ugb200_jpeg_encoder *e)
         cudaFree(e->coef), cudaFree(e->slots), cudaFree(e->out), cudaFree(e->staging);
         cudaFree(e->sizes), cudaFree(e->offsets), cudaFree(e->cta_total), cudaFree(e->total);
         cudaFreeHost(e->h_out), cudaFreeHost(e->h_in), cudaFreeHost(e->h_total);
+        if (e->stats_ev) {
+                cudaEventDestroy(e->stats_ev);
+        }
         delete e;
+}
+
+/// size the fused kernel's per-block bit buffer for the next frame: the last finished frame's largest block + 25 %
+static void adapt_cap(ugb200_jpeg_encoder *e)
+{
+        if (e->last_fused && e->stats_pending) {
+                const int want = (int) ((e->h_total[1] + e->h_total[1] / 4 + 31) / 32);
+                e->cap_words = want <= 16 ? 16 : want <= 24 ? 24 : want <= 32 ? 32 : kBlkWords;
+        }
+        e->stats_pending = false;
 }
 
 int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitch, int width, int height, int codec,
@@ -1022,6 +1038,9 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         const jpeg_geom &g = e->g;
         const bool vec_ok = fmt == FMT_UYVY_422 && !(15 & (size_t) src) && !(pitch & 15);
         e->last_src = src, e->last_pitch = pitch, e->last_vec_ok = vec_ok;
+        if (e->stats_pending && cudaEventQuery(e->stats_ev) == cudaSuccess) {
+                adapt_cap(e);  // the previous frame has finished although nobody fetched its result yet
+        }
         const int bps = g.ri * g.blocks_per_mcu;
         static const bool force_split = getenv("UGB200_JPEG_SPLIT") != nullptr;
         const bool fused = !force_split && (bps == 4 || bps == 8 || bps == 16 || bps == 32);
@@ -1064,11 +1083,15 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         }
         jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
         jpeg_compact_kernel<<<(int) (((long) g.nseg * 32 + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
-                                                                                           segs_per_cta, ctas_per_scan, e->out);
+                                                                                           segs_per_cta, ctas_per_scan, e->out, e->total, (uint32_t) e->out_cap);
         if (cudaGetLastError() != cudaSuccess) {
                 return -2;
         }
         cudaMemcpyAsync(e->h_total, e->total, 12, cudaMemcpyDeviceToHost, e->stream);
+        if (e->stats_ev != nullptr || cudaEventCreateWithFlags(&e->stats_ev, cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(e->stats_ev, e->stream);
+                e->stats_pending = true;
+        }
         e->pending = true;
         return 0;
 }
@@ -1081,13 +1104,13 @@ int ugb200_jpeg_result_device(ugb200_jpeg_encoder *e, const void **dev_ptr, size
         if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
                 return -2;
         }
+        if (*e->h_total > e->out_cap) {
+                return -5;  // the stream does not fit w * h * 3 bytes (the capacity the reference gives libgpujpeg, gpujpeg.cpp:355)
+        }
         if (dev_ptr) {
                 *dev_ptr = e->out;
         }
-        if (e->last_fused) {  // size the fused kernel's per-block bit buffer for the next frame: this frame's largest block + 25 %
-                const int want = (int) ((e->h_total[1] + e->h_total[1] / 4 + 31) / 32);
-                e->cap_words = want <= 16 ? 16 : want <= 24 ? 24 : want <= 32 ? 32 : kBlkWords;
-        }
+        adapt_cap(e);
         if (size) {
                 *size = *e->h_total;
         }
