@@ -53,6 +53,29 @@ UGB_API int ugb200_jpeg_encode(ugb200_jpeg_encoder *enc, const void *src, int sr
 /* Stage access for tests: quantised zig-zag coefficients (int16[blocks][64], scan order) of the last encode, device ptr. */
 UGB_API int ugb200_jpeg_debug_coefficients(ugb200_jpeg_encoder *enc, const int16_t **dev_ptr, size_t *count);
 
+/* ---- decode: what src/video_decompress/gpujpeg.c:74-145,268-330 asks of libgpujpeg ---------------
+ * Baseline sequential Huffman JPEG, 3 components, luma sampling 1x1 / 2x1 / 2x2, interleaved or one scan per component, restart
+ * intervals (the unit of GPU parallelism), tables taken from the stream.  No colour transform inside the codec: a 4:2:2 / 4:2:0
+ * YCbCr stream decodes to UYVY, a 4:4:4 RGB stream (Adobe transform 0) to RGB, a 4:4:4 YCbCr stream to VUYA; any other requested
+ * output goes through UltraGrid's own line converters (ugb200_pixfmt_convert). */
+typedef struct ugb200_jpeg_decoder ugb200_jpeg_decoder;
+struct ugb200_jpeg_image_info {
+        int width, height, components;
+        int h_samp, v_samp;      /* sampling factors of component 0 */
+        int adobe_transform;     /* APP14 transform flag, -1 without an Adobe marker */
+        int restart_interval;
+        int native_codec;        /* enum ugb200_codec the stream decodes to without conversion */
+};
+/* gpujpeg_decoder_get_image_info (gpujpeg.c:212): host only, reads the headers up to the first SOS */
+UGB_API int ugb200_jpeg_get_image_info(const uint8_t *stream, size_t len, struct ugb200_jpeg_image_info *info);
+UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t stream);   /* gpujpeg_decoder_create, gpujpeg.c:93 */
+UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *dec);                      /* gpujpeg_decoder_destroy */
+/* gpujpeg_decoder_decode (gpujpeg.c:289,300): `stream` is a HOST buffer; dst is a host (synchronous) or device (asynchronous on the
+ * decoder's stream) buffer of dst_pitch bytes per row (0 = vc_get_linesize); out_codec UGB_UYVY, UGB_RGB or UGB_RGBA (shifts).
+ * 0 ok, -1 bad arguments, -2 CUDA failure, -3 malformed stream, -4 unsupported stream or output codec. */
+UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *dec, const uint8_t *stream, size_t len, void *dst, int dst_is_device, long dst_pitch,
+                               int out_codec, int rshift, int gshift, int bshift);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,148 @@
+"""Baseline JPEG decode (the stage src/video_decompress/gpujpeg.c:268-330 delegates to libgpujpeg).
+GPUJPEG is absent (parity unpinned against it); pinned instead:
+  * CPU: oracle/jpeg_decode_oracle.c against libjpeg (PIL) on streams of our encoder and on libjpeg-made streams: every sample
+    within 1 (libjpeg's default IDCT is integer, ours float AAN), and the reference's flat-grey round trip (test/gpujpeg_test.cpp:68-106);
+  * GPU: ugb200_jpeg_decode == the oracle, byte for byte; other output codecs == the line converters applied to the native output."""
+import ctypes
+import io
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import util
+from test_jpeg import RGB, UYVY, natural_rgb, orc_encode, psnr
+
+RGBA, VUYA = 1, 4
+
+
+def orc_decode(orc, stream, fmt, w, h):
+    orc.orc_jpeg_decode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+    info = (ctypes.c_int * 6)()
+    pitch = (w + 1) // 2 * 4 if fmt == 0 else w * 3
+    out = np.zeros(pitch * h + 64, np.uint8)
+    b = np.frombuffer(stream, np.uint8)
+    rc = orc.orc_jpeg_decode(b.ctypes.data, len(stream), fmt, out.ctypes.data, pitch, info)
+    assert rc == 0, rc
+    return list(info), out[:pitch * h]
+
+
+def pil_stream(rgb, quality, subsampling, restart_blocks=0):
+    b = io.BytesIO()
+    kw = {"restart_marker_blocks": restart_blocks} if restart_blocks else {}
+    Image.fromarray(rgb).save(b, "JPEG", quality=quality, subsampling=subsampling, **kw)
+    return b.getvalue()
+
+
+def pil_ycc(stream, w, h):
+    im = Image.open(io.BytesIO(stream))
+    im.draft("YCbCr", (w, h))
+    return np.asarray(im)
+
+
+STREAMS = [("ours-uyvy", 200, 120, 90, 0), ("ours-uyvy", 1920, 1080, 75, 8), ("ours-uyvy", 98, 50, 90, 1), ("ours-rgb", 200, 120, 90, 0), ("ours-rgb", 130, 37, 75, 32),
+           ("pil-444", 200, 120, 85, 0), ("pil-444", 64, 64, 95, 3), ("pil-422", 200, 120, 85, 5), ("pil-420", 200, 120, 85, 4), ("pil-420", 150, 75, 60, 0)]
+
+
+def make_stream(orc, kind, w, h, q, ri):
+    rgb = natural_rgb(w, h, 5)
+    if kind == "ours-uyvy":
+        return orc_encode(orc, util.convert_cpu(orc, "orc_convert", RGB, UYVY, rgb.reshape(-1), w, h), w, h, UYVY, q, ri), rgb
+    if kind == "ours-rgb":
+        return orc_encode(orc, rgb.reshape(-1).copy(), w, h, RGB, q, ri), rgb
+    return pil_stream(rgb, q, {"pil-444": 0, "pil-422": 1, "pil-420": 2}[kind], ri), rgb
+
+
+@pytest.mark.parametrize("kind,w,h,q,ri", STREAMS)
+def test_oracle_decoder_matches_libjpeg(orc, kind, w, h, q, ri):
+    s, rgb = make_stream(orc, kind, w, h, q, ri)
+    if kind == "ours-rgb":  # Adobe transform 0: libjpeg hands back the stored RGB
+        info, out = orc_decode(orc, s, 1, w, h)
+        assert info[:3] == [w, h, 3] and info[5] == 0
+        d = np.abs(out.reshape(h, w, 3).astype(int) - np.asarray(Image.open(io.BytesIO(s))).astype(int))
+        assert d.max() <= 1 and d.mean() < 0.05
+        return
+    ycc = pil_ycc(s, w, h)
+    if kind in ("ours-uyvy", "pil-422"):
+        info, out = orc_decode(orc, s, 0, w, h)
+        assert info[3:5] == [2, 1]
+        uy = out.reshape(h, -1)
+        d = np.abs(uy[:, 1::2][:, :w].astype(int) - ycc[:, :, 0].astype(int))  # luma (chroma: libjpeg upsamples with a triangle filter)
+        assert d.max() <= 1 and d.mean() < 0.05
+        cb = uy[:, 0::4].astype(int)
+        assert np.abs(cb - ycc[:, 0::2, 1][:, :cb.shape[1]].astype(int)).mean() < 2.5
+    else:
+        info, out = orc_decode(orc, s, 1, w, h)
+        o = out.reshape(h, w, 3)
+        if kind == "pil-444":
+            d = np.abs(o.astype(int) - ycc.astype(int))
+        else:
+            d = np.abs(o[:, :, 0].astype(int) - ycc[:, :, 0].astype(int))
+        assert d.max() <= 1 and d.mean() < 0.05
+
+
+def test_oracle_flat_grey_roundtrip(orc):
+    """test/gpujpeg_test.cpp:68-106 of the reference: encode a flat grey RGB 1080p frame, decode, max |diff| <= 1"""
+    w, h = 1920, 1080
+    src = np.full(w * h * 3, 127, np.uint8)
+    _, out = orc_decode(orc, orc_encode(orc, src, w, h, RGB, 75), 1, w, h)
+    assert np.abs(out.astype(int) - 127).max() <= 1
+
+
+def test_image_info_host_only(orc):
+    from ultragrid_b200 import _lib
+    lib = _lib.load()
+
+    class Info(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_int) for n in ("width", "height", "components", "h_samp", "v_samp", "adobe", "ri", "native")]
+    for kind, w, h, q, ri in STREAMS[:1] + STREAMS[3:4] + STREAMS[5:6] + STREAMS[8:9]:
+        s, _ = make_stream(orc, kind, w, h, q, ri)
+        info = Info()
+        assert lib.ugb200_jpeg_get_image_info((ctypes.c_uint8 * len(s)).from_buffer_copy(s), len(s), ctypes.byref(info)) == 0
+        assert (info.width, info.height, info.components) == (w, h, 3)
+        assert info.native == {"ours-uyvy": UYVY, "ours-rgb": RGB, "pil-444": VUYA, "pil-420": UYVY}[kind]
+    assert lib.ugb200_jpeg_get_image_info((ctypes.c_uint8 * 4)(1, 2, 3, 4), 4, ctypes.byref(Info())) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,w,h,q,ri", STREAMS + [("ours-uyvy", 3840, 2160, 90, 0), ("ours-rgb", 1920, 1080, 90, 0)])
+def test_gpu_decoder_equals_oracle(orc, kind, w, h, q, ri):
+    from ultragrid_b200 import api
+    s, _ = make_stream(orc, kind, w, h, q, ri)
+    dec = api.JpegDecoder()
+    native = api.jpeg_image_info(s).native_codec
+    if native == UYVY:
+        _, want = orc_decode(orc, s, 0, w, h)
+    elif native == RGB:
+        _, want = orc_decode(orc, s, 1, w, h)
+    else:  # 4:4:4 YCbCr: the oracle's packed Y Cb Cr against VUYA
+        _, ycc = orc_decode(orc, s, 1, w, h)
+        ycc = ycc.reshape(h, w, 3)
+        want = np.stack([ycc[:, :, 2], ycc[:, :, 1], ycc[:, :, 0], np.full((h, w), 255, np.uint8)], axis=2).reshape(-1)
+    got = dec.decode(s, native)
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:8]
+    assert np.array_equal(dec.decode(s, native, device=True).cpu().numpy(), want)
+    # another output codec = UltraGrid's line converter applied to the native frame
+    for out_c in (UYVY, RGB, RGBA):
+        if out_c == native or not api.pixfmt_supported(native, out_c):
+            continue
+        shifts = (16, 8, 0) if out_c == RGBA else (0, 8, 16)
+        conv = util.convert_cpu(orc, "orc_convert", native, out_c, want, w, h, shifts=shifts)
+        assert np.array_equal(dec.decode(s, out_c, shifts=shifts), conv), (native, out_c)
+    dec.close()
+
+
+@pytest.mark.gpu
+def test_gpu_roundtrip_8k(orc):
+    """encode -> decode on the device at BASELINE's size: PSNR of the round trip as the quantiser implies, decoder == oracle on a band"""
+    import torch
+    from ultragrid_b200 import api
+    w, h = 7680, 4320
+    src = util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h, 3).reshape(-1), w, h)
+    enc, dec = api.JpegEncoder(), api.JpegDecoder()
+    enc.encode_device(torch.from_numpy(src).cuda(), w, h, UYVY, quality=90)
+    s = enc.result()
+    out = dec.decode(s, UYVY)
+    assert psnr(out, src) > 38.0
+    _, want = orc_decode(orc, s, 0, w, h)
+    assert np.array_equal(out, want)

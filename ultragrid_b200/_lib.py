@@ -86,6 +86,10 @@ SIGNATURES = {
     "ugb200_jpeg_encode_device": (_i, [_vp, _vp, _l, _i, _i, _i, _vp]),
     "ugb200_jpeg_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ugb200_jpeg_encode": (_i, [_vp, _vp, _i, _l, _i, _i, _i, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    "ugb200_jpeg_get_image_info": (_i, [_vp, _sz, _vp]),
+    "ugb200_jpeg_decoder_create": (_vp, [_vp]),
+    "ugb200_jpeg_decoder_destroy": (None, [_vp]),
+    "ugb200_jpeg_decode": (_i, [_vp, _vp, _sz, _vp, _i, _l, _i, _i, _i, _i]),
     "ugb200_jpeg_debug_coefficients": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     # include/ugb200_vcompress.h
     "ugb200_set_cuda_devices": (_i, [ctypes.POINTER(_i), _i]),

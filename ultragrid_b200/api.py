@@ -185,3 +185,49 @@ class JpegEncoder:
         host = np.empty(n.value, dtype=np.int16)
         _check(_L.cuda_wrapper_memcpy(ctypes.c_void_p(host.ctypes.data), ptr, n.value * 2, 1), "cuda_wrapper_memcpy")
         return host
+
+
+class JpegImageInfo(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("components", ctypes.c_int), ("h_samp", ctypes.c_int), ("v_samp", ctypes.c_int),
+                ("adobe_transform", ctypes.c_int), ("restart_interval", ctypes.c_int), ("native_codec", ctypes.c_int)]
+
+
+def jpeg_image_info(stream):
+    """gpujpeg_decoder_get_image_info (src/video_decompress/gpujpeg.c:212): host-only header probe"""
+    info = JpegImageInfo()
+    buf = (ctypes.c_uint8 * len(stream)).from_buffer_copy(stream)
+    _check(_L.ugb200_jpeg_get_image_info(buf, len(stream), ctypes.byref(info)), "ugb200_jpeg_get_image_info")
+    return info
+
+
+class JpegDecoder:
+    """ugb200_jpeg_decode*: the stage src/video_decompress/gpujpeg.c delegates to libgpujpeg."""
+
+    def __init__(self, stream=None):
+        self._stream = stream if stream is not None else torch.cuda.current_stream()
+        self._h = _L.ugb200_jpeg_decoder_create(ctypes.c_void_p(self._stream.cuda_stream))
+        if not self._h:
+            raise RuntimeError("ugb200_jpeg_decoder_create failed")
+
+    def close(self):
+        if self._h and _L is not None:
+            _L.ugb200_jpeg_decoder_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def decode(self, stream, out_codec, shifts=(0, 8, 16), device=False, pitch=0):
+        """bytes -> numpy array (host) or CUDA tensor (device=True) holding height rows of vc_get_linesize(width, out_codec) bytes"""
+        info = jpeg_image_info(stream)
+        ls = pitch or vc_get_linesize(info.width, out_codec)
+        buf = (ctypes.c_uint8 * len(stream)).from_buffer_copy(stream)
+        if device:
+            out = torch.zeros(ls * info.height, dtype=torch.uint8, device="cuda")
+            _check(_L.ugb200_jpeg_decode(self._h, buf, len(stream), _ptr(out), 1, ls, int(out_codec), *shifts), "ugb200_jpeg_decode")
+            self._stream.synchronize()
+            return out
+        import numpy as np
+        out = np.zeros(ls * info.height, dtype=np.uint8)
+        _check(_L.ugb200_jpeg_decode(self._h, buf, len(stream), ctypes.c_void_p(out.ctypes.data), 0, ls, int(out_codec), *shifts), "ugb200_jpeg_decode")
+        return out

@@ -1,0 +1,656 @@
+// Baseline JPEG decoder (include/ugb200_jpeg.h, decode part): the stage libgpujpeg performs for UltraGrid's
+// src/video_decompress/gpujpeg.c:268-330 and gpujpeg_to_dxt.cpp:117-166.
+//
+//   host   parse_stream     markers up to each SOS (tables, frame, scans) and ONE pass over the entropy-coded bytes that records
+//                           where every restart segment starts (what GPUJPEG's reader does when the stream carries no segment info)
+//   K1     jpeg_decode_huffman_kernel   one thread per restart segment: T.81 F.2.2 Huffman decoding with a 9-bit look-ahead
+//                           table per Huffman table in shared memory (longer codes: min/max-code walk), DC prediction,
+//                           coefficients scattered in natural order into a zeroed int16 [block][64] buffer
+//   K2     jpeg_idct_kernel one thread per 8x8 block: dequantise, float AAN inverse DCT (fixed operation order = bit-exact with
+//                           oracle/jpeg_decode_oracle.c), level shift, clamp, 8 x 8-byte stores into the component plane
+//   pack   the component planes go through the from_planar kernels that already exist (planar_conv_kernels.cu):
+//                           4:2:2 -> UYVY (yuv422p_to_uyvy), 4:2:0 -> UYVY (yuv420p_to_uyvy), 4:4:4 YCbCr -> VUYA (yuv444p_to_vuya),
+//                           RGB -> RGB (rgbpXX_to_rgb), then ugb200_pixfmt_convert when another output codec was asked for.
+// Restart intervals are the unit of parallelism; a stream without DRI decodes correctly but on one thread per scan.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/ugb200.h"
+#include "../../include/ugb200_jpeg.h"
+
+namespace ugb {
+
+static const uint8_t kZigzag[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+
+constexpr int kLook = 9;
+
+struct dec_tables {                   // tables 0,1 = DC (Th 0,1), 2,3 = AC (Th 0,1)
+        uint16_t lut[4][1 << kLook];  // (length << 8) | symbol for codes of up to kLook bits, 0 = longer code
+        int maxcode[4][18];           // T.81 F.2.2.3, -1 = no code of that length
+        int valoff[4][17];            // valptr - mincode
+        uint8_t vals[4][256];
+        uint8_t zz[64];
+        float m[4][64];               // dequantisation x AAN scale, natural order
+};
+
+struct dec_comp {
+        int h, v, tq;
+        int bw, bh;     // blocks per row / rows of the padded plane
+        int blk_off;    // first block of the component in the coefficient buffer
+        long plane_off; // first byte of the plane in the plane buffer
+};
+struct dec_scan {
+        int ns, comp[3], td[3], ta[3];
+        int mcux, nmcu;
+        int seg0, nseg;  // segments [seg0, seg0 + nseg)
+};
+struct dec_geom {
+        int w, h, ncomp, hmax, vmax, ri, nscans, nblocks;
+        dec_comp c[3];
+        dec_scan s[3];
+};
+
+struct bit_reader {  // MSB-first, removes stuffed zero bytes, feeds zeros beyond `end`
+        const uint8_t *p, *end;
+        uint64_t acc;
+        int nbits;
+        __device__ __forceinline__ void refill()
+        {
+                while (nbits <= 56) {
+                        uint32_t b = 0;
+                        if (p < end) {
+                                b = __ldg(p++);
+                                if (b == 0xFF && p < end && __ldg(p) == 0) {
+                                        ++p;
+                                }
+                        }
+                        acc |= (uint64_t) b << (56 - nbits);
+                        nbits += 8;
+                }
+        }
+        __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t) (acc >> (64 - n)); }
+        __device__ __forceinline__ void skip(int n) { acc <<= n, nbits -= n; }
+};
+
+__device__ __forceinline__ int decode_symbol(bit_reader &r, const dec_tables *t, int tab)
+{
+        const uint32_t e = t->lut[tab][r.peek(kLook)];
+        if (e) {
+                r.skip(e >> 8);
+                return e & 0xff;
+        }
+        const uint32_t v16 = r.peek(16);
+        for (int l = kLook + 1; l <= 16; ++l) {
+                const int code = (int) (v16 >> (16 - l));
+                if (code <= t->maxcode[tab][l]) {
+                        r.skip(l);
+                        return t->vals[tab][t->valoff[tab][l] + code];
+                }
+        }
+        r.skip(16);
+        return 0;  // corrupt stream
+}
+__device__ __forceinline__ int receive_extend(bit_reader &r, int n)  // F.2.2.1, n in 1..15
+{
+        const int v = (int) r.peek(n);
+        r.skip(n);
+        return v < (1 << (n - 1)) ? v - (1 << n) + 1 : v;
+}
+
+__global__ void __launch_bounds__(128) jpeg_decode_huffman_kernel(const uint8_t *__restrict__ stream, const uint32_t *__restrict__ seg_begin,
+                                                                  const uint32_t *__restrict__ seg_end, const dec_tables *__restrict__ tables,
+                                                                  dec_geom g, int16_t *__restrict__ coef)
+{
+        extern __shared__ uint8_t smem_raw[];
+        dec_tables *t = (dec_tables *) smem_raw;
+        for (int i = threadIdx.x; i < (int) (sizeof(dec_tables) / 4); i += blockDim.x) {
+                ((uint32_t *) t)[i] = ((const uint32_t *) tables)[i];
+        }
+        __syncthreads();
+        const int s = blockIdx.x * blockDim.x + threadIdx.x;
+        int sc = 0;
+        while (sc < g.nscans && s >= g.s[sc].seg0 + g.s[sc].nseg) {
+                ++sc;
+        }
+        if (sc >= g.nscans) {
+                return;
+        }
+        const dec_scan &S = g.s[sc];
+        const int ls = s - S.seg0;
+        const int m0 = g.ri ? ls * g.ri : 0, m1 = g.ri ? min(m0 + g.ri, S.nmcu) : S.nmcu;
+        bit_reader r = { stream + seg_begin[s], stream + seg_end[s], 0, 0 };
+        int pred[3] = { 0, 0, 0 };
+        for (int m = m0; m < m1; ++m) {
+                const int mx = m % S.mcux, my = m / S.mcux;
+                for (int k = 0; k < S.ns; ++k) {
+                        const dec_comp &c = g.c[S.comp[k]];
+                        const int nh = S.ns == 1 ? 1 : c.h, nv = S.ns == 1 ? 1 : c.v;
+                        for (int by = 0; by < nv; ++by) {
+                                for (int bx = 0; bx < nh; ++bx) {
+                                        const int X = mx * nh + bx, Y = my * nv + by;
+                                        const bool inside = X < c.bw && Y < c.bh;
+                                        int16_t *blk = coef + ((long) c.blk_off + (long) Y * c.bw + X) * 64;
+                                        r.refill();
+                                        const int tt = decode_symbol(r, t, S.td[k]);
+                                        r.refill();
+                                        if (tt) {
+                                                pred[k] += receive_extend(r, tt & 15);
+                                        }
+                                        if (inside && pred[k] != 0) {
+                                                blk[0] = (int16_t) pred[k];
+                                        }
+                                        for (int i = 1; i < 64;) {
+                                                r.refill();
+                                                const int rs = decode_symbol(r, t, 2 + S.ta[k]), run = rs >> 4, sz = rs & 15;
+                                                if (sz == 0) {
+                                                        if (run != 15) {
+                                                                break;  // EOB
+                                                        }
+                                                        i += 16;
+                                                        continue;
+                                                }
+                                                i += run;
+                                                const int v = receive_extend(r, sz);  // refill guarantees >= 57 bits: 16 + 15 fit
+                                                if (i < 64 && inside) {
+                                                        blk[t->zz[i]] = (int16_t) v;
+                                                }
+                                                ++i;
+                                        }
+                                }
+                        }
+                }
+        }
+}
+
+__device__ __forceinline__ void idct8(float &d0, float &d1, float &d2, float &d3, float &d4, float &d5, float &d6, float &d7)
+{
+        const float e0 = __fadd_rn(d0, d4), e1 = __fadd_rn(d0, -d4);
+        const float e3 = __fadd_rn(d2, d6), e2 = __fadd_rn(__fmul_rn(__fadd_rn(d2, -d6), 1.414213562f), -e3);
+        const float a0 = __fadd_rn(e0, e3), a3 = __fadd_rn(e0, -e3), a1 = __fadd_rn(e1, e2), a2 = __fadd_rn(e1, -e2);
+        const float z13 = __fadd_rn(d5, d3), z10 = __fadd_rn(d5, -d3), z11 = __fadd_rn(d1, d7), z12 = __fadd_rn(d1, -d7);
+        const float b7 = __fadd_rn(z11, z13);
+        const float b11 = __fmul_rn(__fadd_rn(z11, -z13), 1.414213562f);
+        const float z5 = __fmul_rn(__fadd_rn(z10, z12), 1.847759065f);
+        const float b10 = __fmaf_rn(1.082392200f, z12, -z5);
+        const float b12 = __fmaf_rn(-2.613125930f, z10, z5);
+        const float b6 = __fadd_rn(b12, -b7), b5 = __fadd_rn(b11, -b6), b4 = __fadd_rn(b10, b5);
+        d0 = __fadd_rn(a0, b7), d7 = __fadd_rn(a0, -b7);
+        d1 = __fadd_rn(a1, b6), d6 = __fadd_rn(a1, -b6);
+        d2 = __fadd_rn(a2, b5), d5 = __fadd_rn(a2, -b5);
+        d4 = __fadd_rn(a3, b4), d3 = __fadd_rn(a3, -b4);
+}
+
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(const int16_t *__restrict__ coef, const dec_tables *__restrict__ tables, dec_geom g,
+                                                        uint8_t *__restrict__ planes)
+{
+        __shared__ float s_m[4][64];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+                s_m[i >> 6][i & 63] = tables->m[i >> 6][i & 63];
+        }
+        __syncthreads();
+        const int b = blockIdx.x * blockDim.x + threadIdx.x;
+        if (b >= g.nblocks) {
+                return;
+        }
+        int ci = 0;
+        while (ci + 1 < g.ncomp && b >= g.c[ci + 1].blk_off) {
+                ++ci;
+        }
+        const dec_comp &c = g.c[ci];
+        const int lb = b - c.blk_off, X = lb % c.bw, Y = lb / c.bw;
+        const float *m = s_m[c.tq];
+        float f[64];
+        const uint4 *src = (const uint4 *) (coef + (long) b * 64);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+                const uint4 v = __ldg(src + q);
+                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {  // int16 -> float without I2F: 1.5 * 2^23 + c is exact
+                        const int lo = (int) (short) (w[j] & 0xffffu), hi = (int) w[j] >> 16;
+                        f[8 * q + 2 * j] = __fmul_rn(__fadd_rn(__uint_as_float(0x4B400000u + (uint32_t) lo), -12582912.0f), m[8 * q + 2 * j]);
+                        f[8 * q + 2 * j + 1] = __fmul_rn(__fadd_rn(__uint_as_float(0x4B400000u + (uint32_t) hi), -12582912.0f), m[8 * q + 2 * j + 1]);
+                }
+        }
+#pragma unroll
+        for (int col = 0; col < 8; ++col) {
+                idct8(f[col], f[8 + col], f[16 + col], f[24 + col], f[32 + col], f[40 + col], f[48 + col], f[56 + col]);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+                idct8(f[8 * r], f[8 * r + 1], f[8 * r + 2], f[8 * r + 3], f[8 * r + 4], f[8 * r + 5], f[8 * r + 6], f[8 * r + 7]);
+        }
+        uint8_t *dst = planes + c.plane_off + ((long) Y * 8) * (c.bw * 8) + X * 8;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+                uint32_t o[8];
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {  // rintf(v + 128) through the 1.5 * 2^23 magic, clamp 0..255
+                        const int v = (int) __float_as_uint(__fadd_rn(__fadd_rn(f[8 * r + x], 128.0f), 12582912.0f)) - 0x4B400000;
+                        o[x] = (uint32_t) min(max(v, 0), 255);
+                }
+                *(uint2 *) (dst + (long) r * (c.bw * 8)) = make_uint2(o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24, o[4] | o[5] << 8 | o[6] << 16 | o[7] << 24);
+        }
+}
+
+}  // namespace ugb
+
+using namespace ugb;
+
+struct ugb200_jpeg_decoder {
+        cudaStream_t stream = nullptr;
+        uint8_t *d_stream = nullptr, *planes = nullptr, *native = nullptr, *staging = nullptr;
+        int16_t *coef = nullptr;
+        uint32_t *d_seg = nullptr;
+        dec_tables *d_tables = nullptr;
+        size_t stream_cap = 0, planes_cap = 0, native_cap = 0, staging_cap = 0, coef_cap = 0, seg_cap = 0;
+        uint8_t *h_stream = nullptr;  // pinned copy: the caller's buffer is pageable and freed right after the call
+        uint32_t *h_seg = nullptr;
+        dec_tables *h_tables = nullptr;
+        size_t h_stream_cap = 0, h_seg_cap = 0;
+};
+
+namespace {
+
+template <class T>
+bool dgrow(T *&ptr, size_t &cap, size_t need)
+{
+        if (need <= cap) {
+                return true;
+        }
+        if (ptr) {
+                cudaFree(ptr);
+        }
+        ptr = nullptr, cap = 0;
+        if (cudaMalloc((void **) &ptr, need * sizeof(T)) != cudaSuccess) {
+                return false;
+        }
+        cap = need;
+        return true;
+}
+template <class T>
+bool hgrow(T *&ptr, size_t &cap, size_t need)
+{
+        if (need <= cap) {
+                return true;
+        }
+        if (ptr) {
+                cudaFreeHost(ptr);
+        }
+        ptr = nullptr, cap = 0;
+        if (cudaMallocHost((void **) &ptr, need * sizeof(T)) != cudaSuccess) {
+                return false;
+        }
+        cap = need;
+        return true;
+}
+
+int be16(const uint8_t *p) { return p[0] << 8 | p[1]; }
+
+struct parsed {
+        dec_geom g{};
+        int adobe = -1, comp_id[3] = { 0, 0, 0 };
+        bool have_sof = false, have_q[4] = { false, false, false, false };
+        uint8_t q[4][64];
+        std::vector<uint32_t> seg_begin, seg_end;
+};
+
+void build_table(dec_tables &t, int tab, const uint8_t *bits, const uint8_t *vals, int n)
+{
+        memset(t.lut[tab], 0, sizeof t.lut[tab]);
+        memcpy(t.vals[tab], vals, n);
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; ++l) {
+                t.valoff[tab][l] = k - code;
+                for (int i = 0; i < bits[l - 1]; ++i, ++k, ++code) {
+                        if (l <= kLook) {
+                                for (int fill = 0; fill < (1 << (kLook - l)); ++fill) {
+                                        t.lut[tab][(code << (kLook - l)) | fill] = (uint16_t) (l << 8 | vals[k]);
+                                }
+                        }
+                }
+                t.maxcode[tab][l] = bits[l - 1] ? code - 1 : -1;
+                code <<= 1;
+        }
+        t.maxcode[tab][17] = 0x7fffffff;
+}
+
+const float kAan[8] = { 1.0f, 1.387039845f, 1.306562965f, 1.175875602f, 1.0f, 0.785694958f, 0.541196100f, 0.275899379f };
+
+/// header markers up to and including every SOS; `full` also walks the entropy-coded data to find the restart segments
+int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool full)
+{
+        const uint8_t *p = s, *end = s + len;
+        if (len < 4 || p[0] != 0xFF || p[1] != 0xD8) {
+                return -1;
+        }
+        p += 2;
+        dec_geom &g = P.g;
+        while (p + 4 <= end) {
+                if (p[0] != 0xFF) {
+                        return -3;
+                }
+                const int mk = p[1];
+                if (mk == 0xD9) {
+                        break;
+                }
+                if (mk == 0xFF) {  // fill byte
+                        ++p;
+                        continue;
+                }
+                const int L = be16(p + 2);
+                const uint8_t *d = p + 4, *dend = p + 2 + L;
+                if (L < 2 || dend > end) {
+                        return -3;
+                }
+                if (mk == 0xDB) {
+                        while (d + 65 <= dend) {
+                                const int pq = d[0] >> 4, tq = d[0] & 15;
+                                if (pq != 0 || tq > 3) {
+                                        return -4;
+                                }
+                                for (int k = 0; k < 64; ++k) {
+                                        P.q[tq][kZigzag[k]] = d[1 + k];
+                                }
+                                P.have_q[tq] = true;
+                                if (T) {
+                                        for (int n = 0; n < 64; ++n) {
+                                                T->m[tq][n] = ((float) P.q[tq][n] * kAan[n >> 3]) * kAan[n & 7] * 0.125f;
+                                        }
+                                }
+                                d += 65;
+                        }
+                } else if (mk == 0xC4) {
+                        while (d + 17 <= dend) {
+                                const int tc = d[0] >> 4, th = d[0] & 15;
+                                int n = 0;
+                                for (int i = 0; i < 16; ++i) {
+                                        n += d[1 + i];
+                                }
+                                if (tc > 1 || th > 1 || n > 256 || d + 17 + n > dend) {
+                                        return -4;  // baseline: two tables per class
+                                }
+                                if (T) {
+                                        build_table(*T, tc * 2 + th, d + 1, d + 17, n);
+                                }
+                                d += 17 + n;
+                        }
+                } else if (mk == 0xC0) {
+                        if (L < 8 + 3 * d[5] || d[0] != 8) {
+                                return -4;
+                        }
+                        g.h = be16(d + 1), g.w = be16(d + 3), g.ncomp = d[5];
+                        if (g.ncomp != 3 || g.w == 0 || g.h == 0) {
+                                return -4;
+                        }
+                        g.hmax = g.vmax = 1;
+                        for (int i = 0; i < 3; ++i) {
+                                P.comp_id[i] = d[6 + 3 * i];
+                                g.c[i].h = d[7 + 3 * i] >> 4, g.c[i].v = d[7 + 3 * i] & 15, g.c[i].tq = d[8 + 3 * i];
+                                g.hmax = g.c[i].h > g.hmax ? g.c[i].h : g.hmax, g.vmax = g.c[i].v > g.vmax ? g.c[i].v : g.vmax;
+                        }
+                        int blk = 0;
+                        long off = 0;
+                        for (int i = 0; i < 3; ++i) {
+                                dec_comp &c = g.c[i];
+                                if (c.h < 1 || c.h > 2 || c.v < 1 || c.v > 2 || (i > 0 && (c.h != 1 || c.v != 1)) || c.tq > 3) {
+                                        return -4;
+                                }
+                                c.bw = (g.w + 8 * g.hmax - 1) / (8 * g.hmax) * c.h, c.bh = (g.h + 8 * g.vmax - 1) / (8 * g.vmax) * c.v;
+                                c.blk_off = blk, c.plane_off = off;
+                                blk += c.bw * c.bh, off += (long) c.bw * c.bh * 64;
+                        }
+                        g.nblocks = blk;
+                        P.have_sof = true;
+                } else if (mk >= 0xC1 && mk <= 0xCF && mk != 0xC4 && mk != 0xC8 && mk != 0xCC) {
+                        return -4;  // not baseline sequential Huffman
+                } else if (mk == 0xDD) {
+                        g.ri = be16(d);
+                } else if (mk == 0xEE && L >= 14 && memcmp(d, "Adobe", 5) == 0) {
+                        P.adobe = d[11];
+                } else if (mk == 0xDA) {
+                        if (!P.have_sof || g.nscans >= 3) {
+                                return -3;
+                        }
+                        dec_scan &S = g.s[g.nscans];
+                        S.ns = d[0];
+                        if (S.ns < 1 || S.ns > 3 || L < 6 + 2 * S.ns) {
+                                return -4;
+                        }
+                        for (int i = 0; i < S.ns; ++i) {
+                                S.comp[i] = -1;
+                                for (int j = 0; j < 3; ++j) {
+                                        if (P.comp_id[j] == d[1 + 2 * i]) {
+                                                S.comp[i] = j;
+                                        }
+                                }
+                                S.td[i] = d[2 + 2 * i] >> 4, S.ta[i] = d[2 + 2 * i] & 15;
+                                if (S.comp[i] < 0 || S.td[i] > 1 || S.ta[i] > 1 || !P.have_q[g.c[S.comp[i]].tq]) {
+                                        return -4;
+                                }
+                        }
+                        int mcuy;
+                        if (S.ns == 1) {
+                                const dec_comp &c = g.c[S.comp[0]];
+                                S.mcux = ((g.w * c.h + g.hmax - 1) / g.hmax + 7) / 8, mcuy = ((g.h * c.v + g.vmax - 1) / g.vmax + 7) / 8;
+                        } else {
+                                S.mcux = (g.w + 8 * g.hmax - 1) / (8 * g.hmax), mcuy = (g.h + 8 * g.vmax - 1) / (8 * g.vmax);
+                        }
+                        S.nmcu = S.mcux * mcuy;
+                        S.seg0 = (int) P.seg_begin.size();
+                        S.nseg = g.ri ? (S.nmcu + g.ri - 1) / g.ri : 1;
+                        ++g.nscans;
+                        p = dend;
+                        if (!full) {
+                                return 0;  // enough for the image info
+                        }
+                        // entropy-coded segment(s): up to the next marker that is neither a stuffed zero nor RSTn
+                        uint32_t begin = (uint32_t) (p - s);
+                        int found = 0;
+                        for (;;) {
+                                const uint8_t *ff = (const uint8_t *) memchr(p, 0xFF, (size_t) (end - p));
+                                if (ff == nullptr || ff + 1 >= end) {
+                                        p = end;
+                                        break;
+                                }
+                                const int c2 = ff[1];
+                                if (c2 == 0 || c2 == 0xFF) {
+                                        p = ff + 1;
+                                        continue;
+                                }
+                                if (c2 >= 0xD0 && c2 <= 0xD7) {
+                                        if (found + 1 < S.nseg) {
+                                                P.seg_begin.push_back(begin), P.seg_end.push_back((uint32_t) (ff - s));
+                                                ++found;
+                                        }
+                                        begin = (uint32_t) (ff + 2 - s);
+                                        p = ff + 2;
+                                        continue;
+                                }
+                                p = ff;
+                                break;
+                        }
+                        P.seg_begin.push_back(begin), P.seg_end.push_back((uint32_t) (p - s));
+                        ++found;
+                        while (found < S.nseg) {  // truncated stream: the missing segments decode as nothing (zero coefficients)
+                                P.seg_begin.push_back((uint32_t) (p - s)), P.seg_end.push_back((uint32_t) (p - s));
+                                ++found;
+                        }
+                        continue;
+                }
+                p = dend;
+        }
+        return P.have_sof && g.nscans > 0 ? 0 : -3;
+}
+
+int native_codec(const parsed &P)
+{
+        const dec_geom &g = P.g;
+        if (g.c[0].h == 2) {
+                return UGB_UYVY;  // 4:2:2 and 4:2:0 land in UYVY
+        }
+        const bool rgb = P.adobe == 0 || (P.comp_id[0] == 'R' && P.comp_id[1] == 'G' && P.comp_id[2] == 'B');
+        return rgb ? UGB_RGB : UGB_VUYA;
+}
+
+}  // namespace
+
+extern "C" {
+
+UGB_API int ugb200_jpeg_get_image_info(const uint8_t *stream, size_t len, struct ugb200_jpeg_image_info *info)
+{
+        if (!stream || !info) {
+                return -1;
+        }
+        parsed P;
+        const int rc = parse_stream(stream, len, P, nullptr, false);
+        if (rc != 0) {
+                return rc;
+        }
+        info->width = P.g.w, info->height = P.g.h, info->components = P.g.ncomp;
+        info->h_samp = P.g.c[0].h, info->v_samp = P.g.c[0].v;
+        info->adobe_transform = P.adobe, info->restart_interval = P.g.ri;
+        info->native_codec = native_codec(P);
+        return 0;
+}
+
+UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t stream)
+{
+        ugb200_jpeg_decoder *d = new (std::nothrow) ugb200_jpeg_decoder;
+        if (!d) {
+                return nullptr;
+        }
+        d->stream = (cudaStream_t) stream;
+        if (cudaMalloc((void **) &d->d_tables, sizeof(dec_tables)) != cudaSuccess || cudaMallocHost((void **) &d->h_tables, sizeof(dec_tables)) != cudaSuccess) {
+                ugb200_jpeg_decoder_destroy(d);
+                return nullptr;
+        }
+        return d;
+}
+
+UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *d)
+{
+        if (!d) {
+                return;
+        }
+        cudaStreamSynchronize(d->stream);
+        cudaFree(d->d_stream), cudaFree(d->planes), cudaFree(d->native), cudaFree(d->staging), cudaFree(d->coef), cudaFree(d->d_seg), cudaFree(d->d_tables);
+        cudaFreeHost(d->h_stream), cudaFreeHost(d->h_seg), cudaFreeHost(d->h_tables);
+        delete d;
+}
+
+UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, size_t len, void *dst, int dst_is_device, long dst_pitch, int out_codec,
+                               int rshift, int gshift, int bshift)
+{
+        if (!d || !stream || !dst || len > 0xFFFFFFF0u) {
+                return -1;
+        }
+        if (out_codec != UGB_UYVY && out_codec != UGB_RGB && out_codec != UGB_RGBA) {
+                return -4;
+        }
+        cudaStreamSynchronize(d->stream);  // the pinned staging buffers of the previous frame are free again
+        parsed P;
+        memset(d->h_tables, 0, sizeof(dec_tables));
+        memcpy(d->h_tables->zz, kZigzag, 64);
+        int rc = parse_stream(stream, len, P, d->h_tables, true);
+        if (rc != 0) {
+                return rc;
+        }
+        const dec_geom &g = P.g;
+        const size_t nseg = P.seg_begin.size();
+        const long plane_bytes = (long) g.nblocks * 64;
+        const int native = native_codec(P);
+        const long npitch = native == UGB_UYVY ? (long) ((g.w + 1) / 2) * 4 : native == UGB_RGB ? (long) g.w * 3 : (long) g.w * 4;
+        const long opitch = out_codec == UGB_UYVY ? (long) ((g.w + 1) / 2) * 4 : out_codec == UGB_RGB ? (long) g.w * 3 : (long) g.w * 4;
+        if (dst_pitch == 0) {
+                dst_pitch = opitch;
+        }
+        if (!dgrow(d->d_stream, d->stream_cap, len + 16) || !dgrow(d->planes, d->planes_cap, (size_t) plane_bytes) || !dgrow(d->coef, d->coef_cap, (size_t) g.nblocks * 64) ||
+            !dgrow(d->d_seg, d->seg_cap, 2 * nseg) || !dgrow(d->native, d->native_cap, (size_t) npitch * g.h + 64) || !hgrow(d->h_stream, d->h_stream_cap, len) ||
+            !hgrow(d->h_seg, d->h_seg_cap, 2 * nseg)) {
+                return -2;
+        }
+        cudaStream_t s = d->stream;
+        memcpy(d->h_stream, stream, len);
+        memcpy(d->h_seg, P.seg_begin.data(), nseg * 4), memcpy(d->h_seg + nseg, P.seg_end.data(), nseg * 4);
+        cudaMemcpyAsync(d->d_stream, d->h_stream, len, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d->d_seg, d->h_seg, 2 * nseg * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d->d_tables, d->h_tables, sizeof(dec_tables), cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
+        static bool attr = false;
+        if (!attr) {
+                cudaFuncSetAttribute(jpeg_decode_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(dec_tables));
+                attr = true;
+        }
+        jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d->d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef);
+        jpeg_idct_kernel<<<(g.nblocks + 127) / 128, 128, 0, s>>>(d->coef, d->d_tables, g, d->planes);
+        if (cudaGetLastError() != cudaSuccess) {
+                return -2;
+        }
+        // component planes -> the stream's native packed format
+        const bool direct = native == out_codec && dst_is_device;
+        uint8_t *nat = direct ? (uint8_t *) dst : d->native;
+        struct ugb200_from_planar_data fp;
+        memset(&fp, 0, sizeof fp);
+        fp.width = native == UGB_UYVY ? (g.w + 1) & ~1 : g.w;  // the padded planes hold the second luma of an odd last pixel pair
+        fp.height = g.h, fp.out_data = nat, fp.out_pitch = (unsigned) (direct ? dst_pitch : npitch);
+        for (int i = 0; i < 3; ++i) {
+                fp.in_data[i] = d->planes + g.c[i].plane_off, fp.in_linesize[i] = (unsigned) (g.c[i].bw * 8);
+        }
+        fp.in_depth = 8;
+        if (native == UGB_UYVY) {
+                rc = g.c[0].v == 2 ? ugb200_yuv420p_to_uyvy(&fp, s) : ugb200_yuv422p_to_uyvy(&fp, s);
+        } else if (native == UGB_RGB) {
+                rc = ugb200_rgbpXX_to_rgb(&fp, s);
+        } else {
+                rc = ugb200_yuv444p_to_vuya(&fp, s);
+        }
+        if (rc != 0) {
+                return rc;
+        }
+        if (direct) {
+                return 0;
+        }
+        // native -> requested codec (UltraGrid's own line converters), then to the caller
+        uint8_t *result = nat;
+        long rpitch = npitch;
+        if (native != out_codec) {
+                if (!ugb200_pixfmt_supported(native, out_codec)) {
+                        return -4;
+                }
+                uint8_t *conv;
+                if (dst_is_device) {
+                        conv = (uint8_t *) dst, rpitch = dst_pitch;
+                } else {
+                        if (!dgrow(d->staging, d->staging_cap, (size_t) opitch * g.h + 64)) {
+                                return -2;
+                        }
+                        conv = d->staging, rpitch = opitch;
+                }
+                const int len_out = out_codec == UGB_UYVY ? ((g.w + 1) / 2) * 4 : out_codec == UGB_RGB ? g.w * 3 : g.w * 4;
+                rc = ugb200_pixfmt_convert(native, out_codec, conv, rpitch, nat, npitch, len_out, g.h, (long) npitch * g.h, rshift, gshift, bshift, s);
+                if (rc != 0) {
+                        return rc;
+                }
+                result = conv;
+                if (dst_is_device) {
+                        return 0;
+                }
+        }
+        if (dst_is_device) {
+                return cudaMemcpy2DAsync(dst, dst_pitch, result, rpitch, opitch, g.h, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : -2;
+        }
+        if (cudaMemcpy2DAsync(dst, dst_pitch, result, rpitch, opitch, g.h, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+                return -2;
+        }
+        return 0;
+}
+
+}  // extern "C"
