@@ -46,6 +46,8 @@ UGB_API int cuda_wrapper_stream_create(cuda_wrapper_stream_t *stream);   /* non-
 UGB_API int cuda_wrapper_stream_destroy(cuda_wrapper_stream_t stream);
 UGB_API int cuda_wrapper_stream_synchronize(cuda_wrapper_stream_t stream);
 UGB_API int cuda_wrapper_memcpy_async(void *dst, const void *src, size_t count, int kind, cuda_wrapper_stream_t stream);
+/* pitched copy (cudaMemcpy2D), synchronous like cuda_wrapper_memcpy */
+UGB_API int cuda_wrapper_memcpy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int kind);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,13 @@ UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *dst, long d
                           int dst_len, int height, long src_size, int rshift, int gshift, int bshift,
                           cuda_wrapper_stream_t stream);
 
+/* ---- block decoders --------------------------------------------------- */
+/* DXT5-YCoCg -> RGB exactly as the reference's CPU tool cuda_dxt/dxt62tga.c:24-108 (double arithmetic); DXT1 -> RGB by the same rule
+ * for the colour block (+ the 3-colour mode).  src: device blocks in raster block order (what the encoders write), out: device, 3 B/px,
+ * out_pitch bytes per row (0 = 3 * w); bgr != 0 swaps R and B (the TGA order of the tool).  w, h multiples of 4.  Asynchronous. */
+UGB_API int ugb200_dxt1_to_rgb(const void *src, void *out, int w, int h, long out_pitch, int bgr, cuda_wrapper_stream_t stream);
+UGB_API int ugb200_dxt5ycocg_to_rgb(const void *src, void *out, int w, int h, long out_pitch, int bgr, cuda_wrapper_stream_t stream);
+
 /* ---- packed -> planar (src/to_planar.h:53-59) ----------------------------------------------------- */
 struct ugb200_to_planar_data { /* same fields as struct to_planar_data; pointers are DEVICE pointers */
         int            width;

@@ -39,6 +39,20 @@ UGB_API int ugb200_compress_pop_ref(ugb200_compress *s, const void **data, size_
 
 UGB_API void ugb200_compress_done(ugb200_compress *s);
 
+/* ---- decompress side (src/video_decompress.h:173-213; modules gpujpeg, gpujpeg_to_dxt, dxt_cuda) --------------------------------------
+ * decompress_init_multi(compression, internal, to, &state, 1): the registered module with the best priority for compression
+ * (UGB_JPEG, UGB_DXT1, UGB_DXT5) -> out_codec (UGB_RGB / RGBA / UYVY / DXT1 / DXT5, or UGB_VIDEO_CODEC_NONE to probe).  NULL if none. */
+typedef struct ugb200_decompress ugb200_decompress;
+UGB_API ugb200_decompress *ugb200_decompress_init(int compression, int out_codec);
+UGB_API const char *ugb200_decompress_module(ugb200_decompress *d);  /* name of the module that was selected */
+/* decompress_reconfigure(state, desc{width, height, compression}, rshift, gshift, bshift, pitch, out_codec): non-zero = ok */
+UGB_API int ugb200_decompress_reconfigure(ugb200_decompress *d, int width, int height, int compression, int rshift, int gshift, int bshift, int pitch,
+                                          int out_codec);
+/* decompress_frame(): src and dst are HOST buffers.  Returns decompress_status: 0 no frame, 1 got frame, 2 got codec (probe: internal_props[3] =
+ * depth, subsampling (4440/4220/4200), rgb), 3 unsupported pixel format. */
+UGB_API int ugb200_decompress_frame(ugb200_decompress *d, void *dst, const void *src, unsigned src_len, int frame_seq, int *internal_props);
+UGB_API void ugb200_decompress_done(ugb200_decompress *d);
+
 /* get_best_decoder_from(in, candidates, &out) (src/pixfmt_conv.c:3148-3172): the codec_t a module converts `in` to when it
  * natively accepts `candidates`; 0 (VIDEO_CODEC_NONE) if no conversion exists. */
 UGB_API int ugb200_get_best_decoder_from(int in_codec, const int *candidates, int count);

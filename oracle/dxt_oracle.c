@@ -300,5 +300,65 @@ API void orc_dxt1_decode(const uint32_t *in, uint8_t *rgb, int sx, int sy)
         }
 }
 
+/* DXT5-YCoCg -> RGB/BGR as the reference tool cuda_dxt/dxt62tga.c:24-108 does it (all in double, (int)(255 v + 0.5), clamp), and DXT1
+ * by the same rule for the colour block (+ 3-colour mode).  Built with -ffp-contract=off like the tool's plain gcc build. */
+static uint8_t to_byte(double s)
+{
+        const int is = (int) (s + 0.5);
+        return is > 255 ? 255 : is < 0 ? 0 : is;
+}
+API void orc_dxt5ycocg_to_rgb(const uint64_t *in, uint8_t *out, int sx, int sy, long pitch, int bgr)
+{
+        for (int by = 0; by < sy / 4; ++by) {
+                for (int bx = 0; bx < sx / 4; ++bx, in += 2) {
+                        uint64_t ac = in[0], cc = in[1];
+                        const double a0 = (ac & 0xFF) / 255.0, a1 = ((ac >> 8) & 0xFF) / 255.0;
+                        double ap[8] = { a0, a1 };
+                        for (int k = 2; k < 8; ++k) {
+                                ap[k] = a0 > a1 ? ((8 - k) * a0 + (k - 1) * a1) / 7.0 : k < 6 ? ((6 - k) * a0 + (k - 1) * a1) / 5.0 : k == 6 ? 0.0 : 1.0;
+                        }
+                        double r[4], g[4], b[4];
+                        for (int k = 0; k < 2; ++k) {
+                                b[k] = ((cc >> (16 * k)) & 0x1F) / 31.0, g[k] = ((cc >> (16 * k + 5)) & 0x3F) / 63.0, r[k] = ((cc >> (16 * k + 11)) & 0x1F) / 31.0;
+                        }
+                        b[2] = (2.0 * b[0] + 1.0 * b[1]) / 3.0, g[2] = (2.0 * g[0] + 1.0 * g[1]) / 3.0, r[2] = (2.0 * r[0] + 1.0 * r[1]) / 3.0;
+                        b[3] = (1.0 * b[0] + 2.0 * b[1]) / 3.0, g[3] = (1.0 * g[0] + 2.0 * g[1]) / 3.0, r[3] = (1.0 * r[0] + 2.0 * r[1]) / 3.0;
+                        ac >>= 16, cc >>= 32;
+                        for (int i = 0; i < 16; ++i, ac >>= 3, cc >>= 2) {
+                                const double a = ap[ac & 7];
+                                const int k = cc & 3;
+                                const double scale = 1.0 / (31.875 * b[k] + 1.0);
+                                const double co = (r[k] - 5.01960814E-01) * scale, cg = (g[k] - 5.01960814E-01) * scale;
+                                uint8_t *p = out + (size_t) (by * 4 + i / 4) * pitch + (size_t) (bx * 4 + i % 4) * 3;
+                                p[bgr ? 2 : 0] = to_byte(((a + co) - cg) * 255.0), p[1] = to_byte((a + cg) * 255.0), p[bgr ? 0 : 2] = to_byte(((a - co) - cg) * 255.0);
+                        }
+                }
+        }
+}
+API void orc_dxt1_to_rgb(const uint32_t *in, uint8_t *out, int sx, int sy, long pitch, int bgr)
+{
+        for (int by = 0; by < sy / 4; ++by) {
+                for (int bx = 0; bx < sx / 4; ++bx, in += 2) {
+                        const uint32_t c0 = in[0] & 0xffff, c1 = in[0] >> 16;
+                        double r[4], g[4], b[4];
+                        r[0] = (c0 >> 11) / 31.0, g[0] = ((c0 >> 5) & 63) / 63.0, b[0] = (c0 & 31) / 31.0;
+                        r[1] = (c1 >> 11) / 31.0, g[1] = ((c1 >> 5) & 63) / 63.0, b[1] = (c1 & 31) / 31.0;
+                        if (c0 > c1) {
+                                r[2] = (2.0 * r[0] + r[1]) / 3.0, g[2] = (2.0 * g[0] + g[1]) / 3.0, b[2] = (2.0 * b[0] + b[1]) / 3.0;
+                                r[3] = (r[0] + 2.0 * r[1]) / 3.0, g[3] = (g[0] + 2.0 * g[1]) / 3.0, b[3] = (b[0] + 2.0 * b[1]) / 3.0;
+                        } else {
+                                r[2] = (r[0] + r[1]) * 0.5, g[2] = (g[0] + g[1]) * 0.5, b[2] = (b[0] + b[1]) * 0.5;
+                                r[3] = g[3] = b[3] = 0.0;
+                        }
+                        uint32_t idx = in[1];
+                        for (int i = 0; i < 16; ++i, idx >>= 2) {
+                                const int k = idx & 3;
+                                uint8_t *p = out + (size_t) (by * 4 + i / 4) * pitch + (size_t) (bx * 4 + i % 4) * 3;
+                                p[bgr ? 2 : 0] = to_byte(r[k] * 255.0), p[1] = to_byte(g[k] * 255.0), p[bgr ? 0 : 2] = to_byte(b[k] * 255.0);
+                        }
+                }
+        }
+}
+
 API void orc_set_threads(int n) { omp_set_num_threads(n > 0 ? n : omp_get_num_procs()); }
 API int orc_get_max_threads(void) { return omp_get_max_threads(); }

@@ -32,6 +32,7 @@ SIGNATURES = {
     "cuda_wrapper_stream_destroy": (_i, [_vp]),
     "cuda_wrapper_stream_synchronize": (_i, [_vp]),
     "cuda_wrapper_memcpy_async": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "cuda_wrapper_memcpy2d": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _i]),
     # include/ugb200.h
     "ugb200_rgb_to_dxt1_async": (_i, [_vp, _vp, _i, _i, _vp]),
     "ugb200_yuv_to_dxt1_async": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -39,6 +40,8 @@ SIGNATURES = {
     "ugb200_yuv_to_dxt6_async": (_i, [_vp, _vp, _i, _i, _vp]),
     "ugb200_uyvy_to_dxt1_async": (_i, [_vp, _vp, _i, _i, _l, _vp]),
     "ugb200_uyvy_to_dxt6_async": (_i, [_vp, _vp, _i, _i, _l, _vp]),
+    "ugb200_dxt1_to_rgb": (_i, [_vp, _vp, _i, _i, _l, _i, _vp]),
+    "ugb200_dxt5ycocg_to_rgb": (_i, [_vp, _vp, _i, _i, _l, _i, _vp]),
     "ugb200_pixfmt_supported": (_i, [_i, _i]),
     "ugb200_pixfmt_convert": (_i, [_i, _i, _vp, _l, _vp, _l, _i, _i, _l, _i, _i, _i, _vp]),
     "ugb200_v210_to_p010le": (_i, [_vp, _l, _vp]),
@@ -98,6 +101,11 @@ SIGNATURES = {
     "ugb200_compress_pop": (_i, [_vp, _vp, _sz, ctypes.POINTER(_sz), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_uint)]),
     "ugb200_compress_pop_ref": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_uint)]),
     "ugb200_compress_done": (None, [_vp]),
+    "ugb200_decompress_init": (_vp, [_i, _i]),
+    "ugb200_decompress_module": (ctypes.c_char_p, [_vp]),
+    "ugb200_decompress_reconfigure": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "ugb200_decompress_frame": (_i, [_vp, _vp, _vp, ctypes.c_uint, _i, _vp]),
+    "ugb200_decompress_done": (None, [_vp]),
     "ugb200_get_best_decoder_from": (_i, [_i, ctypes.POINTER(_i), _i]),
 }
 

@@ -96,6 +96,15 @@ def v210_to_p010le(src, width, height, out_y=None, out_c=None, ls_y=None, ls_c=N
     return out_y, out_c
 
 
+def dxt_to_rgb(src, width, height, dxt_type=1, bgr=False, out=None, out_pitch=0, stream=None):
+    """ugb200_dxt1_to_rgb / ugb200_dxt5ycocg_to_rgb: device blocks -> packed RGB (or BGR) on the device"""
+    if out is None:
+        out = torch.zeros((out_pitch or width * 3) * height, dtype=torch.uint8, device=src.device)
+    fn = _L.ugb200_dxt1_to_rgb if dxt_type == 1 else _L.ugb200_dxt5ycocg_to_rgb
+    _check(fn(_ptr(src), _ptr(out), width, height, out_pitch, int(bgr), _stream(stream)), "ugb200_dxt_to_rgb")
+    return out
+
+
 class FromPlanarData(ctypes.Structure):
     """struct from_planar_data (src/from_planar.h:58-70) with device pointers"""
     _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("out_data", ctypes.c_void_p), ("out_pitch", ctypes.c_uint),

@@ -79,3 +79,43 @@ class Compress:
 
     def __del__(self):
         self.close()
+
+
+class Decompress:
+    """decompress_init_multi / decompress_reconfigure / decompress_frame (src/video_decompress.h:173-213) through the C driver.
+    Host buffers in and out, like UltraGrid's receiver calls it."""
+
+    GOT_FRAME, GOT_CODEC = 1, 2
+
+    def __init__(self, compression, out_codec):
+        self._h = _L.ugb200_decompress_init(int(compression), int(out_codec))
+        if not self._h:
+            raise RuntimeError(f"no decompress module for {compression} -> {out_codec}")
+        self.module = _L.ugb200_decompress_module(self._h).decode()
+        self._out_bytes = 0
+
+    def reconfigure(self, width, height, compression, out_codec, shifts=(0, 8, 16), pitch=None):
+        from .codec import vc_get_linesize
+        pitch = vc_get_linesize(width, out_codec) if pitch is None and int(out_codec) != 0 else (pitch or 0)
+        ok = _L.ugb200_decompress_reconfigure(self._h, width, height, int(compression), shifts[0], shifts[1], shifts[2], pitch, int(out_codec))
+        if not ok:
+            raise RuntimeError("decompress_reconfigure failed")
+        self._out_bytes = pitch * height
+        return pitch
+
+    def frame(self, data, seq=0):
+        """returns (status, output bytes as numpy array or None, [depth, subsampling, rgb])"""
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8)
+        dst = np.zeros(max(self._out_bytes, 1), dtype=np.uint8)
+        props = (ctypes.c_int * 3)()
+        st = _L.ugb200_decompress_frame(self._h, ctypes.c_void_p(dst.ctypes.data), ctypes.c_void_p(src.ctypes.data), len(data), seq, props)
+        return st, (dst if st == self.GOT_FRAME else None), list(props)
+
+    def close(self):
+        if self._h and _L is not None:
+            _L.ugb200_decompress_done(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.close()

@@ -84,4 +84,9 @@ int cuda_wrapper_memcpy_async(void *dst, const void *src, size_t count, int kind
         return (int) cudaMemcpyAsync(dst, src, count, kind_of(kind), (cudaStream_t) stream);
 }
 
+int cuda_wrapper_memcpy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int kind)
+{
+        return (int) cudaMemcpy2D(dst, dpitch, src, spitch, width, height, kind_of(kind));
+}
+
 }  // extern "C"

@@ -1,0 +1,147 @@
+// DXT1 and DXT5-YCoCg block DEcoders.  The reference decodes these textures only on the
+// display side in OpenGL (src/video_decompress/dxt_glsl.c, dxt_compress/display_dxt5ycocg_fp.glsl); its one CPU decoder is the
+// tool cuda_dxt/dxt62tga.c:24-108 (DXT5-YCoCg -> BGR, all arithmetic in double), and that is the contract here: the same
+// operations in the same order with explicit-rounding FP64 intrinsics (no contraction), byte-identical output.
+// DXT1 has no CPU decoder in the tree (parity unpinned): the S3TC rule is evaluated the same way dxt62tga.c does it for the
+// colour block of DXT5 (endpoints / 31.0, / 63.0, thirds in double, (int)(255 * v + 0.5)), plus the 3-colour mode when
+// color0 <= color1 (midpoint, index 3 = black).
+//
+// A thread decodes one 4x4 block: 8 or 16 bytes in, 4 rows x 12 bytes out.  1 B/px + 3 B/px, FP64 on the pixel path
+// (DADD/DMUL run at half the FP32 rate on this part; the double -> int conversion is the slow instruction).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ugb200.h"
+
+namespace ugb {
+
+__device__ __forceinline__ uint32_t to_byte(double s)  // dxt62tga.c:14-21
+{
+        const int is = __double2int_rz(__dadd_rn(s, 0.5));
+        return (uint32_t) min(max(is, 0), 255);
+}
+__device__ __forceinline__ double third(double a, double b)  // (2.0 * a + 1.0 * b) / 3.0, dxt62tga.c:76-81
+{
+        return __ddiv_rn(__dadd_rn(__dmul_rn(2.0, a), b), 3.0);
+}
+
+template <int BGR>
+__device__ __forceinline__ void store_px(uint8_t *p, uint32_t r, uint32_t g, uint32_t b)
+{
+        p[BGR ? 2 : 0] = (uint8_t) r, p[1] = (uint8_t) g, p[BGR ? 0 : 2] = (uint8_t) b;
+}
+
+template <int BGR>
+__global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch)
+{
+        const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
+        if (bx >= bw) {
+                return;
+        }
+        const uint4 blk = __ldg(in + (long) by * bw + bx);
+        uint64_t alpha_code = (uint64_t) blk.x | (uint64_t) blk.y << 32, rgb_code = (uint64_t) blk.z | (uint64_t) blk.w << 32;
+        // alpha palette (dxt62tga.c:38-62): 8 luma levels
+        const double a0 = __ddiv_rn((double) (alpha_code & 0xFF), 255.0), a1 = __ddiv_rn((double) ((alpha_code >> 8) & 0xFF), 255.0);
+        double ap[8];
+        ap[0] = a0, ap[1] = a1;
+        if (a0 > a1) {
+#pragma unroll
+                for (int k = 2; k < 8; ++k) {
+                        ap[k] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (8 - k), a0), __dmul_rn((double) (k - 1), a1)), 7.0);
+                }
+        } else {
+#pragma unroll
+                for (int k = 2; k < 6; ++k) {
+                        ap[k] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (6 - k), a0), __dmul_rn((double) (k - 1), a1)), 5.0);
+                }
+                ap[6] = 0.0, ap[7] = 1.0;
+        }
+        // colour palette (:68-81) and, per entry, the scaled Co / Cg (:24-27 depend on the entry only)
+        double r[4], g[4], b[4], co[4], cg[4];
+        b[0] = __ddiv_rn((double) (rgb_code & 0x1F), 31.0), g[0] = __ddiv_rn((double) ((rgb_code >> 5) & 0x3F), 63.0), r[0] = __ddiv_rn((double) ((rgb_code >> 11) & 0x1F), 31.0);
+        b[1] = __ddiv_rn((double) ((rgb_code >> 16) & 0x1F), 31.0), g[1] = __ddiv_rn((double) ((rgb_code >> 21) & 0x3F), 63.0), r[1] = __ddiv_rn((double) ((rgb_code >> 27) & 0x1F), 31.0);
+        b[2] = third(b[0], b[1]), g[2] = third(g[0], g[1]), r[2] = third(r[0], r[1]);
+        b[3] = __ddiv_rn(__dadd_rn(b[0], __dmul_rn(2.0, b[1])), 3.0), g[3] = __ddiv_rn(__dadd_rn(g[0], __dmul_rn(2.0, g[1])), 3.0),
+        r[3] = __ddiv_rn(__dadd_rn(r[0], __dmul_rn(2.0, r[1])), 3.0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+                const double scale = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(31.875, b[k]), 1.0));
+                co[k] = __dmul_rn(__dadd_rn(r[k], -5.01960814E-01), scale);
+                cg[k] = __dmul_rn(__dadd_rn(g[k], -5.01960814E-01), scale);
+        }
+        alpha_code >>= 16, rgb_code >>= 32;
+        uint8_t *o = out + (long) by * 4 * pitch + (long) bx * 12;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                        const double a = ap[alpha_code & 7];
+                        const int k = (int) (rgb_code & 3);
+                        alpha_code >>= 3, rgb_code >>= 2;
+                        const double R = __dadd_rn(__dadd_rn(a, co[k]), -cg[k]), G = __dadd_rn(a, cg[k]), B = __dadd_rn(__dadd_rn(a, -co[k]), -cg[k]);
+                        store_px<BGR>(o + y * pitch + 3 * x, to_byte(__dmul_rn(R, 255.0)), to_byte(__dmul_rn(G, 255.0)), to_byte(__dmul_rn(B, 255.0)));
+                }
+        }
+}
+
+template <int BGR>
+__global__ void __launch_bounds__(128) dxt1_decode_kernel(const uint2 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch)
+{
+        const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
+        if (bx >= bw) {
+                return;
+        }
+        const uint2 blk = __ldg(in + (long) by * bw + bx);
+        const uint32_t c0 = blk.x & 0xffff, c1 = blk.x >> 16;
+        double r[4], g[4], b[4];
+        r[0] = __ddiv_rn((double) (c0 >> 11), 31.0), g[0] = __ddiv_rn((double) ((c0 >> 5) & 63), 63.0), b[0] = __ddiv_rn((double) (c0 & 31), 31.0);
+        r[1] = __ddiv_rn((double) (c1 >> 11), 31.0), g[1] = __ddiv_rn((double) ((c1 >> 5) & 63), 63.0), b[1] = __ddiv_rn((double) (c1 & 31), 31.0);
+        if (c0 > c1) {
+                r[2] = third(r[0], r[1]), g[2] = third(g[0], g[1]), b[2] = third(b[0], b[1]);
+                r[3] = __ddiv_rn(__dadd_rn(r[0], __dmul_rn(2.0, r[1])), 3.0), g[3] = __ddiv_rn(__dadd_rn(g[0], __dmul_rn(2.0, g[1])), 3.0),
+                b[3] = __ddiv_rn(__dadd_rn(b[0], __dmul_rn(2.0, b[1])), 3.0);
+        } else {
+                r[2] = __dmul_rn(__dadd_rn(r[0], r[1]), 0.5), g[2] = __dmul_rn(__dadd_rn(g[0], g[1]), 0.5), b[2] = __dmul_rn(__dadd_rn(b[0], b[1]), 0.5);
+                r[3] = g[3] = b[3] = 0.0;
+        }
+        uint32_t pr[4], pg[4], pb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+                pr[k] = to_byte(__dmul_rn(r[k], 255.0)), pg[k] = to_byte(__dmul_rn(g[k], 255.0)), pb[k] = to_byte(__dmul_rn(b[k], 255.0));
+        }
+        uint32_t idx = blk.y;
+        uint8_t *o = out + (long) by * 4 * pitch + (long) bx * 12;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                        const int k = idx & 3;
+                        idx >>= 2;
+                        store_px<BGR>(o + y * pitch + 3 * x, pr[k], pg[k], pb[k]);
+                }
+        }
+}
+
+}  // namespace ugb
+
+using namespace ugb;
+
+#define UGB_DECODE(name, KERNEL, T)                                                                                                        \
+        extern "C" UGB_API int name(const void *src, void *out, int w, int h, long out_pitch, int bgr, cuda_wrapper_stream_t stream)       \
+        {                                                                                                                                  \
+                if (src == nullptr || out == nullptr || w <= 0 || h <= 0 || (w & 3) || (h & 3) || (sizeof(T) - 1 & (size_t) src)) {        \
+                        return -1; /* the block codecs need multiples of 4 (cuda_dxt.cu:745) */                                           \
+                }                                                                                                                          \
+                if (out_pitch == 0) {                                                                                                      \
+                        out_pitch = (long) w * 3;                                                                                          \
+                }                                                                                                                          \
+                dim3 grid((w / 4 + 127) / 128, h / 4);                                                                                     \
+                if (bgr) {                                                                                                                 \
+                        KERNEL<1><<<grid, 128, 0, (cudaStream_t) stream>>>((const T *) src, (uint8_t *) out, w / 4, h / 4, out_pitch);    \
+                } else {                                                                                                                   \
+                        KERNEL<0><<<grid, 128, 0, (cudaStream_t) stream>>>((const T *) src, (uint8_t *) out, w / 4, h / 4, out_pitch);    \
+                }                                                                                                                          \
+                return cudaGetLastError() == cudaSuccess ? 0 : -2;                                                                         \
+        }
+UGB_DECODE(ugb200_dxt1_to_rgb, dxt1_decode_kernel, uint2)
+UGB_DECODE(ugb200_dxt5ycocg_to_rgb, dxt5ycocg_decode_kernel, uint4)

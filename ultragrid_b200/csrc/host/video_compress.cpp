@@ -57,6 +57,18 @@ const void *load_library(const char *name, enum library_class cls, int abi_versi
         return nullptr;
 }
 
+int get_libraries_for_class(enum library_class cls, int abi_version, const char **names, const void **infos, int max)
+{
+        int n = 0;
+        for (const lib_entry &e : libraries()) {
+                if (e.cls == cls && e.abi == abi_version && n < max) {
+                        names[n] = e.name.c_str(), infos[n] = e.info;
+                        ++n;
+                }
+        }
+        return n;
+}
+
 // ---- pinned frame pool ------------------------------------------------------------------------------------------
 namespace {
 struct pinned_pool {

@@ -7,7 +7,7 @@
 #include "ug_types.h"
 
 #define VIDEO_COMPRESS_ABI_VERSION 14  // src/video_compress.h:71
-enum library_class { LIBRARY_CLASS_VIDEO_COMPRESS = 7 };
+enum library_class { LIBRARY_CLASS_VIDEO_DECOMPRESS = 7, LIBRARY_CLASS_VIDEO_COMPRESS = 8 };  // positions in src/lib_common.h:73-86
 
 struct module;  // parent in the module tree — unused by the hot path
 
@@ -34,6 +34,8 @@ struct video_compress_info {  // src/video_compress.h:221-236
 
 void register_library(const char *name, const void *info, enum library_class cls, int abi_version);
 const void *load_library(const char *name, enum library_class cls, int abi_version);
+/// every registered module of a class (what list_modules / get_libraries_for_class of src/lib_common.h:96-113 provide)
+int get_libraries_for_class(enum library_class cls, int abi_version, const char **names, const void **infos, int max);
 #define REGISTER_MODULE(name, info, lclass, abi)                                                                                           \
         static struct ugb_reg_##name {                                                                                                     \
                 ugb_reg_##name() { register_library(#name, info, lclass, abi); }                                                           \

@@ -552,7 +552,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         if (!d || !stream || !dst || len > 0xFFFFFFF0u) {
                 return -1;
         }
-        if (out_codec != UGB_UYVY && out_codec != UGB_RGB && out_codec != UGB_RGBA) {
+        if (out_codec != UGB_UYVY && out_codec != UGB_RGB && out_codec != UGB_RGBA && out_codec != UGB_VUYA) {
                 return -4;
         }
         cudaStreamSynchronize(d->stream);  // the pinned staging buffers of the previous frame are free again
