@@ -333,3 +333,6 @@ API void orc_jpeg_coefficients(const uint8_t *src, long pitch, int w, int h, int
                 }
         }
 }
+
+/* the quality-scaled Annex K table (natural order): which = 0 luminance (K.1), 1 chrominance (K.2) */
+API void orc_jpeg_scaled_qtable(int which, int quality, uint8_t out[64]) { ugb_jpeg_scaled_qtable(which ? ugb_jpeg_q_chroma : ugb_jpeg_q_luma, quality, out); }

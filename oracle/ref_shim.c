@@ -91,3 +91,40 @@ API int ref_get_best_decoder_from(int in_codec, const int *candidates, int count
         codec_t out = VIDEO_CODEC_NONE;
         return get_best_decoder_from((codec_t) in_codec, cand, &out) != NULL ? (int) out : 0;
 }
+
+/* jpeg_read_info / jpeg_get_rtp_hdr_data (src/utils/jpeg_reader.c:860-1003, :1092-1160): what an unmodified UltraGrid receiver does with a
+ * JPEG bitstream before RFC 2435 packetisation.  out[]: width, height, comp_count, color_spec, interleaved, restart_interval,
+ * sampling h[0..2], v[0..2], quantisation-table map [0..2], offset of the entropy-coded data; qt = the two 64-byte tables it found */
+#include "utils/jpeg_reader.h"
+API int ref_jpeg_read_info(unsigned char *image, int len, int *out, unsigned char *qt, unsigned char *huff)
+{
+        static struct jpeg_info info;
+        memset(&info, 0, sizeof info);
+        const int rc = jpeg_read_info(image, len, &info);
+        if (rc != 0) {
+                return rc;
+        }
+        out[0] = info.width, out[1] = info.height, out[2] = info.comp_count, out[3] = info.color_spec, out[4] = info.interleaved, out[5] = info.restart_interval;
+        for (int i = 0; i < 3; ++i) {
+                out[6 + i] = info.sampling_factor_h[i], out[9 + i] = info.sampling_factor_v[i], out[12 + i] = info.comp_table_quantization_map[i];
+        }
+        out[15] = (int) (info.data - image);
+        for (int t = 0; t < 2; ++t) {
+                if (info.quantization_tables[t]) {
+                        memcpy(qt + 64 * t, info.quantization_tables[t], 64);
+                }
+        }
+        memcpy(huff, info.huff_lum_dc, 272), memcpy(huff + 272, info.huff_lum_ac, 272), memcpy(huff + 544, info.huff_chm_dc, 272), memcpy(huff + 816, info.huff_chm_ac, 272);
+        return 0;
+}
+/* @returns 1 if the stream can be sent as RFC 2435 RTP/JPEG; out[]: width, height, type, q, restart_interval, data offset */
+API int ref_jpeg_get_rtp_hdr_data(unsigned char *image, int len, int *out)
+{
+        struct jpeg_rtp_data d;
+        memset(&d, 0, sizeof d);
+        if (!jpeg_get_rtp_hdr_data(image, len, &d)) {
+                return 0;
+        }
+        out[0] = d.width, out[1] = d.height, out[2] = d.type, out[3] = d.q, out[4] = d.restart_interval, out[5] = (int) (d.data - image);
+        return 1;
+}
