@@ -9,7 +9,7 @@
  * Scope (ITU-T T.81 baseline sequential DCT, Huffman, 8 bit): 1 or 3 components, luma sampling 1x1, 2x1 or 2x2 with 1x1 chroma,
  * interleaved or one-scan-per-component, restart intervals, byte stuffing, tables from the stream (DQT 8-bit, DHT).  Output
  * is the stream's own colour space, like the reference's default configuration stores it (gpujpeg.cpp:304-305): no transform.
- *   out_fmt 0: UYVY  (needs 3 components, 2x1 luma)          out_fmt 1: packed 3 bytes/pixel, component order of the frame
+ *   out_fmt 0: UYVY  (3 components, 2x1 or 2x2 luma)         out_fmt 1: packed 3 bytes/pixel, component order of the frame
  *   header: SOF0 only (as src/utils/jpeg_reader.c:860-1003 accepts), APPn/COM skipped. */
 #include <math.h>
 #include <stddef.h>
@@ -350,12 +350,13 @@ API int orc_jpeg_decode(const uint8_t *s, size_t len, int out_fmt, uint8_t *out,
                 }
                 if (out) {
                         if (out_fmt == 0) {
-                                if (f.ncomp != 3 || f.c[0].h != 2 || f.c[0].v != 1) {
+                                if (f.ncomp != 3 || f.c[0].h != 2) {
                                         rc = -5;
                                 } else {
                                         for (int y = 0; y < f.h; ++y) {
-                                                const uint8_t *Y = f.c[0].plane + (size_t) y * f.c[0].bw * 8, *B = f.c[1].plane + (size_t) y * f.c[1].bw * 8,
-                                                              *R = f.c[2].plane + (size_t) y * f.c[2].bw * 8;
+                                                const int cy = y / f.c[0].v; /* 4:2:0: a chroma row serves two luma rows (nearest) */
+                                                const uint8_t *Y = f.c[0].plane + (size_t) y * f.c[0].bw * 8, *B = f.c[1].plane + (size_t) cy * f.c[1].bw * 8,
+                                                              *R = f.c[2].plane + (size_t) cy * f.c[2].bw * 8;
                                                 uint8_t *o = out + (size_t) y * pitch;
                                                 for (int x = 0; x < f.w; x += 2) {
                                                         o[2 * x] = B[x / 2], o[2 * x + 1] = Y[x], o[2 * x + 2] = R[x / 2];

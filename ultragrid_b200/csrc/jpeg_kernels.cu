@@ -191,6 +191,71 @@ __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict
         }
 }
 
+// ---- packed (f32x2) helpers of the fused kernel: one issue slot per two lanes, same roundings as the scalar code -------------
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }  // folds into the operand modifier
+__device__ __forceinline__ void fdct8_2(float2 &d0, float2 &d1, float2 &d2, float2 &d3, float2 &d4, float2 &d5, float2 &d6, float2 &d7)
+{
+        const float2 t0 = __fadd2_rn(d0, d7), t7 = __fadd2_rn(d0, neg2(d7)), t1 = __fadd2_rn(d1, d6), t6 = __fadd2_rn(d1, neg2(d6));
+        const float2 t2 = __fadd2_rn(d2, d5), t5 = __fadd2_rn(d2, neg2(d5)), t3 = __fadd2_rn(d3, d4), t4 = __fadd2_rn(d3, neg2(d4));
+        const float2 e0 = __fadd2_rn(t0, t3), e3 = __fadd2_rn(t0, neg2(t3)), e1 = __fadd2_rn(t1, t2), e2 = __fadd2_rn(t1, neg2(t2));
+        d0 = __fadd2_rn(e0, e1);
+        d4 = __fadd2_rn(e0, neg2(e1));
+        const float2 z1 = __fmul2_rn(__fadd2_rn(e2, e3), make_float2(0.707106781f, 0.707106781f));
+        d2 = __fadd2_rn(e3, z1);
+        d6 = __fadd2_rn(e3, neg2(z1));
+        const float2 o0 = __fadd2_rn(t4, t5), o1 = __fadd2_rn(t5, t6), o2 = __fadd2_rn(t6, t7);
+        const float2 z5 = __fmul2_rn(__fadd2_rn(o0, neg2(o2)), make_float2(0.382683433f, 0.382683433f));
+        const float2 z2 = __ffma2_rn(make_float2(0.541196100f, 0.541196100f), o0, z5);
+        const float2 z4 = __ffma2_rn(make_float2(1.306562965f, 1.306562965f), o2, z5);
+        const float2 z3 = __fmul2_rn(o1, make_float2(0.707106781f, 0.707106781f));
+        const float2 z11 = __fadd2_rn(t7, z3), z13 = __fadd2_rn(t7, neg2(z3));
+        d5 = __fadd2_rn(z13, z2);
+        d3 = __fadd2_rn(z13, neg2(z2));
+        d1 = __fadd2_rn(z11, z4);
+        d7 = __fadd2_rn(z11, neg2(z4));
+}
+/// the 8 samples of one row of a block as 2^23 + sample (level shift and conversion happen in one packed add later)
+__device__ __forceinline__ void load_row_magic(const uint8_t *__restrict__ src, long pitch, const jpeg_geom &g, int comp, int bx, int y, bool interior,
+                                               float *m)
+{
+        const uint8_t *row = src + (long) clampi(y, g.h - 1) * pitch;
+        if (g.fmt == FMT_UYVY_422) {
+                if (interior && comp == 0) {
+                        const uint4 v = __ldg((const uint4 *) (row + (long) bx * 16));
+                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                                m[2 * i] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7541u));
+                                m[2 * i + 1] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7543u));
+                        }
+                } else if (interior) {
+                        const uint4 a = __ldg((const uint4 *) (row + (long) bx * 32)), b = __ldg((const uint4 *) (row + (long) bx * 32) + 1);
+                        const uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+                        const unsigned sel = comp == 1 ? 0x7540u : 0x7542u;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                                m[i] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, sel));
+                        }
+                } else {
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) {
+                                uint32_t s;
+                                if (comp == 0) {
+                                        s = row[2 * clampi(bx * 8 + x, g.w - 1) + 1];
+                                } else {
+                                        s = row[4 * clampi(bx * 8 + x, (g.w + 1) / 2 - 1) + (comp == 1 ? 0 : 2)];
+                                }
+                                m[x] = __uint_as_float(0x4B000000u | s);
+                        }
+                }
+        } else {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                        m[x] = __uint_as_float(0x4B000000u | (uint32_t) __ldg(row + 3 * clampi(bx * 8 + x, g.w - 1) + comp));
+                }
+        }
+}
+
 // ---- fused path: DCT + quantise + per-block entropy coding + restart-segment assembly in ONE kernel ----------------------------
 // No int16 coefficient round trip through HBM (2 B/sample written + read by the split path), and the unit of serial work is one
 // 8x8 block instead of one restart segment.  CTA = 128 threads = 128 blocks in scan order:
@@ -326,46 +391,69 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
                 bx = b % g.bw, by = b / g.bw;
                 p = tid;
         }
-        // ---- 1. DCT + quantise -------------------------------------------------------------------------------------------------
-        int q[64];
+        // ---- 1. DCT + quantise, packed: lanes (x, y) of a float2 = rows (2r, 2r + 1) in the row pass, columns (2c, 2c + 1) in the column pass ----
+        float2 g2[8][4];  // after the column pass: g2[r][cp] = coefficients (r, 2cp) and (r, 2cp + 1), still as 1.5 * 2^23 + q
         {
                 const int px_w = (FMT == FMT_UYVY_422 && comp != 0) ? 16 : 8;
                 const bool interior = vec_ok && valid && (bx + 1) * px_w <= g.w && (by + 1) * 8 <= g.h;
-                float f[64];
+                float2 f2[4][8];
 #pragma unroll
-                for (int y = 0; y < 8; ++y) {
-                        load_row(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + y : 0, interior, f + 8 * y);
+                for (int rp = 0; rp < 4; ++rp) {
+                        float ma[8], mb[8];
+                        load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp : 0, interior, ma);
+                        load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp + 1 : 0, interior, mb);
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) {  // (2^23 + s) - (2^23 + 128): level shift, exact
+                                f2[rp][x] = __fadd2_rn(make_float2(ma[x], mb[x]), make_float2(-8388736.0f, -8388736.0f));
+                        }
+                        fdct8_2(f2[rp][0], f2[rp][1], f2[rp][2], f2[rp][3], f2[rp][4], f2[rp][5], f2[rp][6], f2[rp][7]);
                 }
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                        fdct8(f[8 * r], f[8 * r + 1], f[8 * r + 2], f[8 * r + 3], f[8 * r + 4], f[8 * r + 5], f[8 * r + 6], f[8 * r + 7]);
-                }
+                for (int rp = 0; rp < 4; ++rp) {  // re-pair: rows apart, neighbouring columns together
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                        fdct8(f[c], f[8 + c], f[16 + c], f[24 + c], f[32 + c], f[40 + c], f[48 + c], f[56 + c]);
+                        for (int cp = 0; cp < 4; ++cp) {
+                                g2[2 * rp][cp] = make_float2(f2[rp][2 * cp].x, f2[rp][2 * cp + 1].x);
+                                g2[2 * rp + 1][cp] = make_float2(f2[rp][2 * cp].y, f2[rp][2 * cp + 1].y);
+                        }
                 }
-                const float *qm = c_tab.qmul[comp == 0 ? 0 : 1];
+                const float2 *qm = (const float2 *) c_tab.qmul[comp == 0 ? 0 : 1];
 #pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                        q[i] = (int) __float_as_uint(__fadd_rn(__fmul_rn(f[i], qm[i]), 12582912.0f)) - 0x4B400000;
+                for (int cp = 0; cp < 4; ++cp) {
+                        fdct8_2(g2[0][cp], g2[1][cp], g2[2][cp], g2[3][cp], g2[4][cp], g2[5][cp], g2[6][cp], g2[7][cp]);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {  // rint without F2I: low 16 bits of the result = the quantised value
+                                g2[r][cp] = __fadd2_rn(__fmul2_rn(g2[r][cp], qm[4 * r + cp]), make_float2(12582912.0f, 12582912.0f));
+                        }
                 }
         }
         constexpr int zz[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                  41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                  30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
-        uint64_t nz = 0;
+        // word k of the block = zig-zag coefficients k (low half) and k + 32 (high half): the non-zero flags of 16 words then add up
+        // into one register without touching each other (bit k and bit 16 + k), and two byte permutes assemble the 64-bit map
+        uint32_t flags_a = 0, flags_b = 0;
+        int dcv = 0;
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-                int a = q[zz[2 * k]], c2 = q[zz[2 * k + 1]];
-                if (k > 0) {
-                        a = min(max(a, -1023), 1023);
+                const int na = zz[k], nb = zz[k + 32];
+                const float2 pa = g2[na >> 3][(na & 7) >> 1], pb = g2[nb >> 3][(nb & 7) >> 1];
+                const uint32_t ua = __float_as_uint((na & 1) ? pa.y : pa.x), ub = __float_as_uint((nb & 1) ? pb.y : pb.x);
+                uint32_t w = __byte_perm(ua, ub, 0x5410);
+                // AC range of the 10-bit categories (the DC, low half of word 0, keeps its full range)
+                w = __vmins2(__vmaxs2(w, k == 0 ? 0xFC018000u : 0xFC01FC01u), k == 0 ? 0x03FF7FFFu : 0x03FF03FFu);
+                s_coef[k * 128 + p] = w;
+                const uint32_t fl = __vminu2(w, 0x00010001u);
+                if (k < 16) {
+                        flags_a += fl << k;
+                } else {
+                        flags_b += fl << (k - 16);
                 }
-                c2 = min(max(c2, -1023), 1023);
-                s_coef[k * 128 + p] = ((uint32_t) a & 0xffffu) | ((uint32_t) c2 << 16);
-                nz |= ((uint64_t) (a != 0) | (uint64_t) (c2 != 0) << 1) << (2 * k);
+                if (k == 0) {
+                        dcv = (int) (short) (w & 0xffffu);
+                }
         }
+        uint64_t nz = (uint64_t) __byte_perm(flags_a, flags_b, 0x5410) | (uint64_t) __byte_perm(flags_a, flags_b, 0x7632) << 32;
         nz &= ~1ull;
-        const int dcv = q[0];
         s_dc[p] = dcv;
         __syncthreads();
         // ---- 2. entropy-code my block --------------------------------------------------------------------------------------------
@@ -397,7 +485,7 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
                                 bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);  // ZRL
                                 run -= 16;
                         }
-                        const int v = (int) (short) (s_coef[(i >> 1) * 128 + p] >> (16 * (i & 1)));
+                        const int v = (int) (short) (s_coef[(i & 31) * 128 + p] >> (16 * (i >> 5)));
                         sz = category(v);
                         const uint32_t e = s_ac[t][(run << 4) | sz];
                         bw.put(((e & 0xffff) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), (int) (e >> 16) + sz);
@@ -441,7 +529,7 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
                                 uint64_t map = 0;
                                 for (int k = 0; k < 32; ++k) {
                                         const uint32_t w = s_coef[k * 128 + q];
-                                        map |= ((uint64_t) ((w & 0xffffu) != 0) | (uint64_t) ((w >> 16) != 0) << 1) << (2 * k);
+                                        map |= (uint64_t) ((w & 0xffffu) != 0) << k | (uint64_t) ((w >> 16) != 0) << (k + 32);
                                 }
                                 map &= ~1ull;
                                 const int dc = s_dc[q], diff = dc - pred[FMT == FMT_UYVY_422 ? comp : 0];
@@ -461,7 +549,7 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
                                                 bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);
                                                 run -= 16;
                                         }
-                                        const int v = (int) (short) (s_coef[(i >> 1) * 128 + q] >> (16 * (i & 1)));
+                                        const int v = (int) (short) (s_coef[(i & 31) * 128 + q] >> (16 * (i >> 5)));
                                         sz = category(v);
                                         const uint32_t e = s_ac[t][(run << 4) | sz];
                                         bw.put(((e & 0xffff) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), (int) (e >> 16) + sz);
