@@ -296,6 +296,7 @@ def main():
         if world == 1 and not args.no_extra:
             line["extra"] = extra_kernels(api, torch, dev)
             line["extra"]["jpeg"] = extra_jpeg(api, compress, torch, dev)
+            line["extra"]["decode"] = extra_decode(api, torch, dev)
             v, cores, sample = cpu_port_fps()
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
             line["extra"]["cpu_reference_pixfmt"] = cpu_reference_pixfmt()
@@ -405,6 +406,46 @@ def extra_jpeg(api, compress, torch, dev):
         c.pop_into(out)
     res["natural_e2e_module_fps"] = n / (time.perf_counter() - t0)
     c.close()
+    return res
+
+
+def extra_decode(api, torch, dev):
+    """decode side and one planar converter, 8K: kernel-only where the input is device-resident; the JPEG decoder takes a
+    HOST stream (parse + upload + kernels), so that number is wall clock per frame"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    peak, _ = measured_peaks()
+    res = {}
+    w, h = W8K, H8K
+    for t, name in ((1, "dxt1_rgb_8k"), (6, "dxt5ycocg_rgb_8k")):
+        nb = w * h // (2 if t == 1 else 1)
+        blocks = [torch.randint(0, 256, (nb,), dtype=torch.uint8, device=dev) for _ in range(4)]
+        out = torch.empty(w * h * 3, dtype=torch.uint8, device=dev)
+        secs = time_kernel(torch, lambda i: api.dxt_to_rgb(blocks[i % 4], w, h, t, out=out), 12)
+        res[name] = {"us": secs * 1e6, "fps": 1 / secs, "GBps": (nb + w * h * 3) / secs / 1e9, "frac_of_peak": (nb + w * h * 3) / secs / 1e9 / peak}
+        del blocks
+    src = [torch.randint(0, 256, (w * h * 2,), dtype=torch.uint8, device=dev) for _ in range(4)]
+    y, c = torch.empty(w * h, dtype=torch.uint8, device=dev), torch.empty(w * h // 2, dtype=torch.uint8, device=dev)
+    secs = time_kernel(torch, lambda i: api.to_planar("uyvy_to_nv12", src[i % 4], w, h, [y, c], [w, w]), 20)
+    res["uyvy_nv12_8k"] = {"us": secs * 1e6, "GBps": w * h * 3.5 / secs / 1e9, "frac_of_peak": w * h * 3.5 / secs / 1e9 / peak}
+    del src
+    orc = util.oracle()
+    yy, xx = np.mgrid[0:h, 0:w]
+    rgb = np.stack([xx * 255 // (w - 1), yy * 255 // (h - 1), (xx + yy) % 256], axis=2).astype(np.uint8)
+    rgb = (rgb.astype(np.int16) + np.random.default_rng(1).integers(-6, 7, rgb.shape, dtype=np.int16)).clip(0, 255).astype(np.uint8)
+    enc = api.JpegEncoder()
+    enc.encode_device(torch.from_numpy(util.convert_cpu(orc, "orc_convert", 12, 2, rgb.reshape(-1), w, h)).cuda(), w, h, 2, quality=90)
+    stream = enc.result()
+    enc.close()
+    dec = api.JpegDecoder()
+    dec.decode(stream, 2, device=True)
+    t0 = time.perf_counter()
+    n = 5
+    for _ in range(n):
+        dec.decode(stream, 2, device=True)
+    res["jpeg_decode_natural_8k"] = {"ms_wall_per_frame": (time.perf_counter() - t0) / n * 1e3, "stream_bytes": len(stream), "output": "UYVY on the device"}
+    dec.close()
     return res
 
 
