@@ -26,7 +26,7 @@
 
 enum { FMT_UYVY_422 = 0, FMT_RGB_444 = 1 };
 
-/* 8-point AAN forward DCT (Arai/Agui/Nakajima), explicit operation order; the two multiply-adds are fused on
+/* 8-point AAN forward DCT (Arai/Agui/Nakajima), explicit operation order; all multiply-adds are fused on
  * purpose (fmaf) so that CPU and GPU round identically */
 static void fdct8(float *d, int stride)
 {
@@ -37,15 +37,14 @@ static void fdct8(float *d, int stride)
         const float e0 = t0 + t3, e3 = t0 - t3, e1 = t1 + t2, e2 = t1 - t2;
         d[0 * stride] = e0 + e1;
         d[4 * stride] = e0 - e1;
-        const float z1 = (e2 + e3) * 0.707106781f;
-        d[2 * stride] = e3 + z1;
-        d[6 * stride] = e3 - z1;
+        const float s1 = e2 + e3; /* every multiply-add of this transform is ONE fused operation, written out: no product ever feeds a */
+        d[2 * stride] = fmaf(s1, 0.707106781f, e3);  /* separate add, so there is nothing a compiler could contract differently     */
+        d[6 * stride] = fmaf(s1, -0.707106781f, e3);
         const float o0 = t4 + t5, o1 = t5 + t6, o2 = t6 + t7;
         const float z5 = (o0 - o2) * 0.382683433f;
         const float z2 = fmaf(0.541196100f, o0, z5);
         const float z4 = fmaf(1.306562965f, o2, z5);
-        const float z3 = o1 * 0.707106781f;
-        const float z11 = t7 + z3, z13 = t7 - z3;
+        const float z11 = fmaf(o1, 0.707106781f, t7), z13 = fmaf(o1, -0.707106781f, t7);
         d[5 * stride] = z13 + z2;
         d[3 * stride] = z13 - z2;
         d[1 * stride] = z11 + z4;
@@ -67,7 +66,7 @@ static void block_to_coeffs(const uint8_t px[64], const float qmul[64], int16_t 
         }
         for (int k = 0; k < 64; ++k) {
                 const int n = ugb_jpeg_zigzag[k];
-                int v = (int) rintf(f[n] * qmul[n]);
+                int v = (int) (fmaf(f[n], qmul[n], 12582912.0f) - 12582912.0f); /* round-to-nearest-even of the exact product (1.5 * 2^23 trick) */
                 if (k > 0) {
                         v = v < -1023 ? -1023 : v > 1023 ? 1023 : v;
                 }

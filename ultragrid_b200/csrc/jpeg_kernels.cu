@@ -57,15 +57,14 @@ __device__ __forceinline__ void fdct8(float &d0, float &d1, float &d2, float &d3
         const float e0 = __fadd_rn(t0, t3), e3 = __fadd_rn(t0, -t3), e1 = __fadd_rn(t1, t2), e2 = __fadd_rn(t1, -t2);
         d0 = __fadd_rn(e0, e1);
         d4 = __fadd_rn(e0, -e1);
-        const float z1 = __fmul_rn(__fadd_rn(e2, e3), 0.707106781f);
-        d2 = __fadd_rn(e3, z1);
-        d6 = __fadd_rn(e3, -z1);
+        const float s1 = __fadd_rn(e2, e3);  // every multiply-add is one explicit FMA: no product feeds a separate add (ptxas fuses
+        d2 = __fmaf_rn(s1, 0.707106781f, e3);  // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 on its own, so the packed twin of this
+        d6 = __fmaf_rn(s1, -0.707106781f, e3); // function must not contain such a pair either)
         const float o0 = __fadd_rn(t4, t5), o1 = __fadd_rn(t5, t6), o2 = __fadd_rn(t6, t7);
         const float z5 = __fmul_rn(__fadd_rn(o0, -o2), 0.382683433f);
         const float z2 = __fmaf_rn(0.541196100f, o0, z5);
         const float z4 = __fmaf_rn(1.306562965f, o2, z5);
-        const float z3 = __fmul_rn(o1, 0.707106781f);
-        const float z11 = __fadd_rn(t7, z3), z13 = __fadd_rn(t7, -z3);
+        const float z11 = __fmaf_rn(o1, 0.707106781f, t7), z13 = __fmaf_rn(o1, -0.707106781f, t7);
         d5 = __fadd_rn(z13, z2);
         d3 = __fadd_rn(z13, -z2);
         d1 = __fadd_rn(z11, z4);
@@ -168,7 +167,7 @@ __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict
         int q[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
-                q[i] = (int) __float_as_uint(__fadd_rn(__fmul_rn(f[i], qm[i]), 12582912.0f)) - 0x4B400000;  // rint without F2I
+                q[i] = (int) __float_as_uint(__fmaf_rn(f[i], qm[i], 12582912.0f)) - 0x4B400000;  // nearest-even of the exact product, no F2I
         }
         // zig-zag (Figure A.6) + AC clamp to the 10-bit category range, two int16 per word, 8 x 16-byte stores
         constexpr int zz[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
@@ -200,15 +199,14 @@ __device__ __forceinline__ void fdct8_2(float2 &d0, float2 &d1, float2 &d2, floa
         const float2 e0 = __fadd2_rn(t0, t3), e3 = __fadd2_rn(t0, neg2(t3)), e1 = __fadd2_rn(t1, t2), e2 = __fadd2_rn(t1, neg2(t2));
         d0 = __fadd2_rn(e0, e1);
         d4 = __fadd2_rn(e0, neg2(e1));
-        const float2 z1 = __fmul2_rn(__fadd2_rn(e2, e3), make_float2(0.707106781f, 0.707106781f));
-        d2 = __fadd2_rn(e3, z1);
-        d6 = __fadd2_rn(e3, neg2(z1));
+        const float2 s1 = __fadd2_rn(e2, e3);
+        d2 = __ffma2_rn(s1, make_float2(0.707106781f, 0.707106781f), e3);
+        d6 = __ffma2_rn(s1, make_float2(-0.707106781f, -0.707106781f), e3);
         const float2 o0 = __fadd2_rn(t4, t5), o1 = __fadd2_rn(t5, t6), o2 = __fadd2_rn(t6, t7);
         const float2 z5 = __fmul2_rn(__fadd2_rn(o0, neg2(o2)), make_float2(0.382683433f, 0.382683433f));
         const float2 z2 = __ffma2_rn(make_float2(0.541196100f, 0.541196100f), o0, z5);
         const float2 z4 = __ffma2_rn(make_float2(1.306562965f, 1.306562965f), o2, z5);
-        const float2 z3 = __fmul2_rn(o1, make_float2(0.707106781f, 0.707106781f));
-        const float2 z11 = __fadd2_rn(t7, z3), z13 = __fadd2_rn(t7, neg2(z3));
+        const float2 z11 = __ffma2_rn(o1, make_float2(0.707106781f, 0.707106781f), t7), z13 = __ffma2_rn(o1, make_float2(-0.707106781f, -0.707106781f), t7);
         d5 = __fadd2_rn(z13, z2);
         d3 = __fadd2_rn(z13, neg2(z2));
         d1 = __fadd2_rn(z11, z4);
@@ -422,7 +420,7 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
                         fdct8_2(g2[0][cp], g2[1][cp], g2[2][cp], g2[3][cp], g2[4][cp], g2[5][cp], g2[6][cp], g2[7][cp]);
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {  // rint without F2I: low 16 bits of the result = the quantised value
-                                g2[r][cp] = __fadd2_rn(__fmul2_rn(g2[r][cp], qm[4 * r + cp]), make_float2(12582912.0f, 12582912.0f));
+                                g2[r][cp] = __ffma2_rn(g2[r][cp], qm[4 * r + cp], make_float2(12582912.0f, 12582912.0f));
                         }
                 }
         }
