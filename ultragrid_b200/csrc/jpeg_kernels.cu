@@ -214,9 +214,29 @@ __device__ __forceinline__ void fdct8_2(float2 &d0, float2 &d1, float2 &d2, floa
 }
 /// the 8 samples of one row of a block as 2^23 + sample (level shift and conversion happen in one packed add later)
 __device__ __forceinline__ void load_row_magic(const uint8_t *__restrict__ src, long pitch, const jpeg_geom &g, int comp, int bx, int y, bool interior,
-                                               float *m)
+                                               float *m, const uint8_t *tile_row = nullptr, int tile_x = 0)
 {
         const uint8_t *row = src + (long) clampi(y, g.h - 1) * pitch;
+        if (tile_row != nullptr) {  // the CTA's 8 x 1024-byte input tile is in shared memory (UYVY only): tile_x = my MCU within the tile
+                if (comp == 0) {
+                        const uint4 v = *(const uint4 *) (tile_row + tile_x * 32 + (bx & 1) * 16);
+                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                                m[2 * i] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7541u));
+                                m[2 * i + 1] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7543u));
+                        }
+                } else {
+                        const uint4 a = *(const uint4 *) (tile_row + tile_x * 32), b = *(const uint4 *) (tile_row + tile_x * 32 + 16);
+                        const uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+                        const unsigned sel = comp == 1 ? 0x7540u : 0x7542u;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                                m[i] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, sel));
+                        }
+                }
+                return;
+        }
         if (g.fmt == FMT_UYVY_422) {
                 if (interior && comp == 0) {
                         const uint4 v = __ldg((const uint4 *) (row + (long) bx * 16));
@@ -347,7 +367,7 @@ struct block_bits {  // MSB-first bit string of one block in shared memory, word
 };
 
 template <int FMT>
-__global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
+__global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
                                                          uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
                                                          uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats)
 {
@@ -389,6 +409,24 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
                 bx = b % g.bw, by = b / g.bw;
                 p = tid;
         }
+        // ---- 0. stage the CTA's input tile (32 MCUs x 8 rows = 8 x 1024 bytes) through shared memory: coalesced, asynchronous, and the
+        //         luma and chroma warps read every byte from there instead of fetching it twice.  The tile borrows s_bits (free until phase 2).
+        bool staged = false;
+        const uint8_t *tile = (const uint8_t *) s_bits;
+        if (FMT == FMT_UYVY_422) {
+                const int mx0 = first_mcu % g.bw, my0 = first_mcu / g.bw;
+                staged = vec_ok && cap >= 16 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h;
+                if (staged) {
+                        const uint8_t *gsrc = src + (long) (my0 * 8) * pitch + (long) mx0 * 32;
+                        for (int i = tid; i < 512; i += 128) {
+                                const int row = i >> 6, col = i & 63;
+                                const uint32_t dst = (uint32_t) __cvta_generic_to_shared(tile + row * 1024 + col * 16);
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc + (long) row * pitch + col * 16) : "memory");
+                        }
+                        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                        __syncthreads();
+                }
+        }
         // ---- 1. DCT + quantise, packed: lanes (x, y) of a float2 = rows (2r, 2r + 1) in the row pass, columns (2c, 2c + 1) in the column pass ----
         float2 g2[8][4];  // after the column pass: g2[r][cp] = coefficients (r, 2cp) and (r, 2cp + 1), still as 1.5 * 2^23 + q
         {
@@ -398,8 +436,9 @@ __global__ void __launch_bounds__(128) jpeg_fused_kernel(const uint8_t *__restri
 #pragma unroll
                 for (int rp = 0; rp < 4; ++rp) {
                         float ma[8], mb[8];
-                        load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp : 0, interior, ma);
-                        load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp + 1 : 0, interior, mb);
+                        load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp : 0, interior, ma, staged ? tile + (2 * rp) * 1024 : nullptr, tid & 31);
+                        load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp + 1 : 0, interior, mb, staged ? tile + (2 * rp + 1) * 1024 : nullptr,
+                                       tid & 31);
 #pragma unroll
                         for (int x = 0; x < 8; ++x) {  // (2^23 + s) - (2^23 + 128): level shift, exact
                                 f2[rp][x] = __fadd2_rn(make_float2(ma[x], mb[x]), make_float2(-8388736.0f, -8388736.0f));
