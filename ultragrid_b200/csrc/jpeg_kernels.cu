@@ -34,6 +34,9 @@ struct jpeg_tables_dev {
         uint32_t ac[2][256];   // (len << 16) | code, by (run << 4 | size)
 };
 __constant__ jpeg_tables_dev c_tab;
+// the Huffman code tables once more in global memory: a CTA copies them to shared memory with coalesced loads (indexing the constant
+// bank with the thread id serialises into 32 replays per warp)
+__device__ uint32_t g_huff[2 * 16 + 2 * 256];
 
 struct jpeg_geom {
         int fmt, w, h;
@@ -345,9 +348,9 @@ struct block_bits {  // MSB-first bit string of one block in shared memory, word
         uint32_t *base;
         uint64_t acc;
         int nbits, nwords, cap;  // words beyond `cap` are counted but not stored
-        __device__ __forceinline__ void put(uint32_t code, int len)
+        __device__ __forceinline__ void put(uint32_t code, int len)  // code must not have bits above len
         {
-                acc = (acc << len) | (code & ((1u << len) - 1u));
+                acc = (acc << len) | code;
                 nbits += len;
                 if (nbits >= 32) {
                         if (nwords < cap) {
@@ -379,10 +382,10 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
         __shared__ int s_dc[128];
         const int tid = threadIdx.x;
         for (int i = tid; i < 32; i += 128) {
-                s_dctab[i >> 4][i & 15] = c_tab.dc[i >> 4][i & 15];
+                s_dctab[i >> 4][i & 15] = __ldg(g_huff + i);
         }
         for (int i = tid; i < 512; i += 128) {
-                s_ac[i >> 8][i & 255] = c_tab.ac[i >> 8][i & 255];
+                s_ac[i >> 8][i & 255] = __ldg(g_huff + 32 + i);
         }
         for (int i = tid; i < cap * 128; i += 128) {
                 s_seg[i] = 0;
@@ -510,25 +513,34 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 int sz = category(diff);
                 bw.put(s_dctab[t][sz] & 0xffff, s_dctab[t][sz] >> 16);
                 if (sz) {
-                        bw.put((uint32_t) (diff < 0 ? diff - 1 : diff), sz);
+                        bw.put((uint32_t) (diff < 0 ? diff - 1 : diff) & ((1u << sz) - 1u), sz);
                 }
+                // AC: one turn per non-zero coefficient.  The map is walked as two 32-bit halves: bit b of half h is zig-zag index b + 32 h,
+                // stored in half h of word b
                 int prev = 0;
-                while (nz) {
-                        const int i = __ffsll((long long) nz) - 1;
-                        nz &= nz - 1;
-                        int run = i - prev - 1;
-                        prev = i;
-                        while (run > 15) {
-                                bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);  // ZRL
-                                run -= 16;
+                const uint32_t *cw = s_coef + p;
+                const uint32_t *act = s_ac[t];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                        uint32_t m = half ? (uint32_t) (nz >> 32) : (uint32_t) nz;
+                        while (m) {
+                                const int b = __ffs((int) m) - 1;
+                                m &= m - 1;
+                                const int i = b + 32 * half;
+                                int run = i - prev - 1;
+                                prev = i;
+                                while (run > 15) {
+                                        bw.put(act[0xF0] & 0xffff, act[0xF0] >> 16);  // ZRL
+                                        run -= 16;
+                                }
+                                const int v = half ? (int) cw[b * 128] >> 16 : (int) (short) (cw[b * 128] & 0xffffu);
+                                sz = category(v);
+                                const uint32_t e = act[(run << 4) | sz];
+                                bw.put(((e & 0xffff) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), (int) (e >> 16) + sz);
                         }
-                        const int v = (int) (short) (s_coef[(i & 31) * 128 + p] >> (16 * (i >> 5)));
-                        sz = category(v);
-                        const uint32_t e = s_ac[t][(run << 4) | sz];
-                        bw.put(((e & 0xffff) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), (int) (e >> 16) + sz);
                 }
                 if (prev != 63) {
-                        bw.put(s_ac[t][0] & 0xffff, s_ac[t][0] >> 16);  // EOB
+                        bw.put(act[0] & 0xffff, act[0] >> 16);  // EOB
                 }
                 bits = bw.finish();
         }
@@ -1066,7 +1078,8 @@ int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri
                 }
         }
         // the constant bank is per-module state; encoders with different quality on one stream order themselves through the stream
-        if (cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+        if (cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+            cudaMemcpyToSymbolAsync(g_huff, t.dc, sizeof t.dc + sizeof t.ac, 0, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
                 return -2;
         }
         build_header(e, ql, qc);
