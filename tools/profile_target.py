@@ -41,4 +41,34 @@ elif which == "jpeg":
     for i in range(3):
         enc.encode_device(src, W, H, 2, quality=90)
     print("jpeg bytes", len(enc.result()))
+elif which in ("jpegdec", "dxtdec"):
+    import time
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import util
+    if which == "dxtdec":
+        for t in (1, 6):
+            blocks = torch.randint(0, 256, (W * H // (2 if t == 1 else 1),), dtype=torch.uint8, device=dev)
+            out = torch.empty(W * H * 3, dtype=torch.uint8, device=dev)
+            for i in range(3):
+                api.dxt_to_rgb(blocks, W, H, t, out=out)
+    else:
+        orc = util.oracle()
+        yy, xx = np.mgrid[0:H, 0:W]
+        rgb = np.stack([xx * 255 // (W - 1), yy * 255 // (H - 1), (xx + yy) % 256], axis=2).astype(np.uint8)
+        rgb = (rgb.astype(np.int16) + np.random.default_rng(1).integers(-6, 7, rgb.shape, dtype=np.int16)).clip(0, 255).astype(np.uint8)
+        enc = api.JpegEncoder()
+        enc.encode_device(torch.from_numpy(util.convert_cpu(orc, "orc_convert", 12, 2, rgb.reshape(-1), W, H)).cuda(), W, H, 2, quality=90)
+        stream = enc.result()
+        dec = api.JpegDecoder()
+        for i in range(4):
+            t0 = time.perf_counter()
+            dec.decode(stream, 2, device=True)
+            print("decode wall ms", (time.perf_counter() - t0) * 1e3)
+        info = api.JpegImageInfo()
+        buf = (__import__("ctypes").c_uint8 * len(stream)).from_buffer_copy(stream)
+        t0 = time.perf_counter()
+        for i in range(10):
+            api._L.ugb200_jpeg_get_image_info(buf, len(stream), __import__("ctypes").byref(info))
+        print("header probe ms", (time.perf_counter() - t0) * 100)
 torch.cuda.synchronize()

@@ -25,16 +25,31 @@ __device__ __forceinline__ double third(double a, double b)  // (2.0 * a + 1.0 *
         return __ddiv_rn(__dadd_rn(__dmul_rn(2.0, a), b), 3.0);
 }
 
-template <int BGR>
-__device__ __forceinline__ void store_px(uint8_t *p, uint32_t r, uint32_t g, uint32_t b)
+/// four pixels (24-bit colours p0..p3, R in the low byte) = 12 bytes of a row: three 32-bit stores when the row is 4-byte aligned
+__device__ __forceinline__ void store_row(uint8_t *o, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, bool aligned)
 {
-        p[BGR ? 2 : 0] = (uint8_t) r, p[1] = (uint8_t) g, p[BGR ? 0 : 2] = (uint8_t) b;
+        const uint32_t w0 = p0 | p1 << 24, w1 = (p1 >> 8) | p2 << 16, w2 = (p2 >> 16) | p3 << 8;
+        if (aligned) {
+                ((uint32_t *) o)[0] = w0, ((uint32_t *) o)[1] = w1, ((uint32_t *) o)[2] = w2;
+        } else {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                        o[i] = (uint8_t) ((i < 4 ? w0 : i < 8 ? w1 : w2) >> (8 * (i & 3)));
+                }
+        }
+}
+template <int BGR>
+__device__ __forceinline__ uint32_t pack_px(uint32_t r, uint32_t g, uint32_t b)
+{
+        return BGR ? b | g << 8 | r << 16 : r | g << 8 | b << 16;
 }
 
 template <int BGR>
-__global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch)
+__global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch, bool aligned)
 {
-        const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
+        // per-thread palettes live in shared memory ([entry][thread]: conflict-free, dynamically indexable without local memory)
+        __shared__ double s_ap[8][128], s_co[4][128], s_cg[4][128];
+        const int tid = threadIdx.x, bx = blockIdx.x * blockDim.x + tid, by = blockIdx.y;
         if (bx >= bw) {
                 return;
         }
@@ -42,22 +57,21 @@ __global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__re
         uint64_t alpha_code = (uint64_t) blk.x | (uint64_t) blk.y << 32, rgb_code = (uint64_t) blk.z | (uint64_t) blk.w << 32;
         // alpha palette (dxt62tga.c:38-62): 8 luma levels
         const double a0 = __ddiv_rn((double) (alpha_code & 0xFF), 255.0), a1 = __ddiv_rn((double) ((alpha_code >> 8) & 0xFF), 255.0);
-        double ap[8];
-        ap[0] = a0, ap[1] = a1;
+        s_ap[0][tid] = a0, s_ap[1][tid] = a1;
         if (a0 > a1) {
 #pragma unroll
                 for (int k = 2; k < 8; ++k) {
-                        ap[k] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (8 - k), a0), __dmul_rn((double) (k - 1), a1)), 7.0);
+                        s_ap[k][tid] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (8 - k), a0), __dmul_rn((double) (k - 1), a1)), 7.0);
                 }
         } else {
 #pragma unroll
                 for (int k = 2; k < 6; ++k) {
-                        ap[k] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (6 - k), a0), __dmul_rn((double) (k - 1), a1)), 5.0);
+                        s_ap[k][tid] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (6 - k), a0), __dmul_rn((double) (k - 1), a1)), 5.0);
                 }
-                ap[6] = 0.0, ap[7] = 1.0;
+                s_ap[6][tid] = 0.0, s_ap[7][tid] = 1.0;
         }
         // colour palette (:68-81) and, per entry, the scaled Co / Cg (:24-27 depend on the entry only)
-        double r[4], g[4], b[4], co[4], cg[4];
+        double r[4], g[4], b[4];
         b[0] = __ddiv_rn((double) (rgb_code & 0x1F), 31.0), g[0] = __ddiv_rn((double) ((rgb_code >> 5) & 0x3F), 63.0), r[0] = __ddiv_rn((double) ((rgb_code >> 11) & 0x1F), 31.0);
         b[1] = __ddiv_rn((double) ((rgb_code >> 16) & 0x1F), 31.0), g[1] = __ddiv_rn((double) ((rgb_code >> 21) & 0x3F), 63.0), r[1] = __ddiv_rn((double) ((rgb_code >> 27) & 0x1F), 31.0);
         b[2] = third(b[0], b[1]), g[2] = third(g[0], g[1]), r[2] = third(r[0], r[1]);
@@ -66,26 +80,29 @@ __global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__re
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
                 const double scale = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(31.875, b[k]), 1.0));
-                co[k] = __dmul_rn(__dadd_rn(r[k], -5.01960814E-01), scale);
-                cg[k] = __dmul_rn(__dadd_rn(g[k], -5.01960814E-01), scale);
+                s_co[k][tid] = __dmul_rn(__dadd_rn(r[k], -5.01960814E-01), scale);
+                s_cg[k][tid] = __dmul_rn(__dadd_rn(g[k], -5.01960814E-01), scale);
         }
         alpha_code >>= 16, rgb_code >>= 32;
         uint8_t *o = out + (long) by * 4 * pitch + (long) bx * 12;
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
+                uint32_t px[4];
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
-                        const double a = ap[alpha_code & 7];
+                        const double a = s_ap[alpha_code & 7][tid];
                         const int k = (int) (rgb_code & 3);
                         alpha_code >>= 3, rgb_code >>= 2;
-                        const double R = __dadd_rn(__dadd_rn(a, co[k]), -cg[k]), G = __dadd_rn(a, cg[k]), B = __dadd_rn(__dadd_rn(a, -co[k]), -cg[k]);
-                        store_px<BGR>(o + y * pitch + 3 * x, to_byte(__dmul_rn(R, 255.0)), to_byte(__dmul_rn(G, 255.0)), to_byte(__dmul_rn(B, 255.0)));
+                        const double co = s_co[k][tid], cg = s_cg[k][tid];
+                        const double R = __dadd_rn(__dadd_rn(a, co), -cg), G = __dadd_rn(a, cg), B = __dadd_rn(__dadd_rn(a, -co), -cg);
+                        px[x] = pack_px<BGR>(to_byte(__dmul_rn(R, 255.0)), to_byte(__dmul_rn(G, 255.0)), to_byte(__dmul_rn(B, 255.0)));
                 }
+                store_row(o + y * pitch, px[0], px[1], px[2], px[3], aligned);
         }
 }
 
 template <int BGR>
-__global__ void __launch_bounds__(128) dxt1_decode_kernel(const uint2 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch)
+__global__ void __launch_bounds__(128) dxt1_decode_kernel(const uint2 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch, bool aligned)
 {
         const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
         if (bx >= bw) {
@@ -104,21 +121,23 @@ __global__ void __launch_bounds__(128) dxt1_decode_kernel(const uint2 *__restric
                 r[2] = __dmul_rn(__dadd_rn(r[0], r[1]), 0.5), g[2] = __dmul_rn(__dadd_rn(g[0], g[1]), 0.5), b[2] = __dmul_rn(__dadd_rn(b[0], b[1]), 0.5);
                 r[3] = g[3] = b[3] = 0.0;
         }
-        uint32_t pr[4], pg[4], pb[4];
+        uint32_t pal[4];  // the four colours as 24-bit pixels, selected per pixel with two predicated moves
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-                pr[k] = to_byte(__dmul_rn(r[k], 255.0)), pg[k] = to_byte(__dmul_rn(g[k], 255.0)), pb[k] = to_byte(__dmul_rn(b[k], 255.0));
+                pal[k] = pack_px<BGR>(to_byte(__dmul_rn(r[k], 255.0)), to_byte(__dmul_rn(g[k], 255.0)), to_byte(__dmul_rn(b[k], 255.0)));
         }
         uint32_t idx = blk.y;
         uint8_t *o = out + (long) by * 4 * pitch + (long) bx * 12;
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
+                uint32_t px[4];
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
-                        const int k = idx & 3;
+                        const uint32_t lo = (idx & 1) ? pal[1] : pal[0], hi = (idx & 1) ? pal[3] : pal[2];
+                        px[x] = (idx & 2) ? hi : lo;
                         idx >>= 2;
-                        store_px<BGR>(o + y * pitch + 3 * x, pr[k], pg[k], pb[k]);
                 }
+                store_row(o + y * pitch, px[0], px[1], px[2], px[3], aligned);
         }
 }
 
@@ -136,10 +155,11 @@ using namespace ugb;
                         out_pitch = (long) w * 3;                                                                                          \
                 }                                                                                                                          \
                 dim3 grid((w / 4 + 127) / 128, h / 4);                                                                                     \
+                const bool aligned = !(3 & (size_t) out) && !(out_pitch & 3);                                                              \
                 if (bgr) {                                                                                                                 \
-                        KERNEL<1><<<grid, 128, 0, (cudaStream_t) stream>>>((const T *) src, (uint8_t *) out, w / 4, h / 4, out_pitch);    \
+                        KERNEL<1><<<grid, 128, 0, (cudaStream_t) stream>>>((const T *) src, (uint8_t *) out, w / 4, h / 4, out_pitch, aligned);    \
                 } else {                                                                                                                   \
-                        KERNEL<0><<<grid, 128, 0, (cudaStream_t) stream>>>((const T *) src, (uint8_t *) out, w / 4, h / 4, out_pitch);    \
+                        KERNEL<0><<<grid, 128, 0, (cudaStream_t) stream>>>((const T *) src, (uint8_t *) out, w / 4, h / 4, out_pitch, aligned);    \
                 }                                                                                                                          \
                 return cudaGetLastError() == cudaSuccess ? 0 : -2;                                                                         \
         }
