@@ -456,12 +456,14 @@ def extra_decode(api, torch, dev):
     stream = enc.result()
     enc.close()
     dec = api.JpegDecoder()
-    dec.decode(stream, 2, device=True)
+    out = dec.decode(stream, 2, device=True)
     t0 = time.perf_counter()
-    n = 5
+    n = 8
     for _ in range(n):
-        dec.decode(stream, 2, device=True)
-    res["jpeg_decode_natural_8k"] = {"ms_wall_per_frame": (time.perf_counter() - t0) / n * 1e3, "stream_bytes": len(stream), "output": "UYVY on the device"}
+        dec.decode(stream, 2, device=True, out=out, sync=False)
+    torch.cuda.synchronize()
+    res["jpeg_decode_natural_8k"] = {"ms_wall_per_frame": (time.perf_counter() - t0) / n * 1e3, "stream_bytes": len(stream),
+                                     "output": "UYVY on the device; host stream in: marker scan + staged upload + 4 kernels"}
     dec.close()
     return res
 

@@ -68,6 +68,9 @@ struct ugb200_jpeg_image_info {
 };
 /* gpujpeg_decoder_get_image_info (gpujpeg.c:212): host only, reads the headers up to the first SOS */
 UGB_API int ugb200_jpeg_get_image_info(const uint8_t *stream, size_t len, struct ugb200_jpeg_image_info *info);
+/* host only, for tests: the restart segments the stream parser found ([begin, end) byte offsets of their entropy-coded data);
+ * returns their number (may exceed cap) or a negative error */
+UGB_API long ugb200_jpeg_debug_segments(const uint8_t *stream, size_t len, uint32_t *begin, uint32_t *end, long cap);
 UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t stream);   /* gpujpeg_decoder_create, gpujpeg.c:93 */
 UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *dec);                      /* gpujpeg_decoder_destroy */
 /* gpujpeg_decoder_decode (gpujpeg.c:289,300): `stream` is a HOST buffer; dst is a host (synchronous) or device (asynchronous on the

@@ -104,6 +104,31 @@ def test_image_info_host_only(orc):
     assert lib.ugb200_jpeg_get_image_info((ctypes.c_uint8 * 4)(1, 2, 3, 4), 4, ctypes.byref(Info())) != 0
 
 
+@pytest.mark.parametrize("kind,w,h,q,ri", STREAMS)
+def test_stream_parser_finds_restart_segments(orc, kind, w, h, q, ri):
+    """host logic of the decoder: the SSE2 marker scan against a plain numpy search of the same stream"""
+    from ultragrid_b200 import _lib
+    lib = _lib.load()
+    s, _ = make_stream(orc, kind, w, h, q, ri)
+    a = np.frombuffer(s, np.uint8)
+    ff = np.flatnonzero(a[:-1] == 0xFF)
+    nxt = a[ff + 1]
+    sos = ff[nxt == 0xDA]
+    cap = 1 << 16
+    begin, end = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    n = lib.ugb200_jpeg_debug_segments(a.ctypes.data, len(s), begin.ctypes.data, end.ctypes.data, cap)
+    assert n > 0
+    want_b, want_e = [], []
+    for k, so in enumerate(sos):
+        data0 = so + 2 + (int(a[so + 2]) << 8 | int(a[so + 3]))
+        stop = next(p for p, c in zip(ff, nxt) if p >= data0 and c != 0 and not 0xD0 <= c <= 0xD7 and c != 0xFF)
+        rst = [p for p, c in zip(ff, nxt) if data0 <= p < stop and 0xD0 <= c <= 0xD7]
+        want_b += [data0] + [p + 2 for p in rst]
+        want_e += rst + [stop]
+    assert n == len(want_b)
+    assert begin[:n].tolist() == want_b and end[:n].tolist() == want_e
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,w,h,q,ri", STREAMS + [("ours-uyvy", 3840, 2160, 90, 0), ("ours-rgb", 1920, 1080, 90, 0)])
 def test_gpu_decoder_equals_oracle(orc, kind, w, h, q, ri):

@@ -196,6 +196,11 @@ class JpegEncoder:
         return host
 
 
+def _bytes_ptr(b):
+    """address of a bytes object's buffer without copying it (the C side only reads)"""
+    return ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p)
+
+
 class JpegImageInfo(ctypes.Structure):
     _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("components", ctypes.c_int), ("h_samp", ctypes.c_int), ("v_samp", ctypes.c_int),
                 ("adobe_transform", ctypes.c_int), ("restart_interval", ctypes.c_int), ("native_codec", ctypes.c_int)]
@@ -204,8 +209,7 @@ class JpegImageInfo(ctypes.Structure):
 def jpeg_image_info(stream):
     """gpujpeg_decoder_get_image_info (src/video_decompress/gpujpeg.c:212): host-only header probe"""
     info = JpegImageInfo()
-    buf = (ctypes.c_uint8 * len(stream)).from_buffer_copy(stream)
-    _check(_L.ugb200_jpeg_get_image_info(buf, len(stream), ctypes.byref(info)), "ugb200_jpeg_get_image_info")
+    _check(_L.ugb200_jpeg_get_image_info(_bytes_ptr(stream), len(stream), ctypes.byref(info)), "ugb200_jpeg_get_image_info")
     return info
 
 
@@ -226,15 +230,17 @@ class JpegDecoder:
     def __del__(self):
         self.close()
 
-    def decode(self, stream, out_codec, shifts=(0, 8, 16), device=False, pitch=0):
+    def decode(self, stream, out_codec, shifts=(0, 8, 16), device=False, pitch=0, out=None, sync=True):
         """bytes -> numpy array (host) or CUDA tensor (device=True) holding height rows of vc_get_linesize(width, out_codec) bytes"""
         info = jpeg_image_info(stream)
         ls = pitch or vc_get_linesize(info.width, out_codec)
-        buf = (ctypes.c_uint8 * len(stream)).from_buffer_copy(stream)
+        buf = _bytes_ptr(stream)
         if device:
-            out = torch.zeros(ls * info.height, dtype=torch.uint8, device="cuda")
+            if out is None:
+                out = torch.zeros(ls * info.height, dtype=torch.uint8, device="cuda")
             _check(_L.ugb200_jpeg_decode(self._h, buf, len(stream), _ptr(out), 1, ls, int(out_codec), *shifts), "ugb200_jpeg_decode")
-            self._stream.synchronize()
+            if sync:
+                self._stream.synchronize()
             return out
         import numpy as np
         out = np.zeros(ls * info.height, dtype=np.uint8)

@@ -17,7 +17,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <emmintrin.h>
+
+#include <algorithm>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/ugb200.h"
@@ -324,9 +328,44 @@ void build_table(dec_tables &t, int tab, const uint8_t *bits, const uint8_t *val
 
 const float kAan[8] = { 1.0f, 1.387039845f, 1.306562965f, 1.175875602f, 1.0f, 0.785694958f, 0.541196100f, 0.275899379f };
 
-/// header markers up to and including every SOS; `full` also walks the entropy-coded data to find the restart segments
-int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool full)
+/// marker candidates of [lo, hi): positions p with s[p] == 0xFF and s[p + 1] neither a stuffed 0x00 nor a fill 0xFF.  One SSE2 compare per
+/// 16 bytes, then only the 0xFF positions are looked at.  Optionally copies the range to `copy_to` in the same pass (staging for the upload).
+void scan_markers(const uint8_t *s, size_t lo, size_t hi, size_t len, std::vector<uint32_t> &out, uint8_t *copy_to)
 {
+        const __m128i ff16 = _mm_set1_epi8((char) 0xFF), zero = _mm_setzero_si128();
+        size_t i = lo;
+        // 0xFF is frequent in Huffman-coded data (runs of 1-bits), a marker is not: the follower byte is tested in the vector domain too
+        for (; i + 17 <= len && i + 16 <= hi; i += 16) {
+                const __m128i v = _mm_loadu_si128((const __m128i *) (s + i)), nx = _mm_loadu_si128((const __m128i *) (s + i + 1));
+                if (copy_to) {
+                        _mm_storeu_si128((__m128i *) (copy_to + i), v);
+                }
+                const __m128i stuffed = _mm_or_si128(_mm_cmpeq_epi8(nx, zero), _mm_cmpeq_epi8(nx, ff16));
+                unsigned mask = (unsigned) _mm_movemask_epi8(_mm_andnot_si128(stuffed, _mm_cmpeq_epi8(v, ff16)));
+                while (mask) {
+                        out.push_back((uint32_t) (i + (size_t) __builtin_ctz(mask)));
+                        mask &= mask - 1;
+                }
+        }
+        for (; i < hi; ++i) {
+                if (copy_to) {
+                        copy_to[i] = s[i];
+                }
+                if (s[i] == 0xFF && i + 1 < len && s[i + 1] != 0 && s[i + 1] != 0xFF) {
+                        out.push_back((uint32_t) i);
+                }
+        }
+}
+
+/// header markers up to and including every SOS; `full` also finds the restart segments of the entropy-coded data, from the marker
+/// candidates in `markers` (sorted; scanned here when the caller has none)
+int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool full, const std::vector<uint32_t> *markers = nullptr)
+{
+        std::vector<uint32_t> own;
+        if (full && markers == nullptr) {
+                scan_markers(s, 0, len, len, own, nullptr);
+                markers = &own;
+        }
         const uint8_t *p = s, *end = s + len;
         if (len < 4 || p[0] != 0xFF || p[1] != 0xD8) {
                 return -1;
@@ -445,38 +484,29 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
                         }
                         S.nmcu = S.mcux * mcuy;
                         S.seg0 = (int) P.seg_begin.size();
+                        P.seg_begin.reserve(P.seg_begin.size() + (size_t) (g.ri ? (S.nmcu + g.ri - 1) / g.ri : 1)), P.seg_end.reserve(P.seg_begin.capacity());
                         S.nseg = g.ri ? (S.nmcu + g.ri - 1) / g.ri : 1;
                         ++g.nscans;
                         p = dend;
                         if (!full) {
                                 return 0;  // enough for the image info
                         }
-                        // entropy-coded segment(s): up to the next marker that is neither a stuffed zero nor RSTn
+                        // entropy-coded segment(s): RSTn candidates split it, the first other marker ends it
                         uint32_t begin = (uint32_t) (p - s);
                         int found = 0;
-                        for (;;) {
-                                const uint8_t *ff = (const uint8_t *) memchr(p, 0xFF, (size_t) (end - p));
-                                if (ff == nullptr || ff + 1 >= end) {
-                                        p = end;
+                        auto it = std::lower_bound(markers->begin(), markers->end(), begin);
+                        for (; it != markers->end(); ++it) {
+                                const int c2 = s[*it + 1];
+                                if (c2 < 0xD0 || c2 > 0xD7) {
                                         break;
                                 }
-                                const int c2 = ff[1];
-                                if (c2 == 0 || c2 == 0xFF) {
-                                        p = ff + 1;
-                                        continue;
+                                if (found + 1 < S.nseg) {
+                                        P.seg_begin.push_back(begin), P.seg_end.push_back(*it);
+                                        ++found;
                                 }
-                                if (c2 >= 0xD0 && c2 <= 0xD7) {
-                                        if (found + 1 < S.nseg) {
-                                                P.seg_begin.push_back(begin), P.seg_end.push_back((uint32_t) (ff - s));
-                                                ++found;
-                                        }
-                                        begin = (uint32_t) (ff + 2 - s);
-                                        p = ff + 2;
-                                        continue;
-                                }
-                                p = ff;
-                                break;
+                                begin = *it + 2;
                         }
+                        p = it != markers->end() ? s + *it : end;
                         P.seg_begin.push_back(begin), P.seg_end.push_back((uint32_t) (p - s));
                         ++found;
                         while (found < S.nseg) {  // truncated stream: the missing segments decode as nothing (zero coefficients)
@@ -521,6 +551,24 @@ UGB_API int ugb200_jpeg_get_image_info(const uint8_t *stream, size_t len, struct
         return 0;
 }
 
+UGB_API long ugb200_jpeg_debug_segments(const uint8_t *stream, size_t len, uint32_t *begin, uint32_t *end, long cap)
+{
+        if (!stream) {
+                return -1;
+        }
+        parsed P;
+        dec_tables T;
+        const int rc = parse_stream(stream, len, P, &T, true);
+        if (rc != 0) {
+                return rc;
+        }
+        const long n = (long) P.seg_begin.size();
+        for (long i = 0; i < n && i < cap; ++i) {
+                begin[i] = P.seg_begin[i], end[i] = P.seg_end[i];
+        }
+        return n;
+}
+
 UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t stream)
 {
         ugb200_jpeg_decoder *d = new (std::nothrow) ugb200_jpeg_decoder;
@@ -559,7 +607,30 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         parsed P;
         memset(d->h_tables, 0, sizeof(dec_tables));
         memcpy(d->h_tables->zz, kZigzag, 64);
-        int rc = parse_stream(stream, len, P, d->h_tables, true);
+        if (!hgrow(d->h_stream, d->h_stream_cap, len)) {
+                return -2;
+        }
+        // one pass over the caller's (pageable) buffer: copy it to the pinned staging buffer and collect the marker candidates, split over a
+        // few threads when the stream is large (an 8K frame is 5-50 MB)
+        std::vector<uint32_t> markers;
+        {
+                const int nt = len > (1u << 20) ? 4 : 1;
+                std::vector<uint32_t> part[4];
+                std::thread th[4];
+                const size_t chunk = (len / nt + 15) & ~(size_t) 15;
+                for (int i = 1; i < nt; ++i) {
+                        const size_t lo = std::min(len, chunk * i), hi = i == nt - 1 ? len : std::min(len, chunk * (i + 1));
+                        th[i] = std::thread(scan_markers, stream, lo, hi, len, std::ref(part[i]), d->h_stream);
+                }
+                scan_markers(stream, 0, nt == 1 ? len : std::min(len, chunk), len, part[0], d->h_stream);
+                for (int i = 1; i < nt; ++i) {
+                        th[i].join();
+                }
+                for (int i = 0; i < nt; ++i) {
+                        markers.insert(markers.end(), part[i].begin(), part[i].end());
+                }
+        }
+        int rc = parse_stream(stream, len, P, d->h_tables, true, &markers);
         if (rc != 0) {
                 return rc;
         }
@@ -573,14 +644,12 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 dst_pitch = opitch;
         }
         if (!dgrow(d->d_stream, d->stream_cap, len + 16) || !dgrow(d->planes, d->planes_cap, (size_t) plane_bytes) || !dgrow(d->coef, d->coef_cap, (size_t) g.nblocks * 64) ||
-            !dgrow(d->d_seg, d->seg_cap, 2 * nseg) || !dgrow(d->native, d->native_cap, (size_t) npitch * g.h + 64) || !hgrow(d->h_stream, d->h_stream_cap, len) ||
-            !hgrow(d->h_seg, d->h_seg_cap, 2 * nseg)) {
+            !dgrow(d->d_seg, d->seg_cap, 2 * nseg) || !dgrow(d->native, d->native_cap, (size_t) npitch * g.h + 64) || !hgrow(d->h_seg, d->h_seg_cap, 2 * nseg)) {
                 return -2;
         }
         cudaStream_t s = d->stream;
-        memcpy(d->h_stream, stream, len);
-        memcpy(d->h_seg, P.seg_begin.data(), nseg * 4), memcpy(d->h_seg + nseg, P.seg_end.data(), nseg * 4);
         cudaMemcpyAsync(d->d_stream, d->h_stream, len, cudaMemcpyHostToDevice, s);
+        memcpy(d->h_seg, P.seg_begin.data(), nseg * 4), memcpy(d->h_seg + nseg, P.seg_end.data(), nseg * 4);
         cudaMemcpyAsync(d->d_seg, d->h_seg, 2 * nseg * 4, cudaMemcpyHostToDevice, s);
         cudaMemcpyAsync(d->d_tables, d->h_tables, sizeof(dec_tables), cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
