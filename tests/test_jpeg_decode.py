@@ -13,7 +13,7 @@ from PIL import Image
 import util
 from test_jpeg import RGB, UYVY, natural_rgb, orc_encode, psnr
 
-RGBA, VUYA = 1, 4
+RGBA, VUYA, I420 = 1, 4, 29
 
 
 def orc_decode(orc, stream, fmt, w, h):
@@ -147,6 +147,15 @@ def test_gpu_decoder_equals_oracle(orc, kind, w, h, q, ri):
     got = dec.decode(s, native)
     assert np.array_equal(got, want), np.flatnonzero(got != want)[:8]
     assert np.array_equal(dec.decode(s, native, device=True).cpu().numpy(), want)
+    if native == UYVY:  # I420 output (GPUJPEG_420_U8_P0P1P2, gpujpeg.c:113-116) = uyvy_to_i420 of the native frame (to_planar.c:343-378)
+        uy = want.reshape(h, -1).astype(np.int32)
+        rows_b = [min(y + 1, h - 1) for y in range(0, h, 2)]
+        cw = (w + 1) // 2
+        u = (uy[0::2, 0::4][:, :cw] + uy[rows_b, 0::4][:, :cw] + 1) // 2
+        v = (uy[0::2, 2::4][:, :cw] + uy[rows_b, 2::4][:, :cw] + 1) // 2
+        i420 = np.concatenate([uy[:, 1::2][:, :w].reshape(-1), u.reshape(-1), v.reshape(-1)]).astype(np.uint8)
+        assert np.array_equal(dec.decode(s, I420), i420)
+        assert np.array_equal(dec.decode(s, I420, device=True).cpu().numpy(), i420)
     # another output codec = UltraGrid's line converter applied to the native frame
     for out_c in (UYVY, RGB, RGBA):
         if out_c == native or not api.pixfmt_supported(native, out_c):

@@ -234,15 +234,18 @@ class JpegDecoder:
         """bytes -> numpy array (host) or CUDA tensor (device=True) holding height rows of vc_get_linesize(width, out_codec) bytes"""
         info = jpeg_image_info(stream)
         ls = pitch or vc_get_linesize(info.width, out_codec)
+        nbytes = ls * info.height
+        if int(out_codec) == int(Codec.I420):  # three tight planes
+            nbytes = info.width * info.height + 2 * ((info.width + 1) // 2) * ((info.height + 1) // 2)
         buf = _bytes_ptr(stream)
         if device:
             if out is None:
-                out = torch.zeros(ls * info.height, dtype=torch.uint8, device="cuda")
+                out = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
             _check(_L.ugb200_jpeg_decode(self._h, buf, len(stream), _ptr(out), 1, ls, int(out_codec), *shifts), "ugb200_jpeg_decode")
             if sync:
                 self._stream.synchronize()
             return out
         import numpy as np
-        out = np.zeros(ls * info.height, dtype=np.uint8)
+        out = np.zeros(nbytes, dtype=np.uint8)
         _check(_L.ugb200_jpeg_decode(self._h, buf, len(stream), ctypes.c_void_p(out.ctypes.data), 0, ls, int(out_codec), *shifts), "ugb200_jpeg_decode")
         return out

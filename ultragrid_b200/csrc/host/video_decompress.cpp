@@ -119,8 +119,8 @@ static void *gpujpeg_decompress_init(void)
 static int gpujpeg_decompress_reconfigure(void *state, struct video_desc desc, int rshift, int gshift, int bshift, int pitch, codec_t out_codec)
 {
         auto *s = (state_decompress_gpujpeg *) state;
-        if (out_codec != RGB && out_codec != RGBA && out_codec != UYVY && out_codec != VIDEO_CODEC_NONE) {
-                return 0;  // the reference asserts this set (+ I420), gpujpeg.c:181-182
+        if (out_codec != RGB && out_codec != RGBA && out_codec != UYVY && out_codec != I420 && out_codec != VIDEO_CODEC_NONE) {
+                return 0;  // the reference asserts this set, gpujpeg.c:181-182
         }
         s->desc = desc, s->rshift = rshift, s->gshift = gshift, s->bshift = bshift, s->pitch = pitch, s->out_codec = out_codec;
         if (!s->decoder) {
@@ -167,7 +167,7 @@ static int gpujpeg_decompress_get_priority(codec_t compression, struct pixfmt_de
         if (ugc == VIDEO_CODEC_NONE) {
                 return VDEC_PRIO_PROBE_HI;
         }
-        return ugc == RGB || ugc == RGBA || ugc == UYVY ? VDEC_PRIO_PREFERRED : VDEC_PRIO_NA;  // I420 output: not yet
+        return ugc == I420 || ugc == RGB || ugc == RGBA || ugc == UYVY ? VDEC_PRIO_PREFERRED : VDEC_PRIO_NA;
 }
 static const struct video_decompress_info gpujpeg_dec_info = { gpujpeg_decompress_init, gpujpeg_decompress_reconfigure, gpujpeg_decompress, no_corrupted_frames,
                                                                gpujpeg_decompress_done, gpujpeg_decompress_get_priority };

@@ -600,7 +600,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         if (!d || !stream || !dst || len > 0xFFFFFFF0u) {
                 return -1;
         }
-        if (out_codec != UGB_UYVY && out_codec != UGB_RGB && out_codec != UGB_RGBA && out_codec != UGB_VUYA) {
+        if (out_codec != UGB_UYVY && out_codec != UGB_RGB && out_codec != UGB_RGBA && out_codec != UGB_VUYA && out_codec != UGB_I420) {
                 return -4;
         }
         cudaStreamSynchronize(d->stream);  // the pinned staging buffers of the previous frame are free again
@@ -653,11 +653,6 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         cudaMemcpyAsync(d->d_seg, d->h_seg, 2 * nseg * 4, cudaMemcpyHostToDevice, s);
         cudaMemcpyAsync(d->d_tables, d->h_tables, sizeof(dec_tables), cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
-        static bool attr = false;
-        if (!attr) {
-                cudaFuncSetAttribute(jpeg_decode_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(dec_tables));
-                attr = true;
-        }
         jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d->d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef);
         jpeg_idct_kernel<<<(g.nblocks + 127) / 128, 128, 0, s>>>(d->coef, d->d_tables, g, d->planes);
         if (cudaGetLastError() != cudaSuccess) {
@@ -686,6 +681,37 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         }
         if (direct) {
                 return 0;
+        }
+        if (out_codec == UGB_I420) {  // GPUJPEG_420_U8_P0P1P2 (gpujpeg.c:113-116): Y, then Cb, then Cr plane, tightly packed
+                const size_t cw = (size_t) (g.w + 1) / 2, chh = (size_t) (g.h + 1) / 2, total = (size_t) g.w * g.h + 2 * cw * chh;
+                uint8_t *uy = nat;
+                long uy_pitch = npitch;
+                if (native != UGB_UYVY) {
+                        if (!ugb200_pixfmt_supported(native, UGB_UYVY) || !dgrow(d->staging, d->staging_cap, (size_t) ((g.w + 1) / 2) * 4 * g.h + total + 64)) {
+                                return -4;
+                        }
+                        uy = d->staging, uy_pitch = (long) ((g.w + 1) / 2) * 4;
+                        rc = ugb200_pixfmt_convert(native, UGB_UYVY, uy, uy_pitch, nat, npitch, (int) uy_pitch, g.h, (long) npitch * g.h, 0, 8, 16, s);
+                        if (rc != 0) {
+                                return rc;
+                        }
+                } else if (!dgrow(d->staging, d->staging_cap, total + 64)) {
+                        return -2;
+                }
+                uint8_t *planes_out = dst_is_device ? (uint8_t *) dst : d->staging + (native != UGB_UYVY ? (size_t) uy_pitch * g.h : 0);
+                struct ugb200_to_planar_data tp;
+                memset(&tp, 0, sizeof tp);
+                tp.width = g.w, tp.height = g.h, tp.in_data = uy;
+                tp.out_data[0] = planes_out, tp.out_data[1] = planes_out + (size_t) g.w * g.h, tp.out_data[2] = tp.out_data[1] + cw * chh;
+                tp.out_linesize[0] = (unsigned) g.w, tp.out_linesize[1] = tp.out_linesize[2] = (unsigned) cw;
+                if (uy_pitch != (long) ((g.w + 1) / 2) * 4) {
+                        return -4;
+                }
+                rc = ugb200_uyvy_to_i420(&tp, s);
+                if (rc != 0 || dst_is_device) {
+                        return rc;
+                }
+                return cudaMemcpyAsync(dst, planes_out, total, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess ? 0 : -2;
         }
         // native -> requested codec (UltraGrid's own line converters), then to the caller
         uint8_t *result = nat;

@@ -931,6 +931,7 @@ struct ugb200_jpeg_encoder {
         bool last_vec_ok = false, last_fused = false;
         cudaEvent_t stats_ev = nullptr;  // recorded behind the copy of h_total: lets an asynchronous caller adapt the cap too
         bool stats_pending = false;
+        bool attr_set[2] = { false, false };  // cudaFuncSetAttribute done for the fused kernels on this encoder's device
 };
 
 namespace {
@@ -1193,22 +1194,20 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                 if (fmt == FMT_UYVY_422) {
                         ctas_per_scan = (g.mcu_per_scan + 31) / 32;
                         nctas = ctas_per_scan;
-                        static bool attr_set = false;
-                        if (!attr_set) {
+                        if (!e->attr_set[0]) {  // per encoder = per device context: the attribute does not carry over to another GPU
                                 cudaFuncSetAttribute(jpeg_fused_kernel<FMT_UYVY_422>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t)));
-                                attr_set = true;
+                                e->attr_set[0] = true;
                         }
                         jpeg_fused_kernel<FMT_UYVY_422><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
                                                                                        e->cta_total, vec_ok, cap, e->total + 1);
                 } else {
                         ctas_per_scan = (g.mcu_per_scan + 127) / 128;
                         nctas = ctas_per_scan * 3;
-                        static bool attr_set = false;
-                        if (!attr_set) {
+                        if (!e->attr_set[1]) {
                                 cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t)));
-                                attr_set = true;
+                                e->attr_set[1] = true;
                         }
                         jpeg_fused_kernel<FMT_RGB_444><<<dim3(ctas_per_scan, 3), 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes,
                                                                                                        e->offsets, e->cta_total, vec_ok, cap, e->total + 1);
