@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -q -x --timeout 150 -k "dxt_decode or vdecompress" > gpurun_out/pytest_quick.log 2>&1; tail -3 gpurun_out/pytest_quick.log
+timeout 300 python -m pytest tests -m gpu -q -x --timeout 150 -k "jpeg_decode or vdecompress" > gpurun_out/pytest_quick.log 2>&1; tail -3 gpurun_out/pytest_quick.log
 timeout 200 python tools/profile_target.py jpegdec 2>&1 | tail -6
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_dec.csv python tools/profile_target.py jpegdec > gpurun_out/dec_prof.log 2>&1
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 20 --csv --log-file gpurun_out/launches_dxtdec.csv python tools/profile_target.py dxtdec > gpurun_out/dxtdec_prof.log 2>&1

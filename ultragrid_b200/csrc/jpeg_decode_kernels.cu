@@ -244,6 +244,85 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(const int16_t *__restric
         }
 }
 
+/// 4:2:2 streams: IDCT and UYVY packing in one kernel.  CTA = 32 MCUs x (Y0, Y1, Cb, Cr), warp k = block kind k (component-uniform
+/// dequantisation), lane = MCU.  The 8 x 8 samples of each block go to a shared tile as 8-byte rows; then the 8 KB tile leaves as 512
+/// 16-byte UYVY pieces, consecutive pieces consecutive in memory.  Same arithmetic as jpeg_idct_kernel.
+__global__ void __launch_bounds__(128) jpeg_idct_uyvy_kernel(const int16_t *__restrict__ coef, const dec_tables *__restrict__ tables, dec_geom g,
+                                                             uint8_t *__restrict__ out, long pitch, bool vec_ok)
+{
+        __shared__ float s_m[4][64];
+        __shared__ uint2 s_tile[4][8][32];
+        const int tid = threadIdx.x;
+        for (int i = tid; i < 256; i += blockDim.x) {
+                s_m[i >> 6][i & 63] = tables->m[i >> 6][i & 63];
+        }
+        __syncthreads();
+        const int mcux = g.c[1].bw, nmcu = mcux * g.c[1].bh;
+        const int k = tid >> 5, lane = tid & 31, m0 = blockIdx.x * 32, m = m0 + lane;
+        if (m < nmcu) {
+                const int mx = m % mcux, my = m / mcux;
+                const dec_comp &c = g.c[k < 2 ? 0 : k - 1];
+                const int X = k < 2 ? 2 * mx + k : mx;
+                const long b = (long) c.blk_off + (long) my * c.bw + X;
+                const float *mq = s_m[c.tq];
+                float f[64];
+                const uint4 *src = (const uint4 *) (coef + b * 64);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                        const uint4 v = __ldg(src + q);
+                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                                const int lo = (int) (short) (w[j] & 0xffffu), hi = (int) w[j] >> 16;
+                                f[8 * q + 2 * j] = __fmul_rn(__fadd_rn(__uint_as_float(0x4B400000u + (uint32_t) lo), -12582912.0f), mq[8 * q + 2 * j]);
+                                f[8 * q + 2 * j + 1] = __fmul_rn(__fadd_rn(__uint_as_float(0x4B400000u + (uint32_t) hi), -12582912.0f), mq[8 * q + 2 * j + 1]);
+                        }
+                }
+#pragma unroll
+                for (int col = 0; col < 8; ++col) {
+                        idct8(f[col], f[8 + col], f[16 + col], f[24 + col], f[32 + col], f[40 + col], f[48 + col], f[56 + col]);
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                        idct8(f[8 * r], f[8 * r + 1], f[8 * r + 2], f[8 * r + 3], f[8 * r + 4], f[8 * r + 5], f[8 * r + 6], f[8 * r + 7]);
+                        uint32_t o[8];
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) {
+                                const int v = (int) __float_as_uint(__fadd_rn(__fadd_rn(f[8 * r + x], 128.0f), 12582912.0f)) - 0x4B400000;
+                                o[x] = (uint32_t) min(max(v, 0), 255);
+                        }
+                        s_tile[k][r][lane] = make_uint2(o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24, o[4] | o[5] << 8 | o[6] << 16 | o[7] << 24);
+                }
+        }
+        __syncthreads();
+        const int row_bytes = ((g.w + 1) / 2) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+                const int cidx = tid + 128 * i, row = cidx >> 6, within = cidx & 63, mcu = within >> 1, half = within & 1;
+                const int mm = m0 + mcu;
+                if (mm >= nmcu) {
+                        continue;
+                }
+                const int mx = mm % mcux, y = (mm / mcux) * 8 + row, xoff = mx * 32 + half * 16;
+                if (y >= g.h || xoff >= row_bytes) {
+                        continue;
+                }
+                const uint2 Y = s_tile[half][row][mcu], CB = s_tile[2][row][mcu], CR = s_tile[3][row][mcu];
+                const uint32_t C = half ? CB.y : CB.x, R = half ? CR.y : CR.x;
+                const uint32_t w0 = __byte_perm(__byte_perm(C, R, 0x0040), Y.x, 0x5140), w1 = __byte_perm(__byte_perm(C, R, 0x0051), Y.x, 0x7160);
+                const uint32_t w2 = __byte_perm(__byte_perm(C, R, 0x0062), Y.y, 0x5140), w3 = __byte_perm(__byte_perm(C, R, 0x0073), Y.y, 0x7160);
+                uint8_t *d = out + (long) y * pitch + xoff;
+                if (vec_ok && xoff + 16 <= row_bytes) {
+                        *(uint4 *) d = make_uint4(w0, w1, w2, w3);
+                } else {
+                        const uint32_t w[4] = { w0, w1, w2, w3 };
+                        for (int bq = 0; bq < 16 && xoff + bq < row_bytes; ++bq) {
+                                d[bq] = (uint8_t) (w[bq >> 2] >> (8 * (bq & 3)));
+                        }
+                }
+        }
+}
+
 }  // namespace ugb
 
 using namespace ugb;
@@ -255,10 +334,17 @@ struct ugb200_jpeg_decoder {
         uint32_t *d_seg = nullptr;
         dec_tables *d_tables = nullptr;
         size_t stream_cap = 0, planes_cap = 0, native_cap = 0, staging_cap = 0, coef_cap = 0, seg_cap = 0;
-        uint8_t *h_stream = nullptr;  // pinned copy: the caller's buffer is pageable and freed right after the call
-        uint32_t *h_seg = nullptr;
-        dec_tables *h_tables = nullptr;
-        size_t h_stream_cap = 0, h_seg_cap = 0;
+        // pinned staging (the caller's stream buffer is pageable and freed right after the call), two slots: the host side of frame
+        // i + 1 (scan, parse, staging copy) runs while the device still works on frame i
+        struct host_slot {
+                uint8_t *stream = nullptr;
+                uint32_t *seg = nullptr;
+                dec_tables *tables = nullptr;
+                size_t stream_cap = 0, seg_cap = 0;
+                cudaEvent_t uploaded = nullptr;
+                bool pending = false;
+        } hs[2];
+        unsigned frame_no = 0;
 };
 
 namespace {
@@ -576,7 +662,10 @@ UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t st
                 return nullptr;
         }
         d->stream = (cudaStream_t) stream;
-        if (cudaMalloc((void **) &d->d_tables, sizeof(dec_tables)) != cudaSuccess || cudaMallocHost((void **) &d->h_tables, sizeof(dec_tables)) != cudaSuccess) {
+        if (cudaMalloc((void **) &d->d_tables, sizeof(dec_tables)) != cudaSuccess || cudaMallocHost((void **) &d->hs[0].tables, sizeof(dec_tables)) != cudaSuccess ||
+            cudaMallocHost((void **) &d->hs[1].tables, sizeof(dec_tables)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d->hs[0].uploaded, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d->hs[1].uploaded, cudaEventDisableTiming) != cudaSuccess) {
                 ugb200_jpeg_decoder_destroy(d);
                 return nullptr;
         }
@@ -590,7 +679,12 @@ UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *d)
         }
         cudaStreamSynchronize(d->stream);
         cudaFree(d->d_stream), cudaFree(d->planes), cudaFree(d->native), cudaFree(d->staging), cudaFree(d->coef), cudaFree(d->d_seg), cudaFree(d->d_tables);
-        cudaFreeHost(d->h_stream), cudaFreeHost(d->h_seg), cudaFreeHost(d->h_tables);
+        for (auto &h : d->hs) {
+                cudaFreeHost(h.stream), cudaFreeHost(h.seg), cudaFreeHost(h.tables);
+                if (h.uploaded) {
+                        cudaEventDestroy(h.uploaded);
+                }
+        }
         delete d;
 }
 
@@ -603,11 +697,15 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         if (out_codec != UGB_UYVY && out_codec != UGB_RGB && out_codec != UGB_RGBA && out_codec != UGB_VUYA && out_codec != UGB_I420) {
                 return -4;
         }
-        cudaStreamSynchronize(d->stream);  // the pinned staging buffers of the previous frame are free again
+        ugb200_jpeg_decoder::host_slot &H = d->hs[d->frame_no++ & 1];
+        if (H.pending) {
+                cudaEventSynchronize(H.uploaded);  // the uploads of the frame before last left this slot long ago
+                H.pending = false;
+        }
         parsed P;
-        memset(d->h_tables, 0, sizeof(dec_tables));
-        memcpy(d->h_tables->zz, kZigzag, 64);
-        if (!hgrow(d->h_stream, d->h_stream_cap, len)) {
+        memset(H.tables, 0, sizeof(dec_tables));
+        memcpy(H.tables->zz, kZigzag, 64);
+        if (!hgrow(H.stream, H.stream_cap, len)) {
                 return -2;
         }
         // one pass over the caller's (pageable) buffer: copy it to the pinned staging buffer and collect the marker candidates, split over a
@@ -620,9 +718,9 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 const size_t chunk = (len / nt + 15) & ~(size_t) 15;
                 for (int i = 1; i < nt; ++i) {
                         const size_t lo = std::min(len, chunk * i), hi = i == nt - 1 ? len : std::min(len, chunk * (i + 1));
-                        th[i] = std::thread(scan_markers, stream, lo, hi, len, std::ref(part[i]), d->h_stream);
+                        th[i] = std::thread(scan_markers, stream, lo, hi, len, std::ref(part[i]), H.stream);
                 }
-                scan_markers(stream, 0, nt == 1 ? len : std::min(len, chunk), len, part[0], d->h_stream);
+                scan_markers(stream, 0, nt == 1 ? len : std::min(len, chunk), len, part[0], H.stream);
                 for (int i = 1; i < nt; ++i) {
                         th[i].join();
                 }
@@ -630,7 +728,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                         markers.insert(markers.end(), part[i].begin(), part[i].end());
                 }
         }
-        int rc = parse_stream(stream, len, P, d->h_tables, true, &markers);
+        int rc = parse_stream(stream, len, P, H.tables, true, &markers);
         if (rc != 0) {
                 return rc;
         }
@@ -644,23 +742,31 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 dst_pitch = opitch;
         }
         if (!dgrow(d->d_stream, d->stream_cap, len + 16) || !dgrow(d->planes, d->planes_cap, (size_t) plane_bytes) || !dgrow(d->coef, d->coef_cap, (size_t) g.nblocks * 64) ||
-            !dgrow(d->d_seg, d->seg_cap, 2 * nseg) || !dgrow(d->native, d->native_cap, (size_t) npitch * g.h + 64) || !hgrow(d->h_seg, d->h_seg_cap, 2 * nseg)) {
+            !dgrow(d->d_seg, d->seg_cap, 2 * nseg) || !dgrow(d->native, d->native_cap, (size_t) npitch * g.h + 64) || !hgrow(H.seg, H.seg_cap, 2 * nseg)) {
                 return -2;
         }
         cudaStream_t s = d->stream;
-        cudaMemcpyAsync(d->d_stream, d->h_stream, len, cudaMemcpyHostToDevice, s);
-        memcpy(d->h_seg, P.seg_begin.data(), nseg * 4), memcpy(d->h_seg + nseg, P.seg_end.data(), nseg * 4);
-        cudaMemcpyAsync(d->d_seg, d->h_seg, 2 * nseg * 4, cudaMemcpyHostToDevice, s);
-        cudaMemcpyAsync(d->d_tables, d->h_tables, sizeof(dec_tables), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d->d_stream, H.stream, len, cudaMemcpyHostToDevice, s);
+        memcpy(H.seg, P.seg_begin.data(), nseg * 4), memcpy(H.seg + nseg, P.seg_end.data(), nseg * 4);
+        cudaMemcpyAsync(d->d_seg, H.seg, 2 * nseg * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d->d_tables, H.tables, sizeof(dec_tables), cudaMemcpyHostToDevice, s);
+        cudaEventRecord(H.uploaded, s);
+        H.pending = true;
         cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
         jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d->d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef);
-        jpeg_idct_kernel<<<(g.nblocks + 127) / 128, 128, 0, s>>>(d->coef, d->d_tables, g, d->planes);
+        const bool direct = native == out_codec && dst_is_device;
+        uint8_t *nat = direct ? (uint8_t *) dst : d->native;
+        const bool fused_uyvy = native == UGB_UYVY && g.c[0].v == 1;  // 4:2:2: IDCT and packing in one kernel, no component planes
+        if (fused_uyvy) {
+                const long np = direct ? dst_pitch : npitch;
+                jpeg_idct_uyvy_kernel<<<(g.c[1].bw * g.c[1].bh + 31) / 32, 128, 0, s>>>(d->coef, d->d_tables, g, nat, np, !(15 & (size_t) nat) && !(np & 15));
+        } else {
+                jpeg_idct_kernel<<<(g.nblocks + 127) / 128, 128, 0, s>>>(d->coef, d->d_tables, g, d->planes);
+        }
         if (cudaGetLastError() != cudaSuccess) {
                 return -2;
         }
         // component planes -> the stream's native packed format
-        const bool direct = native == out_codec && dst_is_device;
-        uint8_t *nat = direct ? (uint8_t *) dst : d->native;
         struct ugb200_from_planar_data fp;
         memset(&fp, 0, sizeof fp);
         fp.width = native == UGB_UYVY ? (g.w + 1) & ~1 : g.w;  // the padded planes hold the second luma of an odd last pixel pair
@@ -669,7 +775,9 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 fp.in_data[i] = d->planes + g.c[i].plane_off, fp.in_linesize[i] = (unsigned) (g.c[i].bw * 8);
         }
         fp.in_depth = 8;
-        if (native == UGB_UYVY) {
+        if (fused_uyvy) {
+                rc = 0;
+        } else if (native == UGB_UYVY) {
                 rc = g.c[0].v == 2 ? ugb200_yuv420p_to_uyvy(&fp, s) : ugb200_yuv422p_to_uyvy(&fp, s);
         } else if (native == UGB_RGB) {
                 rc = ugb200_rgbpXX_to_rgb(&fp, s);
