@@ -148,6 +148,26 @@ def test_gpu_noise_takes_serial_route_then_adapts(orc, codec, q):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("codec,w,h,pad", [(UYVY, 100, 52, 24), (UYVY, 1920, 64, 64), (RGB, 77, 33, 5), (UYVY, 98, 50, 4)])
+def test_gpu_encoder_honours_the_source_pitch(orc, codec, w, h, pad):
+    """rows further apart than one line (device and host input): the same stream as from the tight frame"""
+    import torch
+    from ultragrid_b200 import api
+    bpp = 2 if codec == UYVY else 3
+    tight = util.rng_bytes(w * bpp * h, 21) if codec == RGB else util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h, 9).reshape(-1), w, h)
+    row = len(tight) // h
+    pitch = row + pad
+    padded = np.full(pitch * h, 0xEE, np.uint8)
+    padded.reshape(h, pitch)[:, :row] = tight.reshape(h, row)
+    want = orc_encode(orc, tight, w, h, codec, 85)
+    assert orc_encode(orc, padded, w, h, codec, 85, pitch=pitch) == want
+    enc = api.JpegEncoder()
+    assert enc.encode(padded, w, h, codec, quality=85, pitch=pitch) == want
+    assert enc.encode(torch.from_numpy(padded).cuda(), w, h, codec, quality=85, pitch=pitch) == want
+    enc.close()
+
+
+@pytest.mark.gpu
 def test_gpu_stream_larger_than_output_buffer_is_an_error(orc):
     """RGB noise at quality 100 codes to more than w * h * 3 bytes (the capacity the reference hands libgpujpeg, gpujpeg.cpp:355)"""
     import torch
