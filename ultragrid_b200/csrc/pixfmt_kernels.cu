@@ -126,24 +126,25 @@ struct conv_yuv422_rgb {
 struct conv_uyvy_rgba {
         static constexpr int IN = 16, OUT = 32;
         static __host__ int out_len(int dst_len) { return dst_len < 8 ? 0 : dst_len / 8 * 8; }
-        static __device__ __forceinline__ uint32_t px(int y, int u, int v, const conv_params &p, uint32_t amask)
-        {
-                const double yy = __dmul_rn(1.164, (double) (y - 16));
-                const double dv = (double) (v - 128), du = (double) (u - 128);
-                const int r = clamp255((int) __dadd_rn(yy, __dmul_rn(1.793, dv)));
-                const int g = clamp255((int) __dadd_rn(__dadd_rn(yy, -__dmul_rn(0.534, dv)), -__dmul_rn(0.213, du)));
-                const int b = clamp255((int) __dadd_rn(yy, __dmul_rn(2.115, du)));
-                return amask | (uint32_t) r << p.rshift | (uint32_t) g << p.gshift | (uint32_t) b << p.bshift;
-        }
+        // The conversions are the slow FP64 instructions on this part (I2F / F2I: 16 lanes/clk/SM against 63 for DADD/DMUL), so both go
+        // through the 2^52 magic: 2^52 + byte is exact, and x + 1.5 * 2^52 rounded toward zero leaves floor(x) in the low word - equal to
+        // the reference's truncation for x >= 0, and below zero both end at 0 after the clamp.
+        static __device__ __forceinline__ double byte_minus(uint32_t b, double bias) { return __dadd_rn(__hiloint2double(0x43300000, (int) b), bias); }
+        static __device__ __forceinline__ uint32_t trunc_clamp(double x) { return (uint32_t) clamp255(__double2loint(__dadd_rz(x, 6755399441055744.0))); }
         static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
         {
                 const uint32_t amask = 0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                         const uint32_t w = in[i];
-                        const int u = w & 0xff, y1 = (w >> 8) & 0xff, v = (w >> 16) & 0xff, y2 = w >> 24;
-                        out[2 * i] = px(y1, u, v, p, amask);
-                        out[2 * i + 1] = px(y2, u, v, p, amask);
+                        const double du = byte_minus(w & 0xff, -4503599627370624.0), dv = byte_minus((w >> 16) & 0xff, -4503599627370624.0);  // - (2^52 + 128)
+                        const double rv = __dmul_rn(1.793, dv), gv = __dmul_rn(0.534, dv), gu = __dmul_rn(0.213, du), bu = __dmul_rn(2.115, du);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                                const double yy = __dmul_rn(1.164, byte_minus((w >> (8 + 16 * k)) & 0xff, -4503599627370512.0));  // - (2^52 + 16)
+                                const uint32_t r = trunc_clamp(__dadd_rn(yy, rv)), g = trunc_clamp(__dadd_rn(__dadd_rn(yy, -gv), -gu)), b = trunc_clamp(__dadd_rn(yy, bu));
+                                out[2 * i + k] = amask | r << p.rshift | g << p.gshift | b << p.bshift;
+                        }
                 }
         }
 };
@@ -358,33 +359,54 @@ struct conv_v210_y416 {
 
 /// vc_copylineV210toRGB, pixfmt_conv.c:2884-2940: top 8 bits of each sample, depth-8 coefficients, CLAMP_FULL (1..254);
 /// the loop runs while x < dst_len in steps of 18 bytes, i.e. it may write past dst_len up to the end of the last group
-struct conv_v210_rgb {
+struct conv_v210_rgb {  // fp32 like conv_yuv422_rgb: the sums stay below 2^24 (8-bit samples, depth-8 coefficients), >> 14 = round-down FMA
         static constexpr int IN = 128, OUT = 144;
         static __host__ int out_len(int dst_len) { return (dst_len + 17) / 18 * 18; }
-        static __device__ __forceinline__ int cf(int v) { return min(max(v, 1), 254); }  // CLAMP_FULL, color_space.h:96-98
+        static __device__ __forceinline__ float magic8(uint32_t w, int sh) { return __uint_as_float(((w >> (sh + 2)) & 0xffu) | 0x4B000000u); }  // top 8 of 10 bits
+        static __device__ __forceinline__ uint32_t floor_clamp2(float2 x)  // {CLAMP_FULL(x.x >> 14), CLAMP_FULL(x.y >> 14)}: 1..254 (color_space.h:96-98)
+        {
+                const float2 f = __ffma2_rd(x, make_float2(0x1p-14f, 0x1p-14f), make_float2(12582912.0f, 12582912.0f));
+                return __vmaxs2(__vmins2(__byte_perm(__float_as_uint(f.x), __float_as_uint(f.y), 0x5410), 0x00FE00FEu), 0x00010001u);
+        }
         static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &, const row_ctx &)
         {
                 constexpr color_coeffs c = coeffs_709(8);
-                uint32_t o[144];
+                const float2 ys = make_float2((float) c.y_scale, (float) c.y_scale), ybias = make_float2(-8388624.0f, -8388624.0f),
+                             cbias = make_float2(-8388736.0f, -8388736.0f);
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                        const uint32_t w0 = in[4 * g], w1 = in[4 * g + 1], w2 = in[4 * g + 2], w3 = in[4 * g + 3];
-#define UGB_S8(w, sh) ((int) (((w) >> ((sh) + 2)) & 0xffu))
-                        const int y[6] = { UGB_S8(w0, 10), UGB_S8(w1, 0), UGB_S8(w1, 20), UGB_S8(w2, 10), UGB_S8(w3, 0), UGB_S8(w3, 20) };
-                        const int u[3] = { UGB_S8(w0, 0) - 128, UGB_S8(w1, 10) - 128, UGB_S8(w2, 20) - 128 };
-                        const int v[3] = { UGB_S8(w0, 20) - 128, UGB_S8(w2, 0) - 128, UGB_S8(w3, 10) - 128 };
-#undef UGB_S8
+                for (int gp = 0; gp < 4; ++gp) {  // lanes of every float2 = the same sample of groups 2 gp and 2 gp + 1 (2 x 6 pixels)
+                        const uint32_t *a = in + 8 * gp, *b = a + 4;
+                        // sample positions inside a v210 group: word, bit shift (pixfmt_conv.c:2907-2925)
+                        constexpr int yw[6] = { 0, 1, 1, 2, 3, 3 }, ysh[6] = { 10, 0, 20, 10, 0, 20 };
+                        constexpr int uw[3] = { 0, 1, 2 }, ush[3] = { 0, 10, 20 }, vw[3] = { 0, 2, 3 }, vsh[3] = { 20, 0, 10 };
+                        float2 rc[3], gc[3], bc[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                                const float2 u = __fadd2_rn(make_float2(magic8(a[uw[k]], ush[k]), magic8(b[uw[k]], ush[k])), cbias);
+                                const float2 v = __fadd2_rn(make_float2(magic8(a[vw[k]], vsh[k]), magic8(b[vw[k]], vsh[k])), cbias);
+                                rc[k] = __fmul2_rn(v, make_float2((float) c.r_cr, (float) c.r_cr));
+                                gc[k] = __ffma2_rn(u, make_float2((float) c.g_cb, (float) c.g_cb), __fmul2_rn(v, make_float2((float) c.g_cr, (float) c.g_cr)));
+                                bc[k] = __fmul2_rn(u, make_float2((float) c.b_cb, (float) c.b_cb));
+                        }
+                        uint32_t val[18];  // R G B of the six pixels; low half-word = group 2 gp, high = group 2 gp + 1
 #pragma unroll
                         for (int i = 0; i < 6; ++i) {
-                                const int ys = c.y_scale * (y[i] - 16), uu = u[i / 2], vv = v[i / 2];
-                                o[18 * g + 3 * i + 0] = cf((ys + vv * c.r_cr) >> COMP_BASE);
-                                o[18 * g + 3 * i + 1] = cf((ys + uu * c.g_cb + vv * c.g_cr) >> COMP_BASE);
-                                o[18 * g + 3 * i + 2] = cf((ys + uu * c.b_cb) >> COMP_BASE);
+                                const float2 y = __fadd2_rn(make_float2(magic8(a[yw[i]], ysh[i]), magic8(b[yw[i]], ysh[i])), ybias);
+                                val[3 * i] = floor_clamp2(__ffma2_rn(y, ys, rc[i / 2]));
+                                val[3 * i + 1] = floor_clamp2(__ffma2_rn(y, ys, gc[i / 2]));
+                                val[3 * i + 2] = floor_clamp2(__ffma2_rn(y, ys, bc[i / 2]));
                         }
-                }
 #pragma unroll
-                for (int i = 0; i < 36; ++i) {
-                        out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                        for (int j = 0; j < 9; ++j) {  // byte n of the 36 output bytes: n < 18 -> val[n] byte 0, else val[n - 18] byte 2
+                                uint32_t t[2];
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                        const int n0 = 4 * j + 2 * h, n1 = n0 + 1;
+                                        const uint32_t A = val[n0 < 18 ? n0 : n0 - 18], B = val[n1 < 18 ? n1 : n1 - 18];
+                                        t[h] = __byte_perm(A, B, (n0 < 18 ? 0u : 2u) | (n1 < 18 ? 4u : 6u) << 4);
+                                }
+                                out[9 * gp + j] = __byte_perm(t[0], t[1], 0x5410);
+                        }
                 }
         }
 };
