@@ -41,6 +41,13 @@ elif which == "jpeg":
     for i in range(3):
         enc.encode_device(src, W, H, 2, quality=90)
     print("jpeg bytes", len(enc.result()))
+elif which == "conv":
+    inc, outc = int(sys.argv[2]), int(sys.argv[3])
+    ls_i, ls_o = vc_get_linesize(W, inc), vc_get_linesize(W, outc)
+    src = [torch.randint(0, 256, (ls_i * H + 4096,), dtype=torch.uint8, device=dev) for _ in range(3)]
+    dst = torch.empty(ls_o * H + 4096, dtype=torch.uint8, device=dev)
+    for i in range(4):
+        api.pixfmt_convert(inc, outc, src[i % 3], W, H, dst=dst)
 elif which in ("jpegdec", "dxtdec"):
     import time
     import numpy as np

@@ -130,10 +130,17 @@ struct conv_uyvy_rgba {
         // through the 2^52 magic: 2^52 + byte is exact, and x + 1.5 * 2^52 rounded toward zero leaves floor(x) in the low word - equal to
         // the reference's truncation for x >= 0, and below zero both end at 0 after the clamp.
         static __device__ __forceinline__ double byte_minus(uint32_t b, double bias) { return __dadd_rn(__hiloint2double(0x43300000, (int) b), bias); }
-        static __device__ __forceinline__ uint32_t trunc_clamp(double x) { return (uint32_t) clamp255(__double2loint(__dadd_rz(x, 6755399441055744.0))); }
+        static __device__ __forceinline__ int trunc_int(double x) { return __double2loint(__dadd_rz(x, 6755399441055744.0)); }
         static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
         {
                 const uint32_t amask = 0xFFFFFFFFu ^ (0xFFu << p.rshift) ^ (0xFFu << p.gshift) ^ (0xFFu << p.bshift);
+                // byte-aligned shifts (every caller in the tree): one permute places the three clamped components, selector built once per thread
+                const bool aligned = !((p.rshift | p.gshift | p.bshift) & 7);
+                uint32_t sel = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                        sel |= (8 * j == p.rshift ? 0u : 8 * j == p.gshift ? 2u : 8 * j == p.bshift ? 4u : 5u) << (4 * j);
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                         const uint32_t w = in[i];
@@ -142,8 +149,11 @@ struct conv_uyvy_rgba {
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
                                 const double yy = __dmul_rn(1.164, byte_minus((w >> (8 + 16 * k)) & 0xff, -4503599627370512.0));  // - (2^52 + 16)
-                                const uint32_t r = trunc_clamp(__dadd_rn(yy, rv)), g = trunc_clamp(__dadd_rn(__dadd_rn(yy, -gv), -gu)), b = trunc_clamp(__dadd_rn(yy, bu));
-                                out[2 * i + k] = amask | r << p.rshift | g << p.gshift | b << p.bshift;
+                                const int r = trunc_int(__dadd_rn(yy, rv)), g = trunc_int(__dadd_rn(__dadd_rn(yy, -gv), -gu)), b = trunc_int(__dadd_rn(yy, bu));
+                                // clamp 0..255 two at a time (the values fit 16 bits): VIMNMX.S16x2.RELU
+                                const uint32_t rg = __vimin_s16x2_relu(__byte_perm((uint32_t) r, (uint32_t) g, 0x5410), 0x00ff00ffu);
+                                const uint32_t bb = __vimin_s16x2_relu((uint32_t) b & 0xffffu, 0x00ff00ffu);
+                                out[2 * i + k] = aligned ? amask | __byte_perm(rg, bb, sel) : amask | (rg & 0xff) << p.rshift | (rg >> 16) << p.gshift | bb << p.bshift;
                         }
                 }
         }
