@@ -53,6 +53,17 @@ UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *dst, long d
                           int dst_len, int height, long src_size, int rshift, int gshift, int bshift,
                           cuda_wrapper_stream_t stream);
 
+/* The line converters pixfmt_conv.h exports OUTSIDE the decoders[] table (pixfmt_conv.h:93-101; callers: screen capture, DeckLink): same
+ * whole-buffer form and return codes as ugb200_pixfmt_convert.  rshift/gshift/bshift are used by UGB_LINE_TO_RGBA_INPLACE only (SOURCE shifts). */
+enum ugb200_line_func {
+        UGB_LINE_ABGR_TO_RGB = 1,      /* vc_copylineABGRtoRGB, pixfmt_conv.c:809-843 */
+        UGB_LINE_BGRA_TO_RGB,          /* vc_copylineBGRAtoRGB, :845-860 */
+        UGB_LINE_TO_RGBA_INPLACE,      /* vc_copylineToRGBA_inplace, :907-921 (dst may equal src) */
+        UGB_LINE_UYVY_TO_GRAYSCALE,    /* vc_copylineUYVYtoGrayscale, :927-938 */
+};
+UGB_API int ugb200_vc_copyline(int func, void *dst, long dst_pitch, const void *src, long src_pitch, int dst_len, int height, long src_size,
+                               int rshift, int gshift, int bshift, cuda_wrapper_stream_t stream);
+
 /* ---- block decoders --------------------------------------------------- */
 /* DXT5-YCoCg -> RGB exactly as the reference's CPU tool cuda_dxt/dxt62tga.c:24-108 (double arithmetic); DXT1 -> RGB by the same rule
  * for the colour block (+ the 3-colour mode).  src: device blocks in raster block order (what the encoders write), out: device, 3 B/px,

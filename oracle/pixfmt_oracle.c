@@ -995,3 +995,39 @@ API void orc_v210_to_p010le(int width, int height, unsigned char *out_y, unsigne
         }
         free(garbage);
 }
+
+/* ---- line converters exported outside decoders[] (pixfmt_conv.h:93-101) -------------------------------------------------------------------
+ * func: 1 vc_copylineABGRtoRGB (pixfmt_conv.c:809-843, SSSE3 build: the scalar tail never advances src), 2 vc_copylineBGRAtoRGB (:845-860),
+ * 3 vc_copylineToRGBA_inplace (:907-921), 4 vc_copylineUYVYtoGrayscale (:927-938).  Same whole-buffer row loop as orc_convert. */
+static void x32_to_rgb(unsigned char *dst, const unsigned char *src, int dst_len, int rs, int gs, int bs, int quirk)
+{
+        const int tail_px = !quirk ? 0x7fffffff : dst_len >= 24 ? ((dst_len - 24) / 12 + 1) * 4 : 0;
+        for (int x = 0, px = 0; x <= dst_len - 3; x += 3, ++px) {
+                const uint32_t in = rd32(src + 4 * (size_t) (px < tail_px ? px : tail_px));
+                dst[x] = (in >> rs) & 0xff, dst[x + 1] = (in >> gs) & 0xff, dst[x + 2] = (in >> bs) & 0xff;
+        }
+}
+API int orc_copyline_named(int func, unsigned char *dst, long dst_pitch, const unsigned char *src, long src_pitch, int dst_len, int height, int rs, int gs, int bs)
+{
+        for (int y = 0; y < height; ++y) {
+                unsigned char *d = dst + (size_t) y * dst_pitch;
+                const unsigned char *s = src + (size_t) y * src_pitch;
+                switch (func) {
+                case 1: x32_to_rgb(d, s, dst_len, 24, 16, 8, 1); break;
+                case 2: x32_to_rgb(d, s, dst_len, 16, 8, 0, 0); break;
+                case 3:
+                        for (int x = 0; x + 4 <= dst_len; x += 4) {
+                                const uint32_t in = rd32(s + x);
+                                wr32(d + x, ((in >> rs) & 0xff) | ((in >> gs) & 0xff) << 8 | ((in >> bs) & 0xff) << 16);
+                        }
+                        break;
+                case 4:
+                        for (int x = 0; x <= dst_len - 2; x += 2) {
+                                d[x] = s[2 * x + 1], d[x + 1] = s[2 * x + 3];
+                        }
+                        break;
+                default: return -4;
+                }
+        }
+        return 0;
+}

@@ -128,3 +128,16 @@ API int ref_jpeg_get_rtp_hdr_data(unsigned char *image, int len, int *out)
         out[0] = d.width, out[1] = d.height, out[2] = d.type, out[3] = d.q, out[4] = d.restart_interval, out[5] = (int) (d.data - image);
         return 1;
 }
+
+/* the exported line converters that are not in decoders[] (pixfmt_conv.h:93-101), row loop as tools/convert.cpp:148-152 */
+API int ref_copyline_named(int func, unsigned char *dst, long dst_pitch, const unsigned char *src, long src_pitch, int dst_len, int height, int rs, int gs, int bs)
+{
+        decoder_t f = func == 1 ? vc_copylineABGRtoRGB : func == 2 ? vc_copylineBGRAtoRGB : func == 3 ? vc_copylineToRGBA_inplace : func == 4 ? vc_copylineUYVYtoGrayscale : NULL;
+        if (!f) {
+                return -4;
+        }
+        for (int y = 0; y < height; ++y) {
+                f(dst + (size_t) y * dst_pitch, src + (size_t) y * src_pitch, dst_len, rs, gs, bs);
+        }
+        return 0;
+}

@@ -42,6 +42,7 @@ SIGNATURES = {
     "ugb200_uyvy_to_dxt6_async": (_i, [_vp, _vp, _i, _i, _l, _vp]),
     "ugb200_dxt1_to_rgb": (_i, [_vp, _vp, _i, _i, _l, _i, _vp]),
     "ugb200_dxt5ycocg_to_rgb": (_i, [_vp, _vp, _i, _i, _l, _i, _vp]),
+    "ugb200_vc_copyline": (_i, [_i, _vp, _l, _vp, _l, _i, _i, _l, _i, _i, _i, _vp]),
     "ugb200_pixfmt_supported": (_i, [_i, _i]),
     "ugb200_pixfmt_convert": (_i, [_i, _i, _vp, _l, _vp, _l, _i, _i, _l, _i, _i, _i, _vp]),
     "ugb200_v210_to_p010le": (_i, [_vp, _l, _vp]),

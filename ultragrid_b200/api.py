@@ -75,6 +75,17 @@ def pixfmt_convert(in_codec, out_codec, src, width, height, dst=None, dst_len=No
     return dst
 
 
+LINE_FUNCS = {"ABGRtoRGB": 1, "BGRAtoRGB": 2, "ToRGBA_inplace": 3, "UYVYtoGrayscale": 4}
+
+
+def vc_copyline(func, src, dst, dst_len, height, src_pitch, dst_pitch, shifts=(0, 8, 16), stream=None):
+    """the exported line converters outside decoders[] (pixfmt_conv.h:93-101); func = a key of LINE_FUNCS; dst may be src for ToRGBA_inplace"""
+    rc = _L.ugb200_vc_copyline(LINE_FUNCS[func], _ptr(dst), dst_pitch, _ptr(src), src_pitch, dst_len, height, src.numel(), shifts[0], shifts[1], shifts[2],
+                               _stream(stream))
+    _check(rc, f"ugb200_vc_copyline({func})")
+    return dst
+
+
 class ToPlanarData(ctypes.Structure):
     _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("out_data", ctypes.c_void_p * 4),
                 ("out_linesize", ctypes.c_uint * 4), ("in_data", ctypes.c_void_p)]

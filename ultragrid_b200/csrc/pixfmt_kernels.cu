@@ -212,17 +212,20 @@ struct conv_rgb_rgba {
         }
 };
 
-/// vc_copylineRGBAtoRGB, pixfmt_conv.c:866-900 (SSSE3 build, which is what tools/Makefile and oracle/_ref build).
-/// QUIRK reproduced for bit-exactness: the scalar tail loop (:889-895) never advances `src`, so every pixel from
-/// the end of the pshufb loop (x <= dst_len - 24) on repeats the first tail pixel.  p.aux = first tail pixel.
-struct conv_rgba_rgb {
+/// 32-bit pixel -> RGB with source shifts RS/GS/BS:
+///   vc_copylineRGBAtoRGB (pixfmt_conv.c:866-900, shifts 0/8/16) and vc_copylineABGRtoRGB (:809-843, 24/16/8) in the SSSE3 build that is the
+///   contract: QUIRK reproduced for bit-exactness - the scalar tail loop (:889-895, :834-839) never advances `src`, so every pixel from the end
+///   of the pshufb loop (x <= dst_len - 24) on repeats the first tail pixel.  p.aux = first tail pixel.
+///   vc_copylineBGRAtoRGB (:845-860, 16/8/0) goes through the plain C loop vc_copylineRGBAtoRGBwithShift (:769-801): no quirk.
+template <int RS, int GS, int BS, bool QUIRK>
+struct conv_x32_rgb {
         static constexpr int IN = 64, OUT = 48;
         static __host__ int out_len(int dst_len) { return dst_len < 3 ? 0 : dst_len / 3 * 3; }
-        static __host__ int aux(int dst_len) { return dst_len >= 24 ? ((dst_len - 24) / 12 + 1) * 4 : 0; }
+        static __host__ int aux(int dst_len) { return !QUIRK ? 0x7fffffff : dst_len >= 24 ? ((dst_len - 24) / 12 + 1) * 4 : 0; }
         static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &rc)
         {
                 uint32_t tail = 0;
-                if ((rc.cx + 1) * 16 > p.aux) {  // this chunk reaches into the tail
+                if (QUIRK && (rc.cx + 1) * 16 > p.aux) {  // this chunk reaches into the tail
                         const long a = rc.row_abs + 4L * p.aux;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -234,14 +237,31 @@ struct conv_rgba_rgb {
                 uint32_t o[48];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                        const uint32_t w = rc.cx * 16 + i >= p.aux ? tail : in[i];
-                        o[3 * i] = w & 0xff;
-                        o[3 * i + 1] = (w >> 8) & 0xff;
-                        o[3 * i + 2] = (w >> 16) & 0xff;
+                        const uint32_t w = QUIRK && rc.cx * 16 + i >= p.aux ? tail : in[i];
+                        o[3 * i] = (w >> RS) & 0xff;
+                        o[3 * i + 1] = (w >> GS) & 0xff;
+                        o[3 * i + 2] = (w >> BS) & 0xff;
                 }
 #pragma unroll
                 for (int i = 0; i < 12; ++i) {
                         out[i] = pack4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+        }
+};
+using conv_rgba_rgb = conv_x32_rgb<0, 8, 16, true>;
+using conv_abgr_rgb = conv_x32_rgb<24, 16, 8, true>;
+using conv_bgra_rgb = conv_x32_rgb<16, 8, 0, false>;
+
+/// vc_copylineToRGBA_inplace, pixfmt_conv.c:907-921: pick R, G, B out of a 32-bit pixel by SOURCE shifts; the fourth byte becomes 0.
+/// dst may be src (a thread reads its whole chunk before it writes it).
+struct conv_to_rgba_inplace {
+        static constexpr int IN = 16, OUT = 16;
+        static __host__ int out_len(int dst_len) { return dst_len < 4 ? 0 : dst_len / 4 * 4; }
+        static __device__ __forceinline__ void run(const uint32_t *in, uint32_t *out, const conv_params &p, const row_ctx &)
+        {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                        out[i] = ((in[i] >> p.rshift) & 0xff) | ((in[i] >> p.gshift) & 0xff) << 8 | ((in[i] >> p.bshift) & 0xff) << 16;
                 }
         }
 };
@@ -483,6 +503,11 @@ struct map_rg48_rgb {  // vc_copylineRG48toRGB, pixfmt_conv.c:2030-2042: the hig
         static constexpr int IN = 96, OUT = 48;
         static __host__ int out_len(int n) { return n < 3 ? 0 : n / 3 * 3; }
         static constexpr int src(int j) { return 6 * (j / 3) + 2 * (j % 3) + 1; }
+};
+struct map_uyvy_gray {  // vc_copylineUYVYtoGrayscale, pixfmt_conv.c:927-938: the luma bytes
+        static constexpr int IN = 32, OUT = 16;
+        static __host__ int out_len(int n) { return n / 2 * 2; }
+        static constexpr int src(int j) { return 2 * j + 1; }
 };
 struct map_dvs10_uyvy {  // vc_copylineDVS10 (C variant, pixfmt_conv.c:690-720): bytes 0..2 of every 32-bit word; src_len = dst_len / 1.5
         static constexpr int IN = 64, OUT = 48;
@@ -1171,6 +1196,30 @@ static int copy_rows(void *dst, long dst_pitch, const void *src, long src_pitch,
 }  // namespace ugb
 
 using namespace ugb;
+
+extern "C" UGB_API int ugb200_vc_copyline(int func, void *dst, long dst_pitch, const void *src, long src_pitch, int dst_len, int height, long src_size,
+                                          int rshift, int gshift, int bshift, cuda_wrapper_stream_t stream)
+{
+        if (dst == nullptr || src == nullptr || dst_len < 0 || height < 0 || dst_pitch <= 0 || src_pitch <= 0) {
+                return -1;
+        }
+        cudaStream_t s = (cudaStream_t) stream;
+        switch (func) {
+        case UGB_LINE_ABGR_TO_RGB:
+                return launch_line<conv_abgr_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, conv_params{ 0, 8, 16, conv_abgr_rgb::aux(dst_len) }, s);
+        case UGB_LINE_BGRA_TO_RGB:
+                return launch_line<conv_bgra_rgb>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, conv_params{ 0, 8, 16, conv_bgra_rgb::aux(dst_len) }, s);
+        case UGB_LINE_TO_RGBA_INPLACE:
+                if ((unsigned) rshift > 24 || (unsigned) gshift > 24 || (unsigned) bshift > 24) {
+                        return -1;
+                }
+                return launch_line<conv_to_rgba_inplace>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, conv_params{ rshift, gshift, bshift, 0 }, s);
+        case UGB_LINE_UYVY_TO_GRAYSCALE:
+                return launch_line<conv_bytemap<map_uyvy_gray>>(dst, dst_pitch, src, src_pitch, dst_len, height, src_size, conv_params{ 0, 8, 16, 0 }, s);
+        default:
+                return -4;
+        }
+}
 
 extern "C" UGB_API int ugb200_pixfmt_supported(int in_codec, int out_codec)
 {
