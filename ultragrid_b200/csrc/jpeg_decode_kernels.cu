@@ -20,6 +20,8 @@
 #include <emmintrin.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <new>
 #include <thread>
 #include <vector>
@@ -416,7 +418,7 @@ const float kAan[8] = { 1.0f, 1.387039845f, 1.306562965f, 1.175875602f, 1.0f, 0.
 
 /// marker candidates of [lo, hi): positions p with s[p] == 0xFF and s[p + 1] neither a stuffed 0x00 nor a fill 0xFF.  One SSE2 compare per
 /// 16 bytes, then only the 0xFF positions are looked at.  Optionally copies the range to `copy_to` in the same pass (staging for the upload).
-void scan_markers(const uint8_t *s, size_t lo, size_t hi, size_t len, std::vector<uint32_t> &out, uint8_t *copy_to)
+void scan_markers(const uint8_t *s, size_t lo, size_t hi, size_t len, std::vector<uint64_t> &out, uint8_t *copy_to)
 {
         const __m128i ff16 = _mm_set1_epi8((char) 0xFF), zero = _mm_setzero_si128();
         size_t i = lo;
@@ -428,8 +430,9 @@ void scan_markers(const uint8_t *s, size_t lo, size_t hi, size_t len, std::vecto
                 }
                 const __m128i stuffed = _mm_or_si128(_mm_cmpeq_epi8(nx, zero), _mm_cmpeq_epi8(nx, ff16));
                 unsigned mask = (unsigned) _mm_movemask_epi8(_mm_andnot_si128(stuffed, _mm_cmpeq_epi8(v, ff16)));
-                while (mask) {
-                        out.push_back((uint32_t) (i + (size_t) __builtin_ctz(mask)));
+                while (mask) {  // entry = marker code << 32 | position: the parser never has to touch the stream again (one cache miss per marker)
+                        const size_t p = i + (size_t) __builtin_ctz(mask);
+                        out.push_back((uint64_t) s[p + 1] << 32 | p);
                         mask &= mask - 1;
                 }
         }
@@ -438,16 +441,16 @@ void scan_markers(const uint8_t *s, size_t lo, size_t hi, size_t len, std::vecto
                         copy_to[i] = s[i];
                 }
                 if (s[i] == 0xFF && i + 1 < len && s[i + 1] != 0 && s[i + 1] != 0xFF) {
-                        out.push_back((uint32_t) i);
+                        out.push_back((uint64_t) s[i + 1] << 32 | i);
                 }
         }
 }
 
 /// header markers up to and including every SOS; `full` also finds the restart segments of the entropy-coded data, from the marker
 /// candidates in `markers` (sorted; scanned here when the caller has none)
-int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool full, const std::vector<uint32_t> *markers = nullptr)
+int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool full, const std::vector<uint64_t> *markers = nullptr)
 {
-        std::vector<uint32_t> own;
+        std::vector<uint64_t> own;
         if (full && markers == nullptr) {
                 scan_markers(s, 0, len, len, own, nullptr);
                 markers = &own;
@@ -580,19 +583,21 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
                         // entropy-coded segment(s): RSTn candidates split it, the first other marker ends it
                         uint32_t begin = (uint32_t) (p - s);
                         int found = 0;
-                        auto it = std::lower_bound(markers->begin(), markers->end(), begin);
+                        auto it = std::lower_bound(markers->begin(), markers->end(), (uint64_t) begin,
+                                                   [](uint64_t e, uint64_t pos) { return (uint32_t) e < pos; });
                         for (; it != markers->end(); ++it) {
-                                const int c2 = s[*it + 1];
+                                const int c2 = (int) (*it >> 32);
+                                const uint32_t pos = (uint32_t) *it;
                                 if (c2 < 0xD0 || c2 > 0xD7) {
                                         break;
                                 }
                                 if (found + 1 < S.nseg) {
-                                        P.seg_begin.push_back(begin), P.seg_end.push_back(*it);
+                                        P.seg_begin.push_back(begin), P.seg_end.push_back(pos);
                                         ++found;
                                 }
-                                begin = *it + 2;
+                                begin = pos + 2;
                         }
-                        p = it != markers->end() ? s + *it : end;
+                        p = it != markers->end() ? s + (uint32_t) *it : end;
                         P.seg_begin.push_back(begin), P.seg_end.push_back((uint32_t) (p - s));
                         ++found;
                         while (found < S.nseg) {  // truncated stream: the missing segments decode as nothing (zero coefficients)
@@ -697,6 +702,13 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         if (out_codec != UGB_UYVY && out_codec != UGB_RGB && out_codec != UGB_RGBA && out_codec != UGB_VUYA && out_codec != UGB_I420) {
                 return -4;
         }
+        static const bool timing = getenv("UGB200_JPEG_TIMING") != nullptr;  // stage times of the host side on stderr
+        const auto t_start = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+                if (timing) {
+                        fprintf(stderr, "[jpeg decode] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+                }
+        };
         ugb200_jpeg_decoder::host_slot &H = d->hs[d->frame_no++ & 1];
         if (H.pending) {
                 cudaEventSynchronize(H.uploaded);  // the uploads of the frame before last left this slot long ago
@@ -710,11 +722,12 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         }
         // one pass over the caller's (pageable) buffer: copy it to the pinned staging buffer and collect the marker candidates, split over a
         // few threads when the stream is large (an 8K frame is 5-50 MB)
-        std::vector<uint32_t> markers;
+        std::vector<uint64_t> markers;
         {
-                const int nt = len > (1u << 20) ? 4 : 1;
-                std::vector<uint32_t> part[4];
-                std::thread th[4];
+                constexpr int kMaxThreads = 8;
+                const int nt = len > (4u << 20) ? kMaxThreads : len > (1u << 20) ? 4 : 1;
+                std::vector<uint64_t> part[kMaxThreads];
+                std::thread th[kMaxThreads];
                 const size_t chunk = (len / nt + 15) & ~(size_t) 15;
                 for (int i = 1; i < nt; ++i) {
                         const size_t lo = std::min(len, chunk * i), hi = i == nt - 1 ? len : std::min(len, chunk * (i + 1));
@@ -728,10 +741,12 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                         markers.insert(markers.end(), part[i].begin(), part[i].end());
                 }
         }
+        lap("scan+stage");
         int rc = parse_stream(stream, len, P, H.tables, true, &markers);
         if (rc != 0) {
                 return rc;
         }
+        lap("parse");
         const dec_geom &g = P.g;
         const size_t nseg = P.seg_begin.size();
         const long plane_bytes = (long) g.nblocks * 64;
@@ -752,6 +767,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         cudaMemcpyAsync(d->d_tables, H.tables, sizeof(dec_tables), cudaMemcpyHostToDevice, s);
         cudaEventRecord(H.uploaded, s);
         H.pending = true;
+        lap("uploads queued");
         cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
         jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d->d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef);
         const bool direct = native == out_codec && dst_is_device;
@@ -766,6 +782,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         if (cudaGetLastError() != cudaSuccess) {
                 return -2;
         }
+        lap("kernels queued");
         // component planes -> the stream's native packed format
         struct ugb200_from_planar_data fp;
         memset(&fp, 0, sizeof fp);
