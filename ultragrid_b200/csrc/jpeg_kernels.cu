@@ -369,10 +369,53 @@ struct block_bits {  // MSB-first bit string of one block in shared memory, word
         }
 };
 
+/// byte stuffing of one assembled restart segment (T bits in `seg`, MSB first) by the bps threads of its group; appends RSTn when rst >= 0.
+/// @returns the number of bytes written (identical in every thread of the group)
+__device__ __forceinline__ uint32_t stuff_segment(uint8_t *__restrict__ dst, const uint32_t *seg, uint32_t T, int bps, int gl, unsigned lane32, unsigned gmask,
+                                                  int rst)
+{
+        uint32_t written = 0;
+        const uint32_t n = (T + 7) >> 3;
+        for (uint32_t base = 0; base < n; base += bps) {
+                const uint32_t i = base + gl;
+                const uint32_t b = i < n ? (seg[i >> 2] >> (24 - 8 * (i & 3))) & 0xffu : 0u;
+                const unsigned ff = __ballot_sync(gmask, b == 0xFF) & gmask;
+                const uint32_t before = __popc(ff & ((1u << lane32) - 1u));
+                if (i < n) {
+                        dst[written + gl + before] = (uint8_t) b;
+                        if (b == 0xFF) {
+                                dst[written + gl + before + 1] = 0;
+                        }
+                }
+                written += min((uint32_t) bps, n - base) + __popc(ff);
+        }
+        if (rst >= 0) {
+                if (gl == 0) {
+                        dst[written] = 0xFF, dst[written + 1] = (uint8_t) rst;
+                }
+                written += 2;
+        }
+        return written;
+}
+
+/// Single-pass stream compaction (decoupled look-back): when `state` is set the kernel writes the stuffed segments straight to their final
+/// position in the stream, so that neither the per-segment slots nor the scan / compact kernels are needed.  A CTA takes a ticket (its
+/// logical index: every CTA with a smaller one has started), publishes the byte count of its segments, adds up the counts of its
+/// predecessors until it meets one that already knows its own prefix, publishes its prefix, and writes.
+struct jpeg_lookback {
+        unsigned long long *state;  // per CTA: flag << 62 | bytes; flag 1 = own count, 2 = inclusive prefix (zeroed before the launch)
+        uint32_t *ticket;           // zeroed before the launch
+        uint8_t *out;
+        uint32_t out_cap;
+        uint32_t *total;
+        int ctas_per_scan;
+};
+
 template <int FMT>
 __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
                                                          uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
-                                                         uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats)
+                                                         uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats,
+                                                         jpeg_lookback lb)
 {
         extern __shared__ uint32_t smem[];
         uint32_t *s_coef = smem;                // [32][128] zig-zag coefficients, two int16 per word
@@ -380,7 +423,17 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
         uint32_t *s_seg = s_bits + cap * 128;   // [segments of the CTA][bps * cap]
         __shared__ uint32_t s_dctab[2][16], s_ac[2][256], s_len[128], s_warp[4], s_max[4];
         __shared__ int s_dc[128];
+        __shared__ uint32_t s_ticket, s_tot, s_base;
         const int tid = threadIdx.x;
+        int cta_x = blockIdx.x, cta_y = blockIdx.y, ticket = 0;
+        if (lb.state != nullptr) {
+                if (tid == 0) {
+                        s_ticket = atomicAdd(lb.ticket, 1u);
+                }
+                __syncthreads();
+                ticket = (int) s_ticket;
+                cta_x = FMT == FMT_UYVY_422 ? ticket : ticket % lb.ctas_per_scan, cta_y = FMT == FMT_UYVY_422 ? 0 : ticket / lb.ctas_per_scan;
+        }
         for (int i = tid; i < 32; i += 128) {
                 s_dctab[i >> 4][i & 15] = __ldg(g_huff + i);
         }
@@ -397,7 +450,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
         int first_mcu;                            // scan-local index of the CTA's first MCU
         if (FMT == FMT_UYVY_422) {
                 const int k = tid >> 5, lane = tid & 31;
-                first_mcu = blockIdx.x * 32;
+                first_mcu = cta_x * 32;
                 const int m = first_mcu + lane;
                 valid = m < g.mcu_per_scan;
                 comp = k < 2 ? 0 : k - 1;
@@ -405,10 +458,10 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 bx = comp == 0 ? mx * 2 + k : mx, by = m / g.bw;
                 p = lane * 4 + k;
         } else {
-                first_mcu = blockIdx.x * 128;
+                first_mcu = cta_x * 128;
                 const int b = first_mcu + tid;
                 valid = b < g.mcu_per_scan;
-                comp = blockIdx.y;
+                comp = cta_y;
                 bx = b % g.bw, by = b / g.bw;
                 p = tid;
         }
@@ -559,9 +612,12 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
         const int sg = tid / bps, gl = tid % bps;          // segment within the CTA, my lane within the segment's group
         const unsigned lane32 = tid & 31;
         const int ls = first_mcu / g.ri + sg;              // index of the segment within its scan
-        const int seg_global = FMT == FMT_UYVY_422 ? ls : blockIdx.y * g.seg_per_scan + ls;
+        const int seg_global = FMT == FMT_UYVY_422 ? ls : cta_y * g.seg_per_scan + ls;
         const bool seg_valid = ls < g.seg_per_scan && (long) ls * g.ri < g.mcu_per_scan;
         uint32_t written = 0;
+        const unsigned gmask = bps == 32 ? 0xffffffffu : (((1u << bps) - 1u) << (lane32 - gl));
+        uint32_t T = 0;                                    // bits of my segment (fast route)
+        uint32_t *seg = s_seg + sg * bps * cap;            // its assembled bit string
         if (overflow) {
                 // ---- serial route: the segment's first thread codes all its blocks into the slot --------------------------------------
                 if (gl == 0 && seg_valid) {
@@ -573,7 +629,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                                 if (m >= g.mcu_per_scan) {
                                         break;
                                 }
-                                const int comp = FMT == FMT_UYVY_422 ? ((q & 3) < 2 ? 0 : (q & 3) - 1) : (int) blockIdx.y;
+                                const int comp = FMT == FMT_UYVY_422 ? ((q & 3) < 2 ? 0 : (q & 3) - 1) : cta_y;
                                 const int t = comp == 0 ? 0 : 1;
                                 uint64_t map = 0;
                                 for (int k = 0; k < 32; ++k) {
@@ -617,7 +673,6 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 }
         } else {
                 // ---- 3. assemble restart segments: thread tid now owns scan-order block tid ---------------------------------------------
-                const unsigned gmask = bps == 32 ? 0xffffffffu : (((1u << bps) - 1u) << (lane32 - gl));
                 const uint32_t L = s_len[tid];
                 uint32_t incl = L;
                 for (int d = 1; d < bps; d <<= 1) {
@@ -626,8 +681,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                                 incl += o;
                         }
                 }
-                const uint32_t T = __shfl_sync(gmask, incl, bps - 1, bps);  // bits of the whole segment
-                uint32_t *seg = s_seg + sg * bps * cap;
+                T = __shfl_sync(gmask, incl, bps - 1, bps);  // bits of the whole segment
                 {
                         const uint32_t off = incl - L, sh = off & 31;
                         uint32_t *d = seg + (off >> 5);
@@ -644,28 +698,20 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                         }
                 }
                 __syncthreads();
-                // ---- 4. byte stuffing into the slot ----------------------------------------------------------------------------------
-                if (seg_valid) {
-                        uint8_t *slot = slots + (long) seg_global * g.slot;
+                // ---- 4. byte stuffing into the slot - or, with the single-pass compaction, only the SIZE of the stuffed segment for now -------
+                if (seg_valid && lb.state != nullptr) {
                         const uint32_t n = (T + 7) >> 3;
-                        for (uint32_t base = 0; base < n; base += bps) {
-                                const uint32_t i = base + gl;
-                                const uint32_t b = i < n ? (seg[i >> 2] >> (24 - 8 * (i & 3))) & 0xffu : 0u;
-                                const unsigned ff = __ballot_sync(gmask, b == 0xFF) & gmask;
-                                const uint32_t before = __popc(ff & ((1u << lane32) - 1u));
-                                if (i < n) {
-                                        slot[written + gl + before] = (uint8_t) b;
-                                        if (b == 0xFF) {
-                                                slot[written + gl + before + 1] = 0;
-                                        }
-                                }
-                                written += min((uint32_t) bps, n - base) + __popc(ff);
+                        uint32_t cnt = 0;
+                        for (uint32_t wi = gl; wi * 4 < n; wi += bps) {  // bytes beyond n are zero: whole words can be tested
+                                cnt += __popc(__vcmpeq4(seg[wi], 0xFFFFFFFFu)) >> 3;
                         }
+                        for (int d = bps >> 1; d > 0; d >>= 1) {
+                                cnt += __shfl_xor_sync(gmask, cnt, d, bps);
+                        }
+                        written = n + cnt + (ls != g.seg_per_scan - 1 ? 2u : 0u);
+                } else if (seg_valid) {
+                        written = stuff_segment(slots + (long) seg_global * g.slot, seg, T, bps, gl, lane32, gmask, ls != g.seg_per_scan - 1 ? 0xD0 + (ls & 7) : -1);
                         if (gl == 0) {
-                                if (ls != g.seg_per_scan - 1) {
-                                        slot[written] = 0xFF, slot[written + 1] = (uint8_t) (0xD0 + (ls & 7));
-                                        written += 2;
-                                }
                                 sizes[seg_global] = written;
                         }
                 }
@@ -688,15 +734,75 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
         for (int w = 0; w < (tid >> 5); ++w) {
                 before += s_warp[w];
         }
-        if (gl == 0 && seg_valid) {
-                local_off[seg_global] = before + inc2 - mine;
-        }
         if (tid == 127) {
-                const int cta = FMT == FMT_UYVY_422 ? blockIdx.x : blockIdx.y * gridDim.x + blockIdx.x;
-                cta_total[cta] = before + inc2;
                 atomicMax(stats, max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3])));
                 if (overflow) {
                         atomicAdd(stats + 1, 1u);
+                }
+        }
+        if (lb.state == nullptr) {  // two-level scan + compaction kernels follow
+                if (gl == 0 && seg_valid) {
+                        local_off[seg_global] = before + inc2 - mine;
+                }
+                if (tid == 127) {
+                        const int cta = FMT == FMT_UYVY_422 ? cta_x : cta_y * gridDim.x + cta_x;
+                        cta_total[cta] = before + inc2;
+                }
+                return;
+        }
+        // ---- 6. single-pass compaction: my CTA's offset in the stream by decoupled look-back, then the segments go to their final place -------
+        if (tid == 127) {
+                s_tot = before + inc2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+                constexpr unsigned long long kAgg = 1ull << 62, kPfx = 2ull << 62, kMask = (1ull << 62) - 1;
+                unsigned long long base = 0;
+                if (ticket > 0) {
+                        atomicExch(lb.state + ticket, kAgg | s_tot);
+                        for (int j = ticket - 1;; ) {
+                                const unsigned long long v = *(volatile unsigned long long *) (lb.state + j);
+                                if ((v >> 62) == 0) {
+                                        continue;  // that CTA has started (tickets are handed out in order) and will publish
+                                }
+                                base += v & kMask;
+                                if ((v >> 62) == 2) {
+                                        break;
+                                }
+                                --j;
+                        }
+                }
+                atomicExch(lb.state + ticket, kPfx | (base + s_tot));
+                s_base = (uint32_t) base;
+        }
+        __syncthreads();
+        const uint32_t seg_off = __shfl_sync(gmask, before + inc2 - mine, 0, bps), seg_size = __shfl_sync(gmask, written, 0, bps);
+        const unsigned long long pos0 = (unsigned long long) g.header_len + (unsigned long long) g.sos_len * cta_y + s_base;
+        if (seg_valid && pos0 + seg_off + seg_size <= lb.out_cap) {  // a stream larger than the buffer is reported by the host, never written
+                uint8_t *dstp = lb.out + pos0 + seg_off;
+                if (overflow) {  // the serial route left the finished segment in its slot
+                        const uint8_t *slot = slots + (long) seg_global * g.slot;
+                        for (uint32_t i = gl; i < seg_size; i += bps) {
+                                dstp[i] = slot[i];
+                        }
+                } else {
+                        stuff_segment(dstp, seg, T, bps, gl, lane32, gmask, ls != g.seg_per_scan - 1 ? 0xD0 + (ls & 7) : -1);
+                }
+        }
+        if (tid == 0) {
+                if (FMT == FMT_RGB_444 && cta_x == 0 && cta_y > 0 && pos0 <= lb.out_cap) {  // SOS header of a later scan, right in front of its data
+                        uint8_t *h = lb.out + pos0 - g.sos_len;
+                        const uint8_t sos[10] = { 0xFF, 0xDA, 0, 8, 1, (uint8_t) (cta_y + 1), 0x11, 0, 63, 0 };
+                        for (int i = 0; i < 10; ++i) {
+                                h[i] = sos[i];
+                        }
+                }
+                if (ticket == (int) gridDim.x - 1) {  // the last CTA of the stream: EOI and the total
+                        const unsigned long long end = pos0 + s_tot;
+                        if (end + 2 <= lb.out_cap) {
+                                lb.out[end] = 0xFF, lb.out[end + 1] = 0xD9;
+                        }
+                        *lb.total = (uint32_t) (end + 2);
                 }
         }
 }
@@ -919,6 +1025,8 @@ struct ugb200_jpeg_encoder {
         int16_t *coef = nullptr;
         uint8_t *slots = nullptr, *out = nullptr, *staging = nullptr;
         uint32_t *sizes = nullptr, *offsets = nullptr, *cta_total = nullptr, *total = nullptr;
+        unsigned long long *lb_state = nullptr;  // look-back state of the single-pass compaction ([0] = ticket counter)
+        size_t lb_cap = 0;
         size_t coef_cap = 0, slots_cap = 0, out_cap = 0, seg_cap = 0, staging_cap = 0, cta_cap = 0;
         // pinned host buffers
         uint8_t *h_out = nullptr, *h_in = nullptr;
@@ -1135,7 +1243,7 @@ void ugb200_jpeg_encoder_destroy(ugb200_jpeg_encoder *e)
         }
         cudaStreamSynchronize(e->stream);
         cudaFree(e->coef), cudaFree(e->slots), cudaFree(e->out), cudaFree(e->staging);
-        cudaFree(e->sizes), cudaFree(e->offsets), cudaFree(e->cta_total), cudaFree(e->total);
+        cudaFree(e->sizes), cudaFree(e->offsets), cudaFree(e->cta_total), cudaFree(e->total), cudaFree(e->lb_state);
         cudaFreeHost(e->h_out), cudaFreeHost(e->h_in), cudaFreeHost(e->h_total);
         if (e->stats_ev) {
                 cudaEventDestroy(e->stats_ev);
@@ -1185,32 +1293,46 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         const bool fused = !force_split && (bps == 4 || bps == 8 || bps == 16 || bps == 32);
         e->last_fused = fused;
         int nctas, segs_per_cta, ctas_per_scan;
+        bool single_pass = false;
         if (fused) {  // one kernel: DCT + entropy coding + segment assembly
                 static const char *cap_env = getenv("UGB200_JPEG_CAP");
                 const int cap = cap_env ? atoi(cap_env) : e->cap_words;
                 const size_t smem = (size_t) (32 * 128 + 2 * cap * 128) * sizeof(uint32_t);
                 segs_per_cta = 128 / bps;
                 cudaMemsetAsync(e->total + 1, 0, 8, e->stream);
+                ctas_per_scan = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.mcu_per_scan + 127) / 128;
+                nctas = fmt == FMT_UYVY_422 ? ctas_per_scan : ctas_per_scan * 3;
+                static const bool two_pass = getenv("UGB200_JPEG_COMPACT") != nullptr;  // cross-check: slots + scan + compact kernels
+                single_pass = !two_pass;
+                jpeg_lookback lb = { nullptr, nullptr, e->out, (uint32_t) e->out_cap, e->total, ctas_per_scan };
+                if (single_pass) {
+                        if (!grow(e->lb_state, e->lb_cap, (size_t) nctas + 1)) {
+                                return -2;
+                        }
+                        cudaMemsetAsync(e->lb_state, 0, ((size_t) nctas + 1) * sizeof(unsigned long long), e->stream);
+                        lb.state = e->lb_state + 1, lb.ticket = (uint32_t *) e->lb_state;  // word 0 of the array = the ticket counter
+                }
                 if (fmt == FMT_UYVY_422) {
-                        ctas_per_scan = (g.mcu_per_scan + 31) / 32;
-                        nctas = ctas_per_scan;
                         if (!e->attr_set[0]) {  // per encoder = per device context: the attribute does not carry over to another GPU
                                 cudaFuncSetAttribute(jpeg_fused_kernel<FMT_UYVY_422>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t)));
                                 e->attr_set[0] = true;
                         }
                         jpeg_fused_kernel<FMT_UYVY_422><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
-                                                                                       e->cta_total, vec_ok, cap, e->total + 1);
+                                                                                       e->cta_total, vec_ok, cap, e->total + 1, lb);
                 } else {
-                        ctas_per_scan = (g.mcu_per_scan + 127) / 128;
-                        nctas = ctas_per_scan * 3;
                         if (!e->attr_set[1]) {
                                 cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t)));
                                 e->attr_set[1] = true;
                         }
-                        jpeg_fused_kernel<FMT_RGB_444><<<dim3(ctas_per_scan, 3), 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes,
-                                                                                                       e->offsets, e->cta_total, vec_ok, cap, e->total + 1);
+                        if (single_pass) {  // tickets run over the three scans
+                                jpeg_fused_kernel<FMT_RGB_444><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
+                                                                                              e->cta_total, vec_ok, cap, e->total + 1, lb);
+                        } else {
+                                jpeg_fused_kernel<FMT_RGB_444><<<dim3(ctas_per_scan, 3), 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes,
+                                                                                                               e->offsets, e->cta_total, vec_ok, cap, e->total + 1, lb);
+                        }
                 }
         } else {  // split path: any restart interval
                 const int dct_ctas = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
@@ -1218,9 +1340,11 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                 nctas = (g.nseg + 127) / 128, segs_per_cta = 128, ctas_per_scan = 0;
                 jpeg_huffman_kernel<<<nctas, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes, e->offsets, e->cta_total);
         }
-        jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
-        jpeg_compact_kernel<<<(int) (((long) g.nseg * 32 + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
-                                                                                           segs_per_cta, ctas_per_scan, e->out, e->total, (uint32_t) e->out_cap);
+        if (!single_pass) {
+                jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
+                jpeg_compact_kernel<<<(int) (((long) g.nseg * 32 + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
+                                                                                                   segs_per_cta, ctas_per_scan, e->out, e->total, (uint32_t) e->out_cap);
+        }
         if (cudaGetLastError() != cudaSuccess) {
                 return -2;
         }
