@@ -755,25 +755,39 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 s_tot = before + inc2;
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid < 32) {  // warp 0 looks back 32 predecessors at a time
                 constexpr unsigned long long kAgg = 1ull << 62, kPfx = 2ull << 62, kMask = (1ull << 62) - 1;
                 unsigned long long base = 0;
                 if (ticket > 0) {
-                        atomicExch(lb.state + ticket, kAgg | s_tot);
-                        for (int j = ticket - 1;; ) {
-                                const unsigned long long v = *(volatile unsigned long long *) (lb.state + j);
-                                if ((v >> 62) == 0) {
-                                        continue;  // that CTA has started (tickets are handed out in order) and will publish
+                        if (tid == 0) {
+                                atomicExch(lb.state + ticket, kAgg | s_tot);
+                        }
+                        for (int j = ticket - 1;;) {
+                                const int idx = j - tid;
+                                const unsigned long long v = idx >= 0 ? *(volatile unsigned long long *) (lb.state + idx) : kPfx;  // nothing before CTA 0
+                                const unsigned flag = (unsigned) (v >> 62);
+                                const unsigned pfx = __ballot_sync(0xffffffffu, flag == 2), inv = __ballot_sync(0xffffffffu, flag == 0);
+                                const int first = pfx ? __ffs((int) pfx) - 1 : 31;           // nearest predecessor that knows its prefix
+                                const unsigned window = first == 31 ? 0xffffffffu : (2u << first) - 1u;
+                                if (inv & window) {
+                                        continue;  // one of them has not published yet (it has started: tickets are handed out in order)
                                 }
-                                base += v & kMask;
-                                if ((v >> 62) == 2) {
+                                unsigned long long part = (window >> tid) & 1u ? v & kMask : 0ull;
+#pragma unroll
+                                for (int d = 16; d > 0; d >>= 1) {
+                                        part += __shfl_xor_sync(0xffffffffu, part, d);
+                                }
+                                base += part;
+                                if (pfx) {
                                         break;
                                 }
-                                --j;
+                                j -= 32;
                         }
                 }
-                atomicExch(lb.state + ticket, kPfx | (base + s_tot));
-                s_base = (uint32_t) base;
+                if (tid == 0) {
+                        atomicExch(lb.state + ticket, kPfx | (base + s_tot));
+                        s_base = (uint32_t) base;
+                }
         }
         __syncthreads();
         const uint32_t seg_off = __shfl_sync(gmask, before + inc2 - mine, 0, bps), seg_size = __shfl_sync(gmask, written, 0, bps);
