@@ -168,6 +168,27 @@ def test_gpu_encoder_honours_the_source_pitch(orc, codec, w, h, pad):
 
 
 @pytest.mark.gpu
+def test_gpu_two_encoders_with_different_quality_interleaved(orc):
+    """no module-level table state: encoders of different quality (and format) share a device, their launches interleave on two streams"""
+    import torch
+    from ultragrid_b200 import api
+    w, h = 640, 360
+    uy = util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h, 11).reshape(-1), w, h)
+    rgb = natural_rgb(w, h, 12).reshape(-1).copy()
+    d_uy, d_rgb = torch.from_numpy(uy).cuda(), torch.from_numpy(rgb).cuda()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    a, b = api.JpegEncoder(stream=s1), api.JpegEncoder(stream=s2)
+    want_a, want_b = orc_encode(orc, uy, w, h, UYVY, 50), orc_encode(orc, rgb, w, h, RGB, 95)
+    for _ in range(4):
+        a.encode_device(d_uy, w, h, UYVY, quality=50)
+        b.encode_device(d_rgb, w, h, RGB, quality=95)
+        assert a.result() == want_a
+        assert b.result() == want_b
+    a.close(), b.close()
+
+
+@pytest.mark.gpu
 def test_gpu_stream_larger_than_output_buffer_is_an_error(orc):
     """RGB noise at quality 100 codes to more than w * h * 3 bytes (the capacity the reference hands libgpujpeg, gpujpeg.cpp:355)"""
     import torch

@@ -28,15 +28,18 @@ enum { FMT_UYVY_422 = 0, FMT_RGB_444 = 1 };
 constexpr int kSlotBytesPerBlock = 416;  // worst case: 1658 bits/block = 208 B, every byte stuffed
 constexpr int kSlotExtra = 8;            // final pad byte + RSTn
 
-struct jpeg_tables_dev {
+// Per-encoder tables, no module-level state (encoders with different quality may run concurrently on one device):
+//   the quantiser multipliers travel BY VALUE as a kernel parameter - they sit in the constant bank of that launch and are read with
+//   immediate offsets exactly like a __constant__ array;
+//   the Huffman code tables live in a small per-encoder global buffer; a CTA copies them to shared memory with coalesced loads
+//   (indexing a constant bank with the thread id would serialise into 32 replays per warp).
+struct jpeg_qtab {
         float qmul[2][64];     // [luma|chroma][natural index]
+};
+struct jpeg_hufftab {
         uint32_t dc[2][16];    // (len << 16) | code, by category
         uint32_t ac[2][256];   // (len << 16) | code, by (run << 4 | size)
 };
-__constant__ jpeg_tables_dev c_tab;
-// the Huffman code tables once more in global memory: a CTA copies them to shared memory with coalesced loads (indexing the constant
-// bank with the thread id serialises into 32 replays per warp)
-__device__ uint32_t g_huff[2 * 16 + 2 * 256];
 
 struct jpeg_geom {
         int fmt, w, h;
@@ -125,7 +128,7 @@ __device__ __forceinline__ void load_row(const uint8_t *__restrict__ src, long p
 }
 
 __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, int16_t *__restrict__ coef,
-                                                       bool vec_ok)
+                                                       bool vec_ok, const __grid_constant__ jpeg_qtab qt)
 {
         int b = blockIdx.x * blockDim.x + threadIdx.x;
         int comp, bx, by;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict
         for (int c = 0; c < 8; ++c) {
                 fdct8(f[c], f[8 + c], f[16 + c], f[24 + c], f[32 + c], f[40 + c], f[48 + c], f[56 + c]);
         }
-        const float *qm = c_tab.qmul[comp == 0 ? 0 : 1];
+        const float *qm = qt.qmul[comp == 0 ? 0 : 1];
         int q[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
@@ -415,7 +418,7 @@ template <int FMT>
 __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
                                                          uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
                                                          uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats,
-                                                         jpeg_lookback lb)
+                                                         jpeg_lookback lb, const __grid_constant__ jpeg_qtab qt, const uint32_t *__restrict__ huff)
 {
         extern __shared__ uint32_t smem[];
         uint32_t *s_coef = smem;                // [32][128] zig-zag coefficients, two int16 per word
@@ -435,10 +438,10 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 cta_x = FMT == FMT_UYVY_422 ? ticket : ticket % lb.ctas_per_scan, cta_y = FMT == FMT_UYVY_422 ? 0 : ticket / lb.ctas_per_scan;
         }
         for (int i = tid; i < 32; i += 128) {
-                s_dctab[i >> 4][i & 15] = __ldg(g_huff + i);
+                s_dctab[i >> 4][i & 15] = __ldg(huff + i);
         }
         for (int i = tid; i < 512; i += 128) {
-                s_ac[i >> 8][i & 255] = __ldg(g_huff + 32 + i);
+                s_ac[i >> 8][i & 255] = __ldg(huff + 32 + i);
         }
         for (int i = tid; i < cap * 128; i += 128) {
                 s_seg[i] = 0;
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                                 g2[2 * rp + 1][cp] = make_float2(f2[rp][2 * cp].y, f2[rp][2 * cp + 1].y);
                         }
                 }
-                const float2 *qm = (const float2 *) c_tab.qmul[comp == 0 ? 0 : 1];
+                const float2 *qm = (const float2 *) qt.qmul[comp == 0 ? 0 : 1];
 #pragma unroll
                 for (int cp = 0; cp < 4; ++cp) {
                         fdct8_2(g2[0][cp], g2[1][cp], g2[2][cp], g2[3][cp], g2[4][cp], g2[5][cp], g2[6][cp], g2[7][cp]);
@@ -827,14 +830,14 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
 /// The CTA also produces the exclusive prefix of its 128 segment sizes and its total (first level of the stream scan).
 __global__ void __launch_bounds__(128) jpeg_huffman_kernel(const int16_t *__restrict__ coef, jpeg_geom g, uint8_t *__restrict__ slots,
                                                            uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
-                                                           uint32_t *__restrict__ cta_total)
+                                                           uint32_t *__restrict__ cta_total, const uint32_t *__restrict__ huff)
 {
         __shared__ uint32_t s_dc[2][16], s_ac[2][256], s_warp[4];
         for (int i = threadIdx.x; i < 32; i += blockDim.x) {
-                s_dc[i >> 4][i & 15] = c_tab.dc[i >> 4][i & 15];
+                s_dc[i >> 4][i & 15] = __ldg(huff + i);
         }
         for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-                s_ac[i >> 8][i & 255] = c_tab.ac[i >> 8][i & 255];
+                s_ac[i >> 8][i & 255] = __ldg(huff + 32 + i);
         }
         __syncthreads();
         const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1039,6 +1042,8 @@ struct ugb200_jpeg_encoder {
         int16_t *coef = nullptr;
         uint8_t *slots = nullptr, *out = nullptr, *staging = nullptr;
         uint32_t *sizes = nullptr, *offsets = nullptr, *cta_total = nullptr, *total = nullptr;
+        jpeg_qtab qt{};                  // quantiser multipliers of the current quality (kernel parameter)
+        uint32_t *d_huff = nullptr;      // jpeg_hufftab on the device
         unsigned long long *lb_state = nullptr;  // look-back state of the single-pass compaction ([0] = ticket counter)
         size_t lb_cap = 0;
         size_t coef_cap = 0, slots_cap = 0, out_cap = 0, seg_cap = 0, staging_cap = 0, cta_cap = 0;
@@ -1184,9 +1189,9 @@ int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri
         uint8_t ql[64], qc[64];
         ugb_jpeg_scaled_qtable(ugb_jpeg_q_luma, quality, ql);
         ugb_jpeg_scaled_qtable(ugb_jpeg_q_chroma, quality, qc);
-        jpeg_tables_dev t;
-        ugb_jpeg_quant_multipliers(ql, t.qmul[0]);
-        ugb_jpeg_quant_multipliers(qc, t.qmul[1]);
+        jpeg_hufftab t;
+        ugb_jpeg_quant_multipliers(ql, e->qt.qmul[0]);
+        ugb_jpeg_quant_multipliers(qc, e->qt.qmul[1]);
         uint16_t code[256];
         uint8_t len[256];
         for (int k = 0; k < 2; ++k) {
@@ -1200,9 +1205,8 @@ int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri
                         t.ac[k][i] = ((uint32_t) len[i] << 16) | code[i];
                 }
         }
-        // the constant bank is per-module state; encoders with different quality on one stream order themselves through the stream
-        if (cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
-            cudaMemcpyToSymbolAsync(g_huff, t.dc, sizeof t.dc + sizeof t.ac, 0, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+        if ((e->d_huff == nullptr && cudaMalloc((void **) &e->d_huff, sizeof t) != cudaSuccess) ||
+            cudaMemcpyAsync(e->d_huff, &t, sizeof t, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
                 return -2;
         }
         build_header(e, ql, qc);
@@ -1257,7 +1261,7 @@ void ugb200_jpeg_encoder_destroy(ugb200_jpeg_encoder *e)
         }
         cudaStreamSynchronize(e->stream);
         cudaFree(e->coef), cudaFree(e->slots), cudaFree(e->out), cudaFree(e->staging);
-        cudaFree(e->sizes), cudaFree(e->offsets), cudaFree(e->cta_total), cudaFree(e->total), cudaFree(e->lb_state);
+        cudaFree(e->sizes), cudaFree(e->offsets), cudaFree(e->cta_total), cudaFree(e->total), cudaFree(e->lb_state), cudaFree(e->d_huff);
         cudaFreeHost(e->h_out), cudaFreeHost(e->h_in), cudaFreeHost(e->h_total);
         if (e->stats_ev) {
                 cudaEventDestroy(e->stats_ev);
@@ -1333,7 +1337,7 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                                 e->attr_set[0] = true;
                         }
                         jpeg_fused_kernel<FMT_UYVY_422><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
-                                                                                       e->cta_total, vec_ok, cap, e->total + 1, lb);
+                                                                                       e->cta_total, vec_ok, cap, e->total + 1, lb, e->qt, e->d_huff);
                 } else {
                         if (!e->attr_set[1]) {
                                 cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1342,17 +1346,17 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                         }
                         if (single_pass) {  // tickets run over the three scans
                                 jpeg_fused_kernel<FMT_RGB_444><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
-                                                                                              e->cta_total, vec_ok, cap, e->total + 1, lb);
+                                                                                              e->cta_total, vec_ok, cap, e->total + 1, lb, e->qt, e->d_huff);
                         } else {
                                 jpeg_fused_kernel<FMT_RGB_444><<<dim3(ctas_per_scan, 3), 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes,
-                                                                                                               e->offsets, e->cta_total, vec_ok, cap, e->total + 1, lb);
+                                                                                                               e->offsets, e->cta_total, vec_ok, cap, e->total + 1, lb, e->qt, e->d_huff);
                         }
                 }
         } else {  // split path: any restart interval
                 const int dct_ctas = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
-                jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok);
+                jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok, e->qt);
                 nctas = (g.nseg + 127) / 128, segs_per_cta = 128, ctas_per_scan = 0;
-                jpeg_huffman_kernel<<<nctas, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes, e->offsets, e->cta_total);
+                jpeg_huffman_kernel<<<nctas, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes, e->offsets, e->cta_total, e->d_huff);
         }
         if (!single_pass) {
                 jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
@@ -1445,7 +1449,7 @@ int ugb200_jpeg_debug_coefficients(ugb200_jpeg_encoder *e, const int16_t **dev_p
         {  // recompute them with the stand-alone DCT kernel from the last source frame (which must still be alive)
                 const jpeg_geom &g = e->g;
                 const int dct_ctas = g.fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
-                jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) e->last_src, e->last_pitch, g, e->coef, e->last_vec_ok);
+                jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) e->last_src, e->last_pitch, g, e->coef, e->last_vec_ok, e->qt);
         }
         cudaStreamSynchronize(e->stream);
         *dev_ptr = e->coef;
