@@ -239,10 +239,9 @@ static int launch_uyvy(const void *src, void *out, int sx, int sy, long pitch, c
                 return 0;
         }
         const int threads = 128;
-        static const bool tune_bpt1 = getenv("UGB200_DXT_BPT1") != nullptr;  // experiment knob: one block per thread
         // DXT5-YCoCg: one block per thread — two unrolled blocks (~50 KB of SASS) overflow the instruction cache (ncu: the top stall
         // was no_instruction); DXT1: two blocks per thread for 128-bit loads/stores
-        const bool pair = DXT_TYPE == 1 && !tune_bpt1 && !(wb & 1) && !(15 & (size_t) src) && !(pitch & 15) && !(15 & (size_t) out);
+        const bool pair = DXT_TYPE == 1 && !(wb & 1) && !(15 & (size_t) src) && !(pitch & 15) && !(15 & (size_t) out);
         if (hb > 65535) {
                 return -1;
         }
@@ -250,20 +249,13 @@ static int launch_uyvy(const void *src, void *out, int sx, int sy, long pitch, c
         const dim3 grid((groups + threads - 1) / threads, hb);
         const uint8_t *s = (const uint8_t *) src;
 #define UGB_LAUNCH(BPT, MIR) dxt_uyvy_kernel<DXT_TYPE, BPT, MIR><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch)
-        static const int tune_minb = getenv("UGB200_DXT_MINB") ? atoi(getenv("UGB200_DXT_MINB")) : 0;  // occupancy experiment knob
-        if (DXT_TYPE == 1 && pair && !mirrored && (tune_minb == 1 || tune_minb >= 7)) {
-                if (tune_minb == 1) {
-                        dxt_uyvy_kernel<DXT_TYPE, 2, false, 1><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch);
-                } else if (tune_minb == 7) {
-                        dxt_uyvy_kernel<DXT_TYPE, 2, false, 7><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch);
-                } else {
-                        dxt_uyvy_kernel<DXT_TYPE, 2, false, 8><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch);
-                }
-        } else if (pair) {
-                if (mirrored) {
-                        UGB_LAUNCH(2, true);
-                } else {
-                        UGB_LAUNCH(2, false);
+        if (DXT_TYPE == 1 && pair) {
+                if constexpr (DXT_TYPE == 1) {  // (the two-block variant is not even instantiated for DXT5-YCoCg)
+                        if (mirrored) {
+                                UGB_LAUNCH(2, true);
+                        } else {
+                                UGB_LAUNCH(2, false);
+                        }
                 }
         } else {
                 if (mirrored) {
