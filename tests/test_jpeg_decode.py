@@ -180,3 +180,61 @@ def test_gpu_roundtrip_8k(orc):
     assert psnr(out, src) > 38.0
     _, want = orc_decode(orc, s, 0, w, h)
     assert np.array_equal(out, want)
+
+
+def test_stream_parser_survives_corruption(orc):
+    """host logic: truncated and randomly damaged streams are rejected or parsed, never read out of bounds (segments stay inside the stream)"""
+    from ultragrid_b200 import _lib
+    lib = _lib.load()
+    s, _ = make_stream(orc, "ours-uyvy", 200, 120, 90, 0)
+    rng = np.random.default_rng(5)
+    cap = 1 << 12
+    begin, end = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+
+    class Info(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_int) for n in ("width", "height", "components", "h_samp", "v_samp", "adobe", "ri", "native")]
+    for trial in range(400):
+        a = np.frombuffer(s, np.uint8).copy()
+        kind = trial % 4
+        if kind == 0:
+            a = a[:rng.integers(2, len(a))]                       # truncated anywhere
+        elif kind == 1:
+            pos = rng.integers(0, len(a), rng.integers(1, 8))     # a few damaged bytes, headers included
+            a[pos] = rng.integers(0, 256, len(pos))
+        elif kind == 2:
+            pos = rng.integers(0, min(len(a), 700))               # a damaged header length / marker
+            a[pos] = 0xFF
+        else:
+            a = np.concatenate([a[:rng.integers(2, 600)], rng.integers(0, 256, rng.integers(1, 300)).astype(np.uint8)])
+        a = np.ascontiguousarray(a)
+        rc = lib.ugb200_jpeg_get_image_info(a.ctypes.data, len(a), ctypes.byref(Info()))
+        n = lib.ugb200_jpeg_debug_segments(a.ctypes.data, len(a), begin.ctypes.data, end.ctypes.data, cap)
+        if n > 0:
+            k = min(n, cap)
+            assert (begin[:k] <= end[:k]).all() and (end[:k] <= len(a)).all(), (trial, kind)
+        assert rc <= 0
+
+
+@pytest.mark.gpu
+def test_gpu_decoder_survives_corruption(orc):
+    """damaged entropy-coded data decodes to *something* of the right size (or is rejected) without faulting the device"""
+    import torch
+    from ultragrid_b200 import api
+    s, _ = make_stream(orc, "ours-uyvy", 200, 120, 90, 0)
+    rng = np.random.default_rng(6)
+    dec = api.JpegDecoder()
+    good = dec.decode(s, UYVY)
+    for trial in range(40):
+        a = np.frombuffer(s, np.uint8).copy()
+        if trial % 2:
+            a = a[:rng.integers(700, len(a))]
+        else:
+            pos = rng.integers(640, len(a), rng.integers(1, 30))
+            a[pos] = rng.integers(0, 256, len(pos))
+        try:
+            out = dec.decode(a.tobytes(), UYVY)
+            assert out.size == good.size
+        except RuntimeError:
+            pass
+    torch.cuda.synchronize()
+    assert np.array_equal(dec.decode(s, UYVY), good)  # the decoder is still healthy
