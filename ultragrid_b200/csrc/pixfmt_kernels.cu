@@ -17,8 +17,6 @@ namespace ugb {
 struct conv_params {
         int rshift, gshift, bshift;
         int aux;  // converter-specific, computed on the host from dst_len (see conv_rgba_rgb)
-        int l1;   // set by the launcher: multi-piece vector loads go through L1
-        int stage;  // set by the launcher: warp-coalesced stores through shared memory
 };
 /// where a chunk sits, for the rare converter whose result depends on more than its own chunk
 struct row_ctx {
@@ -1105,7 +1103,6 @@ __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ ds
                                                         conv_params p)
 {
         constexpr int NI = C::IN / 4, NO = C::OUT / 4;
-        constexpr bool STAGE = C::OUT >= 32 && C::OUT <= 64;
         const int cx = blockIdx.x * blockDim.x + threadIdx.x;
         const long out_off = (long) cx * C::OUT;
         if (out_off >= wlen) {
@@ -1127,7 +1124,9 @@ __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ ds
 #pragma unroll
                         for (int i = 0; i < NI / 4; ++i) {
                                 uint4 v;
-                                if (NI > 4 && p.l1) {  // several 16-byte pieces per thread: lanes stride over the sectors, let L1 keep them for the next piece
+                                if (NI >= 16) {  // four or more 16-byte pieces per thread: neighbouring lanes are 64+ bytes apart and every piece touches a
+                                                 // fresh part of lines the previous one already pulled in - let L1 keep them (measured: RG48->RGB 64 -> 46 us,
+                                                 // RGBA->RGB 44 -> 38 us at 8K; with two or three pieces per thread the streaming load is as good or better)
                                         v = __ldg(s + i);
                                 } else {
                                         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -1154,24 +1153,7 @@ __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ ds
                 C::run(in, out, p, rc);
                 uint8_t *d = dst + row * dst_pitch + out_off;
                 const bool full = vec_ok && out_off + C::OUT <= wlen;
-                if (STAGE && p.stage && __activemask() == 0xffffffffu && __all_sync(0xffffffffu, full)) {  // the whole warp is here with full chunks
-                        // a thread's 2-4 pieces are 32-64 bytes apart from its neighbour's: through shared memory the warp stores 512 contiguous
-                        // bytes per instruction instead of 32 scattered 16-byte pieces (conflict-free both ways for 2, 3 and 4 pieces per lane)
-                        __shared__ uint4 s_out[4][NO / 4 * 32];
-                        uint4 *buf = s_out[threadIdx.x >> 5];
-                        const int lane = threadIdx.x & 31;
-#pragma unroll
-                        for (int i = 0; i < NO / 4; ++i) {
-                                buf[lane * (NO / 4) + i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
-                        }
-                        __syncwarp();
-                        uint4 *wd = (uint4 *) (d - (long) lane * C::OUT);  // the warp's first chunk
-#pragma unroll
-                        for (int i = 0; i < NO / 4; ++i) {
-                                wd[i * 32 + lane] = buf[i * 32 + lane];
-                        }
-                        __syncwarp();
-                } else if (full) {
+                if (full) {
 #pragma unroll
                         for (int i = 0; i < NO / 4; ++i) {
                                 ((uint4 *) d)[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
@@ -1202,10 +1184,6 @@ static int launch_line(void *dst, long dst_pitch, const void *src, long src_pitc
                 src_size = src_pitch * height;
         }
         const bool vec_ok = !(15 & (size_t) dst) && !(15 & (size_t) src) && !(dst_pitch & 15) && !(src_pitch & 15);
-        static const bool l1 = getenv("UGB200_LINE_L1") != nullptr;  // experiment knob
-        p.l1 = l1;
-        static const bool stage = getenv("UGB200_LINE_STAGE") != nullptr;  // experiment knob
-        p.stage = stage;
         const int chunks = (wlen + C::OUT - 1) / C::OUT;
         const int threads = 128;
         dim3 grid((chunks + threads - 1) / threads, height > 65535 ? 65535 : height);
