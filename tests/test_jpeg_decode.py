@@ -104,7 +104,7 @@ def test_image_info_host_only(orc):
     assert lib.ugb200_jpeg_get_image_info((ctypes.c_uint8 * 4)(1, 2, 3, 4), 4, ctypes.byref(Info())) != 0
 
 
-@pytest.mark.parametrize("kind,w,h,q,ri", STREAMS)
+@pytest.mark.parametrize("kind,w,h,q,ri", STREAMS + [("ours-uyvy", 3840, 2160, 90, 0), ("ours-uyvy", 7680, 4320, 90, 0)])  # the last two: 4 / 8 scan threads
 def test_stream_parser_finds_restart_segments(orc, kind, w, h, q, ri):
     """host logic of the decoder: the SSE2 marker scan against a plain numpy search of the same stream"""
     from ultragrid_b200 import _lib
@@ -114,7 +114,7 @@ def test_stream_parser_finds_restart_segments(orc, kind, w, h, q, ri):
     ff = np.flatnonzero(a[:-1] == 0xFF)
     nxt = a[ff + 1]
     sos = ff[nxt == 0xDA]
-    cap = 1 << 16
+    cap = 1 << 17
     begin, end = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
     n = lib.ugb200_jpeg_debug_segments(a.ctypes.data, len(s), begin.ctypes.data, end.ctypes.data, cap)
     assert n > 0

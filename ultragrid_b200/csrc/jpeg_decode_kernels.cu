@@ -20,6 +20,9 @@
 #include <emmintrin.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <chrono>
 #include <cstdio>
 #include <new>
@@ -329,8 +332,74 @@ __global__ void __launch_bounds__(128) jpeg_idct_uyvy_kernel(const int16_t *__re
 
 using namespace ugb;
 
+/// A handful of persistent host threads for the marker scan (creating threads per frame costs more than the scan of an 8K stream).
+class scan_pool {
+public:
+        explicit scan_pool(int n)
+        {
+                for (int i = 0; i < n; ++i) {
+                        workers.emplace_back([this, i] { run(i); });
+                }
+        }
+        ~scan_pool()
+        {
+                {
+                        std::lock_guard<std::mutex> lk(m);
+                        quit = true;
+                }
+                cv.notify_all();
+                for (auto &t : workers) {
+                        t.join();
+                }
+        }
+        int size() const { return (int) workers.size(); }
+        /// runs job(i) for i in 0..n-1 on the workers (n <= size()) while the caller does its own share; returns when all are done
+        void parallel(int n, const std::function<void(int)> &job_, const std::function<void()> &own)
+        {
+                {
+                        std::lock_guard<std::mutex> lk(m);
+                        job = &job_, todo = n, left = n, ++generation;
+                }
+                cv.notify_all();
+                own();
+                std::unique_lock<std::mutex> lk(m);
+                done.wait(lk, [this] { return left == 0; });
+                job = nullptr;
+        }
+
+private:
+        void run(int i)
+        {
+                unsigned seen = 0;
+                for (;;) {
+                        const std::function<void(int)> *j;
+                        {
+                                std::unique_lock<std::mutex> lk(m);
+                                cv.wait(lk, [&] { return quit || (generation != seen && i < todo); });
+                                if (quit) {
+                                        return;
+                                }
+                                seen = generation, j = job;
+                        }
+                        (*j)(i);
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--left == 0) {
+                                done.notify_one();
+                        }
+                }
+        }
+        std::vector<std::thread> workers;
+        std::mutex m;
+        std::condition_variable cv, done;
+        const std::function<void(int)> *job = nullptr;
+        int todo = 0, left = 0;
+        unsigned generation = 0;
+        bool quit = false;
+};
+
 struct ugb200_jpeg_decoder {
         cudaStream_t stream = nullptr;
+        scan_pool pool{ 7 };
         uint8_t *d_stream = nullptr, *planes = nullptr, *native = nullptr, *staging = nullptr;
         int16_t *coef = nullptr;
         uint32_t *d_seg = nullptr;
@@ -611,6 +680,30 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
         return P.have_sof && g.nscans > 0 ? 0 : -3;
 }
 
+/// all marker candidates of the stream, in order; large streams are split over the pool (piece 0 on the calling thread)
+void collect_markers(const uint8_t *stream, size_t len, scan_pool *pool, uint8_t *copy_to, std::vector<uint64_t> &markers)
+{
+        constexpr int kMaxThreads = 8;
+        int nt = len > (4u << 20) ? kMaxThreads : len > (1u << 20) ? 4 : 1;
+        if (pool == nullptr || pool->size() + 1 < nt) {
+                nt = pool ? pool->size() + 1 : 1;
+        }
+        std::vector<uint64_t> part[kMaxThreads];
+        const size_t chunk = (len / nt + 15) & ~(size_t) 15;
+        auto range = [&](int i) {
+                const size_t lo = std::min(len, chunk * i), hi = i == nt - 1 ? len : std::min(len, chunk * (i + 1));
+                scan_markers(stream, lo, hi, len, part[i], copy_to);
+        };
+        if (nt == 1) {
+                range(0);
+        } else {
+                pool->parallel(nt - 1, [&](int w) { range(w + 1); }, [&] { range(0); });
+        }
+        for (int i = 0; i < nt; ++i) {
+                markers.insert(markers.end(), part[i].begin(), part[i].end());
+        }
+}
+
 int native_codec(const parsed &P)
 {
         const dec_geom &g = P.g;
@@ -649,7 +742,14 @@ UGB_API long ugb200_jpeg_debug_segments(const uint8_t *stream, size_t len, uint3
         }
         parsed P;
         dec_tables T;
-        const int rc = parse_stream(stream, len, P, &T, true);
+        std::vector<uint64_t> markers;
+        if (len > (1u << 20)) {  // the same threaded scan the decoder uses
+                scan_pool pool(7);
+                collect_markers(stream, len, &pool, nullptr, markers);
+        } else {
+                collect_markers(stream, len, nullptr, nullptr, markers);
+        }
+        const int rc = parse_stream(stream, len, P, &T, true, &markers);
         if (rc != 0) {
                 return rc;
         }
@@ -723,24 +823,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         // one pass over the caller's (pageable) buffer: copy it to the pinned staging buffer and collect the marker candidates, split over a
         // few threads when the stream is large (an 8K frame is 5-50 MB)
         std::vector<uint64_t> markers;
-        {
-                constexpr int kMaxThreads = 8;
-                const int nt = len > (4u << 20) ? kMaxThreads : len > (1u << 20) ? 4 : 1;
-                std::vector<uint64_t> part[kMaxThreads];
-                std::thread th[kMaxThreads];
-                const size_t chunk = (len / nt + 15) & ~(size_t) 15;
-                for (int i = 1; i < nt; ++i) {
-                        const size_t lo = std::min(len, chunk * i), hi = i == nt - 1 ? len : std::min(len, chunk * (i + 1));
-                        th[i] = std::thread(scan_markers, stream, lo, hi, len, std::ref(part[i]), H.stream);
-                }
-                scan_markers(stream, 0, nt == 1 ? len : std::min(len, chunk), len, part[0], H.stream);
-                for (int i = 1; i < nt; ++i) {
-                        th[i].join();
-                }
-                for (int i = 0; i < nt; ++i) {
-                        markers.insert(markers.end(), part[i].begin(), part[i].end());
-                }
-        }
+        collect_markers(stream, len, &d->pool, H.stream, markers);
         lap("scan+stage");
         int rc = parse_stream(stream, len, P, H.tables, true, &markers);
         if (rc != 0) {
