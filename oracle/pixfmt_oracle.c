@@ -1031,3 +1031,37 @@ API int orc_copyline_named(int func, unsigned char *dst, long dst_pitch, const u
         }
         return 0;
 }
+
+/* ---- src/utils/cuda_pix_conv.cu (device-to-device helpers of the reference), restated on the CPU ---------------------------------------------
+ * kind 0 RGB->RGBA (:7-29), 1 RGBA->RGB (:32-54), 2 UYVY->RGBA (:60-92), 3 RGBA->UYVY (:95-133).  The float matrix of kind 2 follows the FMA
+ * contraction of the reference's sm_100a build (read from its SASS): y = 1.164f * (Y - 16); R = fma(v, 1.793f, y);
+ * G = fma(v, -0.534f, y) - 0.213f * u; B = fma(u, 2.115f, y); x > 0 ? (x < 255 ? trunc : 255) : 0.  Pinned on the GPU against the unmodified file. */
+#include <math.h>
+static uint32_t sat_trunc(float x) { return x > 0.0f ? (x < 255.0f ? (uint32_t) (int) x : 255u) : 0u; }
+API void orc_cuda_pix_conv(int kind, unsigned char *dst, size_t dpitch, const unsigned char *src, size_t spitch, int width, int height)
+{
+        for (int y = 0; y < height; ++y) {
+                const unsigned char *s = src + (size_t) y * spitch;
+                unsigned char *d = dst + (size_t) y * dpitch;
+                for (int x = 0; x < width; ++x) {
+                        if (kind == 0) {
+                                d[4 * x] = s[3 * x], d[4 * x + 1] = s[3 * x + 1], d[4 * x + 2] = s[3 * x + 2], d[4 * x + 3] = 0;
+                        } else if (kind == 1) {
+                                d[3 * x] = s[4 * x], d[3 * x + 1] = s[4 * x + 1], d[3 * x + 2] = s[4 * x + 2];
+                        } else if (kind == 2) {
+                                const unsigned char *b = s + 4 * (x / 2);
+                                const float u = (float) (b[0] - 128), v = (float) (b[2] - 128), yy = (float) (b[1 + 2 * (x & 1)] - 16) * 1.164f;
+                                d[4 * x] = sat_trunc(fmaf(v, 1.793f, yy)), d[4 * x + 1] = sat_trunc(fmaf(v, -0.534f, yy) - u * 0.213f), d[4 * x + 2] = sat_trunc(fmaf(u, 2.115f, yy));
+                                d[4 * x + 3] = 0;
+                        } else if (x % 2 == 0 && x + 1 < width) {
+                                const unsigned char *p = s + 4 * x;
+                                const int y1 = 11993 * p[0] + 40239 * p[1] + 4063 * p[2] + (1 << 20), y2 = 11993 * p[4] + 40239 * p[5] + 4063 * p[6] + (1 << 20);
+                                int u = (-6619 * p[0] - 22151 * p[1] + 28770 * p[2]) + (-6619 * p[4] - 22151 * p[5] + 28770 * p[6]);
+                                int v = (28770 * p[0] - 26149 * p[1] - 2621 * p[2]) + (28770 * p[4] - 26149 * p[5] - 2621 * p[6]);
+                                u = u / 2 + (1 << 23), v = v / 2 + (1 << 23);
+                                const int lim = (1 << 24) - 1;
+                                d[2 * x] = clampr(u, 0, lim) >> 16, d[2 * x + 1] = clampr(y1, 0, lim) >> 16, d[2 * x + 2] = clampr(v, 0, lim) >> 16, d[2 * x + 3] = clampr(y2, 0, lim) >> 16;
+                        }
+                }
+        }
+}
