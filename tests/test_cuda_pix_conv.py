@@ -32,7 +32,7 @@ def test_gpu_equals_reference_kernels_and_restatement(orc, name):
     sym, kind, bi, bo = NAMES[name]
     orc.orc_cuda_pix_conv.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
     orc.orc_cuda_pix_conv.restype = None
-    for i, (w, h, pad) in enumerate([(2, 1, 0), (5, 3, 0), (16, 2, 0), (17, 5, 6), (64, 4, 16), (130, 3, 2), (1920, 1080, 0), (7680, 16, 0)]):
+    for i, (w, h, pad) in enumerate([(2, 1, 0), (5, 3, 0), (16, 2, 0), (17, 5, 4), (64, 4, 16), (130, 3, 8), (1920, 1080, 0), (7680, 16, 0)]):  # pitches stay 4-byte aligned: the reference stores uchar4
         wi = (w + 1) // 2 * 2 if bi == 2 else w  # UYVY rows hold whole pairs
         sp, dp = wi * bi + pad, ((w + 1) // 2 * 2 if bo == 2 else w) * bo + pad
         src = util.rng_bytes(sp * h, 900 + i)

@@ -3,6 +3,7 @@ valid baseline stream, PSNR equal to libjpeg's own encoder at the same quality/t
 round-trip criterion (test/gpujpeg_test.cpp:68-106).  GPU part: the CUDA encoder emits the oracle's bytes exactly."""
 import ctypes
 import io
+import os
 
 import numpy as np
 import pytest
@@ -218,3 +219,16 @@ def test_gpu_8k_uyvy_jpeg_decodes_with_expected_psnr(orc):
     Y, Cb, _ = uyvy_planes(uyvy, w, h)
     assert psnr(dec[:, :, 0], Y) > 36 and psnr(dec[:, ::2, 1], Cb) > 36
     enc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("knob", ["UGB200_JPEG_SINGLE_PASS", "UGB200_JPEG_SPLIT"])
+def test_gpu_alternative_routes_give_the_same_bytes(knob):
+    """the single-pass compaction (decoupled look-back) and the forced split path are process-wide switches: the byte-exactness tests run
+    once more in a child process with the switch set"""
+    import subprocess
+    import sys
+    env = dict(os.environ, **{knob: "1"})
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "equals_oracle_bytes or serial_route or source_pitch or larger_than_output"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -1320,8 +1320,11 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                 cudaMemsetAsync(e->total + 1, 0, 8, e->stream);
                 ctas_per_scan = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.mcu_per_scan + 127) / 128;
                 nctas = fmt == FMT_UYVY_422 ? ctas_per_scan : ctas_per_scan * 3;
-                static const bool two_pass = getenv("UGB200_JPEG_COMPACT") != nullptr;  // cross-check: slots + scan + compact kernels
-                single_pass = !two_pass;
+                // Single-pass compaction (decoupled look-back inside the fused kernel) is implemented and byte-exact, but measured no faster than
+                // slots + scan + compact on this part (8K natural 184 vs 181 us, testcard 127 vs 113 us, noise 393 vs 397 us: the ticket, the size
+                // pre-pass and two more barriers cost what the two small kernels cost) - it stays behind a switch.
+                static const bool want_single_pass = getenv("UGB200_JPEG_SINGLE_PASS") != nullptr;
+                single_pass = want_single_pass;
                 jpeg_lookback lb = { nullptr, nullptr, e->out, (uint32_t) e->out_cap, e->total, ctas_per_scan };
                 if (single_pass) {
                         if (!grow(e->lb_state, e->lb_cap, (size_t) nctas + 1)) {
