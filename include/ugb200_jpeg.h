@@ -50,6 +50,12 @@ UGB_API int ugb200_jpeg_result_device(ugb200_jpeg_encoder *enc, const void **dev
 UGB_API int ugb200_jpeg_encode(ugb200_jpeg_encoder *enc, const void *src, int src_is_device, long pitch, int width, int height,
                                int codec, const struct ugb200_jpeg_params *params, uint8_t **out, size_t *out_size);
 
+/* Same, but the stream goes straight into the caller's host buffer `dst` (capacity dst_cap; pinned memory keeps the copy
+ * asynchronous to other streams) - the module writes into its pooled output frame without the memcpy of gpujpeg.cpp:629-630.
+ * -5 if the stream does not fit. */
+UGB_API int ugb200_jpeg_encode_into(ugb200_jpeg_encoder *enc, const void *src, int src_is_device, long pitch, int width, int height,
+                                    int codec, const struct ugb200_jpeg_params *params, uint8_t *dst, size_t dst_cap, size_t *out_size);
+
 /* Stage access for tests: quantised zig-zag coefficients (int16[blocks][64], scan order) of the last encode, device ptr. */
 UGB_API int ugb200_jpeg_debug_coefficients(ugb200_jpeg_encoder *enc, const int16_t **dev_ptr, size_t *count);
 

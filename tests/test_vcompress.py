@@ -18,6 +18,8 @@ def test_registry_and_option_parsing_fail_cleanly():
         compress.Compress("cuda_dxt:DXT3")  # usage error like cuda_dxt.cpp:113-117
     with pytest.raises(RuntimeError):
         compress.Compress("GPUJPEG:bogus=1")
+    with pytest.raises(RuntimeError):
+        compress.Compress("GPUJPEG:lanes=0")
 
 
 @pytest.mark.parametrize("cands", [(RGB, UYVY), (UYVY, RGB), (UYVY, RGB, RGBA), (RGBA, RGB), (UYVY,), (YUYV, UYVY)])
@@ -89,17 +91,18 @@ def test_cuda_dxt_module_equals_kernel_path(orc, cfg, inc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("devices", [[0], [0, 0, 0]])
-def test_gpujpeg_module_keeps_order_and_matches_oracle(orc, devices):
-    """async frame API with 1 encoder (inline) and with 3 worker threads (all on GPU 0): results pop in submission order
-    and carry the oracle's bytes"""
+@pytest.mark.parametrize("devices,cfg", [([0], "GPUJPEG:q=90:lanes=1"), ([0], "GPUJPEG:q=90"), ([0, 0, 0], "GPUJPEG:q=90:lanes=1"),
+                                         ([0, 0], "GPUJPEG:q=90:lanes=2")])
+def test_gpujpeg_module_keeps_order_and_matches_oracle(orc, devices, cfg):
+    """async frame API with 1 encoder (inline, the reference's single-device shape), with the default 3 lanes on one device, with one
+    worker per cuda_devices[] entry (all on GPU 0) and with both: results pop in submission order and carry the oracle's bytes"""
     from ultragrid_b200 import compress
     compress.set_cuda_devices(devices)
     try:
         w, h, n = 640, 360, 7
         frames = [util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h, 100 + i).reshape(-1), w, h) for i in range(n)]
         want = [orc_encode(orc, f, w, h, UYVY, 90) for f in frames]
-        c = compress.Compress("GPUJPEG:q=90")
+        c = compress.Compress(cfg)
         for f in frames:
             c.push(f, w, h, UYVY)
         c.push(None, 0, 0, 0)

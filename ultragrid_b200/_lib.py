@@ -90,6 +90,7 @@ SIGNATURES = {
     "ugb200_jpeg_encode_device": (_i, [_vp, _vp, _l, _i, _i, _i, _vp]),
     "ugb200_jpeg_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ugb200_jpeg_encode": (_i, [_vp, _vp, _i, _l, _i, _i, _i, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    "ugb200_jpeg_encode_into": (_i, [_vp, _vp, _i, _l, _i, _i, _i, _vp, _vp, _sz, ctypes.POINTER(_sz)]),
     "ugb200_jpeg_get_image_info": (_i, [_vp, _sz, _vp]),
     "ugb200_jpeg_debug_segments": (_l, [_vp, _sz, _vp, _vp, _l]),
     "ugb200_jpeg_decoder_create": (_vp, [_vp]),

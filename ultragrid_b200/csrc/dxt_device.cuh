@@ -212,6 +212,9 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float px(const float2 (&v)[8], int i) { return ((i & 3) >> 1) ? v[2 * (i >> 2) + (i & 1)].y : v[2 * (i >> 2) + (i & 1)].x; }
 
+/// BRANCH = false computes the indices of a flat block (max_code == min_code) too and discards them: straight-line code, so that
+/// the scheduler may interleave the two blocks of a thread
+template <bool BRANCH = true>
 __device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][2])
 {
         float2 R[8], G[8], B[8];
@@ -266,7 +269,7 @@ __device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][
         const uint32_t min_code = (__float_as_uint(qnr) << 11) + (__float_as_uint(qng) << 5) + __float_as_uint(qnb) - kCodeBias;
 
         uint32_t indices = 0;
-        if (max_code != min_code) {
+        if (!BRANCH || max_code != min_code) {
                 const float ex_r = __fmul_rn(__fadd_rn(qxr, -kRoundMagic), kInv31);
                 const float ex_g = __fmul_rn(__fadd_rn(qxg, -kRoundMagic), kInv63);
                 const float ex_b = __fmul_rn(__fadd_rn(qxb, -kRoundMagic), kInv31);
@@ -290,6 +293,9 @@ __device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][
                 }
                 constexpr uint32_t kIdxBias = 0x4B000000u * 0x55555555u;
                 indices = acc0 + acc1 - kIdxBias;
+                if (!BRANCH) {
+                        indices = max_code != min_code ? indices : 0u;
+                }
         }
         const bool swap_end = max_code < min_code;
         if (swap_end) {

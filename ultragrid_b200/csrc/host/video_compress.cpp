@@ -426,6 +426,7 @@ struct encoder_state {  // one per CUDA device, gpujpeg.cpp:103-252
 
 struct state_video_compress_gpujpeg {
         int quality = -1, restart_interval = 0;
+        int lanes = 3;  // workers (encoder + stream + thread) per CUDA device: the H2D of one frame overlaps kernel + D2H of the previous ones
         std::vector<encoder_state *> workers;
         bool uses_worker_threads = false;
         synchronized_queue<std::shared_ptr<video_frame>> out_queue;
@@ -516,18 +517,18 @@ std::shared_ptr<video_frame> encoder_state::compress_step(std::shared_ptr<video_
                 p.quality = parent->quality;
         }
         p.restart_interval = parent->restart_interval;
-        uint8_t *compressed = nullptr;
-        size_t size = 0;
-        if (ugb200_jpeg_encode(encoder, in, 1, 0, (int) w, (int) h, enc_input_codec, &p, &compressed, &size) != 0) {  // :624
+        // the stream goes straight into the pooled (pinned) output frame: no encoder-owned buffer + memcpy as at :629-630
+        const size_t out_cap = (size_t) w * h * 3;  // :355
+        std::shared_ptr<video_frame> out = pinned_pool_get(out_cap);
+        if (!out) {
                 return {};
         }
-        std::shared_ptr<video_frame> out = pinned_pool_get((size_t) w * h * 3);  // :355
-        if (!out) {
+        size_t size = 0;
+        if (ugb200_jpeg_encode_into(encoder, in, 1, 0, (int) w, (int) h, enc_input_codec, &p, (uint8_t *) out->tiles[0].data, out_cap, &size) != 0) {  // :624
                 return {};
         }
         out->color_spec = JPEG, out->fps = tx->fps, out->interlacing = tx->interlacing;
         out->tiles[0].width = w, out->tiles[0].height = h, out->tiles[0].data_len = (unsigned) size;
-        memcpy(out->tiles[0].data, compressed, size);  // :629-630
         return out;
 }
 
@@ -583,18 +584,27 @@ void *gpujpeg_compress_init(struct module *, const char *opts)
                         s->quality = atoi(item.c_str() + 2);
                 } else if (item.rfind("restart=", 0) == 0) {
                         s->restart_interval = atoi(item.c_str() + 8);
+                } else if (item.rfind("lanes=", 0) == 0) {  // B200 addition; lanes=1 on one device = the reference's synchronous push
+                        s->lanes = atoi(item.c_str() + 6);
+                        if (s->lanes < 1 || s->lanes > 8) {
+                                fprintf(stderr, "[GPUJPEG] lanes must be 1..8\n");
+                                delete s;
+                                return nullptr;
+                        }
                 } else if (!item.empty() && isdigit((unsigned char) item[0])) {
                         s->quality = atoi(item.c_str());  // legacy "GPUJPEG:<quality>"
                 } else if (!item.empty()) {
-                        fprintf(stderr, "[GPUJPEG] unknown option: %s\nusage:\n\t-c GPUJPEG[:q=<quality>][:restart=<interval>]\n", item.c_str());
+                        fprintf(stderr, "[GPUJPEG] unknown option: %s\nusage:\n\t-c GPUJPEG[:q=<quality>][:restart=<interval>][:lanes=<frames in flight per device>]\n", item.c_str());
                         delete s;
                         return nullptr;
                 }
         }
-        for (unsigned i = 0; i < cuda_devices_count; ++i) {  // one encoder per device, :446-466
-                s->workers.push_back(new encoder_state(s, (int) cuda_devices[i]));
+        for (int l = 0; l < s->lanes; ++l) {  // one encoder per device (:446-466), times `lanes`; lane-major so that the first idle
+                for (unsigned i = 0; i < cuda_devices_count; ++i) {  // workers found by push() spread over the devices first
+                        s->workers.push_back(new encoder_state(s, (int) cuda_devices[i]));
+                }
         }
-        s->uses_worker_threads = cuda_devices_count > 1;
+        s->uses_worker_threads = s->workers.size() > 1;
         if (s->uses_worker_threads) {
                 for (encoder_state *w : s->workers) {
                         w->thread = std::thread(&encoder_state::worker, w);

@@ -1399,10 +1399,11 @@ int ugb200_jpeg_result_device(ugb200_jpeg_encoder *e, const void **dev_ptr, size
         return 0;
 }
 
-int ugb200_jpeg_encode(ugb200_jpeg_encoder *e, const void *src, int src_is_device, long pitch, int width, int height, int codec,
-                       const struct ugb200_jpeg_params *params, uint8_t **out, size_t *out_size)
+/// shared body of ugb200_jpeg_encode / ugb200_jpeg_encode_into: upload (host source), encode, wait, stream to `dst` (host)
+static int encode_to_host(ugb200_jpeg_encoder *e, const void *src, int src_is_device, long pitch, int width, int height, int codec,
+                          const struct ugb200_jpeg_params *params, uint8_t *dst, size_t dst_cap, uint8_t **out, size_t *out_size)
 {
-        if (!e || !src || !out || !out_size || width <= 0 || height <= 0) {
+        if (!e || !src || !out_size || width <= 0 || height <= 0) {
                 return -1;
         }
         const int bpp = codec == UGB_UYVY ? 2 : codec == UGB_RGB ? 3 : 0;
@@ -1432,16 +1433,41 @@ int ugb200_jpeg_encode(ugb200_jpeg_encoder *e, const void *src, int src_is_devic
         if (rc != 0) {
                 return rc;
         }
-        if (!grow_host(e->h_out, e->h_out_cap, e->out_cap)) {
-                return -2;
+        if (dst == nullptr) {  // encoder-owned pinned buffer
+                if (!grow_host(e->h_out, e->h_out_cap, e->out_cap)) {
+                        return -2;
+                }
+                dst = e->h_out;
+        } else if (n > dst_cap) {
+                return -5;
         }
-        if (cudaMemcpyAsync(e->h_out, e->out, n, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess ||
+        if (cudaMemcpyAsync(dst, e->out, n, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess ||
             cudaStreamSynchronize(e->stream) != cudaSuccess) {
                 return -2;
         }
-        *out = e->h_out;
+        if (out) {
+                *out = dst;
+        }
         *out_size = n;
         return 0;
+}
+
+int ugb200_jpeg_encode(ugb200_jpeg_encoder *e, const void *src, int src_is_device, long pitch, int width, int height, int codec,
+                       const struct ugb200_jpeg_params *params, uint8_t **out, size_t *out_size)
+{
+        if (!out) {
+                return -1;
+        }
+        return encode_to_host(e, src, src_is_device, pitch, width, height, codec, params, nullptr, 0, out, out_size);
+}
+
+int ugb200_jpeg_encode_into(ugb200_jpeg_encoder *e, const void *src, int src_is_device, long pitch, int width, int height, int codec,
+                            const struct ugb200_jpeg_params *params, uint8_t *dst, size_t dst_cap, size_t *out_size)
+{
+        if (!dst) {
+                return -1;
+        }
+        return encode_to_host(e, src, src_is_device, pitch, width, height, codec, params, dst, dst_cap, nullptr, out_size);
 }
 
 int ugb200_jpeg_debug_coefficients(ugb200_jpeg_encoder *e, const int16_t **dev_ptr, size_t *count)
