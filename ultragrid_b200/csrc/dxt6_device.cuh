@@ -17,19 +17,74 @@ __device__ __forceinline__ float roundu_magic(float x)
 }
 __device__ __forceinline__ uint32_t magic_bits(float m) { return __float_as_uint(m) - 0x4B000000u; }
 
+/// Colour index of one pixel from its distances to the four palette entries (cuda_dxt.cu:337-345): b0 = d0 > d3, b1 = d1 > d2, b2 = d0 > d2,
+/// b3 = d1 > d3, b4 = d2 > d3; index = (b0 & b4) | (((b1 & b2) | (b0 & b3)) << 1).  Written with predicate-combining compares
+/// (FSETP...AND) and predicated ORs: 9 instructions where selects on 0/1 integers take 14.  `>` is false for NaN in both forms.
+__device__ __forceinline__ void color_index_bits(uint32_t &cidx, float d0, float d1, float d2, float d3, uint32_t lo_bit, uint32_t hi_bit)
+{
+        asm("{\n\t"
+            ".reg .pred q, s, p, r;\n\t"
+            "setp.gt.f32 q, %1, %4;\n\t"         // b0
+            "setp.gt.and.f32 s, %3, %4, q;\n\t"  // b4 & b0
+            "setp.gt.f32 p, %2, %3;\n\t"         // b1
+            "setp.gt.and.f32 p, %1, %3, p;\n\t"  // b2 & b1
+            "setp.gt.and.f32 r, %2, %4, q;\n\t"  // b3 & b0
+            "or.pred p, p, r;\n\t"
+            "@s or.b32 %0, %0, %5;\n\t"
+            "@p or.b32 %0, %0, %6;\n\t"
+            "}"
+            : "+r"(cidx)
+            : "f"(d0), "f"(d1), "f"(d2), "f"(d3), "r"(lo_bit), "r"(hi_bit));
+}
+
+/// count = #{k : a <= T_k} of one pixel by binary search over the ordered thresholds (T0 >= T1 >= ... >= T6), its three bits ORed into
+/// `acc` at `unit` (predicated ORs, no integer selects)
+__device__ __forceinline__ void alpha_count_bits(uint32_t &acc, float a, float T0, float T1, float T2, float T3, float T4, float T5, float T6,
+                                                 uint32_t unit)
+{
+        asm("{\n\t"
+            ".reg .pred p1, p2, p3;\n\t"
+            ".reg .f32 t, u;\n\t"
+            "setp.le.f32 p1, %1, %5;\n\t"   // a <= T3
+            "selp.f32 t, %7, %3, p1;\n\t"   // T5 : T1
+            "setp.le.f32 p2, %1, t;\n\t"
+            "selp.f32 t, %8, %6, p2;\n\t"   // p1: T6 : T4
+            "selp.f32 u, %4, %2, p2;\n\t"   // !p1: T2 : T0
+            "selp.f32 t, t, u, p1;\n\t"
+            "setp.le.f32 p3, %1, t;\n\t"
+            "@p1 or.b32 %0, %0, %9;\n\t"
+            "@p2 or.b32 %0, %0, %10;\n\t"
+            "@p3 or.b32 %0, %0, %11;\n\t"
+            "}"
+            : "+r"(acc)
+            : "f"(a), "f"(T0), "f"(T1), "f"(T2), "f"(T3), "f"(T4), "f"(T5), "f"(T6), "r"(unit * 4u), "r"(unit * 2u), "r"(unit));
+}
+
+/// index = 1 + count, & 7, ^ (2 > index) (cuda_dxt.cu:376-388), i.e. 0 -> 0, 1..6 -> 2..7, 7 -> 1, on all 3-bit fields of a word at once
+__device__ __forceinline__ uint32_t alpha_count_to_index(uint32_t x)
+{
+        constexpr uint32_t kLsb = 0x09249249u;  // bit 0 of each of the ten fields
+        const uint32_t x1 = x >> 1, x2 = x >> 2;
+        const uint32_t all7 = x & x1 & x2 & kLsb;           // fields equal to 7
+        const uint32_t inc = (x | x1 | x2) & kLsb & ~all7;  // non-zero fields below 7 get + 1 (6 + 1 does not carry out of the field)
+        return ((x & ~(all7 * 7u)) + inc) | all7;
+}
+
 /// dxt_encode<6>, cuda_dxt.cu:471-509 with helpers :141-410
 __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (&g)[16], const float (&b)[16])
 {
         const double offd = (double) kOffset;
         float Y[16], Co[16], Cg[16];
-        // ConvertRGBToYCoCg (:141-148): unsuffixed literals make these double expressions, narrowed once
+        // ConvertRGBToYCoCg (:141-148): unsuffixed literals make these double expressions, narrowed once.  As compiled:
+        //   Y  = ((r + 2 g) + b) * 0.25,  Co = fma((2 r - 2 b), 0.25, off),  Cg = fma(((-r + 2 g) - b), 0.25, off)
+        // with g2 = g + g.  Written here with fewer FP64 instructions, each step the same real number rounded once: r + g2 = fma(g, 2, r)
+        // (2 g is exact), 2 r - 2 b = 2 (r - b) exactly (scaling by 2 commutes with rounding) and fma(2 d, 0.25, off) = fma(d, 0.5, off).
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
                 const double dr = (double) r[i], dg = (double) g[i], db = (double) b[i];
-                const double g2 = __dadd_rn(dg, dg);
-                Y[i] = __double2float_rn(__dmul_rn(__dadd_rn(__dadd_rn(dr, g2), db), 0.25));
-                Co[i] = __double2float_rn(__fma_rn(__dadd_rn(__dadd_rn(dr, dr), -__dadd_rn(db, db)), 0.25, offd));
-                Cg[i] = __double2float_rn(__fma_rn(__dadd_rn(__dadd_rn(-dr, g2), -db), 0.25, offd));
+                Y[i] = __double2float_rn(__dmul_rn(__dadd_rn(__fma_rn(dg, 2.0, dr), db), 0.25));
+                Co[i] = __double2float_rn(__fma_rn(__dadd_rn(dr, -db), 0.5, offd));
+                Cg[i] = __double2float_rn(__fma_rn(__dadd_rn(__fma_rn(dg, 2.0, -dr), -db), 0.25, offd));
         }
         // FindMinMaxColorsBox (:159-168)
         float mnY = Y[0], mxY = Y[0], mnCo = Co[0], mxCo = Co[0], mnCg = Cg[0], mxCg = Cg[0];
@@ -43,9 +98,12 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
         {
                 const float sCo = __fadd_rn(mnCo, mxCo), sCg = __fadd_rn(mnCg, mxCg);
                 float cov = 0.0f;
+                const float2 so2 = dup(sCo), sg2 = dup(sCg), mh = dup(-0.5f);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                        cov = __fmaf_rn(__fmaf_rn(sCo, -0.5f, Co[i]), __fmaf_rn(sCg, -0.5f, Cg[i]), cov);
+                for (int i = 0; i < 16; i += 2) {  // the two deviations of pixels i, i + 1 packed; the chain itself stays sequential
+                        const float2 eo = __ffma2_rn(so2, mh, f2(Co[i], Co[i + 1])), eg = __ffma2_rn(sg2, mh, f2(Cg[i], Cg[i + 1]));
+                        cov = __fmaf_rn(eo.x, eg.x, cov);
+                        cov = __fmaf_rn(eo.y, eg.y, cov);
                 }
                 if (cov < 0.0f) {  // :485-489
                         const float t = mxCg;
@@ -110,14 +168,8 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
                 UGB_DIST2(n2o, n2g, d2)
                 UGB_DIST2(n3o, n3g, d3)
 #undef UGB_DIST2
-                {
-                        const uint32_t bx = d0.x > d3.x, by = d1.x > d2.x, bz = d0.x > d2.x, bw = d1.x > d3.x, b4 = d2.x > d3.x;
-                        cidx |= ((bx & b4) | (((by & bz) | (bx & bw)) << 1)) << (2 * i);
-                }
-                {
-                        const uint32_t bx = d0.y > d3.y, by = d1.y > d2.y, bz = d0.y > d2.y, bw = d1.y > d3.y, b4 = d2.y > d3.y;
-                        cidx |= ((bx & b4) | (((by & bz) | (bx & bw)) << 1)) << (2 * i + 2);
-                }
+                color_index_bits(cidx, d0.x, d1.x, d2.x, d3.x, 1u << (2 * i), 2u << (2 * i));
+                color_index_bits(cidx, d0.y, d1.y, d2.y, d3.y, 1u << (2 * i + 2), 2u << (2 * i + 2));
         }
         outp.w = cidx;
 
@@ -142,27 +194,17 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
         // (rounding is monotone and max >= min), so the count is a 3-step binary search instead of 7 compares, and the
         // "& 7, ^ (2 > idx)" fix-up is the nibble table 0,2,3,4,5,6,7,1 indexed by the count.
         const float T0 = ab[1], T1 = ab[2], T2 = ab[3], T3 = ab[4], T4 = ab[5], T5 = ab[6], T6 = ab[0];
-        uint32_t ix = 0, iy = 0;
+        // count fields (3 bits per pixel) of pixels 0..9 in cntA, 10..15 in cntB; the map count -> index runs once per word afterwards
+        uint32_t cntA = 0, cntB = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-                const float a = Y[i];
-                const bool p1 = a <= T3;
-                const bool p2 = a <= (p1 ? T5 : T1);
-                const bool p3 = a <= (p1 ? (p2 ? T6 : T4) : (p2 ? T2 : T0));
-                const uint32_t cnt = (p1 ? 4u : 0u) + (p2 ? 2u : 0u) + (p3 ? 1u : 0u);
-                const uint32_t idx = (0x17654320u >> (4u * cnt)) & 7u;
-                if (i < 6) {
-                        ix |= idx << (3 * i + 16);  // pixel 5 keeps only its bit 0 here (:389) ...
-                }
-                if (i == 5) {
-                        iy = idx >> 1;  // ... and the rest opens the second word (:392)
-                }
-                if (i > 5) {
-                        iy |= idx << (3 * i - 16);
-                }
+                alpha_count_bits(i < 10 ? cntA : cntB, Y[i], T0, T1, T2, T3, T4, T5, T6, 1u << (3 * (i < 10 ? i : i - 10)));
         }
-        outp.x = (a0 << 8) | a1 | ix;
-        outp.y = iy;
+        const uint32_t idxA = alpha_count_to_index(cntA), idxB = alpha_count_to_index(cntB);
+        // the 48-bit index string (pixel i at bit 3 i) follows the two endpoint bytes (:389-392)
+        const uint32_t s_lo = idxA | (idxB << 30), s_hi = idxB >> 2;
+        outp.x = (a0 << 8) | a1 | (s_lo << 16);
+        outp.y = (s_lo >> 16) | (s_hi << 16);
         return outp;
 }
 

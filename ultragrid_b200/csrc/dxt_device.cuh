@@ -210,6 +210,22 @@ namespace ugb {
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
+/// load_row_uyvy() with the operations of pixels x and x + 2 paired in f32x2 instructions (same operation tree, half the issue slots)
+__device__ __forceinline__ void load_row_uyvy_packed(uint32_t w0, uint32_t w1, float *r, float *g, float *b)
+{
+        const float2 c2 = dup(kInv255);
+        const float2 u = __ffma2_rn(f2(magic_byte(w0, 0), magic_byte(w1, 0)), c2, dup(kBiasC));
+        const float2 v = __ffma2_rn(f2(magic_byte(w0, 2), magic_byte(w1, 2)), c2, dup(kBiasC));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {  // k = 0: pixels 0, 2;  k = 1: pixels 1, 3
+                const float2 yy = __fmul2_rn(__ffma2_rn(f2(magic_byte(w0, 1 + 2 * k), magic_byte(w1, 1 + 2 * k)), c2, dup(kBiasY)), dup(1.1643f));
+                const float2 R = __ffma2_rn(v, dup(1.7926f), yy);
+                const float2 G = __ffma2_rn(v, dup(-0.5328f), __ffma2_rn(u, dup(-0.2132f), yy));
+                const float2 B = __ffma2_rn(u, dup(2.1124f), yy);
+                r[k] = R.x, r[k + 2] = R.y, g[k] = G.x, g[k + 2] = G.y, b[k] = B.x, b[k + 2] = B.y;
+        }
+}
+
 __device__ __forceinline__ float px(const float2 (&v)[8], int i) { return ((i & 3) >> 1) ? v[2 * (i >> 2) + (i & 1)].y : v[2 * (i >> 2) + (i & 1)].x; }
 
 /// BRANCH = false computes the indices of a flat block (max_code == min_code) too and discards them: straight-line code, so that

@@ -66,8 +66,16 @@ __device__ __forceinline__ uint4 encode_block<6>(const float (&r)[16], const flo
 // ------------------------------------------------------------------------------------------------
 // fused UYVY -> DXT.  One thread = BPT horizontally adjacent blocks.
 // ------------------------------------------------------------------------------------------------
-template <int DXT_TYPE, int BPT, bool MIRROR, int MINB = 6>
-__global__ void __launch_bounds__(128, MINB) dxt_uyvy_kernel(const uint8_t *__restrict__ src, void *__restrict__ out,
+/// CTA shape: 80 registers per thread either way (24 warps per SM); DXT1 runs as 12 CTAs of 64 threads per SM - measured 32.8 us against
+/// 34.4 us for 6 CTAs of 128 on an 8K frame (finer-grained CTA turnover; 32-thread CTAs give the same, 256 is slower) - DXT5-YCoCg is
+/// indifferent and keeps 128.
+template <int DXT_TYPE>
+struct uyvy_cta {
+        static constexpr int threads = DXT_TYPE == 1 ? 64 : 128, min_ctas = DXT_TYPE == 1 ? 12 : 6;
+};
+
+template <int DXT_TYPE, int BPT, bool MIRROR>
+__global__ void __launch_bounds__(uyvy_cta<DXT_TYPE>::threads, uyvy_cta<DXT_TYPE>::min_ctas) dxt_uyvy_kernel(const uint8_t *__restrict__ src, void *__restrict__ out,
                                                         int wb /* blocks per row */, int h, long pitch)
 {
         typedef typename block_out<DXT_TYPE>::type out_t;
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(128, MINB) dxt_uyvy_kernel(const uint8_t *__re
                         float r[16], g[16], b[16];
 #pragma unroll
                         for (int y = 0; y < 4; ++y) {
-                                load_row_uyvy(w[y][2 * k], w[y][2 * k + 1], r + 4 * y, g + 4 * y, b + 4 * y);
+                                load_row_uyvy_packed(w[y][2 * k], w[y][2 * k + 1], r + 4 * y, g + 4 * y, b + 4 * y);
                         }
                         res[k] = encode_block<DXT_TYPE>(r, g, b);
                 }
@@ -238,7 +246,7 @@ static int launch_uyvy(const void *src, void *out, int sx, int sy, long pitch, c
         if (wb == 0 || hb == 0) {
                 return 0;
         }
-        const int threads = 128;
+        const int threads = uyvy_cta<DXT_TYPE>::threads;
         // DXT5-YCoCg: one block per thread — two unrolled blocks (~50 KB of SASS) overflow the instruction cache (ncu: the top stall
         // was no_instruction); DXT1: two blocks per thread for 128-bit loads/stores
         const bool pair = DXT_TYPE == 1 && !(wb & 1) && !(15 & (size_t) src) && !(pitch & 15) && !(15 & (size_t) out);

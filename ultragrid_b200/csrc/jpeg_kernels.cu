@@ -300,6 +300,11 @@ constexpr int kCapDefault = 16;
 
 __device__ __forceinline__ int category(int v) { return 32 - __clz(abs(v)); }
 
+/// Shared-memory column of scan-order block p (0..127).  The arrays indexed by block ([k][128] words) are touched in two patterns: phases 1-2
+/// with p = 4 * lane + component (stride 4: a 4-way bank conflict on a plain layout) and phase 3 with p = tid (stride 1).  Rotating each
+/// group of 32 columns by its group index makes both conflict-free: bank = (p + p / 32) mod 32.
+__device__ __forceinline__ int blk_col(int p) { return (p & ~31) | ((p + (p >> 5)) & 31); }
+
 /// MSB-first bit writer with byte stuffing; bytes are gathered into aligned 32-bit words before they go to memory
 struct bit_writer {
         uint32_t *p;     // next aligned word of the slot
@@ -522,6 +527,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                         }
                 }
         }
+        const int pc = blk_col(p);  // my block's column in the [k][128] arrays
         constexpr int zz[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                  41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                  30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
@@ -537,7 +543,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 uint32_t w = __byte_perm(ua, ub, 0x5410);
                 // AC range of the 10-bit categories (the DC, low half of word 0, keeps its full range)
                 w = __vmins2(__vmaxs2(w, k == 0 ? 0xFC018000u : 0xFC01FC01u), k == 0 ? 0x03FF7FFFu : 0x03FF03FFu);
-                s_coef[k * 128 + p] = w;
+                s_coef[k * 128 + pc] = w;
                 const uint32_t fl = __vminu2(w, 0x00010001u);
                 if (k < 16) {
                         flags_a += fl << k;
@@ -550,7 +556,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
         }
         uint64_t nz = (uint64_t) __byte_perm(flags_a, flags_b, 0x5410) | (uint64_t) __byte_perm(flags_a, flags_b, 0x7632) << 32;
         nz &= ~1ull;
-        s_dc[p] = dcv;
+        s_dc[pc] = dcv;
         __syncthreads();
         // ---- 2. entropy-code my block --------------------------------------------------------------------------------------------
         uint32_t bits = 0;
@@ -560,11 +566,11 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 if (FMT == FMT_UYVY_422) {  // MCU = Y0 Y1 Cb Cr; a segment starts every ri MCUs (ri divides the CTA's 32 MCUs)
                         const int k = tid >> 5;
                         const bool first = (p % bps) < 4;
-                        pred = k == 1 ? s_dc[p - 1] : first ? 0 : k == 0 ? s_dc[p - 3] : s_dc[p - 4];
+                        pred = k == 1 ? s_dc[blk_col(p - 1)] : first ? 0 : k == 0 ? s_dc[blk_col(p - 3)] : s_dc[blk_col(p - 4)];
                 } else {
-                        pred = (p % bps) == 0 ? 0 : s_dc[p - 1];
+                        pred = (p % bps) == 0 ? 0 : s_dc[blk_col(p - 1)];
                 }
-                block_bits bw = { s_bits + p, 0, 0, 0, cap };
+                block_bits bw = { s_bits + pc, 0, 0, 0, cap };
                 const int diff = dcv - pred;
                 int sz = category(diff);
                 bw.put(s_dctab[t][sz] & 0xffff, s_dctab[t][sz] >> 16);
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 // AC: one turn per non-zero coefficient.  The map is walked as two 32-bit halves: bit b of half h is zig-zag index b + 32 h,
                 // stored in half h of word b
                 int prev = 0;
-                const uint32_t *cw = s_coef + p;
+                const uint32_t *cw = s_coef + pc;
                 const uint32_t *act = s_ac[t];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -600,7 +606,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 }
                 bits = bw.finish();
         }
-        s_len[p] = bits;
+        s_len[pc] = bits;
         const bool overflow = __syncthreads_or(bits > (uint32_t) cap * 32u) != 0;
         {  // largest block of the CTA (reported at the end: the host sizes the next frame's cap from the frame maximum)
                 uint32_t mx = bits;
@@ -633,14 +639,14 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                                         break;
                                 }
                                 const int comp = FMT == FMT_UYVY_422 ? ((q & 3) < 2 ? 0 : (q & 3) - 1) : cta_y;
-                                const int t = comp == 0 ? 0 : 1;
+                                const int t = comp == 0 ? 0 : 1, qc = blk_col(q);
                                 uint64_t map = 0;
                                 for (int k = 0; k < 32; ++k) {
-                                        const uint32_t w = s_coef[k * 128 + q];
+                                        const uint32_t w = s_coef[k * 128 + qc];
                                         map |= (uint64_t) ((w & 0xffffu) != 0) << k | (uint64_t) ((w >> 16) != 0) << (k + 32);
                                 }
                                 map &= ~1ull;
-                                const int dc = s_dc[q], diff = dc - pred[FMT == FMT_UYVY_422 ? comp : 0];
+                                const int dc = s_dc[qc], diff = dc - pred[FMT == FMT_UYVY_422 ? comp : 0];
                                 pred[FMT == FMT_UYVY_422 ? comp : 0] = dc;
                                 int sz = category(diff);
                                 bw.put(s_dctab[t][sz] & 0xffff, s_dctab[t][sz] >> 16);
@@ -657,7 +663,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                                                 bw.put(s_ac[t][0xF0] & 0xffff, s_ac[t][0xF0] >> 16);
                                                 run -= 16;
                                         }
-                                        const int v = (int) (short) (s_coef[(i & 31) * 128 + q] >> (16 * (i >> 5)));
+                                        const int v = (int) (short) (s_coef[(i & 31) * 128 + qc] >> (16 * (i >> 5)));
                                         sz = category(v);
                                         const uint32_t e = s_ac[t][(run << 4) | sz];
                                         bw.put(((e & 0xffff) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), (int) (e >> 16) + sz);
@@ -676,7 +682,8 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 }
         } else {
                 // ---- 3. assemble restart segments: thread tid now owns scan-order block tid ---------------------------------------------
-                const uint32_t L = s_len[tid];
+                const int tc = blk_col(tid);
+                const uint32_t L = s_len[tc];
                 uint32_t incl = L;
                 for (int d = 1; d < bps; d <<= 1) {
                         const uint32_t o = __shfl_up_sync(gmask, incl, d, bps);
@@ -689,7 +696,7 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                         const uint32_t off = incl - L, sh = off & 31;
                         uint32_t *d = seg + (off >> 5);
                         for (uint32_t w = 0; w * 32 < L; ++w) {
-                                const uint32_t v = s_bits[w * 128 + tid];
+                                const uint32_t v = s_bits[w * 128 + tc];
                                 atomicOr(d + w, v >> sh);
                                 if (sh && (v << (32 - sh))) {
                                         atomicOr(d + w + 1, v << (32 - sh));
