@@ -222,13 +222,15 @@ def test_gpu_8k_uyvy_jpeg_decodes_with_expected_psnr(orc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("knob", ["UGB200_JPEG_SINGLE_PASS", "UGB200_JPEG_SPLIT"])
-def test_gpu_alternative_routes_give_the_same_bytes(knob):
-    """the single-pass compaction (decoupled look-back) and the forced split path are process-wide switches: the byte-exactness tests run
-    once more in a child process with the switch set"""
+@pytest.mark.parametrize("knob,value", [("UGB200_JPEG_SINGLE_PASS", "1"), ("UGB200_JPEG_SPLIT", "1"), ("UGB200_JPEG_CAP", "12"),
+                                        ("UGB200_JPEG_CAP", "8"), ("UGB200_JPEG_CAP", "24")])
+def test_gpu_alternative_routes_give_the_same_bytes(knob, value):
+    """the single-pass compaction (decoupled look-back), the forced split path and the bit-buffer cap (12 words and fewer = the instantiation
+    for seven CTAs per SM, with the input tile reaching into the segment images; 24 = a larger cap) are process-wide switches: the
+    byte-exactness tests run once more in a child process with the switch set"""
     import subprocess
     import sys
-    env = dict(os.environ, **{knob: "1"})
+    env = dict(os.environ, **{knob: value})
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
                         "equals_oracle_bytes or serial_route or source_pitch or larger_than_output"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]

@@ -74,7 +74,8 @@ __device__ __forceinline__ uint32_t alpha_count_to_index(uint32_t x)
 __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (&g)[16], const float (&b)[16])
 {
         const double offd = (double) kOffset;
-        float Y[16], Co[16], Cg[16];
+        float Y[16];
+        float2 Co[8], Cg[8];  // pixels 2 j (.x) and 2 j + 1 (.y): the pairing of the packed instructions below
         // ConvertRGBToYCoCg (:141-148): unsuffixed literals make these double expressions, narrowed once.  As compiled:
         //   Y  = ((r + 2 g) + b) * 0.25,  Co = fma((2 r - 2 b), 0.25, off),  Cg = fma(((-r + 2 g) - b), 0.25, off)
         // with g2 = g + g.  Written here with fewer FP64 instructions, each step the same real number rounded once: r + g2 = fma(g, 2, r)
@@ -83,16 +84,24 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
         for (int i = 0; i < 16; ++i) {
                 const double dr = (double) r[i], dg = (double) g[i], db = (double) b[i];
                 Y[i] = __double2float_rn(__dmul_rn(__dadd_rn(__fma_rn(dg, 2.0, dr), db), 0.25));
-                Co[i] = __double2float_rn(__fma_rn(__dadd_rn(dr, -db), 0.5, offd));
-                Cg[i] = __double2float_rn(__fma_rn(__dadd_rn(__fma_rn(dg, 2.0, -dr), -db), 0.25, offd));
+                const float co = __double2float_rn(__fma_rn(__dadd_rn(dr, -db), 0.5, offd));
+                const float cg = __double2float_rn(__fma_rn(__dadd_rn(__fma_rn(dg, 2.0, -dr), -db), 0.25, offd));
+                if (i & 1) {
+                        Co[i >> 1].y = co, Cg[i >> 1].y = cg;
+                } else {
+                        Co[i >> 1].x = co, Cg[i >> 1].x = cg;
+                }
         }
         // FindMinMaxColorsBox (:159-168)
-        float mnY = Y[0], mxY = Y[0], mnCo = Co[0], mxCo = Co[0], mnCg = Cg[0], mxCg = Cg[0];
+        float mnY = Y[0], mxY = Y[0], mnCo = Co[0].x, mxCo = Co[0].x, mnCg = Cg[0].x, mxCg = Cg[0].x;
 #pragma unroll
         for (int i = 1; i < 16; ++i) {
                 mnY = fminf(mnY, Y[i]), mxY = fmaxf(mxY, Y[i]);
-                mnCo = fminf(mnCo, Co[i]), mxCo = fmaxf(mxCo, Co[i]);
-                mnCg = fminf(mnCg, Cg[i]), mxCg = fmaxf(mxCg, Cg[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+                mnCo = fminf(mnCo, fminf(Co[j].x, Co[j].y)), mxCo = fmaxf(mxCo, fmaxf(Co[j].x, Co[j].y));
+                mnCg = fminf(mnCg, fminf(Cg[j].x, Cg[j].y)), mxCg = fmaxf(mxCg, fmaxf(Cg[j].x, Cg[j].y));
         }
         // SelectYCoCgDiagonal (:260-270): t = c - (max+min)*0.5 is fma(max+min, -0.5, c); cov sequential from +0
         {
@@ -100,8 +109,8 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
                 float cov = 0.0f;
                 const float2 so2 = dup(sCo), sg2 = dup(sCg), mh = dup(-0.5f);
 #pragma unroll
-                for (int i = 0; i < 16; i += 2) {  // the two deviations of pixels i, i + 1 packed; the chain itself stays sequential
-                        const float2 eo = __ffma2_rn(so2, mh, f2(Co[i], Co[i + 1])), eg = __ffma2_rn(sg2, mh, f2(Cg[i], Cg[i + 1]));
+                for (int j = 0; j < 8; ++j) {  // the two deviations of pixels 2 j, 2 j + 1 packed; the chain itself stays sequential
+                        const float2 eo = __ffma2_rn(so2, mh, Co[j]), eg = __ffma2_rn(sg2, mh, Cg[j]);
                         cov = __fmaf_rn(eo.x, eg.x, cov);
                         cov = __fmaf_rn(eo.y, eg.y, cov);
                 }
@@ -156,7 +165,7 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
                      n3g = dup(-c3g);
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-                const float2 co = f2(Co[i], Co[i + 1]), cg = f2(Cg[i], Cg[i + 1]);
+                const float2 co = Co[i >> 1], cg = Cg[i >> 1];
 #define UGB_DIST2(no, ng, d)                                                                                                               \
         {                                                                                                                                  \
                 const float2 eo = __fadd2_rn(co, no), eg = __fadd2_rn(cg, ng);                                                             \

@@ -419,8 +419,10 @@ struct jpeg_lookback {
         int ctas_per_scan;
 };
 
-template <int FMT>
-__global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
+/// MINB = resident CTAs per SM the register allocation aims at: 6 (80 registers) for any cap, 7 (72 registers) when the bit buffers are
+/// capped at 12 words or fewer (28 KB of dynamic shared memory per CTA)
+template <int FMT, int MINB>
+__global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
                                                          uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
                                                          uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats,
                                                          jpeg_lookback lb, const __grid_constant__ jpeg_qtab qt, const uint32_t *__restrict__ huff)
@@ -448,9 +450,6 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
         for (int i = tid; i < 512; i += 128) {
                 s_ac[i >> 8][i & 255] = __ldg(huff + 32 + i);
         }
-        for (int i = tid; i < cap * 128; i += 128) {
-                s_seg[i] = 0;
-        }
         // ---- which block is mine -------------------------------------------------------------------------------------------
         const int bps = g.ri * g.blocks_per_mcu;  // blocks per restart segment: 4, 8, 16 or 32 (checked by the host)
         int comp, bx, by, p;                      // p = position of my block in the CTA's scan order
@@ -474,12 +473,13 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
                 p = tid;
         }
         // ---- 0. stage the CTA's input tile (32 MCUs x 8 rows = 8 x 1024 bytes) through shared memory: coalesced, asynchronous, and the
-        //         luma and chroma warps read every byte from there instead of fetching it twice.  The tile borrows s_bits (free until phase 2).
+        //         luma and chroma warps read every byte from there instead of fetching it twice.  The tile borrows s_bits and, for a cap below 16
+        //         words, the start of s_seg behind it (both are free until phase 2; s_seg is cleared after the DCT).
         bool staged = false;
         const uint8_t *tile = (const uint8_t *) s_bits;
         if (FMT == FMT_UYVY_422) {
                 const int mx0 = first_mcu % g.bw, my0 = first_mcu / g.bw;
-                staged = vec_ok && cap >= 16 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h;
+                staged = vec_ok && cap >= 8 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h;
                 if (staged) {
                         const uint8_t *gsrc = src + (long) (my0 * 8) * pitch + (long) mx0 * 32;
                         for (int i = tid; i < 512; i += 128) {
@@ -558,6 +558,9 @@ __global__ void __launch_bounds__(128, 6) jpeg_fused_kernel(const uint8_t *__res
         nz &= ~1ull;
         s_dc[pc] = dcv;
         __syncthreads();
+        for (int i = tid; i < cap * 128; i += 128) {  // the segment images start empty (the input tile, dead by now, may have reached into them)
+                s_seg[i] = 0;
+        }
         // ---- 2. entropy-code my block --------------------------------------------------------------------------------------------
         uint32_t bits = 0;
         if (valid) {
@@ -1281,7 +1284,7 @@ static void adapt_cap(ugb200_jpeg_encoder *e)
 {
         if (e->last_fused && e->stats_pending) {
                 const int want = (int) ((e->h_total[1] + e->h_total[1] / 4 + 31) / 32);
-                e->cap_words = want <= 16 ? 16 : want <= 24 ? 24 : want <= 32 ? 32 : kBlkWords;
+                e->cap_words = want <= 12 ? 12 : want <= 16 ? 16 : want <= 24 ? 24 : want <= 32 ? 32 : kBlkWords;
         }
         e->stats_pending = false;
 }
@@ -1340,28 +1343,34 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                         cudaMemsetAsync(e->lb_state, 0, ((size_t) nctas + 1) * sizeof(unsigned long long), e->stream);
                         lb.state = e->lb_state + 1, lb.ticket = (uint32_t *) e->lb_state;  // word 0 of the array = the ticket counter
                 }
-                if (fmt == FMT_UYVY_422) {
-                        if (!e->attr_set[0]) {  // per encoder = per device context: the attribute does not carry over to another GPU
-                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_UYVY_422>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t)));
-                                e->attr_set[0] = true;
-                        }
-                        jpeg_fused_kernel<FMT_UYVY_422><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
-                                                                                       e->cta_total, vec_ok, cap, e->total + 1, lb, e->qt, e->d_huff);
-                } else {
-                        if (!e->attr_set[1]) {
-                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t)));
-                                e->attr_set[1] = true;
-                        }
-                        if (single_pass) {  // tickets run over the three scans
-                                jpeg_fused_kernel<FMT_RGB_444><<<nctas, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets,
-                                                                                              e->cta_total, vec_ok, cap, e->total + 1, lb, e->qt, e->d_huff);
+                const bool seven = cap <= 12;  // 28 KB per CTA: seven CTAs (28 warps) fit an SM
+                const int max_smem = (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t));
+                if (!e->attr_set[fmt == FMT_UYVY_422 ? 0 : 1]) {  // per encoder = per device context: the attribute does not carry over to another GPU
+                        if (fmt == FMT_UYVY_422) {
+                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_UYVY_422, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
                         } else {
-                                jpeg_fused_kernel<FMT_RGB_444><<<dim3(ctas_per_scan, 3), 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes,
-                                                                                                               e->offsets, e->cta_total, vec_ok, cap, e->total + 1, lb, e->qt, e->d_huff);
+                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+                        }
+                        e->attr_set[fmt == FMT_UYVY_422 ? 0 : 1] = true;
+                }
+                const dim3 grid = fmt == FMT_UYVY_422 || single_pass ? dim3(nctas) : dim3(ctas_per_scan, 3);  // single pass: tickets run over the three scans
+#define UGB_FUSED(FMT, MINB)                                                                                                                              \
+        jpeg_fused_kernel<FMT, MINB><<<grid, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, vec_ok, cap, \
+                                                                     e->total + 1, lb, e->qt, e->d_huff)
+                if (fmt == FMT_UYVY_422) {
+                        if (seven) {
+                                UGB_FUSED(FMT_UYVY_422, 7);
+                        } else {
+                                UGB_FUSED(FMT_UYVY_422, 6);
+                        }
+                } else {
+                        if (seven) {
+                                UGB_FUSED(FMT_RGB_444, 7);
+                        } else {
+                                UGB_FUSED(FMT_RGB_444, 6);
                         }
                 }
+#undef UGB_FUSED
         } else {  // split path: any restart interval
                 const int dct_ctas = fmt == FMT_UYVY_422 ? (g.mcu_per_scan + 31) / 32 : (g.nblocks + 127) / 128;
                 jpeg_dct_kernel<<<dct_ctas, 128, 0, e->stream>>>((const uint8_t *) src, pitch, g, e->coef, vec_ok, e->qt);
