@@ -130,6 +130,51 @@ def test_gpu_encoder_equals_oracle_bytes(orc, codec, w, h, q, ri):
     enc.close()
 
 
+def extreme_ac_frame(codec, w, h):
+    """samples +-full scale in the sign pattern of cos((2x+1) 4 pi / 16) in x, y or both: the largest AC coefficients a block can have
+    (F(4,4) = F(4,0) = F(0,4) = 1020 in magnitude at quantiser step 1), in every block and every component"""
+    sgn = np.array([1, -1, -1, 1, 1, -1, -1, 1])
+    yy, xx = np.mgrid[0:h, 0:w]
+    kind = ((xx // 8) + (yy // 8)) % 4
+    pat = np.where(kind == 0, sgn[xx % 8] * sgn[yy % 8], np.where(kind == 1, sgn[xx % 8], np.where(kind == 2, sgn[yy % 8], -sgn[xx % 8] * sgn[yy % 8])))
+    plane = np.where(pat > 0, 255, 0).astype(np.uint8)
+    if codec == RGB:
+        return np.repeat(plane[:, :, None], 3, axis=2).reshape(-1).copy()
+    out = np.empty((h, w, 2), np.uint8)
+    out[:, :, 1] = plane                 # luma
+    cx = np.where(sgn[(xx // 2) % 8] * sgn[yy % 8] > 0, 255, 0).astype(np.uint8)  # chroma samples sit at every second pixel
+    out[:, :, 0] = cx
+    return out.reshape(-1).copy()
+
+
+@pytest.mark.parametrize("codec", [UYVY, RGB])
+def test_oracle_largest_ac_coefficients_stay_in_range(orc, codec):
+    """the fused kernel does not clamp AC coefficients to the 10-bit categories: the bound is 1020 (jpeg_kernels.cu); the oracle's own
+    coefficients of the worst-case frame confirm it at quality 100 (all quantiser steps 1)"""
+    w, h = 64, 32
+    src = extreme_ac_frame(codec, w, h)
+    nblk = (w // 16) * (h // 8) * 4 if codec == UYVY else (w // 8) * (h // 8) * 3
+    co = np.zeros(nblk * 64, dtype=np.int16)
+    orc.orc_jpeg_coefficients.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    orc.orc_jpeg_coefficients(src.ctypes.data, w * (2 if codec == UYVY else 3), w, h, 0 if codec == UYVY else 1, 100, co.ctypes.data)
+    ac = co.reshape(-1, 64)[:, 1:]
+    assert 1015 <= np.abs(ac).max() <= 1020, np.abs(ac).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("codec", [UYVY, RGB])
+def test_gpu_largest_ac_coefficients_equal_oracle_bytes(orc, codec):
+    import torch
+    from ultragrid_b200 import api
+    w, h = 64, 32
+    src = extreme_ac_frame(codec, w, h)
+    enc = api.JpegEncoder()
+    for q in (100, 97):
+        enc.encode_device(torch.from_numpy(src).cuda(), w, h, codec, quality=q)
+        assert enc.result() == orc_encode(orc, src, w, h, codec, q, 0), q
+    enc.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("codec,q", [(UYVY, 100), (UYVY, 85), (RGB, 90)])
 def test_gpu_noise_takes_serial_route_then_adapts(orc, codec, q):
@@ -232,5 +277,5 @@ def test_gpu_alternative_routes_give_the_same_bytes(knob, value):
     import sys
     env = dict(os.environ, **{knob: value})
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
-                        "equals_oracle_bytes or serial_route or source_pitch or larger_than_output"], env=env, capture_output=True, text=True, timeout=600)
+                        "equals_oracle_bytes or serial_route or source_pitch or larger_than_output or largest_ac"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]

@@ -66,12 +66,13 @@ __device__ __forceinline__ uint4 encode_block<6>(const float (&r)[16], const flo
 // ------------------------------------------------------------------------------------------------
 // fused UYVY -> DXT.  One thread = BPT horizontally adjacent blocks.
 // ------------------------------------------------------------------------------------------------
-/// CTA shape: 80 registers per thread either way (24 warps per SM); DXT1 runs as 12 CTAs of 64 threads per SM - measured 32.8 us against
-/// 34.4 us for 6 CTAs of 128 on an 8K frame (finer-grained CTA turnover; 32-thread CTAs give the same, 256 is slower) - DXT5-YCoCg is
-/// indifferent and keeps 128.
+/// CTA shape (measured on 8K frames, tools/exp_dxt.cu).  DXT1: 12 CTAs of 64 threads per SM (80 registers, 24 warps): 32.8 us against 34.4 us
+/// for 6 CTAs of 128 - a block row of an 8K frame is 960 threads, i.e. 15 CTAs of 64 but 7.5 of 128 (32-thread CTAs give the same, 256 is
+/// slower); more warps with fewer registers do not pay (72 registers: spills; one block per thread: more instructions).  DXT5-YCoCg: 7 CTAs of
+/// 128 (72 registers, 8 bytes of spill, 28 warps): 86.1 us against 88.2 us for 6.
 template <int DXT_TYPE>
 struct uyvy_cta {
-        static constexpr int threads = DXT_TYPE == 1 ? 64 : 128, min_ctas = DXT_TYPE == 1 ? 12 : 6;
+        static constexpr int threads = DXT_TYPE == 1 ? 64 : 128, min_ctas = DXT_TYPE == 1 ? 12 : 7;
 };
 
 template <int DXT_TYPE, int BPT, bool MIRROR>

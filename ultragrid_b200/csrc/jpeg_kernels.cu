@@ -540,9 +540,10 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 const int na = zz[k], nb = zz[k + 32];
                 const float2 pa = g2[na >> 3][(na & 7) >> 1], pb = g2[nb >> 3][(nb & 7) >> 1];
                 const uint32_t ua = __float_as_uint((na & 1) ? pa.y : pa.x), ub = __float_as_uint((nb & 1) ? pb.y : pb.x);
-                uint32_t w = __byte_perm(ua, ub, 0x5410);
-                // AC range of the 10-bit categories (the DC, low half of word 0, keeps its full range)
-                w = __vmins2(__vmaxs2(w, k == 0 ? 0xFC018000u : 0xFC01FC01u), k == 0 ? 0x03FF7FFFu : 0x03FF03FFu);
+                // No clamp to the 10-bit AC categories is needed: with samples in [-128, 127] the largest AC coefficient is F(4,4) (all |cos| =
+                // 1/sqrt(2)) = 1/4 * 1/2 * 32 * (127 + 128) = 1020 before quantisation, as is F(4,0); every other one is below 930.  The oracle
+                // keeps its clamp, which therefore never acts.  (DC: up to 1024 in magnitude, differences in category 11 of the DC table.)
+                const uint32_t w = __byte_perm(ua, ub, 0x5410);
                 s_coef[k * 128 + pc] = w;
                 const uint32_t fl = __vminu2(w, 0x00010001u);
                 if (k < 16) {
