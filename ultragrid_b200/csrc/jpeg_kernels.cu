@@ -8,7 +8,7 @@
 //   K2 jpeg_huffman_kernel  one thread per restart segment: non-zero map per block, one loop turn per NON-ZERO coefficient,
 //                           Annex K codes + byte stuffing into a private worst-case slot (32-bit stores), RSTn, byte count
 //   K3 jpeg_scan_kernel     second level of the stream-offset prefix sum (first level: inside K2's CTAs); no host round trip
-//   K4 jpeg_compact_kernel  eight lanes per segment: slot -> final position; writes SOS headers of scans 2,3 and EOI
+//   K4 jpeg_compact_kernel  one warp per segment: slot -> final position; writes SOS headers of scans 2,3 and EOI
 // Arithmetic is float with an explicit operation order so that oracle/jpeg_oracle.c reproduces the bytes exactly.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -1007,17 +1007,12 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *__restrict__ 
 }
 
 // ---- K4 -------------------------------------------------------------------------------------------------------------
-constexpr int kCompactLanes = 8;
 __global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ sizes,
                                                            const uint32_t *__restrict__ local_off, const uint32_t *__restrict__ cta_base,
                                                            jpeg_geom g, int segs_per_cta, int ctas_per_scan, uint8_t *__restrict__ out,
                                                            const uint32_t *__restrict__ total, uint32_t out_cap)
 {
-        // kCompactLanes lanes per segment: a typical segment is ~100 bytes, and what bounds this kernel is the chain size -> offsets -> slot -> stream
-        // of dependent accesses per segment, so a warp walks four chains at once; a lane reads aligned words of the slot (four of them in flight)
-        // and writes their bytes to the (unaligned) position in the stream
-        const int t = blockIdx.x * blockDim.x + threadIdx.x;
-        const int s = t / kCompactLanes, lane = t % kCompactLanes;
+        const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
         if (s >= g.nseg || *total > out_cap) {  // a stream larger than the output buffer is reported by the host, never written
                 return;
         }
@@ -1025,29 +1020,9 @@ __global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__rest
         // which CTA of the entropy kernel produced this segment: split path = 128 consecutive segments; fused path = per scan
         const int cta = ctas_per_scan ? scan * ctas_per_scan + (s - scan * g.seg_per_scan) / segs_per_cta : s / segs_per_cta;
         const uint32_t n = sizes[s], off = g.header_len + cta_base[cta] + local_off[s] + g.sos_len * scan;
-        const uint32_t *src = (const uint32_t *) (slots + (long) s * g.slot);  // slots are 8-byte aligned (g.slot is a multiple of 8)
-        uint8_t *dst = out + off;
-        const uint32_t nw = (n + 3) >> 2;
-        auto put_word = [&](uint32_t j, uint32_t w) {  // bytes 4 j .. 4 j + 3 of the segment, as far as they exist
-                const uint32_t b = 4 * j;
-                dst[b] = (uint8_t) w;
-                if (b + 1 < n) {
-                        dst[b + 1] = (uint8_t) (w >> 8);
-                }
-                if (b + 2 < n) {
-                        dst[b + 2] = (uint8_t) (w >> 16);
-                }
-                if (b + 3 < n) {
-                        dst[b + 3] = (uint8_t) (w >> 24);
-                }
-        };
-        uint32_t j = lane;
-        for (; j + 3 * kCompactLanes < nw; j += 4 * kCompactLanes) {
-                const uint32_t w0 = src[j], w1 = src[j + kCompactLanes], w2 = src[j + 2 * kCompactLanes], w3 = src[j + 3 * kCompactLanes];
-                put_word(j, w0), put_word(j + kCompactLanes, w1), put_word(j + 2 * kCompactLanes, w2), put_word(j + 3 * kCompactLanes, w3);
-        }
-        for (; j < nw; j += kCompactLanes) {
-                put_word(j, src[j]);
+        const uint8_t *src = slots + (long) s * g.slot;
+        for (uint32_t i = lane; i < n; i += 32) {
+                out[off + i] = src[i];
         }
         if (lane == 0 && s > 0 && s % g.seg_per_scan == 0) {  // SOS header of a later scan (RGB: one component per scan)
                 uint8_t *h = out + off - g.sos_len;
@@ -1405,7 +1380,7 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         }
         if (!single_pass) {
                 jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
-                jpeg_compact_kernel<<<(int) (((long) g.nseg * kCompactLanes + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
+                jpeg_compact_kernel<<<(int) (((long) g.nseg * 32 + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
                                                                                                    segs_per_cta, ctas_per_scan, e->out, e->total, (uint32_t) e->out_cap);
         }
         if (cudaGetLastError() != cudaSuccess) {
