@@ -398,8 +398,9 @@ def extra_jpeg(api, compress, torch, dev):
               "noise": torch.randint(0, 256, (W8K * H8K * 2,), dtype=torch.uint8, device=dev)}
     enc = api.JpegEncoder()
     for name, src in inputs.items():
-        enc.encode_device(src, W8K, H8K, 2, quality=90)
-        nbytes = len(enc.result())
+        for _ in range(3):  # the encoder sizes its bit buffers (and with them the kernel instantiation) from the previous frame's statistics
+            enc.encode_device(src, W8K, H8K, 2, quality=90)
+            nbytes = len(enc.result())
         n = 6
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
