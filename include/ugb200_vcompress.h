@@ -20,7 +20,8 @@ UGB_API int ugb200_set_cuda_devices(const int *devices, int count);
 
 /* compress_init(parent, config): "cuda_dxt[:DXT1|:DXT5]" (src/video_compress/cuda_dxt.cpp:108-119; asynchronous, 3 frames in
  * flight; "cuda_dxt_sync" is the same module behind the reference's synchronous tile API) or
- * "GPUJPEG[:q=<1-100>][:restart=<n>]" (src/video_compress/gpujpeg.cpp:371-424).  NULL on error. */
+ * "GPUJPEG[:q=<1-100>][:restart=<n>][:lanes=<1-8>]" (src/video_compress/gpujpeg.cpp:371-424; lanes = frames in flight per CUDA device,
+ * default 3, B200 addition; 1 on a single device = the reference's synchronous push).  NULL on error. */
 UGB_API ugb200_compress *ugb200_compress_init(const char *config);
 
 /* compress_frame(): hand one frame to the compressor.  data is a host pointer (mem_location 0 = CPU_MEM) or a device

@@ -201,7 +201,7 @@ __device__ __forceinline__ uint4 dxt6_encode(const float (&r)[16], const float (
         ab[6] = __double2float_rn(__fma_rn(__fma_rn(dN, 6.0, dX), k7, dM));
         // index = 1 + #{k : Y <= ab_k}, & 7, ^ (2 > index)  (:376-388).  The thresholds are ordered ab2 >= ab3 >= ... >= ab7 >= ab1
         // (rounding is monotone and max >= min), so the count is a 3-step binary search instead of 7 compares, and the
-        // "& 7, ^ (2 > idx)" fix-up is the nibble table 0,2,3,4,5,6,7,1 indexed by the count.
+        // "& 7, ^ (2 > idx)" fix-up is the map 0,2,3,4,5,6,7,1 of the count (alpha_count_to_index).
         const float T0 = ab[1], T1 = ab[2], T2 = ab[3], T3 = ab[4], T4 = ab[5], T5 = ab[6], T6 = ab[0];
         // count fields (3 bits per pixel) of pixels 0..9 in cntA, 10..15 in cntB; the map count -> index runs once per word afterwards
         uint32_t cntA = 0, cntB = 0;
