@@ -294,13 +294,21 @@ def main():
             "clocks": clk,
         }
         if world == 1 and not args.no_extra:
-            line["extra"] = extra_kernels(api, torch, dev)
-            line["extra"]["jpeg"] = extra_jpeg(api, compress, torch, dev)
-            line["extra"]["decode"] = extra_decode(api, torch, dev)
-            v, cores, sample = cpu_port_fps()
-            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
-            line["extra"]["cpu_reference_pixfmt"] = cpu_reference_pixfmt()
-            line["extra"]["reference_gpu_kernels"] = reference_gpu_kernels(torch, dev)
+            def guarded(fn, *a):  # a failing secondary measurement must not cost the headline line
+                try:
+                    return fn(*a)
+                except Exception as e:  # noqa: BLE001
+                    return {"error": f"{type(e).__name__}: {e}"[:300]}
+            line["extra"] = guarded(extra_kernels, api, torch, dev)
+            line["extra"]["jpeg"] = guarded(extra_jpeg, api, compress, torch, dev)
+            line["extra"]["decode"] = guarded(extra_decode, api, torch, dev)
+            try:
+                v, cores, sample = cpu_port_fps()
+                line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": None, "kind": "port", "sample": f"failed: {e}"[:200]}
+            line["extra"]["cpu_reference_pixfmt"] = guarded(cpu_reference_pixfmt)
+            line["extra"]["reference_gpu_kernels"] = guarded(reference_gpu_kernels, torch, dev)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
