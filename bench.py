@@ -420,6 +420,26 @@ def extra_jpeg(api, compress, torch, dev):
         res[name] = {"us": secs * 1e6, "fps": 1 / secs, "stream_bytes": nbytes, "algorithmic_GBps": (W8K * H8K * 2 + nbytes) / secs / 1e9}
     nbytes_natural = res["natural"]["stream_bytes"]
     enc.close()
+    # two encoders on two streams, frames alternating: scan + compact of frame n run beside the fused kernel of frame n + 1 (what the GPUJPEG
+    # module's lanes do on one device); wall clock between two device synchronisations around 24 frames
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    encs = [api.JpegEncoder(stream=st) for st in streams]
+    src = inputs["natural"]
+    for e in encs:
+        for _ in range(3):
+            e.encode_device(src, W8K, H8K, 2, quality=90)
+            assert len(e.result()) == nbytes_natural
+    torch.cuda.synchronize()
+    n = 24
+    t0 = time.perf_counter()
+    for i in range(n):
+        encs[i % 2].encode_device(src, W8K, H8K, 2, quality=90)
+    torch.cuda.synchronize()
+    secs = (time.perf_counter() - t0) / n
+    res["natural_two_streams"] = {"us": secs * 1e6, "fps": 1 / secs}
+    for e in encs:
+        e.result()
+        e.close()
     # through the module with pinned host frames (compress_init("GPUJPEG:q=90") / compress_frame / compress_pop): H2D, kernels and the D2H
     # of the stream into the pooled output frame are inside the timed region.  lanes=1 is the reference's single-device shape
     # (push returns when the frame is done), the default keeps 3 frames in flight on one device.
