@@ -12,6 +12,170 @@
 
 namespace ugb {
 
+/// experiment: dxt6_encode() with the alpha thresholds computed before the colour indices and both index computations in one loop over pixel
+/// pairs (ALU-only alpha compares between the FMA-heavy colour distances); same operations, same bits
+__device__ __forceinline__ uint4 dxt6_encode_fused(const float (&r)[16], const float (&g)[16], const float (&b)[16])
+{
+        const double offd = (double) kOffset;
+        float Y[16];
+        float2 Co[8], Cg[8];  // pixels 2 j (.x) and 2 j + 1 (.y): the pairing of the packed instructions below
+        // ConvertRGBToYCoCg (:141-148): unsuffixed literals make these double expressions, narrowed once.  As compiled:
+        //   Y  = ((r + 2 g) + b) * 0.25,  Co = fma((2 r - 2 b), 0.25, off),  Cg = fma(((-r + 2 g) - b), 0.25, off)
+        // with g2 = g + g.  Written here with fewer FP64 instructions, each step the same real number rounded once: r + g2 = fma(g, 2, r)
+        // (2 g is exact), 2 r - 2 b = 2 (r - b) exactly (scaling by 2 commutes with rounding) and fma(2 d, 0.25, off) = fma(d, 0.5, off).
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+                const double dr = (double) r[i], dg = (double) g[i], db = (double) b[i];
+                Y[i] = __double2float_rn(__dmul_rn(__dadd_rn(__fma_rn(dg, 2.0, dr), db), 0.25));
+                const float co = __double2float_rn(__fma_rn(__dadd_rn(dr, -db), 0.5, offd));
+                const float cg = __double2float_rn(__fma_rn(__dadd_rn(__fma_rn(dg, 2.0, -dr), -db), 0.25, offd));
+                if (i & 1) {
+                        Co[i >> 1].y = co, Cg[i >> 1].y = cg;
+                } else {
+                        Co[i >> 1].x = co, Cg[i >> 1].x = cg;
+                }
+        }
+        // FindMinMaxColorsBox (:159-168)
+        float mnY = Y[0], mxY = Y[0], mnCo = Co[0].x, mxCo = Co[0].x, mnCg = Cg[0].x, mxCg = Cg[0].x;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+                mnY = fminf(mnY, Y[i]), mxY = fmaxf(mxY, Y[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+                mnCo = fminf(mnCo, fminf(Co[j].x, Co[j].y)), mxCo = fmaxf(mxCo, fmaxf(Co[j].x, Co[j].y));
+                mnCg = fminf(mnCg, fminf(Cg[j].x, Cg[j].y)), mxCg = fmaxf(mxCg, fmaxf(Cg[j].x, Cg[j].y));
+        }
+        // SelectYCoCgDiagonal (:260-270): t = c - (max+min)*0.5 is fma(max+min, -0.5, c); cov sequential from +0
+        {
+                const float sCo = __fadd_rn(mnCo, mxCo), sCg = __fadd_rn(mnCg, mxCg);
+                float cov = 0.0f;
+                const float2 so2 = dup(sCo), sg2 = dup(sCg), mh = dup(-0.5f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {  // the two deviations of pixels 2 j, 2 j + 1 packed; the chain itself stays sequential
+                        const float2 eo = __ffma2_rn(so2, mh, Co[j]), eg = __ffma2_rn(sg2, mh, Cg[j]);
+                        cov = __fmaf_rn(eo.x, eg.x, cov);
+                        cov = __fmaf_rn(eo.y, eg.y, cov);
+                }
+                if (cov < 0.0f) {  // :485-489
+                        const float t = mxCg;
+                        mxCg = mnCg, mnCg = t;
+                }
+        }
+        // ScaleYCoCg (:241-258)
+        const float eXo = __fadd_rn(mxCo, -kOffset), eXg = __fadd_rn(mxCg, -kOffset);
+        const float eNo = __fadd_rn(mnCo, -kOffset), eNg = __fadd_rn(mnCg, -kOffset);
+        const float m = fmaxf(fmaxf(fabsf(eNo), fabsf(eNg)), fmaxf(fabsf(eXo), fabsf(eXg)));
+        uint32_t scale = 1u;
+        if (m < 0.2509804069995880127f) {  // (float)(64.0/255.0)
+                scale = 2u;
+        }
+        if (m < 0.12549020349979400635f) {  // (float)(32.0/255.0)
+                scale = 4u;
+        }
+        const float fs = (float) scale, inv_s = scale == 1u ? 1.0f : scale == 2u ? 0.5f : 0.25f;  // rcp.rn of 1,2,4 is exact
+
+        // EmitEndPointsYCoCgDXT5 (:272-313)
+        const float sXo = __fmaf_rn(eXo, fs, kOffset), sXg = __fmaf_rn(eXg, fs, kOffset);  // (c - off)*scale + off
+        const float sNo = __fmaf_rn(eNo, fs, kOffset), sNg = __fmaf_rn(eNg, fs, kOffset);
+        // InsetCoCgBBox (:182-187): (max-min)*(1/16) - (float)((8/255)/16) in one FMA
+        const float kIns = (float) ((8.0 / 255.0) / 16.0);  // 0.0019607844...
+        const float insO = __fmaf_rn(__fadd_rn(sXo, -sNo), 0.0625f, -kIns), insG = __fmaf_rn(__fadd_rn(sXg, -sNg), 0.0625f, -kIns);
+        const float cXo = add_sat_rn(sXo, -insO), cXg = add_sat_rn(sXg, -insG);  // clamp(max - inset, 0, 1)
+        const float cNo = add_sat_rn(sNo, insO), cNg = add_sat_rn(sNg, insG);    // clamp(min + inset, 0, 1)
+        const uint32_t qXo = magic_bits(roundu_magic(__fmul_rn(cXo, 31.0f))), qXg = magic_bits(roundu_magic(__fmul_rn(cXg, 63.0f)));
+        const uint32_t qNo = magic_bits(roundu_magic(__fmul_rn(cNo, 31.0f))), qNg = magic_bits(roundu_magic(__fmul_rn(cNg, 63.0f)));
+        uint4 outp;
+        outp.z = ((qXo << 11) | (qXg << 5) | (scale - 1u)) | (((qNo << 11) | (qNg << 5) | (scale - 1u)) << 16);
+        // expand to 8 bits, back to unit range, undo the scale: fma(fma(float(e), 1/255, -off), 1/scale, off)
+        const float k255 = 0.0039215688593685626984f;  // (float)(1.0/255.0)
+#define UGB_EXPAND(q5or6, e)                                                                                           \
+        __fmaf_rn(__fmaf_rn((float) (e), k255, -kOffset), inv_s, kOffset)
+        const float pXo = UGB_EXPAND(qXo, (qXo << 3) | (qXo >> 2)), pXg = UGB_EXPAND(qXg, (qXg << 2) | (qXg >> 4));
+        const float pNo = UGB_EXPAND(qNo, (qNo << 3) | (qNo >> 2)), pNg = UGB_EXPAND(qNg, (qNg << 2) | (qNg >> 4));
+#undef UGB_EXPAND
+
+        // EmitIndicesYCoCgDXT5 (:315-348).  Palette c0 = max, c1 = min, c2/c3 = lerp with (float)(1/3), (float)(2/3);
+        // which product is the plain multiply and which rides the FMA differs between Co and Cg (as compiled).
+        const float c2o = __fmaf_rn(pNo, 0.3333333432674407959f, __fmul_rn(pXo, 0.66666662693023681641f));
+        const float c2g = __fmaf_rn(pXg, 0.66666662693023681641f, __fmul_rn(pNg, 0.3333333432674407959f));
+        const float c3o = __fmaf_rn(pXo, 0.3333333134651184082f, __fmul_rn(pNo, 0.6666666865348815918f));
+        const float c3g = __fmaf_rn(pXg, 0.3333333134651184082f, __fmul_rn(pNg, 0.6666666865348815918f));
+        // InsetYBBox (:176-181): (max - min)/32.0 - (16.0/255.0)/32.0 in double, narrowed once
+        const float insY = __double2float_rn(__fma_rn((double) __fadd_rn(mxY, -mnY), 1.0 / 32.0, -((16.0 / 255.0) / 32.0)));
+        const float nY = add_sat_rn(mnY, insY), xY = add_sat_rn(mxY, -insY);
+        // EmitAlphaEndPointsYCoCgDXT5 (:350-357): roundf(c * 255.0); the double product narrows to the float product
+        const uint32_t a0 = magic_bits(roundu_magic(__fmul_rn(nY, 255.0f))), a1 = magic_bits(roundu_magic(__fmul_rn(xY, 255.0f)));
+        // EmitAlphaIndicesYCoCgDXT5 (:360-410)
+        const float mid = __fdiv_rn(__fadd_rn(xY, -nY), 14.0f);  // (max-min)/(2.0*7.0): float division is what was compiled
+        const double dX = (double) xY, dN = (double) nY, dM = (double) mid;
+        const double k7 = 1.0 / 7.0;
+        float ab[7];
+        ab[0] = __fadd_rn(nY, mid);
+        ab[1] = __double2float_rn(__fma_rn(__fma_rn(dX, 6.0, dN), k7, dM));
+        ab[2] = __double2float_rn(__fma_rn(__fma_rn(dX, 5.0, __dadd_rn(dN, dN)), k7, dM));
+        ab[3] = __double2float_rn(__fma_rn(__fma_rn(dX, 4.0, __dmul_rn(dN, 3.0)), k7, dM));
+        ab[4] = __double2float_rn(__fma_rn(__fma_rn(dX, 3.0, __dmul_rn(dN, 4.0)), k7, dM));
+        ab[5] = __double2float_rn(__fma_rn(__fma_rn(dX, 2.0, __dmul_rn(dN, 5.0)), k7, dM));
+        ab[6] = __double2float_rn(__fma_rn(__fma_rn(dN, 6.0, dX), k7, dM));
+        // index = 1 + #{k : Y <= ab_k}, & 7, ^ (2 > index)  (:376-388).  The thresholds are ordered ab2 >= ab3 >= ... >= ab7 >= ab1
+        // (rounding is monotone and max >= min), so the count is a 3-step binary search instead of 7 compares, and the
+        // "& 7, ^ (2 > idx)" fix-up is the map 0,2,3,4,5,6,7,1 of the count (alpha_count_to_index).
+        const float T0 = ab[1], T1 = ab[2], T2 = ab[3], T3 = ab[4], T4 = ab[5], T5 = ab[6], T6 = ab[0];
+        uint32_t cntA = 0, cntB = 0;
+        // colorDistance = fma(dCo, dCo, dCg*dCg) for the four palette entries; pixels i and i+1 share packed (f32x2) instructions —
+        // same operations, half the issue slots
+        uint32_t cidx = 0;
+        const float2 nXo = dup(-pXo), nXg = dup(-pXg), nNo = dup(-pNo), nNg = dup(-pNg), n2o = dup(-c2o), n2g = dup(-c2g), n3o = dup(-c3o),
+                     n3g = dup(-c3g);
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+                const float2 co = Co[i >> 1], cg = Cg[i >> 1];
+#define UGB_DIST2(no, ng, d)                                                                                                               \
+        {                                                                                                                                  \
+                const float2 eo = __fadd2_rn(co, no), eg = __fadd2_rn(cg, ng);                                                             \
+                d = __ffma2_rn(eo, eo, __fmul2_rn(eg, eg));                                                                                \
+        }
+                float2 d0, d1, d2, d3;
+                UGB_DIST2(nXo, nXg, d0)
+                UGB_DIST2(nNo, nNg, d1)
+                UGB_DIST2(n2o, n2g, d2)
+                UGB_DIST2(n3o, n3g, d3)
+#undef UGB_DIST2
+                color_index_bits(cidx, d0.x, d1.x, d2.x, d3.x, 1u << (2 * i), 2u << (2 * i));
+                color_index_bits(cidx, d0.y, d1.y, d2.y, d3.y, 1u << (2 * i + 2), 2u << (2 * i + 2));
+                alpha_count_bits(i < 10 ? cntA : cntB, Y[i], T0, T1, T2, T3, T4, T5, T6, 1u << (3 * (i < 10 ? i : i - 10)));
+                alpha_count_bits(i + 1 < 10 ? cntA : cntB, Y[i + 1], T0, T1, T2, T3, T4, T5, T6, 1u << (3 * (i + 1 < 10 ? i + 1 : i - 9)));
+        }
+        outp.w = cidx;
+
+        const uint32_t idxA = alpha_count_to_index(cntA), idxB = alpha_count_to_index(cntB);
+        // the 48-bit index string (pixel i at bit 3 i) follows the two endpoint bytes (:389-392)
+        const uint32_t s_lo = idxA | (idxB << 30), s_hi = idxB >> 2;
+        outp.x = (a0 << 8) | a1 | (s_lo << 16);
+        outp.y = (s_lo >> 16) | (s_hi << 16);
+        return outp;
+}
+
+
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) exp_fused6_kernel(const uint8_t *__restrict__ src, void *__restrict__ out, int wb, int h, long pitch)
+{
+        const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+        const int by = blockIdx.y;
+        if (gx >= wb) {
+                return;
+        }
+        const uint8_t *p = src + (long) (by * 4) * pitch + gx * 8;
+        float r[16], g[16], b[16];
+#pragma unroll
+        for (int y = 0; y < 4; ++y, p += pitch) {
+                const uint2 v = ld_stream_v2(p);
+                load_row_uyvy_packed(v.x, v.y, r + 4 * y, g + 4 * y, b + 4 * y);
+        }
+        ((uint4 *) out)[(long) by * wb + gx] = dxt6_encode_fused(r, g, b);
+}
+
 template <int DXT_TYPE, int BPT, int TPB, int MINB, bool BRANCH>
 __global__ void __launch_bounds__(TPB, MINB) exp_kernel(const uint8_t *__restrict__ src, void *__restrict__ out, int wb, int h, long pitch)
 {
@@ -263,6 +427,7 @@ struct variant {
 
 #define V(D, B, T, M, BR) { "d" #D "_b" #B "_t" #T "_m" #M "_" #BR, D, B, T, 0, ugb::exp_kernel<D, B, T, M, BR>, nullptr }
 #define S(D, B, T, M, SK) { "d" #D "_b" #B "_t" #T "_m" #M "_skew" #SK, D, B, T, 0, ugb::exp_skew_kernel<D, B, T, M, SK>, nullptr }
+#define F6(T, M) { "d6_fusedloops_t" #T "_m" #M, 6, 1, T, 0, ugb::exp_fused6_kernel<T, M>, nullptr }
 #define P(D, B, T, M, DYN, SK) { "d" #D "_b" #B "_t" #T "_m" #M "_persist_" #DYN "_skew" #SK, D, B, T, M, nullptr, ugb::exp_persist_kernel<D, B, T, M, DYN, SK> }
 #define Q(D, B, T, M, DYN, SK, PF) { "d" #D "_b" #B "_t" #T "_m" #M "_persist_" #DYN "_skew" #SK "_pf" #PF, D, B, T, M, nullptr, ugb::exp_persist_kernel<D, B, T, M, DYN, SK, PF> }
 
@@ -276,7 +441,7 @@ int main(int argc, char **argv)
                 V(1, 1, 64, 14, true), V(1, 1, 128, 8, true), S(1, 2, 64, 12, 2000), S(1, 2, 64, 12, 8000),
                 P(1, 2, 128, 5, false, 1400), P(1, 2, 128, 5, true, 0), Q(1, 2, 128, 6, true, 1400, 2), Q(1, 2, 128, 6, true, 1400, 0),
                 // DXT5-YCoCg
-                V(6, 1, 128, 6, true), V(6, 1, 64, 12, true), V(6, 1, 128, 5, true), V(6, 1, 128, 4, true), V(6, 1, 128, 7, true), V(6, 1, 256, 3, true),
+                V(6, 1, 128, 7, true), F6(128, 7), F6(128, 6), F6(128, 5), V(6, 1, 128, 6, true), V(6, 1, 64, 12, true), V(6, 1, 128, 5, true), V(6, 1, 128, 4, true), V(6, 1, 128, 7, true), V(6, 1, 256, 3, true),
                 S(6, 1, 64, 12, 4000), P(6, 1, 128, 4, true, 1800), Q(6, 1, 128, 6, true, 1800, 2),
         };
         const char *only = argc > 2 && !strcmp(argv[1], "one") ? argv[2] : nullptr;
