@@ -177,33 +177,6 @@ __global__ void __launch_bounds__(TPB, MINB) exp_fused6_kernel(const uint8_t *__
 }
 
 
-/// DXT1, two blocks per thread, with some of the byte -> float conversions on the conversion (XU) pipe instead of the ALU pipe (I2F_SEL: see
-/// dxt1_encode_uyvy_packed)
-template <int TPB, int MINB, int I2F_SEL>
-__global__ void __launch_bounds__(TPB, MINB) exp_i2f_kernel(const uint8_t *__restrict__ src, void *__restrict__ out, int wb, int h, long pitch)
-{
-        const int gx = blockIdx.x * blockDim.x + threadIdx.x;
-        const int by = blockIdx.y;
-        if (gx >= wb / 2) {
-                return;
-        }
-        const uint8_t *p = src + (long) (by * 4) * pitch + gx * 16;
-        uint32_t w[4][4];
-#pragma unroll
-        for (int y = 0; y < 4; ++y, p += pitch) {
-                const uint4 v = ld_stream_v4(p);
-                w[y][0] = v.x, w[y][1] = v.y, w[y][2] = v.z, w[y][3] = v.w;
-        }
-        uint2 res[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-                const uint32_t wk[4][2] = { { w[0][2 * k], w[0][2 * k + 1] }, { w[1][2 * k], w[1][2 * k + 1] },
-                                            { w[2][2 * k], w[2][2 * k + 1] }, { w[3][2 * k], w[3][2 * k + 1] } };
-                res[k] = dxt1_encode_uyvy_packed<true, I2F_SEL>(wk);
-        }
-        *(uint4 *) ((uint2 *) out + ((long) by * wb + gx * 2)) = make_uint4(res[0].x, res[0].y, res[1].x, res[1].y);
-}
-
 template <int DXT_TYPE, int BPT, int TPB, int MINB, bool BRANCH>
 __global__ void __launch_bounds__(TPB, MINB) exp_kernel(const uint8_t *__restrict__ src, void *__restrict__ out, int wb, int h, long pitch)
 {
@@ -455,7 +428,6 @@ struct variant {
 
 #define V(D, B, T, M, BR) { "d" #D "_b" #B "_t" #T "_m" #M "_" #BR, D, B, T, 0, ugb::exp_kernel<D, B, T, M, BR>, nullptr }
 #define S(D, B, T, M, SK) { "d" #D "_b" #B "_t" #T "_m" #M "_skew" #SK, D, B, T, 0, ugb::exp_skew_kernel<D, B, T, M, SK>, nullptr }
-#define I2F(T, M, SEL) { "d1_b2_t" #T "_m" #M "_i2fsel" #SEL, 1, 2, T, 0, ugb::exp_i2f_kernel<T, M, SEL>, nullptr }
 #define F6(T, M) { "d6_fusedloops_t" #T "_m" #M, 6, 1, T, 0, ugb::exp_fused6_kernel<T, M>, nullptr }
 #define P(D, B, T, M, DYN, SK) { "d" #D "_b" #B "_t" #T "_m" #M "_persist_" #DYN "_skew" #SK, D, B, T, M, nullptr, ugb::exp_persist_kernel<D, B, T, M, DYN, SK> }
 #define Q(D, B, T, M, DYN, SK, PF) { "d" #D "_b" #B "_t" #T "_m" #M "_persist_" #DYN "_skew" #SK "_pf" #PF, D, B, T, M, nullptr, ugb::exp_persist_kernel<D, B, T, M, DYN, SK, PF> }
@@ -466,7 +438,7 @@ int main(int argc, char **argv)
         const long frame = (long) W * H * 2;
         std::vector<variant> vs = {
                 // DXT1: shipped shape first (two blocks per thread, 64-thread CTAs), then the alternatives that were measured
-                V(1, 2, 64, 12, true), I2F(64, 12, 1), I2F(64, 12, 5), I2F(64, 12, 10), I2F(64, 12, 15), I2F(64, 12, 4), I2F(64, 12, 2), V(1, 2, 128, 6, true), V(1, 2, 32, 24, true), V(1, 2, 256, 3, true), V(1, 2, 64, 12, false), V(1, 2, 64, 10, true),
+                V(1, 2, 64, 12, true), V(1, 2, 128, 6, true), V(1, 2, 32, 24, true), V(1, 2, 256, 3, true), V(1, 2, 64, 12, false), V(1, 2, 64, 10, true),
                 V(1, 1, 64, 14, true), V(1, 1, 128, 8, true), S(1, 2, 64, 12, 2000), S(1, 2, 64, 12, 8000),
                 P(1, 2, 128, 5, false, 1400), P(1, 2, 128, 5, true, 0), Q(1, 2, 128, 6, true, 1400, 2), Q(1, 2, 128, 6, true, 1400, 0),
                 // DXT5-YCoCg

@@ -230,28 +230,19 @@ __device__ __forceinline__ float px(const float2 (&v)[8], int i) { return ((i & 
 
 /// BRANCH = false computes the indices of a flat block (max_code == min_code) too and discards them: straight-line code, so that
 /// the scheduler may interleave the two blocks of a thread
-/// I2F_SEL (experiment, tools/exp_dxt.cu): bit s set = the sample pair at byte s of the two words (0 = U, 1 = Y of pixels 0/2, 2 = V, 3 = Y of
-/// pixels 1/3) is converted with I2F on the otherwise idle conversion pipe - fma(float(b), 1/255, -k), the reference's own form - instead of the
-/// byte permute into a 2^23 + b word on the ALU pipe; the same value either way
-template <bool BRANCH = true, int I2F_SEL = 0>
+template <bool BRANCH = true>
 __device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][2])
 {
         float2 R[8], G[8], B[8];
-        const float2 c2 = dup(kInv255);
-        auto sample_pair = [&](uint32_t w0, uint32_t w1, int sel, float bias_magic, float bias_plain) -> float2 {
-                if ((I2F_SEL >> sel) & 1) {
-                        return __ffma2_rn(f2((float) ((w0 >> (8 * sel)) & 0xffu), (float) ((w1 >> (8 * sel)) & 0xffu)), c2, dup(bias_plain));
-                }
-                return __ffma2_rn(f2(magic_byte(w0, sel), magic_byte(w1, sel)), c2, dup(bias_magic));
-        };
+        const float2 c2 = dup(kInv255), ky2 = dup(kBiasY), kc2 = dup(kBiasC);
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
                 const uint32_t w0 = w[y][0], w1 = w[y][1];
-                const float2 u = sample_pair(w0, w1, 0, kBiasC, -0.5f);
-                const float2 v = sample_pair(w0, w1, 2, kBiasC, -0.5f);
+                const float2 u = __ffma2_rn(f2(magic_byte(w0, 0), magic_byte(w1, 0)), c2, kc2);
+                const float2 v = __ffma2_rn(f2(magic_byte(w0, 2), magic_byte(w1, 2)), c2, kc2);
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {  // k = 0: pixels x = 0, 2;  k = 1: pixels x = 1, 3
-                        const float2 yy = __fmul2_rn(sample_pair(w0, w1, 1 + 2 * k, kBiasY, -0.0625f), dup(1.1643f));
+                        const float2 yy = __fmul2_rn(__ffma2_rn(f2(magic_byte(w0, 1 + 2 * k), magic_byte(w1, 1 + 2 * k)), c2, ky2), dup(1.1643f));
                         R[2 * y + k] = __ffma2_rn(v, dup(1.7926f), yy);
                         G[2 * y + k] = __ffma2_rn(v, dup(-0.5328f), __ffma2_rn(u, dup(-0.2132f), yy));
                         B[2 * y + k] = __ffma2_rn(u, dup(2.1124f), yy);
