@@ -1,7 +1,9 @@
 """CPU-side pins of three pieces of reasoning the kernels rely on (no GPU, no product code involved):
   * the 8-operation FP64 form of the YCoCg transform in dxt6_device.cuh equals the reference's 11-operation form on every possible pixel;
   * the SWAR count -> index map of the DXT5 alpha indices equals the per-pixel formula of cuda_dxt.cu:376-392, including the 48-bit layout;
-  * the shared-memory column rotation of the fused JPEG kernel (blk_col) is free of bank conflicts in both access patterns."""
+  * the shared-memory column rotation of the fused JPEG kernel (blk_col) is free of bank conflicts in both access patterns;
+  * the per-segment routine of the JPEG compact kernel (csrc/jpeg_compact.cuh: aligned word stores through a funnel shift), compiled for the host,
+    equals memcpy for every size and alignment and touches no byte outside its segment."""
 import os
 import shutil
 import subprocess
@@ -60,3 +62,14 @@ def test_jpeg_block_columns_are_conflict_free():
         assert len({blk_col(4 * lane + k) % 32 for lane in range(32)}) == 32
     for w in range(4):  # phase 3: thread tid works on block tid
         assert len({blk_col(32 * w + lane) % 32 for lane in range(32)}) == 32
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="needs nvcc (host compilation of a .cu file)")
+def test_jpeg_compact_segment_routine_equals_memcpy(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = tmp_path / "exp_compact"
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(exe), os.path.join(ROOT, "tools", "exp_compact.cu")],
+                   check=True, capture_output=True)
+    r = subprocess.run([str(exe), "check"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "cpu check ok" in r.stdout, r.stdout + r.stderr
+

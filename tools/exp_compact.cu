@@ -1,8 +1,9 @@
 // Experiment harness (not product code): the JPEG stream compaction step in isolation.  64 800 restart segments of ~100 bytes sit in
 // worst-case slots (6 664 bytes apart, as jpeg_kernels.cu lays them out for an 8K UYVY frame); the kernel moves each to its byte offset in
-// the stream.  Variants: the shipped form (a warp per segment, byte loads and byte stores) and aligned 32-bit stores fed by a funnel shift of
+// the stream.  Variants: the earlier form (a warp per segment, byte loads and byte stores) and the shipped one, aligned 32-bit stores fed by a funnel shift of
 // two aligned source words (head and tail bytes of a segment as byte stores; interior words belong to exactly one segment, so there is no race).
-// The per-segment routine is __host__ __device__: `tools/exp_compact check` runs it on the CPU against memcpy for random sizes and alignments.
+// The per-segment routine (ultragrid_b200/csrc/jpeg_compact.cuh, shared with the product kernel) is __host__ __device__: `tools/exp_compact check`
+// runs it on the CPU against memcpy for random sizes and alignments.
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/exp_compact tools/exp_compact.cu
 #include <cstdint>
 #include <cstdio>
@@ -12,38 +13,7 @@
 
 #include <cuda_runtime.h>
 
-__host__ __device__ inline uint32_t src_byte(const uint32_t *src32, uint32_t i) { return (src32[i >> 2] >> (8 * (i & 3))) & 0xffu; }
-
-/// lanes `lane` of `nlanes` cooperate on one segment: n bytes from the 4-byte aligned slot `src32` to the arbitrarily aligned `dst`
-__host__ __device__ inline void compact_segment_aligned(int lane, int nlanes, const uint32_t *src32, uint32_t n, uint8_t *dst)
-{
-        const uint32_t mis = (uint32_t) ((uintptr_t) dst & 3u);
-        const uint32_t head = mis ? (4u - mis < n ? 4u - mis : n) : 0u;  // bytes in front of the first aligned word of the stream
-        if ((uint32_t) lane < head) {
-                dst[lane] = (uint8_t) src_byte(src32, (uint32_t) lane);
-        }
-        const uint32_t body = (n - head) >> 2;  // whole aligned words
-        uint32_t *dw = (uint32_t *) (dst + head);
-        const uint32_t bs = 8u * (head & 3u);   // the source runs `head` bytes ahead of a word boundary: the same shift for every word
-        for (uint32_t j = (uint32_t) lane; j < body; j += (uint32_t) nlanes) {
-                const uint32_t wi = (head + 4u * j) >> 2;
-                const uint32_t lo = src32[wi];
-                uint32_t v = lo;
-                if (bs) {
-                        const uint32_t hi = src32[wi + 1];  // at most one word beyond the last byte: inside the slot's 8 spare bytes
-#ifdef __CUDA_ARCH__
-                        v = __funnelshift_r(lo, hi, bs);
-#else
-                        v = (lo >> bs) | (hi << (32u - bs));
-#endif
-                }
-                dw[j] = v;
-        }
-        const uint32_t done = head + 4u * body;
-        if ((uint32_t) lane < n - done) {
-                dst[done + lane] = (uint8_t) src_byte(src32, done + (uint32_t) lane);
-        }
-}
+#include "../ultragrid_b200/csrc/jpeg_compact.cuh"  // the product's per-segment routine
 
 template <int LANES>
 __global__ void __launch_bounds__(256) compact_aligned_kernel(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ sizes,
@@ -53,10 +23,10 @@ __global__ void __launch_bounds__(256) compact_aligned_kernel(const uint8_t *__r
         if (s >= nseg) {
                 return;
         }
-        compact_segment_aligned(lane, LANES, (const uint32_t *) (slots + (long) s * slot), sizes[s], out + offs[s]);
+        ugb::compact_segment(lane, LANES, (const uint32_t *) (slots + (long) s * slot), sizes[s], out + offs[s]);
 }
 
-/// the shipped form (jpeg_compact_kernel): a warp per segment, bytes
+/// the form shipped until the end of round 1: a warp per segment, bytes
 __global__ void __launch_bounds__(256) compact_bytes_kernel(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ sizes,
                                                             const uint32_t *__restrict__ offs, int nseg, long slot, uint8_t *__restrict__ out)
 {
@@ -87,7 +57,7 @@ static int cpu_check()
                 memset(want.data(), 0xEE, want.size());
                 memcpy(want.data() + off, slot.data(), n);
                 for (int lane = 0; lane < lanes; ++lane) {
-                        compact_segment_aligned(lane, lanes, slot.data(), n, out.data() + off);
+                        ugb::compact_segment(lane, lanes, slot.data(), n, out.data() + off);
                 }
                 if (memcmp(out.data(), want.data(), out.size()) != 0) {
                         printf("MISMATCH n=%u off=%u lanes=%d\n", n, off, lanes);
@@ -163,7 +133,7 @@ int main(int argc, char **argv)
                 }
                 cudaMemcpy(got.data(), d_out, total + 64, cudaMemcpyDeviceToHost);
                 same = memcmp(got.data(), ref.data(), total + 64) == 0;
-                const char *names[] = { "bytes, warp per segment (shipped)", "aligned words, 32 lanes", "aligned words, 8 lanes", "aligned words, 16 lanes" };
+                const char *names[] = { "bytes, warp per segment (earlier)", "aligned words, 32 lanes", "aligned words, 8 lanes (shipped)", "aligned words, 16 lanes" };
                 printf("%-36s %7.2f us  %s  (%u bytes, %d segments)\n", names[v], sum / iters * 1e3, same ? "identical" : "MISMATCH", total, nseg);
         }
         return 0;

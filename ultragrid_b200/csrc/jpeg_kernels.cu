@@ -20,6 +20,7 @@
 
 #include "../../include/ugb200.h"
 #include "../../include/ugb200_jpeg.h"
+#include "jpeg_compact.cuh"
 #include "jpeg_tables.h"
 
 namespace ugb {
@@ -1007,13 +1008,10 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *__restrict__ 
 }
 
 // ---- K4 -------------------------------------------------------------------------------------------------------------
-// Eight lanes per segment (a typical segment is ~100 bytes).  The stream position of a segment has any alignment, its slot is 8-byte aligned:
-// the bytes in front of the first aligned word of the stream and behind the last one go out as bytes, everything between as aligned 32-bit
-// words assembled from two aligned slot words by a funnel shift.  Interior words belong to one segment only, so neighbours never write the
-// same word.  Measured on the 8K layout (tools/exp_compact.cu, profiles/r01_g_exp_compact.txt): 15.3 us against 24.4 us for a warp per
-// segment moving bytes; the routine is checked on the CPU against memcpy there (`tools/exp_compact check`).
+// Eight lanes per segment (a typical segment is ~100 bytes); the per-segment routine, aligned 32-bit stores through a funnel shift, is
+// compact_segment() in jpeg_compact.cuh.  Measured on the 8K layout (tools/exp_compact.cu, profiles/r01_g_exp_compact.txt): 15.3 us against
+// 24.4 us for a warp per segment moving bytes; the same routine is checked on the CPU against memcpy (tests/test_device_identities.py).
 constexpr int kCompactLanes = 8;
-__device__ __forceinline__ uint32_t slot_byte(const uint32_t *src32, uint32_t i) { return (src32[i >> 2] >> (8 * (i & 3))) & 0xffu; }
 
 __global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ sizes,
                                                            const uint32_t *__restrict__ local_off, const uint32_t *__restrict__ cta_base,
@@ -1029,26 +1027,7 @@ __global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__rest
         // which CTA of the entropy kernel produced this segment: split path = 128 consecutive segments; fused path = per scan
         const int cta = ctas_per_scan ? scan * ctas_per_scan + (s - scan * g.seg_per_scan) / segs_per_cta : s / segs_per_cta;
         const uint32_t n = sizes[s], off = g.header_len + cta_base[cta] + local_off[s] + g.sos_len * scan;
-        const uint32_t *src32 = (const uint32_t *) (slots + (long) s * g.slot);  // g.slot is a multiple of 8
-        uint8_t *dst = out + off;
-        const uint32_t mis = (uint32_t) ((size_t) dst & 3u);
-        const uint32_t head = mis ? min(4u - mis, n) : 0u;  // bytes in front of the first aligned word of the stream
-        if ((uint32_t) lane < head) {
-                dst[lane] = (uint8_t) slot_byte(src32, (uint32_t) lane);
-        }
-        const uint32_t body = (n - head) >> 2;  // whole aligned words
-        uint32_t *dw = (uint32_t *) (dst + head);
-        const uint32_t bs = 8u * (head & 3u);   // the slot runs `head` bytes ahead of a word boundary: the same shift for every word
-        for (uint32_t j = (uint32_t) lane; j < body; j += kCompactLanes) {
-                const uint32_t wi = (head + 4u * j) >> 2;
-                const uint32_t lo = src32[wi];
-                // the second word lies at most one word behind the last byte: inside the 8 spare bytes of the slot
-                dw[j] = bs ? __funnelshift_r(lo, src32[wi + 1], bs) : lo;
-        }
-        const uint32_t done = head + 4u * body;
-        if ((uint32_t) lane < n - done) {
-                dst[done + lane] = (uint8_t) slot_byte(src32, done + (uint32_t) lane);
-        }
+        compact_segment(lane, kCompactLanes, (const uint32_t *) (slots + (long) s * g.slot), n, out + off);  // g.slot is a multiple of 8
         if (lane == 0 && s > 0 && s % g.seg_per_scan == 0) {  // SOS header of a later scan (RGB: one component per scan)
                 uint8_t *h = out + off - g.sos_len;
                 const uint8_t sos[10] = { 0xFF, 0xDA, 0, 8, 1, (uint8_t) (scan + 1), 0x11, 0, 63, 0 };
