@@ -22,6 +22,18 @@ def test_registry_and_option_parsing_fail_cleanly():
         compress.Compress("GPUJPEG:lanes=0")
 
 
+@pytest.mark.parametrize("cfg", ["GPUJPEG", "GPUJPEG:q=90:lanes=1", "GPUJPEG:lanes=4", "cuda_dxt:DXT5", "cuda_dxt_sync"])
+def test_module_lifecycle_without_frames(cfg):
+    """init / done with no frame in between, and the poison pill through every lane (src/video_compress.h:143-147): host logic only, no GPU work"""
+    from ultragrid_b200 import compress
+    c = compress.Compress(cfg)
+    c.close()
+    c = compress.Compress(cfg)
+    c.push(None, 0, 0, 0)
+    assert c.pop(16) is None
+    c.close()
+
+
 @pytest.mark.parametrize("cands", [(RGB, UYVY), (UYVY, RGB), (UYVY, RGB, RGBA), (RGBA, RGB), (UYVY,), (YUYV, UYVY)])
 def test_get_best_decoder_from_matches_reference(ref_cpu, cands):
     """where both sides have the converters, the selection (pixfmt_desc ranking 'dsc') must agree with the reference"""
