@@ -79,6 +79,10 @@ UGB_API int ugb200_jpeg_get_image_info(const uint8_t *stream, size_t len, struct
 UGB_API long ugb200_jpeg_debug_segments(const uint8_t *stream, size_t len, uint32_t *begin, uint32_t *end, long cap);
 UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t stream);   /* gpujpeg_decoder_create, gpujpeg.c:93 */
 UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *dec);                      /* gpujpeg_decoder_destroy */
+/* The destination of ugb200_jpeg_decode is sized by the CALLER (video_desc of reconfigure(), gpujpeg.c:176-203) while the stream's SOF0
+ * says how much is written: after this call a stream whose dimensions differ is refused with -3 before anything is decoded
+ * (width = height = 0 switches the check off).  The decompress modules always set it. */
+UGB_API int ugb200_jpeg_decoder_expect(ugb200_jpeg_decoder *dec, int width, int height);
 /* gpujpeg_decoder_decode (gpujpeg.c:289,300): `stream` is a HOST buffer; dst is a host (synchronous) or device (asynchronous on the
  * decoder's stream) buffer of dst_pitch bytes per row (0 = vc_get_linesize); out_codec UGB_UYVY, UGB_RGB or UGB_RGBA (shifts).
  * 0 ok, -1 bad arguments, -2 CUDA failure, -3 malformed stream, -4 unsupported stream or output codec. */

@@ -238,3 +238,56 @@ def test_gpu_decoder_survives_corruption(orc):
             pass
     torch.cuda.synchronize()
     assert np.array_equal(dec.decode(s, UYVY), good)  # the decoder is still healthy
+
+
+def test_oversubscribed_huffman_table_is_rejected(orc):
+    """untrusted DHT: 255 codes of length 1 pass the 'sum <= 256' check but violate Kraft; the look-up fill would then write far past the
+    table (libjpeg: JERR_BAD_HUFF_TABLE).  Host-side parser only."""
+    from ultragrid_b200 import _lib
+    lib = _lib.load()
+    s, _ = make_stream(orc, "ours-uyvy", 64, 32, 90, 0)
+    a = np.frombuffer(s, np.uint8).copy()
+    ff = np.flatnonzero((a[:-1] == 0xFF) & (a[1:] == 0xC4))
+    assert len(ff) >= 1
+    begin, end = np.zeros(64, np.uint32), np.zeros(64, np.uint32)
+    assert lib.ugb200_jpeg_debug_segments(a.ctypes.data, len(a), begin.ctypes.data, end.ctypes.data, 64) > 0
+    for bits in ([255] + [0] * 15, [2, 1] + [0] * 14, [0] * 7 + [250, 7] + [0] * 7):
+        b = a.copy()
+        p = int(ff[0]) + 5  # marker(2) length(2) Tc/Th(1)
+        n_old = int(b[p:p + 16].sum())
+        n_new = sum(bits)
+        body = np.concatenate([np.array(bits, np.uint8), np.arange(n_new, dtype=np.uint8)])
+        seglen = 2 + 1 + 16 + n_new
+        b = np.concatenate([b[:int(ff[0]) + 2], np.array([seglen >> 8, seglen & 255, b[int(ff[0]) + 4]], np.uint8), body, b[p + 16 + n_old:]])
+        b = np.ascontiguousarray(b)
+        assert lib.ugb200_jpeg_debug_segments(b.ctypes.data, len(b), begin.ctypes.data, end.ctypes.data, 64) < 0, bits
+
+
+def test_absurd_dimensions_are_refused_before_allocation(orc):
+    """DRI = 1 with 65535 x 65535 in SOF0 would reserve tens of millions of segment entries: refused by the pixel bound"""
+    from ultragrid_b200 import _lib
+    lib = _lib.load()
+    s, _ = make_stream(orc, "ours-uyvy", 64, 32, 90, 0)
+    a = np.frombuffer(s, np.uint8).copy()
+    sof = int(np.flatnonzero((a[:-1] == 0xFF) & (a[1:] == 0xC0))[0])
+    a[sof + 5:sof + 9] = 0xFF
+    begin, end = np.zeros(64, np.uint32), np.zeros(64, np.uint32)
+    assert lib.ugb200_jpeg_debug_segments(a.ctypes.data, len(a), begin.ctypes.data, end.ctypes.data, 64) < 0
+
+
+@pytest.mark.gpu
+def test_decoder_refuses_stream_of_another_size(orc):
+    """the destination is sized from reconfigure()'s video_desc, the stream's SOF0 says how much is written: a mismatch must be refused
+    (module: DECODER_NO_FRAME) instead of overflowing the buffer"""
+    from ultragrid_b200 import compress
+    small, _ = make_stream(orc, "ours-uyvy", 64, 32, 90, 0)
+    big, _ = make_stream(orc, "ours-uyvy", 128, 64, 90, 0)
+    d = compress.Decompress(13, UYVY)  # JPEG
+    d.reconfigure(64, 32, 13, UYVY)
+    st, out, _ = d.frame(small)
+    assert st == d.GOT_FRAME and out is not None
+    st, out, _ = d.frame(big)
+    assert st != d.GOT_FRAME and out is None
+    st, out, _ = d.frame(small)
+    assert st == d.GOT_FRAME
+    d.close()

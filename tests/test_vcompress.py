@@ -143,3 +143,30 @@ def test_gpujpeg_module_rgb_and_conversion_input(orc):
     uyvy = util.convert_cpu(orc, "orc_convert", YUYV, UYVY, yuyv, w, h)
     assert got.tobytes() == orc_encode(orc, uyvy, w, h, UYVY, 75, ri=16)
     c.close()
+
+
+@pytest.mark.parametrize("cfg", ["cuda_dxt", "cuda_dxt_sync"])
+def test_cuda_dxt_bad_format_does_not_hang_and_recovers_sequence(cfg):
+    """a frame whose size is not divisible by 4 fails configure_with() before any CUDA call (cuda_dxt.cpp:148-151).  The reference returns
+    NULL; here push + pop must stay in step: an empty result comes back (pop reports failure) instead of pop blocking for ever.  Host logic only."""
+    import threading
+    from ultragrid_b200 import compress
+    c = compress.Compress(cfg)
+    bad = np.zeros(6 * 6 * 2, dtype=np.uint8)
+    result = []
+
+    def work():
+        for _ in range(2):  # twice: the failed configuration must not be remembered as the current one
+            c.push(bad, 6, 6, UYVY)
+            try:
+                result.append(c.pop(64))
+            except RuntimeError as e:
+                result.append(str(e))
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    t.join(timeout=20)
+    assert not t.is_alive(), "pop() blocked after a failed reconfiguration"
+    assert len(result) == 2 and all(isinstance(r, str) and "compress_pop failed" in r for r in result), result
+    c.push(None, 0, 0, 0)
+    assert c.pop(16) is None
+    c.close()

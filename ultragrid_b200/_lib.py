@@ -95,6 +95,7 @@ SIGNATURES = {
     "ugb200_jpeg_debug_segments": (_l, [_vp, _sz, _vp, _vp, _l]),
     "ugb200_jpeg_decoder_create": (_vp, [_vp]),
     "ugb200_jpeg_decoder_destroy": (None, [_vp]),
+    "ugb200_jpeg_decoder_expect": (_i, [_vp, _i, _i]),
     "ugb200_jpeg_decode": (_i, [_vp, _vp, _sz, _vp, _i, _l, _i, _i, _i, _i]),
     "ugb200_jpeg_debug_coefficients": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     # include/ugb200_vcompress.h

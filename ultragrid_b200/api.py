@@ -252,6 +252,8 @@ class JpegDecoder:
         if device:
             if out is None:
                 out = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+            elif out.numel() * out.element_size() < nbytes:
+                raise ValueError(f"out holds {out.numel() * out.element_size()} bytes, the stream decodes to {nbytes}")
             _check(_L.ugb200_jpeg_decode(self._h, buf, len(stream), _ptr(out), 1, ls, int(out_codec), *shifts), "ugb200_jpeg_decode")
             if sync:
                 self._stream.synchronize()

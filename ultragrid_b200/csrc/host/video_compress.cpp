@@ -296,7 +296,16 @@ void cuda_dxt_compress_push(void *state, std::shared_ptr<video_frame> tx)
                 if (configure_with(s, desc)) {
                         s->saved_desc = desc;
                 } else {
+                        // the reference returns NULL here (cuda_dxt.cpp:198-204).  In the push/pop shape that is an EMPTY frame with this frame's seq:
+                        // pop() stays in step with push() (cuda_dxt_compress_tile = push + pop must not block), and since cleanup() has already freed
+                        // the device buffers the saved description is forgotten, so that the next good frame configures again
                         fprintf(stderr, "[CUDA DXT] Reconfiguration failed!\n");
+                        s->saved_desc = {};
+                        std::shared_ptr<video_frame> bad(new video_frame());
+                        bad->seq = tx->seq;
+                        s->ready.push_back(bad);
+                        lk.unlock();
+                        s->cv.notify_all();
                         return;
                 }
         }
@@ -307,6 +316,8 @@ void cuda_dxt_compress_push(void *state, std::shared_ptr<video_frame> tx)
         if (!enqueue(s, sl, tx)) {  // failed frame: empty marker keeps the sequence complete (video_compress.cpp:396-398)
                 std::shared_ptr<video_frame> bad(new video_frame());
                 bad->seq = tx->seq;
+                cuda_wrapper_stream_synchronize(sl.stream);  // an H2D from tx may already be queued on the slot's stream
+                sl.out.reset();
                 while (s->tail != s->head) {
                         retire_oldest(s);
                 }
@@ -518,7 +529,8 @@ std::shared_ptr<video_frame> encoder_state::compress_step(std::shared_ptr<video_
         }
         p.restart_interval = parent->restart_interval;
         // the stream goes straight into the pooled (pinned) output frame: no encoder-owned buffer + memcpy as at :629-630
-        const size_t out_cap = (size_t) w * h * 3;  // :355
+        const size_t out_cap = (size_t) w * h * 3 + 4096;  // :355 plus the header allowance of the encoder's own buffer (ugb200_jpeg.h): tiny or
+                                                           // noisy frames at high quality exceed the raw size by their ~600-byte header
         std::shared_ptr<video_frame> out = pinned_pool_get(out_cap);
         if (!out) {
                 return {};
@@ -537,7 +549,12 @@ void encoder_state::compress(std::shared_ptr<video_frame> frame)
 {
         if (frame) {
                 const uint32_t seq = frame->seq;
-                std::shared_ptr<video_frame> out = compress_step(std::move(frame));
+                std::shared_ptr<video_frame> keep = frame;  // a failed step may have queued an asynchronous H2D from this frame: it must
+                std::shared_ptr<video_frame> out = compress_step(std::move(frame));  // not be released before the stream is idle
+                if (!out && stream) {
+                        cuda_wrapper_stream_synchronize(stream);
+                }
+                keep.reset();
                 if (!out) {  // an empty frame marks the error; pop() skips it (:194-198)
                         out = std::shared_ptr<video_frame>(new video_frame());
                         out->tiles[0].data_len = 0;

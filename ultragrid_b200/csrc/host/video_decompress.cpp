@@ -126,7 +126,8 @@ static int gpujpeg_decompress_reconfigure(void *state, struct video_desc desc, i
         if (!s->decoder) {
                 s->decoder = ugb200_jpeg_decoder_create(nullptr);
         }
-        return s->decoder != nullptr;
+        // dst holds pitch * desc.height bytes: a stream that declares another size must not be decoded into it
+        return s->decoder != nullptr && ugb200_jpeg_decoder_expect(s->decoder, (int) desc.width, (int) desc.height) == 0;
 }
 /// gpujpeg_probe_internal_codec, gpujpeg.c:205-262
 static decompress_status gpujpeg_probe_internal_codec(unsigned char *buffer, size_t len, struct pixfmt_desc *internal_prop)
@@ -218,7 +219,7 @@ static int gpujpeg_to_dxt_reconfigure(void *state, struct video_desc desc, int, 
                 s->dxt_cap = dxt;
         }
         s->desc = desc, s->out_codec = out_codec;
-        return 1;
+        return ugb200_jpeg_decoder_expect(s->decoder, (int) desc.width, (int) desc.height) == 0;  // s->rgb holds width * height * 3 bytes
 }
 /// worker_thread, gpujpeg_to_dxt.cpp:134-166: decode to RGB on the device, encode with mirrored height, copy the blocks out
 static decompress_status gpujpeg_to_dxt_decompress(void *state, unsigned char *dst, unsigned char *buffer, unsigned int src_len, int, struct video_frame_callbacks *,

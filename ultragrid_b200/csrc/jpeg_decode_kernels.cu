@@ -416,6 +416,7 @@ struct ugb200_jpeg_decoder {
                 bool pending = false;
         } hs[2];
         unsigned frame_no = 0;
+        int expect_w = 0, expect_h = 0;  // ugb200_jpeg_decoder_expect: the destination was sized for these; 0 = unchecked
 };
 
 namespace {
@@ -455,6 +456,8 @@ bool hgrow(T *&ptr, size_t &cap, size_t need)
 
 int be16(const uint8_t *p) { return p[0] << 8 | p[1]; }
 
+constexpr long kMaxPixels = 16384L * 16384L;  // four 8K frames side by side; larger SOF dimensions are refused before anything is allocated
+
 struct parsed {
         dec_geom g{};
         int adobe = -1, comp_id[3] = { 0, 0, 0 };
@@ -463,8 +466,17 @@ struct parsed {
         std::vector<uint32_t> seg_begin, seg_end;
 };
 
-void build_table(dec_tables &t, int tab, const uint8_t *bits, const uint8_t *vals, int n)
+/// @returns false for an over-subscribed code-length histogram (the Kraft check behind libjpeg's JERR_BAD_HUFF_TABLE): after the codes of
+/// length l are assigned the next code must still fit in l bits, otherwise the look-up fill below would run past the table
+bool build_table(dec_tables &t, int tab, const uint8_t *bits, const uint8_t *vals, int n)
 {
+        for (int l = 1, code = 0; l <= 16; ++l) {
+                code += bits[l - 1];
+                if (code > (1 << l)) {
+                        return false;
+                }
+                code <<= 1;
+        }
         memset(t.lut[tab], 0, sizeof t.lut[tab]);
         memcpy(t.vals[tab], vals, n);
         int code = 0, k = 0;
@@ -481,6 +493,7 @@ void build_table(dec_tables &t, int tab, const uint8_t *bits, const uint8_t *val
                 code <<= 1;
         }
         t.maxcode[tab][17] = 0x7fffffff;
+        return true;
 }
 
 const float kAan[8] = { 1.0f, 1.387039845f, 1.306562965f, 1.175875602f, 1.0f, 0.785694958f, 0.541196100f, 0.275899379f };
@@ -574,17 +587,20 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
                                 if (tc > 1 || th > 1 || n > 256 || d + 17 + n > dend) {
                                         return -4;  // baseline: two tables per class
                                 }
-                                if (T) {
-                                        build_table(*T, tc * 2 + th, d + 1, d + 17, n);
+                                if (T && !build_table(*T, tc * 2 + th, d + 1, d + 17, n)) {
+                                        return -4;  // over-subscribed Huffman table
                                 }
                                 d += 17 + n;
                         }
                 } else if (mk == 0xC0) {
-                        if (L < 8 + 3 * d[5] || d[0] != 8) {
+                        if (L < 8 || L < 8 + 3 * d[5] || d[0] != 8) {  // L first: d[5] lies inside the segment only then
                                 return -4;
                         }
                         g.h = be16(d + 1), g.w = be16(d + 3), g.ncomp = d[5];
                         if (g.ncomp != 3 || g.w == 0 || g.h == 0) {
+                                return -4;
+                        }
+                        if ((long) g.w * g.h > kMaxPixels) {  // header fields are untrusted: they size every host and device allocation below
                                 return -4;
                         }
                         g.hmax = g.vmax = 1;
@@ -609,6 +625,9 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
                 } else if (mk >= 0xC1 && mk <= 0xCF && mk != 0xC4 && mk != 0xC8 && mk != 0xCC) {
                         return -4;  // not baseline sequential Huffman
                 } else if (mk == 0xDD) {
+                        if (L < 4) {
+                                return -3;
+                        }
                         g.ri = be16(d);
                 } else if (mk == 0xEE && L >= 14 && memcmp(d, "Adobe", 5) == 0) {
                         P.adobe = d[11];
@@ -617,6 +636,9 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
                                 return -3;
                         }
                         dec_scan &S = g.s[g.nscans];
+                        if (L < 3) {
+                                return -3;
+                        }
                         S.ns = d[0];
                         if (S.ns < 1 || S.ns > 3 || L < 6 + 2 * S.ns) {
                                 return -4;
@@ -642,8 +664,10 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
                         }
                         S.nmcu = S.mcux * mcuy;
                         S.seg0 = (int) P.seg_begin.size();
-                        P.seg_begin.reserve(P.seg_begin.size() + (size_t) (g.ri ? (S.nmcu + g.ri - 1) / g.ri : 1)), P.seg_end.reserve(P.seg_begin.capacity());
                         S.nseg = g.ri ? (S.nmcu + g.ri - 1) / g.ri : 1;
+                        // every segment but the last ends in a 2-byte RSTn: a stream of `len` bytes cannot hold more than len / 2 + 1 of them (the
+                        // rest of a truncated stream is filled in below, bounded by kMaxPixels)
+                        P.seg_begin.reserve(P.seg_begin.size() + std::min((size_t) S.nseg, len / 2 + 1)), P.seg_end.reserve(P.seg_begin.capacity());
                         ++g.nscans;
                         p = dend;
                         if (!full) {
@@ -793,6 +817,15 @@ UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *d)
         delete d;
 }
 
+UGB_API int ugb200_jpeg_decoder_expect(ugb200_jpeg_decoder *d, int width, int height)
+{
+        if (!d || width < 0 || height < 0) {
+                return -1;
+        }
+        d->expect_w = width, d->expect_h = height;
+        return 0;
+}
+
 UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, size_t len, void *dst, int dst_is_device, long dst_pitch, int out_codec,
                                int rshift, int gshift, int bshift)
 {
@@ -809,6 +842,16 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                         fprintf(stderr, "[jpeg decode] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
                 }
         };
+        if (d->expect_w > 0) {  // the SOF dimensions are untrusted input and decide how much is written to dst: check them before anything else
+                parsed head;
+                const int hrc = parse_stream(stream, len, head, nullptr, false);
+                if (hrc != 0) {
+                        return hrc;
+                }
+                if (head.g.w != d->expect_w || head.g.h != d->expect_h) {
+                        return -3;
+                }
+        }
         ugb200_jpeg_decoder::host_slot &H = d->hs[d->frame_no++ & 1];
         if (H.pending) {
                 cudaEventSynchronize(H.uploaded);  // the uploads of the frame before last left this slot long ago
