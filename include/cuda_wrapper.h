@@ -46,6 +46,12 @@ UGB_API int cuda_wrapper_stream_create(cuda_wrapper_stream_t *stream);   /* non-
 UGB_API int cuda_wrapper_stream_destroy(cuda_wrapper_stream_t stream);
 UGB_API int cuda_wrapper_stream_synchronize(cuda_wrapper_stream_t stream);
 UGB_API int cuda_wrapper_memcpy_async(void *dst, const void *src, size_t count, int kind, cuda_wrapper_stream_t stream);
+/* NUMA placement (two-socket 8-GPU boxes): node of a device (-1 unknown); move the calling thread (affinity + preferred memory node) next to
+ * a device, returns the node or -1; pinned allocation whose pages live on the device's node (falls back to cudaMallocHost; freed with
+ * cuda_wrapper_free_host like any other) */
+UGB_API int cuda_wrapper_device_numa_node(int device);
+UGB_API int cuda_wrapper_bind_thread_to_device(int device);
+UGB_API int cuda_wrapper_malloc_host_near(void **buffer, size_t data_len, int device);
 /* pitched copy (cudaMemcpy2D), synchronous like cuda_wrapper_memcpy */
 UGB_API int cuda_wrapper_memcpy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int kind);
 

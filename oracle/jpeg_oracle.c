@@ -15,6 +15,7 @@
  * RFC 2435 writer (src/utils/jpeg_writer.c:215-382): SOI, APPn, DQT, SOF0, DHT x4, DRI, SOS.
  */
 #include <math.h>
+#include <omp.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -301,6 +302,107 @@ API size_t orc_jpeg_encode(const uint8_t *src, long pitch, int w, int h, int fmt
                 }
         }
         *p++ = 0xFF, *p++ = 0xD9; /* EOI */
+        return (size_t) (p - out);
+}
+
+/* The same stream produced by all host threads (bench.py's cpu_baseline for the JPEG workloads): restart segments are independent
+ * (DC prediction restarts, the bit stream is byte aligned), so contiguous chunks of segments are coded by different threads into
+ * private buffers and concatenated.  Byte-identical to orc_jpeg_encode (tests/test_jpeg.py). */
+static size_t encode_segments(const uint8_t *src, long pitch, int w, int h, int fmt, int comp_of_scan, int ri, int seg0, int seg1, int nseg, int nmcu,
+                              const float *ml, const float *mc, const struct huff *dcl, const struct huff *acl, const struct huff *dcc,
+                              const struct huff *acc, uint8_t *dst)
+{
+        struct bitw bw = { dst, 0, 0 };
+        uint8_t px[64];
+        int16_t zz[64];
+        const int mw = fmt == FMT_UYVY_422 ? (w + 15) / 16 : (w + 7) / 8;
+        for (int s = seg0; s < seg1; ++s) {
+                int pred[3] = { 0, 0, 0 };
+                const int m1 = (s + 1) * ri < nmcu ? (s + 1) * ri : nmcu;
+                for (int m = s * ri; m < m1; ++m) {
+                        if (fmt == FMT_UYVY_422) {
+                                for (int k = 0; k < 4; ++k) {
+                                        const int comp = k < 2 ? 0 : k - 1;
+                                        gather(src, pitch, w, h, fmt, comp, comp == 0 ? (m % mw) * 2 + k : m % mw, m / mw, px);
+                                        block_to_coeffs(px, comp == 0 ? ml : mc, zz);
+                                        encode_block(&bw, zz, &pred[comp], comp == 0 ? dcl : dcc, comp == 0 ? acl : acc);
+                                }
+                        } else {
+                                gather(src, pitch, w, h, fmt, comp_of_scan, m % mw, m / mw, px);
+                                block_to_coeffs(px, comp_of_scan == 0 ? ml : mc, zz);
+                                encode_block(&bw, zz, &pred[0], comp_of_scan == 0 ? dcl : dcc, comp_of_scan == 0 ? acl : acc);
+                        }
+                }
+                flush_bits(&bw);
+                if (s != nseg - 1) {
+                        *bw.p++ = 0xFF, *bw.p++ = (uint8_t) (0xD0 + (s & 7));
+                }
+        }
+        return (size_t) (bw.p - dst);
+}
+
+API size_t orc_jpeg_encode_parallel(const uint8_t *src, long pitch, int w, int h, int fmt, int quality, int ri, uint8_t *out, size_t cap)
+{
+        const size_t nblk = fmt == FMT_UYVY_422 ? (size_t) ((w + 15) / 16) * ((h + 7) / 8) * 4 : (size_t) ((w + 7) / 8) * ((h + 7) / 8) * 3;
+        if (w <= 0 || h <= 0 || cap < 2048 + nblk * 418) {
+                return 0;
+        }
+        if (ri <= 0) {
+                ri = orc_jpeg_default_restart_interval(fmt);
+        }
+        uint8_t ql[64], qc[64];
+        float ml[64], mc[64];
+        ugb_jpeg_scaled_qtable(ugb_jpeg_q_luma, quality, ql);
+        ugb_jpeg_scaled_qtable(ugb_jpeg_q_chroma, quality, qc);
+        ugb_jpeg_quant_multipliers(ql, ml);
+        ugb_jpeg_quant_multipliers(qc, mc);
+        struct huff dcl, acl, dcc, acc;
+        ugb_jpeg_build_codes(ugb_jpeg_dc_luma_bits, ugb_jpeg_dc_vals, 12, dcl.code, dcl.len);
+        ugb_jpeg_build_codes(ugb_jpeg_ac_luma_bits, ugb_jpeg_ac_luma_vals, 162, acl.code, acl.len);
+        ugb_jpeg_build_codes(ugb_jpeg_dc_chroma_bits, ugb_jpeg_dc_vals, 12, dcc.code, dcc.len);
+        ugb_jpeg_build_codes(ugb_jpeg_ac_chroma_bits, ugb_jpeg_ac_chroma_vals, 162, acc.code, acc.len);
+        const int nscan = fmt == FMT_UYVY_422 ? 1 : 3, bpm = fmt == FMT_UYVY_422 ? 4 : 1;
+        const int nmcu = fmt == FMT_UYVY_422 ? ((w + 15) / 16) * ((h + 7) / 8) : ((w + 7) / 8) * ((h + 7) / 8);
+        const int nseg = (nmcu + ri - 1) / ri;
+        int nchunk = omp_get_max_threads() * 4;
+        nchunk = nchunk > nseg ? nseg : nchunk;
+        const int per = (nseg + nchunk - 1) / nchunk;
+        nchunk = (nseg + per - 1) / per;
+        const size_t chunk_cap = (size_t) per * ((size_t) ri * bpm * 418 + 8);
+        uint8_t *tmp = (uint8_t *) malloc(chunk_cap * nchunk);
+        size_t *len = (size_t *) malloc(sizeof(size_t) * nchunk);
+        if (!tmp || !len) {
+                free(tmp), free(len);
+                return 0;
+        }
+        uint8_t *p = write_headers(out, w, h, fmt, ql, qc, ri);
+        for (int scan = 0; scan < nscan; ++scan) {
+                p = write_sos(p, scan, fmt == FMT_UYVY_422 ? 3 : 1);
+#pragma omp parallel for schedule(dynamic, 1)
+                for (int c = 0; c < nchunk; ++c) {
+                        const int s0 = c * per, s1 = s0 + per < nseg ? s0 + per : nseg;
+                        len[c] = encode_segments(src, pitch, w, h, fmt, scan, ri, s0, s1, nseg, nmcu, ml, mc, &dcl, &acl, &dcc, &acc, tmp + chunk_cap * c);
+                }
+                size_t off = 0;
+                for (int c = 0; c < nchunk; ++c) {
+                        off += len[c];
+                }
+                size_t *start = len;  /* exclusive prefix in place, then a parallel copy */
+                size_t run = 0;
+                for (int c = 0; c < nchunk; ++c) {
+                        const size_t l = len[c];
+                        start[c] = run;
+                        run += l;
+                }
+#pragma omp parallel for schedule(static)
+                for (int c = 0; c < nchunk; ++c) {
+                        const size_t l = (c + 1 < nchunk ? start[c + 1] : off) - start[c];
+                        memcpy(p + start[c], tmp + chunk_cap * c, l);
+                }
+                p += off;
+        }
+        free(tmp), free(len);
+        *p++ = 0xFF, *p++ = 0xD9;
         return (size_t) (p - out);
 }
 

@@ -25,6 +25,18 @@ def orc_encode(orc, src, w, h, codec, quality, ri=0, pitch=0):
     return out[:n].tobytes()
 
 
+def orc_encode_parallel(orc, src, w, h, codec, quality, ri=0, pitch=0):
+    """the all-threads CPU port (bench.py's cpu_baseline for the JPEG workloads)"""
+    orc.orc_jpeg_encode_parallel.restype = ctypes.c_size_t
+    orc.orc_jpeg_encode_parallel.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_size_t]
+    out = np.zeros(((w + 15) // 16 * 16) * ((h + 7) // 8 * 8) * 3 // 64 * 418 + 4096, dtype=np.uint8)
+    pitch = pitch or w * (2 if codec == UYVY else 3)
+    n = orc.orc_jpeg_encode_parallel(src.ctypes.data, pitch, w, h, 0 if codec == UYVY else 1, quality, ri, out.ctypes.data, out.size)
+    assert n > 0
+    return out[:n].tobytes()
+
+
 def psnr(a, b):
     mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
     return 99.0 if mse == 0 else 10 * np.log10(255 ** 2 / mse)
@@ -95,6 +107,56 @@ def test_restart_markers_and_header_layout(orc):
     rst = sum(body.count(bytes([0xFF, 0xD0 + k])) for k in range(8))
     assert rst == (nm + 1) // 2 - 1
     decode_ycc(data, w, h)
+
+
+@pytest.mark.parametrize("codec,w,h,q,ri", [(UYVY, 16, 8, 90, 0), (UYVY, 100, 52, 75, 3), (UYVY, 1920, 1080, 90, 0), (RGB, 8, 8, 90, 0), (RGB, 130, 37, 50, 3),
+                                            (RGB, 640, 360, 90, 0), (UYVY, 640, 360, 100, 1)])
+def test_parallel_cpu_port_equals_serial_oracle(orc, codec, w, h, q, ri):
+    """the OpenMP form that bench.py times as the CPU baseline is the same encoder: identical bytes for any thread count"""
+    src = util.rng_bytes(w * h * (2 if codec == UYVY else 3), 31)
+    src[len(src) // 3:] = 128  # part noise, part flat
+    want = orc_encode(orc, src, w, h, codec, q, ri)
+    for threads in (1, 3, 0):
+        orc.orc_set_threads(threads)
+        assert orc_encode_parallel(orc, src, w, h, codec, q, ri) == want, threads
+    orc.orc_set_threads(0)
+
+
+def dqt_tables(data):
+    """{table id: 64 values in natural order} from the DQT segments of a stream"""
+    zig = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43,
+           36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
+    out, i = {}, 2
+    while i + 4 <= len(data) and data[i] == 0xFF and data[i + 1] != 0xDA:
+        L = data[i + 2] << 8 | data[i + 3]
+        if data[i + 1] == 0xDB:
+            d = data[i + 4:i + 2 + L]
+            while len(d) >= 65:
+                t = [0] * 64
+                for k in range(64):
+                    t[zig[k]] = d[1 + k]
+                out[d[0] & 15] = t
+                d = d[65:]
+        i += 2 + L
+    return out
+
+
+@pytest.mark.parametrize("q", [1, 25, 50, 75, 90, 95, 100])
+def test_quant_tables_equal_libjpegs_entry_by_entry(orc, q):
+    """Annex K.1 / K.2 scaled by the IJG quality rule: both tables of the UYVY stream and both tables of the RGB stream (component 0 -> table 0 =
+    K.1, components 1, 2 -> table 1 = K.2, the assignment DESIGN.md section 2 states) equal the tables libjpeg itself writes at that quality"""
+    w, h = 32, 16
+    b = io.BytesIO()
+    PIL.fromarray(natural_rgb(w, h), mode="RGB").save(b, format="JPEG", quality=q, subsampling="4:2:2")
+    theirs = dqt_tables(b.getvalue())
+    assert set(theirs) == {0, 1}
+    uy = orc_encode(orc, util.rng_bytes(w * h * 2, 1), w, h, UYVY, q)
+    rgb = orc_encode(orc, util.rng_bytes(w * h * 3, 1), w, h, RGB, q)
+    for mine in (dqt_tables(uy), dqt_tables(rgb)):
+        assert mine[0] == theirs[0] and mine[1] == theirs[1]
+    # SOF0 of the RGB stream: three components, 1x1 sampling each, quantiser tables 0, 1, 1
+    i = rgb.index(b"\xff\xc0")
+    assert rgb[i + 9] == 3 and [rgb[i + 10 + 3 * c + 2] for c in range(3)] == [0, 1, 1] and [rgb[i + 10 + 3 * c + 1] for c in range(3)] == [0x11] * 3
 
 
 # ---- GPU ---------------------------------------------------------------------------------------------------------------
@@ -264,6 +326,37 @@ def test_gpu_8k_uyvy_jpeg_decodes_with_expected_psnr(orc):
     Y, Cb, _ = uyvy_planes(uyvy, w, h)
     assert psnr(dec[:, :, 0], Y) > 36 and psnr(dec[:, ::2, 1], Cb) > 36
     enc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(3840, 2160), (7680, 4320)])
+def test_gpu_rgb_jpeg_config3_sizes(orc, w, h):
+    """BASELINE config 3 (RGB -> JPEG q = 90: stored as RGB, three scans, gpujpeg.cpp:303-305) at 4K and at the full 8K size: the stream equals
+    the CPU restatement byte for byte, libjpeg decodes it as RGB, and its PSNR is within 0.3 dB of libjpeg's own encoder with the same tables"""
+    import torch
+    from ultragrid_b200 import api
+    PIL.MAX_IMAGE_PIXELS = None
+    rgb = natural_rgb(w, h, 13)
+    src = rgb.reshape(-1)
+    enc = api.JpegEncoder()
+    enc.encode_device(torch.from_numpy(src).cuda(), w, h, RGB, quality=90)
+    got = enc.result()
+    enc.close()
+    orc.orc_set_threads(0)
+    assert got == orc_encode_parallel(orc, src, w, h, RGB, 90)
+    im = PIL.open(io.BytesIO(got))
+    im.load()
+    assert im.mode == "RGB" and im.size == (w, h)
+    mine = psnr(np.asarray(im), rgb)
+    b = io.BytesIO()
+    # libjpeg's encoder on the same samples with the same colour handling (no transform: the planes go in as if they were YCbCr, 4:4:4)
+    PIL.fromarray(rgb, mode="YCbCr").save(b, format="JPEG", quality=90, subsampling="4:4:4")
+    lib = PIL.open(io.BytesIO(b.getvalue()))
+    lib.draft("YCbCr", (w, h))
+    lib.load()
+    theirs = psnr(np.asarray(lib), rgb)
+    assert abs(mine - theirs) < 0.3, (mine, theirs)
+    assert mine > 36
 
 
 @pytest.mark.gpu

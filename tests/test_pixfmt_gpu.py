@@ -97,3 +97,27 @@ def test_v210_to_p010_8k_properties(api):
     cv = c.view(torch.int16).to(torch.int64).bitwise_and(0xffff).reshape(h // 2, w)
     assert torch.equal(yv, luma.expand(h, w))
     assert torch.equal(cv, chroma.expand(h // 2, w))
+
+
+def test_v210_to_p010_8k_full_frame_vs_reference(api, orc):
+    """BASELINE config 4 at its full size with real arithmetic in every chroma sample: a 7680x4320 frame of 30-bit noise (rows all different, so
+    the (row0 + row1) / 2 average of to_planar.c:133-138 is exercised everywhere) memcmp-equal to the UNMODIFIED reference function
+    (oracle/_ref: ref_v210_to_p010le) and to the restatement"""
+    w, h = 7680, 4320
+    src = util.v210_noise(w, h, 77)
+    gy, gc = api.v210_to_p010le(dev(src), w, h)
+    gy, gc = gy.cpu().numpy(), gc.cpu().numpy()
+    checked = 0
+    for lib, fn in ((util.ref_cpu(), "ref_v210_to_p010le"), (orc, "orc_v210_to_p010le")):
+        if lib is None:
+            continue
+        y, c = np.zeros(w * 2 * h, np.uint8), np.zeros(w * h, np.uint8)
+        getattr(lib, fn)(w, h, y.ctypes.data, w * 2, c.ctypes.data, w * 2, src.ctypes.data)
+        assert np.array_equal(gy, y), fn
+        assert np.array_equal(gc, c), fn
+        checked += 1
+    assert checked >= 1
+    # the average is not the identity on this frame: more than a third of the chroma words differ from plain row 0
+    words = src.view(np.uint32).reshape(h, -1, 4)[0::2]
+    cb0 = ((words[:, :, 0] & 0x3ff) << 6).astype(np.uint16)
+    assert np.count_nonzero(gc.view(np.uint16).reshape(h // 2, w)[:, 0::6] != cb0[:, : w // 6]) > cb0[:, : w // 6].size // 3

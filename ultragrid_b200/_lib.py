@@ -33,6 +33,9 @@ SIGNATURES = {
     "cuda_wrapper_stream_synchronize": (_i, [_vp]),
     "cuda_wrapper_memcpy_async": (_i, [_vp, _vp, _sz, _i, _vp]),
     "cuda_wrapper_memcpy2d": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _i]),
+    "cuda_wrapper_device_numa_node": (_i, [_i]),
+    "cuda_wrapper_bind_thread_to_device": (_i, [_i]),
+    "cuda_wrapper_malloc_host_near": (_i, [ctypes.POINTER(_vp), _sz, _i]),
     # include/ugb200.h
     "ugb200_rgb_to_dxt1_async": (_i, [_vp, _vp, _i, _i, _vp]),
     "ugb200_yuv_to_dxt1_async": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -91,6 +94,8 @@ SIGNATURES = {
     "ugb200_jpeg_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ugb200_jpeg_encode": (_i, [_vp, _vp, _i, _l, _i, _i, _i, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ugb200_jpeg_encode_into": (_i, [_vp, _vp, _i, _l, _i, _i, _i, _vp, _vp, _sz, ctypes.POINTER(_sz)]),
+    "ugb200_jpeg_encoder_stage_timing": (_i, [_vp, _i]),
+    "ugb200_jpeg_encoder_stage_times": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "ugb200_jpeg_get_image_info": (_i, [_vp, _sz, _vp]),
     "ugb200_jpeg_debug_segments": (_l, [_vp, _sz, _vp, _vp, _l]),
     "ugb200_jpeg_decoder_create": (_vp, [_vp]),

@@ -144,6 +144,19 @@ def from_planar(name, planes, linesizes, width, height, out, out_pitch, in_depth
     return out
 
 
+def bind_host_to_device(device):
+    """cuda_wrapper_bind_thread_to_device: CPU affinity + preferred memory node of the calling thread := the GPU's NUMA node; returns the node or -1"""
+    return _L.cuda_wrapper_bind_thread_to_device(int(device))
+
+
+def pinned_near(nbytes, device):
+    """pinned host buffer whose pages live on the GPU's NUMA node (cuda_wrapper_malloc_host_near); returns a numpy uint8 view (never freed: bench buffers)"""
+    import numpy as np
+    p = ctypes.c_void_p()
+    _check(_L.cuda_wrapper_malloc_host_near(ctypes.byref(p), nbytes, int(device)), "cuda_wrapper_malloc_host_near")
+    return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes,))
+
+
 class JpegParams(ctypes.Structure):
     _fields_ = [("quality", ctypes.c_int), ("restart_interval", ctypes.c_int)]
 
@@ -197,6 +210,21 @@ class JpegEncoder:
         _check(_L.ugb200_jpeg_encode(self._h, sp, is_dev, pitch, width, height, int(codec), ctypes.byref(p), ctypes.byref(out), ctypes.byref(n)),
                "ugb200_jpeg_encode")
         return ctypes.string_at(out.value, n.value)
+
+    def result_size(self):
+        """waits for the encode; returns the stream length only (the stream stays on the device)"""
+        n = ctypes.c_size_t()
+        _check(_L.ugb200_jpeg_result_device(self._h, None, ctypes.byref(n)), "ugb200_jpeg_result_device")
+        return n.value
+
+    def stage_timing(self, enable=True):
+        _check(_L.ugb200_jpeg_encoder_stage_timing(self._h, 1 if enable else 0), "ugb200_jpeg_encoder_stage_timing")
+
+    def stage_times(self):
+        """device microseconds of the last encode: (fused DCT + entropy kernel, offset scan, compaction)"""
+        us = (ctypes.c_float * 3)()
+        _check(_L.ugb200_jpeg_encoder_stage_times(self._h, us), "ugb200_jpeg_encoder_stage_times")
+        return tuple(float(x) for x in us)
 
     def coefficients(self):
         ptr, n = ctypes.c_void_p(), ctypes.c_size_t()

@@ -70,14 +70,18 @@ int get_libraries_for_class(enum library_class cls, int abi_version, const char 
 }
 
 // ---- pinned frame pool ------------------------------------------------------------------------------------------
+// One free list per CUDA device: a frame that is pinned next to GPU k (cuda_wrapper_malloc_host_near) is only handed out for GPU k
+// again, so that no D2H crosses the socket interconnect on a two-socket box.
 namespace {
 struct pinned_pool {
         std::mutex m;
-        std::multimap<size_t, void *> free_bufs;
+        std::multimap<size_t, void *> free_bufs[MAX_CUDA_DEVICES + 1];
         ~pinned_pool()
         {
-                for (auto &kv : free_bufs) {
-                        cuda_wrapper_free_host(kv.second);
+                for (auto &fb : free_bufs) {
+                        for (auto &kv : fb) {
+                                cuda_wrapper_free_host(kv.second);
+                        }
                 }
         }
 };
@@ -92,29 +96,31 @@ uint64_t now_ns()
 }
 }  // namespace
 
-std::shared_ptr<video_frame> pinned_pool_get(size_t bytes)
+std::shared_ptr<video_frame> pinned_pool_get(size_t bytes, int device)
 {
+        const int list = device >= 0 && device < MAX_CUDA_DEVICES ? device : MAX_CUDA_DEVICES;
         void *buf = nullptr;
         {
                 std::lock_guard<std::mutex> lk(pool().m);
-                auto it = pool().free_bufs.lower_bound(bytes);
-                if (it != pool().free_bufs.end() && it->first <= bytes * 2) {
+                auto &fb = pool().free_bufs[list];
+                auto it = fb.lower_bound(bytes);
+                if (it != fb.end() && it->first <= bytes * 2) {
                         buf = it->second;
                         bytes = it->first;
-                        pool().free_bufs.erase(it);
+                        fb.erase(it);
                 }
         }
-        if (!buf && cuda_wrapper_malloc_host(&buf, bytes) != CUDA_WRAPPER_SUCCESS) {
+        if (!buf && cuda_wrapper_malloc_host_near(&buf, bytes, device) != CUDA_WRAPPER_SUCCESS) {
                 return {};
         }
         video_frame *f = new video_frame();
         f->tile_count = 1;
         f->tiles[0].data = (char *) buf;
         const size_t cap = bytes;
-        return std::shared_ptr<video_frame>(f, [cap](video_frame *fr) {  // back to the pool when the last reference drops
+        return std::shared_ptr<video_frame>(f, [cap, list](video_frame *fr) {  // back to the pool when the last reference drops
                 {
                         std::lock_guard<std::mutex> lk(pool().m);
-                        pool().free_bufs.emplace(cap, fr->tiles[0].data);
+                        pool().free_bufs[list].emplace(cap, fr->tiles[0].data);
                 }
                 delete fr;
         });
@@ -249,7 +255,7 @@ bool enqueue(state_video_compress_cuda_dxt *s, dxt_slot &sl, const std::shared_p
                 fprintf(stderr, "[CUDA DXT] Encoding failed (%d)\n", rc);
                 return false;
         }
-        sl.out = pinned_pool_get(s->out_len);
+        sl.out = pinned_pool_get(s->out_len, (int) cuda_devices[0]);
         if (!sl.out) {
                 return false;
         }
@@ -531,7 +537,7 @@ std::shared_ptr<video_frame> encoder_state::compress_step(std::shared_ptr<video_
         // the stream goes straight into the pooled (pinned) output frame: no encoder-owned buffer + memcpy as at :629-630
         const size_t out_cap = (size_t) w * h * 3 + 4096;  // :355 plus the header allowance of the encoder's own buffer (ugb200_jpeg.h): tiny or
                                                            // noisy frames at high quality exceed the raw size by their ~600-byte header
-        std::shared_ptr<video_frame> out = pinned_pool_get(out_cap);
+        std::shared_ptr<video_frame> out = pinned_pool_get(out_cap, device_id);
         if (!out) {
                 return {};
         }
@@ -570,6 +576,7 @@ void encoder_state::compress(std::shared_ptr<video_frame> frame)
 /// gpujpeg.cpp:209-225
 void encoder_state::worker()
 {
+        cuda_wrapper_bind_thread_to_device(device_id);  // this thread feeds one GPU: run (and allocate) on that GPU's socket
         while (true) {
                 std::shared_ptr<video_frame> frame = in_queue.pop();
                 if (!frame) {

@@ -50,4 +50,4 @@ void compress_done(struct compress_state *);
 
 // pooled output frames in pinned host memory (the role of video_frame_pool + cuda_buffer_data_allocator,
 // src/video_compress/cuda_dxt.cpp:68-83)
-std::shared_ptr<video_frame> pinned_pool_get(size_t bytes);
+std::shared_ptr<video_frame> pinned_pool_get(size_t bytes, int device);

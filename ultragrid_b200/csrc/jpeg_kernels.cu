@@ -1074,6 +1074,8 @@ struct ugb200_jpeg_encoder {
         cudaEvent_t stats_ev = nullptr;  // recorded behind the copy of h_total: lets an asynchronous caller adapt the cap too
         bool stats_pending = false;
         bool attr_set[2] = { false, false };  // cudaFuncSetAttribute done for the fused kernels on this encoder's device
+        bool stage_timing = false;       // ugb200_jpeg_encoder_stage_timing: events between the kernels of an encode
+        cudaEvent_t stage_ev[4] = { nullptr, nullptr, nullptr, nullptr };
 };
 
 namespace {
@@ -1281,6 +1283,11 @@ void ugb200_jpeg_encoder_destroy(ugb200_jpeg_encoder *e)
         if (e->stats_ev) {
                 cudaEventDestroy(e->stats_ev);
         }
+        for (cudaEvent_t ev : e->stage_ev) {
+                if (ev) {
+                        cudaEventDestroy(ev);
+                }
+        }
         delete e;
 }
 
@@ -1327,6 +1334,9 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         e->last_fused = fused;
         int nctas, segs_per_cta, ctas_per_scan;
         bool single_pass = false;
+        if (e->stage_timing) {
+                cudaEventRecord(e->stage_ev[0], e->stream);
+        }
         if (fused) {  // one kernel: DCT + entropy coding + segment assembly
                 static const char *cap_env = getenv("UGB200_JPEG_CAP");
                 const int cap = cap_env ? atoi(cap_env) : e->cap_words;
@@ -1382,10 +1392,22 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                 nctas = (g.nseg + 127) / 128, segs_per_cta = 128, ctas_per_scan = 0;
                 jpeg_huffman_kernel<<<nctas, 128, 0, e->stream>>>(e->coef, g, e->slots, e->sizes, e->offsets, e->cta_total, e->d_huff);
         }
+        if (e->stage_timing) {
+                cudaEventRecord(e->stage_ev[1], e->stream);
+        }
         if (!single_pass) {
                 jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
+                if (e->stage_timing) {
+                        cudaEventRecord(e->stage_ev[2], e->stream);
+                }
                 jpeg_compact_kernel<<<(int) (((long) g.nseg * kCompactLanes + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
                                                                                                    segs_per_cta, ctas_per_scan, e->out, e->total, (uint32_t) e->out_cap);
+        }
+        if (e->stage_timing) {
+                if (single_pass) {
+                        cudaEventRecord(e->stage_ev[2], e->stream);
+                }
+                cudaEventRecord(e->stage_ev[3], e->stream);
         }
         if (cudaGetLastError() != cudaSuccess) {
                 return -2;
@@ -1396,6 +1418,40 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                 e->stats_pending = true;
         }
         e->pending = true;
+        return 0;
+}
+
+int ugb200_jpeg_encoder_stage_timing(ugb200_jpeg_encoder *e, int enable)
+{
+        if (!e) {
+                return -1;
+        }
+        if (enable) {
+                for (cudaEvent_t &ev : e->stage_ev) {
+                        if (ev == nullptr && cudaEventCreate(&ev) != cudaSuccess) {
+                                return -2;
+                        }
+                }
+        }
+        e->stage_timing = enable != 0;
+        return 0;
+}
+
+int ugb200_jpeg_encoder_stage_times(ugb200_jpeg_encoder *e, float us[3])
+{
+        if (!e || !us || !e->stage_timing || !e->pending) {
+                return -1;
+        }
+        if (cudaEventSynchronize(e->stage_ev[3]) != cudaSuccess) {
+                return -2;
+        }
+        for (int i = 0; i < 3; ++i) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, e->stage_ev[i], e->stage_ev[i + 1]) != cudaSuccess) {
+                        return -2;
+                }
+                us[i] = ms * 1000.0f;
+        }
         return 0;
 }
 
