@@ -24,8 +24,10 @@ import sys
 import threading
 import time
 
-os.environ.setdefault("OMP_PROC_BIND", "close")   # CPU arm: threads stay where they start (set before libgomp loads)
-os.environ.setdefault("OMP_PLACES", "cores")
+LAUNCH_AFFINITY = os.sched_getaffinity(0)  # before anything loads libgomp: with OMP_PROC_BIND its initialisation pins the calling thread
+if "--impl" in sys.argv and "reference" in sys.argv:  # CPU arm only: OpenMP threads stay where they start (must be set before libgomp loads;
+    os.environ.setdefault("OMP_PROC_BIND", "close")   # the GPU arm leaves torch's OpenMP runtime alone)
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -72,8 +74,9 @@ def traffic_of(key):
 
 
 def effective_cpus():
-    """CPUs this process may really use: affinity mask capped by the cgroup quota (cpu.max) — OpenMP's own view ignores the quota"""
-    aff = len(os.sched_getaffinity(0))
+    """CPUs this process may really use: affinity mask at launch capped by the cgroup quota (cpu.max) — OpenMP's own view ignores the quota
+    (round 1: 128 threads on a 16-CPU quota ran the port at a sixth of its speed)"""
+    aff = len(LAUNCH_AFFINITY)
     quota = None
     for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
         try:
@@ -497,7 +500,6 @@ def main():
     from ultragrid_b200 import api, compress, sharding  # raises if libugb200.so is missing: no fallback
 
     assert torch.cuda.is_available(), "bench.py needs a GPU"
-    launch_affinity = os.sched_getaffinity(0)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = api.bind_host_to_device(local_rank)  # before any pinned allocation and before the modules start their threads
@@ -663,7 +665,7 @@ def main():
                     "BASELINE config 3: 8K RGB->JPEG q=90 (stored as RGB, 4:4:4, three scans, restart interval 8; gpujpeg.cpp:303-305)")
         if rank == 0:
             if world == 1:  # CPU baselines: rank 0 at N = 1 only, on every CPU the launcher gave us (not just the GPU's NUMA node)
-                os.sched_setaffinity(0, launch_affinity)
+                os.sched_setaffinity(0, LAUNCH_AFFINITY)
                 api.bind_host_to_device(-1)
                 import util
                 cpus = effective_cpus()  # before libgomp loads (see reference_arm)

@@ -426,6 +426,9 @@ struct variant {
         void (*pkern)(const uint8_t *, void *, int, int, long, unsigned *);
 };
 
+#define KF(T, M) { "d1_fine_t" #T "_m" #M, 1, 2, T, 0, ugb::dxt1_uyvy_skew_kernel<false, T, M, 1>, nullptr }
+#define KR(T, M) { "d1_regions_t" #T "_m" #M, 1, 2, T, 0, ugb::dxt1_uyvy_skew_kernel<false, T, M, 2>, nullptr }
+#define K(T, M) { "d1_skew_t" #T "_m" #M, 1, 2, T, 0, ugb::dxt1_uyvy_skew_kernel<false, T, M>, nullptr }
 #define V(D, B, T, M, BR) { "d" #D "_b" #B "_t" #T "_m" #M "_" #BR, D, B, T, 0, ugb::exp_kernel<D, B, T, M, BR>, nullptr }
 #define S(D, B, T, M, SK) { "d" #D "_b" #B "_t" #T "_m" #M "_skew" #SK, D, B, T, 0, ugb::exp_skew_kernel<D, B, T, M, SK>, nullptr }
 #define F6(T, M) { "d6_fusedloops_t" #T "_m" #M, 6, 1, T, 0, ugb::exp_fused6_kernel<T, M>, nullptr }
@@ -438,7 +441,7 @@ int main(int argc, char **argv)
         const long frame = (long) W * H * 2;
         std::vector<variant> vs = {
                 // DXT1: shipped shape first (two blocks per thread, 64-thread CTAs), then the alternatives that were measured
-                V(1, 2, 64, 12, true), V(1, 2, 128, 6, true), V(1, 2, 32, 24, true), V(1, 2, 256, 3, true), V(1, 2, 64, 12, false), V(1, 2, 64, 10, true),
+                V(1, 2, 64, 12, true), K(64, 8), K(64, 10), K(64, 12), K(64, 6), K(128, 4), K(128, 5), K(32, 16), K(32, 20), KF(64, 8), KF(64, 10), KF(64, 6), KF(128, 4), KF(32, 16), KR(64, 8), KR(64, 10), KR(64, 6), KR(128, 4), KR(32, 16), KR(64, 12), V(1, 2, 128, 6, true), V(1, 2, 32, 24, true), V(1, 2, 256, 3, true), V(1, 2, 64, 12, false), V(1, 2, 64, 10, true),
                 V(1, 1, 64, 14, true), V(1, 1, 128, 8, true), S(1, 2, 64, 12, 2000), S(1, 2, 64, 12, 8000),
                 P(1, 2, 128, 5, false, 1400), P(1, 2, 128, 5, true, 0), Q(1, 2, 128, 6, true, 1400, 2), Q(1, 2, 128, 6, true, 1400, 0),
                 // DXT5-YCoCg

@@ -324,3 +324,267 @@ __device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][
 }
 
 }  // namespace ugb
+
+// ================================================================================================
+// Two blocks per thread, phases SKEWED by hand (round 2).
+//
+// The encode of one block alternates long FMA-pipe-only stretches (deviations + covariance chains, index projection) with ALU-pipe-only
+// stretches (bounding box: 48 FMNMX3, index packing), and on sm_100 an f32x2 instruction holds the FMA pipe for two cycles, an ALU-pipe
+// instruction the ALU pipe for two: a warp inside a one-pipe stretch issues every second cycle at best, and the SM only reaches one
+// instruction per cycle when other warps happen to be in the complementary stretch (measured: issue 68.7 %, math_pipe_throttle +
+// not_selected on top; profiles/r01_g_dxt_shipped.md).  Here the two blocks of a thread are one phase apart, statement by statement:
+//     A: unpack+RGB | bbox        | dev + cov   | endpoints + indices | pack
+//     B:            | unpack+RGB  | bbox        | dev + cov           | endpoints + indices | pack
+// so that the ALU-only bounding box of one block sits between the FMA-only instructions of the other.  Same operation tree per block as
+// dxt1_encode_uyvy_packed(), hence the same bits.
+// ================================================================================================
+namespace ugb {
+
+struct dxt1_blk {
+        float2 R[8], G[8], B[8];
+        float mnr, mng, mnb, mxr, mxg, mxb;
+        float lor, hir, log_, hig, lob, hib;
+        float2 sr2, sg2, sb2;
+        float covx, covy;
+        float qxr, qxg, qxb, qnr, qng, qnb;
+        uint32_t max_code, min_code;
+        float2 tr2, tg2, tb2;
+        float nbias;
+        uint32_t acc0, acc1;
+};
+
+__device__ __forceinline__ void d1_rgb_row(dxt1_blk &s, uint32_t w0, uint32_t w1, int y)
+{
+        const float2 c2 = dup(kInv255), ky2 = dup(kBiasY), kc2 = dup(kBiasC);
+        const float2 u = __ffma2_rn(f2(magic_byte(w0, 0), magic_byte(w1, 0)), c2, kc2);
+        const float2 v = __ffma2_rn(f2(magic_byte(w0, 2), magic_byte(w1, 2)), c2, kc2);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+                const float2 yy = __fmul2_rn(__ffma2_rn(f2(magic_byte(w0, 1 + 2 * k), magic_byte(w1, 1 + 2 * k)), c2, ky2), dup(1.1643f));
+                s.R[2 * y + k] = __ffma2_rn(v, dup(1.7926f), yy);
+                s.G[2 * y + k] = __ffma2_rn(v, dup(-0.5328f), __ffma2_rn(u, dup(-0.2132f), yy));
+                s.B[2 * y + k] = __ffma2_rn(u, dup(2.1124f), yy);
+        }
+}
+__device__ __forceinline__ void d1_bbox_init(dxt1_blk &s)
+{
+        s.mnr = s.mxr = s.R[0].x, s.mng = s.mxg = s.G[0].x, s.mnb = s.mxb = s.B[0].x;
+}
+__device__ __forceinline__ void d1_bbox_step(dxt1_blk &s, int j)
+{
+        s.mnr = fminf(s.mnr, fminf(s.R[j].x, s.R[j].y)), s.mxr = fmaxf(s.mxr, fmaxf(s.R[j].x, s.R[j].y));
+        s.mng = fminf(s.mng, fminf(s.G[j].x, s.G[j].y)), s.mxg = fmaxf(s.mxg, fmaxf(s.G[j].x, s.G[j].y));
+        s.mnb = fminf(s.mnb, fminf(s.B[j].x, s.B[j].y)), s.mxb = fmaxf(s.mxb, fmaxf(s.B[j].x, s.B[j].y));
+}
+__device__ __forceinline__ void d1_inset(dxt1_blk &s)
+{
+        const float dr = __fadd_rn(s.mxr, -s.mnr), dg = __fadd_rn(s.mxg, -s.mng), db = __fadd_rn(s.mxb, -s.mnb);
+        s.lor = __fmaf_rn(dr, 0.0625f, s.mnr), s.hir = __fmaf_rn(dr, -0.0625f, s.mxr);
+        s.log_ = __fmaf_rn(dg, 0.0625f, s.mng), s.hig = __fmaf_rn(dg, -0.0625f, s.mxg);
+        s.lob = __fmaf_rn(db, 0.0625f, s.mnb), s.hib = __fmaf_rn(db, -0.0625f, s.mxb);
+        s.sr2 = dup(__fadd_rn(s.lor, s.hir)), s.sg2 = dup(__fadd_rn(s.log_, s.hig)), s.sb2 = dup(__fadd_rn(s.lob, s.hib));
+        s.covx = 0.0f, s.covy = 0.0f;
+}
+/// deviations of pixel pair j and their four covariance terms.  The chain order i = 0..15 is pixel order: element j holds pixels
+/// 4 (j >> 1) + (j & 1) (.x) and that + 2 (.y), so the pairs are consumed as j = 0, 1 (pixels 0, 1 then 2, 3 of row 0), 2, 3, ...
+__device__ __forceinline__ void d1_cov_row(dxt1_blk &s, int y)
+{
+        const float2 mh = dup(-0.5f);
+        const float2 er0 = __ffma2_rn(s.sr2, mh, s.R[2 * y]), er1 = __ffma2_rn(s.sr2, mh, s.R[2 * y + 1]);
+        const float2 eg0 = __ffma2_rn(s.sg2, mh, s.G[2 * y]), eg1 = __ffma2_rn(s.sg2, mh, s.G[2 * y + 1]);
+        const float2 eb0 = __ffma2_rn(s.sb2, mh, s.B[2 * y]), eb1 = __ffma2_rn(s.sb2, mh, s.B[2 * y + 1]);
+        // pixels 4y, 4y+1, 4y+2, 4y+3 = (j0.x, j1.x, j0.y, j1.y)
+        s.covx = __fmaf_rn(er0.x, eb0.x, s.covx), s.covy = __fmaf_rn(eg0.x, eb0.x, s.covy);
+        s.covx = __fmaf_rn(er1.x, eb1.x, s.covx), s.covy = __fmaf_rn(eg1.x, eb1.x, s.covy);
+        s.covx = __fmaf_rn(er0.y, eb0.y, s.covx), s.covy = __fmaf_rn(eg0.y, eb0.y, s.covy);
+        s.covx = __fmaf_rn(er1.y, eb1.y, s.covx), s.covy = __fmaf_rn(eg1.y, eb1.y, s.covy);
+}
+__device__ __forceinline__ void d1_endpoints(dxt1_blk &s)
+{
+        const bool swr = s.covx < 0.0f, swg = s.covy < 0.0f;
+        const float maxr = swr ? s.lor : s.hir, minr = swr ? s.hir : s.lor;
+        const float maxg = swg ? s.log_ : s.hig, ming = swg ? s.hig : s.log_;
+        s.qxr = quant_magic(maxr, 31.0f), s.qxg = quant_magic(maxg, 63.0f), s.qxb = quant_magic(s.hib, 31.0f);
+        s.qnr = quant_magic(minr, 31.0f), s.qng = quant_magic(ming, 63.0f), s.qnb = quant_magic(s.lob, 31.0f);
+        constexpr uint32_t kCodeBias = 0x4B400000u * 2081u;
+        s.max_code = (__float_as_uint(s.qxr) << 11) + (__float_as_uint(s.qxg) << 5) + __float_as_uint(s.qxb) - kCodeBias;
+        s.min_code = (__float_as_uint(s.qnr) << 11) + (__float_as_uint(s.qng) << 5) + __float_as_uint(s.qnb) - kCodeBias;
+        const float ex_r = __fmul_rn(__fadd_rn(s.qxr, -kRoundMagic), kInv31);
+        const float ex_g = __fmul_rn(__fadd_rn(s.qxg, -kRoundMagic), kInv63);
+        const float ex_b = __fmul_rn(__fadd_rn(s.qxb, -kRoundMagic), kInv31);
+        const float dir_r = __fmaf_rn(__fadd_rn(s.qnr, -kRoundMagic), kInv31, -ex_r);
+        const float dir_g = __fmaf_rn(__fadd_rn(s.qng, -kRoundMagic), kInv63, -ex_g);
+        const float dir_b = __fmaf_rn(__fadd_rn(s.qnb, -kRoundMagic), kInv31, -ex_b);
+        const float len2 = __fmaf_rn(dir_b, dir_b, __fmaf_rn(dir_r, dir_r, __fmul_rn(dir_g, dir_g)));
+        const float inv = __fdividef(1.0f, len2);
+        const float tr = __fmul_rn(dir_r, inv), tg = __fmul_rn(dir_g, inv), tb = __fmul_rn(dir_b, inv);
+        s.nbias = -__fmaf_rn(ex_b, tb, __fmaf_rn(ex_r, tr, __fmul_rn(ex_g, tg)));
+        s.tr2 = dup(tr), s.tg2 = dup(tg), s.tb2 = dup(tb);
+        s.acc0 = 0, s.acc1 = 0;
+}
+__device__ __forceinline__ void d1_index_step(dxt1_blk &s, int j)
+{
+        const float2 t = __ffma2_rn(s.B[j], s.tb2, __ffma2_rn(s.R[j], s.tr2, __fmul2_rn(s.G[j], s.tg2)));
+        const float2 x = __ffma2_rn(f2(add_sat_rn(t.x, s.nbias), add_sat_rn(t.y, s.nbias)), dup(3.0f), dup(0.5f));
+        const float2 m = __fadd2_rd(x, dup(kFloorMagic));
+        const int i0 = 4 * (j >> 1) + (j & 1);
+        s.acc0 += __float_as_uint(m.x) << (2 * i0);
+        s.acc1 += __float_as_uint(m.y) << (2 * (i0 + 2));
+}
+__device__ __forceinline__ uint2 d1_pack(const dxt1_blk &s)
+{
+        constexpr uint32_t kIdxBias = 0x4B000000u * 0x55555555u;
+        uint32_t indices = s.acc0 + s.acc1 - kIdxBias;
+        indices = s.max_code != s.min_code ? indices : 0u;  // a flat block's indices are computed too (inf / NaN arithmetic has no side effect) and dropped
+        const bool swap_end = s.max_code < s.min_code;
+        if (swap_end) {
+                indices = ~indices;
+        }
+        const uint32_t lsbs = indices & 0x55555555u, msbs = indices & 0xaaaaaaaau;
+        indices = msbs ^ (2 * lsbs + (msbs >> 1));
+        const uint32_t palette = swap_end ? s.min_code + (s.max_code << 16) : s.max_code + (s.min_code << 16);
+        return make_uint2(palette, indices);
+}
+
+// ---- the same phases cut into single statements, so that the source order can alternate FMA-pipe and ALU-pipe work instruction by instruction
+//      (kept by ptxas at -O1; at -O3 its list scheduler clusters the pipes again)
+struct d1_rgb_tmp {
+        float2 u, v, yy;
+};
+#define D1_UV(s, t, w0, w1)                                                                                      \
+        t.u = __ffma2_rn(f2(magic_byte(w0, 0), magic_byte(w1, 0)), dup(kInv255), dup(kBiasC));                    \
+        t.v = __ffma2_rn(f2(magic_byte(w0, 2), magic_byte(w1, 2)), dup(kInv255), dup(kBiasC))
+#define D1_YY(s, t, w0, w1, k) t.yy = __fmul2_rn(__ffma2_rn(f2(magic_byte(w0, 1 + 2 * (k)), magic_byte(w1, 1 + 2 * (k))), dup(kInv255), dup(kBiasY)), dup(1.1643f))
+#define D1_R(s, t, i) s.R[i] = __ffma2_rn(t.v, dup(1.7926f), t.yy)
+#define D1_G(s, t, i) s.G[i] = __ffma2_rn(t.v, dup(-0.5328f), __ffma2_rn(t.u, dup(-0.2132f), t.yy))
+#define D1_B(s, t, i) s.B[i] = __ffma2_rn(t.u, dup(2.1124f), t.yy)
+#define D1_BB(s, C, mn, mx, j) s.mn = fminf(s.mn, fminf(s.C[j].x, s.C[j].y)), s.mx = fmaxf(s.mx, fmaxf(s.C[j].x, s.C[j].y))
+
+/// fine-grained form of dxt1_encode_uyvy_pair_skewed(): same operations per block, statement-level alternation of the two blocks
+/// @param opaque  a value the compiler cannot know (never equal to a small negative number): with D1_REGIONS the statements of one row sit in their
+///                own basic block behind a never-taken branch on it, which is where ptxas' scheduler has to stop
+#define D1_IF(n) if (!REGIONS || opaque != -(long) (n))
+template <bool REGIONS>
+__device__ __forceinline__ uint4 dxt1_encode_uyvy_pair_fine(const uint4 (&v)[4], long opaque)
+{
+        dxt1_blk a, b;
+        d1_rgb_tmp t;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+                d1_rgb_row(a, v[y].x, v[y].y, y);
+        }
+        d1_bbox_init(a);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) D1_IF(3 + y) {  // B: unpack + RGB of row y (14 packed FMA-pipe instructions, 8 PRMT)   A: bounding box of pixel pairs 2y, 2y+1 (12 FMNMX3)
+                D1_UV(b, t, v[y].z, v[y].w);
+                D1_BB(a, R, mnr, mxr, 2 * y);
+                D1_YY(b, t, v[y].z, v[y].w, 0);
+                D1_BB(a, G, mng, mxg, 2 * y);
+                D1_R(b, t, 2 * y);
+                D1_BB(a, B, mnb, mxb, 2 * y);
+                D1_G(b, t, 2 * y);
+                D1_B(b, t, 2 * y);
+                D1_BB(a, R, mnr, mxr, 2 * y + 1);
+                D1_YY(b, t, v[y].z, v[y].w, 1);
+                D1_BB(a, G, mng, mxg, 2 * y + 1);
+                D1_R(b, t, 2 * y + 1);
+                D1_G(b, t, 2 * y + 1);
+                D1_BB(a, B, mnb, mxb, 2 * y + 1);
+                D1_B(b, t, 2 * y + 1);
+        }
+        d1_inset(a);
+        d1_bbox_init(b);
+        const float2 mh = dup(-0.5f);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) D1_IF(11 + y) {  // A: deviations + covariance chains of row y (6 packed + 8 scalar FMA)   B: bounding box
+                const float2 er0 = __ffma2_rn(a.sr2, mh, a.R[2 * y]), eb0 = __ffma2_rn(a.sb2, mh, a.B[2 * y]);
+                D1_BB(b, R, mnr, mxr, 2 * y);
+                const float2 eg0 = __ffma2_rn(a.sg2, mh, a.G[2 * y]);
+                a.covx = __fmaf_rn(er0.x, eb0.x, a.covx);
+                D1_BB(b, G, mng, mxg, 2 * y);
+                const float2 er1 = __ffma2_rn(a.sr2, mh, a.R[2 * y + 1]), eb1 = __ffma2_rn(a.sb2, mh, a.B[2 * y + 1]);
+                a.covy = __fmaf_rn(eg0.x, eb0.x, a.covy);
+                D1_BB(b, B, mnb, mxb, 2 * y);
+                const float2 eg1 = __ffma2_rn(a.sg2, mh, a.G[2 * y + 1]);
+                a.covx = __fmaf_rn(er1.x, eb1.x, a.covx);
+                D1_BB(b, R, mnr, mxr, 2 * y + 1);
+                a.covy = __fmaf_rn(eg1.x, eb1.x, a.covy);
+                a.covx = __fmaf_rn(er0.y, eb0.y, a.covx);
+                D1_BB(b, G, mng, mxg, 2 * y + 1);
+                a.covy = __fmaf_rn(eg0.y, eb0.y, a.covy);
+                a.covx = __fmaf_rn(er1.y, eb1.y, a.covx);
+                D1_BB(b, B, mnb, mxb, 2 * y + 1);
+                a.covy = __fmaf_rn(eg1.y, eb1.y, a.covy);
+        }
+        d1_endpoints(a);
+        d1_inset(b);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) D1_IF(19 + y) {  // A: indices of pixel pairs 2y, 2y+1   B: deviations + covariance of row y
+                d1_index_step(a, 2 * y);
+                d1_cov_row(b, y);
+                d1_index_step(a, 2 * y + 1);
+        }
+        d1_endpoints(b);
+        // A's packing (ALU pipe) goes between B's index steps (FMA pipe)
+        constexpr uint32_t kIdxBias = 0x4B000000u * 0x55555555u;
+        uint32_t ia = a.acc0 + a.acc1 - kIdxBias;
+        d1_index_step(b, 0);
+        ia = a.max_code != a.min_code ? ia : 0u;
+        const bool swa = a.max_code < a.min_code;
+        d1_index_step(b, 1);
+        ia = swa ? ~ia : ia;
+        const uint32_t la = ia & 0x55555555u, ma = ia & 0xaaaaaaaau;
+        d1_index_step(b, 2);
+        ia = ma ^ (2 * la + (ma >> 1));
+        d1_index_step(b, 3);
+        const uint32_t pa = swa ? a.min_code + (a.max_code << 16) : a.max_code + (a.min_code << 16);
+#pragma unroll
+        for (int j = 4; j < 8; ++j) {
+                d1_index_step(b, j);
+        }
+        const uint2 rb = d1_pack(b);
+        return make_uint4(pa, ia, rb.x, rb.y);
+}
+
+/// two horizontally adjacent blocks: v[y] = the 16 bytes (8 pixels) of row y
+__device__ __forceinline__ uint4 dxt1_encode_uyvy_pair_skewed(const uint4 (&v)[4])
+{
+        dxt1_blk a, b;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+                d1_rgb_row(a, v[y].x, v[y].y, y);
+        }
+        d1_bbox_init(a);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {  // B: unpack + RGB (FMA pipe, PRMT)   A: bounding box (ALU pipe)
+                d1_rgb_row(b, v[y].z, v[y].w, y);
+                d1_bbox_step(a, 2 * y);
+                d1_bbox_step(a, 2 * y + 1);
+        }
+        d1_inset(a);
+        d1_bbox_init(b);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {  // A: deviations + covariance chains (FMA pipe)   B: bounding box (ALU pipe)
+                d1_cov_row(a, y);
+                d1_bbox_step(b, 2 * y);
+                d1_bbox_step(b, 2 * y + 1);
+        }
+        d1_endpoints(a);
+        d1_inset(b);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {  // A: indices   B: deviations + covariance
+                d1_index_step(a, 2 * y);
+                d1_cov_row(b, y);
+                d1_index_step(a, 2 * y + 1);
+        }
+        d1_endpoints(b);
+        const uint2 ra = d1_pack(a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+                d1_index_step(b, j);
+        }
+        const uint2 rb = d1_pack(b);
+        return make_uint4(ra.x, ra.y, rb.x, rb.y);
+}
+
+}  // namespace ugb

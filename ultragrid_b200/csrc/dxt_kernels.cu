@@ -129,6 +129,29 @@ __global__ void __launch_bounds__(uyvy_cta<DXT_TYPE>::threads, uyvy_cta<DXT_TYPE
         }
 }
 
+/// fused UYVY -> DXT1, two blocks per thread with their phases one apart (dxt1_encode_uyvy_pair_skewed): the ALU-only bounding box of one
+/// block between the FMA-only deviation / covariance / projection instructions of the other.  More live registers (both blocks' 48 colour
+/// values), hence fewer resident warps than dxt_uyvy_kernel<1, 2, .>; the kernel is not latency-bound.
+template <bool MIRROR, int TPB, int MINB, int FINE = 0>  // FINE: 0 phases skewed, 1 statement-level alternation, 2 the same in basic blocks of one row
+__global__ void __launch_bounds__(TPB, MINB) dxt1_uyvy_skew_kernel(const uint8_t *__restrict__ src, void *__restrict__ out, int wb, int h, long pitch)
+{
+        const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+        const int by = blockIdx.y;
+        if (gx >= wb / 2) {
+                return;
+        }
+        const int row0 = MIRROR ? h - 1 - by * 4 : by * 4;
+        const uint8_t *p = src + (long) row0 * pitch + gx * 16;
+        const long step = MIRROR ? -pitch : pitch;
+        uint4 v[4];
+#pragma unroll
+        for (int y = 0; y < 4; ++y, p += step) {
+                v[y] = ld_stream_v4(p);
+        }
+        *((uint4 *) out + ((long) by * (wb / 2) + gx)) =
+            FINE == 2 ? dxt1_encode_uyvy_pair_fine<true>(v, pitch) : FINE == 1 ? dxt1_encode_uyvy_pair_fine<false>(v, pitch) : dxt1_encode_uyvy_pair_skewed(v);
+}
+
 // ------------------------------------------------------------------------------------------------
 // packed 3-byte source (RGB or YUV 4:4:4), ABI of cuda_dxt.h
 // ------------------------------------------------------------------------------------------------
@@ -260,6 +283,8 @@ static int launch_uyvy(const void *src, void *out, int sx, int sy, long pitch, c
 #define UGB_LAUNCH(BPT, MIR) dxt_uyvy_kernel<DXT_TYPE, BPT, MIR><<<grid, threads, 0, str>>>(s, out, wb, sy, pitch)
         if (DXT_TYPE == 1 && pair) {
                 if constexpr (DXT_TYPE == 1) {  // (the two-block variant is not even instantiated for DXT5-YCoCg)
+                        // (dxt1_uyvy_skew_kernel - the two blocks of a thread one phase apart - measures the same 32.8 us in every launch shape:
+                        // profiles/r02_b_exp_dxt.txt; it stays in this file for tools/exp_dxt.cu only)
                         if (mirrored) {
                                 UGB_LAUNCH(2, true);
                         } else {

@@ -281,6 +281,24 @@ __device__ __forceinline__ void load_row_magic(const uint8_t *__restrict__ src, 
         }
 }
 
+/// the 8 samples of component `comp` of one block row from the staged packed-RGB tile: 24 bytes at an 8-byte aligned shared address.  The row is
+/// shifted down by `comp` bytes (funnel shifts), after which the samples sit at the fixed byte offsets 0, 3, 6 ... 21
+__device__ __forceinline__ void load_row_rgb_tile(const uint8_t *p, int comp, float *m)
+{
+        const uint2 a = *(const uint2 *) p, b = *(const uint2 *) (p + 8), c = *(const uint2 *) (p + 16);
+        const unsigned sh = 8u * (unsigned) comp;
+        const uint32_t v0 = __funnelshift_r(a.x, a.y, sh), v1 = __funnelshift_r(a.y, b.x, sh), v2 = __funnelshift_r(b.x, b.y, sh);
+        const uint32_t v3 = __funnelshift_r(b.y, c.x, sh), v4 = __funnelshift_r(c.x, c.y, sh), v5 = __funnelshift_r(c.y, 0u, sh);
+        m[0] = __uint_as_float(__byte_perm(v0, 0x4B000000u, 0x7540u));  // byte 0
+        m[1] = __uint_as_float(__byte_perm(v0, 0x4B000000u, 0x7543u));  // byte 3
+        m[2] = __uint_as_float(__byte_perm(v1, 0x4B000000u, 0x7542u));  // byte 6
+        m[3] = __uint_as_float(__byte_perm(v2, 0x4B000000u, 0x7541u));  // byte 9
+        m[4] = __uint_as_float(__byte_perm(v3, 0x4B000000u, 0x7540u));  // byte 12
+        m[5] = __uint_as_float(__byte_perm(v3, 0x4B000000u, 0x7543u));  // byte 15
+        m[6] = __uint_as_float(__byte_perm(v4, 0x4B000000u, 0x7542u));  // byte 18
+        m[7] = __uint_as_float(__byte_perm(v5, 0x4B000000u, 0x7541u));  // byte 21
+}
+
 // ---- fused path: DCT + quantise + per-block entropy coding + restart-segment assembly in ONE kernel ----------------------------
 // No int16 coefficient round trip through HBM (2 B/sample written + read by the split path), and the unit of serial work is one
 // 8x8 block instead of one restart segment.  CTA = 128 threads = 128 blocks in scan order:
@@ -407,6 +425,71 @@ __device__ __forceinline__ uint32_t stuff_segment(uint8_t *__restrict__ dst, con
         return written;
 }
 
+/// The same stuffing a 32-bit word (four segment bytes) per lane and round instead of a byte: the stuffed segment is built in the CTA's shared
+/// staging area `stage` (capacity `cap_bytes`; the dead per-block bit strings) with byte stores there, and leaves for its slot as aligned
+/// 32-bit words.  A round handles 4 * bps bytes with one prefix scan - the byte-wise routine above needs four times as many rounds and
+/// writes every byte to global memory by itself.  @returns the stuffed size, or 0xFFFFFFFF if it did not fit the staging area (nothing
+/// written to the slot then: the caller falls back to stuff_segment()).
+__device__ __forceinline__ uint32_t stuff_segment_words(uint8_t *__restrict__ slot, uint8_t *stage, uint32_t cap_bytes, const uint32_t *seg, uint32_t T, int bps,
+                                                        int gl, unsigned gmask, int rst)
+{
+        const uint32_t n = (T + 7) >> 3, nw = (n + 3) >> 2;
+        uint32_t written = 0;
+        for (uint32_t base = 0; base < nw; base += bps) {
+                const uint32_t wi = base + gl;
+                const uint32_t w = wi < nw ? seg[wi] : 0u;                       // bytes beyond n are zero (the segment image starts cleared)
+                const uint32_t nb = wi < nw ? min(4u, n - 4u * wi) : 0u;
+                const uint32_t ff = __vcmpeq4(w, 0xFFFFFFFFu);                   // 0xFF in every byte that needs a stuffed zero behind it
+                const uint32_t mine = nb + (__popc(ff) >> 3);
+                uint32_t incl = mine;
+                for (int d = 1; d < bps; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(gmask, incl, d, bps);
+                        if (gl >= d) {
+                                incl += o;
+                        }
+                }
+                uint32_t pos = written + incl - mine;
+                written += __shfl_sync(gmask, incl, bps - 1, bps);
+                if (pos + mine <= cap_bytes) {
+                        if (ff == 0) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                        if ((uint32_t) k < nb) {
+                                                stage[pos + k] = (uint8_t) (w >> (24 - 8 * k));
+                                        }
+                                }
+                        } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                        if ((uint32_t) k < nb) {
+                                                const uint32_t b = (w >> (24 - 8 * k)) & 0xffu;
+                                                stage[pos++] = (uint8_t) b;
+                                                if (b == 0xFF) {
+                                                        stage[pos++] = 0;
+                                                }
+                                        }
+                                }
+                        }
+                }
+        }
+        if (rst >= 0) {
+                if (gl == 0 && written + 2 <= cap_bytes) {
+                        stage[written] = 0xFF, stage[written + 1] = (uint8_t) rst;
+                }
+                written += 2;
+        }
+        if (written > cap_bytes) {
+                return 0xFFFFFFFFu;
+        }
+        __syncwarp(gmask);
+        const uint32_t *sw = (const uint32_t *) stage;  // stage and slot are both 8-byte aligned; the bytes behind `written` in the last word are
+        uint32_t *dw = (uint32_t *) slot;               // don't-care (the compaction copies `written` bytes)
+        for (uint32_t i = gl; i * 4 < written; i += bps) {
+                dw[i] = sw[i];
+        }
+        return written;
+}
+
 /// Single-pass stream compaction (decoupled look-back): when `state` is set the kernel writes the stuffed segments straight to their final
 /// position in the stream, so that neither the per-segment slots nor the scan / compact kernels are needed.  A CTA takes a ticket (its
 /// logical index: every CTA with a smaller one has started), publishes the byte count of its segments, adds up the counts of its
@@ -444,6 +527,10 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 __syncthreads();
                 ticket = (int) s_ticket;
                 cta_x = FMT == FMT_UYVY_422 ? ticket : ticket % lb.ctas_per_scan, cta_y = FMT == FMT_UYVY_422 ? 0 : ticket / lb.ctas_per_scan;
+        } else if (FMT == FMT_RGB_444) {
+                // one-dimensional grid, component fastest: the three CTAs that read the same 24 KB of packed RGB run next to each other (L2 / L1 hits
+                // instead of three passes over the frame)
+                cta_x = blockIdx.x / 3, cta_y = blockIdx.x - 3 * cta_x;
         }
         for (int i = tid; i < 32; i += 128) {
                 s_dctab[i >> 4][i & 15] = __ldg(huff + i);
@@ -477,7 +564,31 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         //         luma and chroma warps read every byte from there instead of fetching it twice.  The tile borrows s_bits and, for a cap below 16
         //         words, the start of s_seg behind it (both are free until phase 2; s_seg is cleared after the DCT).
         bool staged = false;
-        const uint8_t *tile = (const uint8_t *) s_bits;
+        const uint8_t *tile = FMT == FMT_UYVY_422 ? (const uint8_t *) s_bits : (const uint8_t *) s_coef;
+        if (FMT == FMT_RGB_444) {
+                // The CTA's 128 blocks are consecutive in raster order of ONE component: 8 rows x 3072 bytes of packed RGB (the run may wrap into the
+                // next block row; the tile keeps block order, not image order).  cp.async in 8-byte pieces - a block starts at a multiple of 24 bytes -
+                // instead of 64 single-byte loads per thread.  24 KB: the tile lies over the coefficient array, the bit strings and the segment images,
+                // all of which are written only after the last sample has been read (barrier below).
+                staged = vec_ok && cap >= 8 && first_mcu + 128 <= g.mcu_per_scan && (g.w & 7) == 0 && (g.h & 7) == 0;
+                if (staged) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                                const int c = tid + 128 * j;            // 8-byte piece c of a 3072-byte tile row
+                                const int blk = c / 3, part = c - 3 * blk;
+                                const int b = first_mcu + blk;
+                                const int bxx = b % g.bw, byy = b / g.bw;
+                                const uint8_t *gp = src + (long) (byy * 8) * pitch + (long) bxx * 24 + part * 8;
+                                uint32_t dst = (uint32_t) __cvta_generic_to_shared(tile + c * 8);
+#pragma unroll
+                                for (int r = 0; r < 8; ++r, gp += pitch, dst += 3072) {
+                                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gp) : "memory");
+                                }
+                        }
+                        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                        __syncthreads();
+                }
+        }
         if (FMT == FMT_UYVY_422) {
                 const int mx0 = first_mcu % g.bw, my0 = first_mcu / g.bw;
                 staged = vec_ok && cap >= 8 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h;
@@ -501,9 +612,15 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
 #pragma unroll
                 for (int rp = 0; rp < 4; ++rp) {
                         float ma[8], mb[8];
-                        load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp : 0, interior, ma, staged ? tile + (2 * rp) * 1024 : nullptr, tid & 31);
-                        load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp + 1 : 0, interior, mb, staged ? tile + (2 * rp + 1) * 1024 : nullptr,
-                                       tid & 31);
+                        if (FMT == FMT_RGB_444 && staged) {
+                                load_row_rgb_tile(tile + (2 * rp) * 3072 + tid * 24, comp, ma);
+                                load_row_rgb_tile(tile + (2 * rp + 1) * 3072 + tid * 24, comp, mb);
+                        } else {
+                                load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp : 0, interior, ma,
+                                               staged ? tile + (2 * rp) * 1024 : nullptr, tid & 31);
+                                load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp + 1 : 0, interior, mb,
+                                               staged ? tile + (2 * rp + 1) * 1024 : nullptr, tid & 31);
+                        }
 #pragma unroll
                         for (int x = 0; x < 8; ++x) {  // (2^23 + s) - (2^23 + 128): level shift, exact
                                 f2[rp][x] = __fadd2_rn(make_float2(ma[x], mb[x]), make_float2(-8388736.0f, -8388736.0f));
@@ -532,6 +649,9 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         constexpr int zz[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                  41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                  30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+        if (FMT == FMT_RGB_444 && staged) {
+                __syncthreads();  // the RGB tile lies over the coefficient array: every thread has its samples in registers before the first store
+        }
         // word k of the block = zig-zag coefficients k (low half) and k + 32 (high half): the non-zero flags of 16 words then add up
         // into one register without touching each other (bit k and bit 16 + k), and two byte permutes assemble the 64-bit map
         uint32_t flags_a = 0, flags_b = 0;
@@ -725,7 +845,13 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                         }
                         written = n + cnt + (ls != g.seg_per_scan - 1 ? 2u : 0u);
                 } else if (seg_valid) {
-                        written = stuff_segment(slots + (long) seg_global * g.slot, seg, T, bps, gl, lane32, gmask, ls != g.seg_per_scan - 1 ? 0xD0 + (ls & 7) : -1);
+                        const int rst = ls != g.seg_per_scan - 1 ? 0xD0 + (ls & 7) : -1;
+                        uint8_t *slot = slots + (long) seg_global * g.slot;
+                        // staging area of this segment: its share of the per-block bit strings, which nobody reads any more (barrier above)
+                        written = stuff_segment_words(slot, (uint8_t *) s_bits + (size_t) sg * bps * cap * 4, (uint32_t) (bps * cap * 4), seg, T, bps, gl, gmask, rst);
+                        if (written == 0xFFFFFFFFu) {  // more 0xFF bytes than the staging area has room for: byte-wise, straight to the slot
+                                written = stuff_segment(slot, seg, T, bps, gl, lane32, gmask, rst);
+                        }
                         if (gl == 0) {
                                 sizes[seg_global] = written;
                         }
@@ -760,7 +886,7 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                         local_off[seg_global] = before + inc2 - mine;
                 }
                 if (tid == 127) {
-                        const int cta = FMT == FMT_UYVY_422 ? cta_x : cta_y * gridDim.x + cta_x;
+                        const int cta = FMT == FMT_UYVY_422 ? cta_x : cta_y * lb.ctas_per_scan + cta_x;
                         cta_total[cta] = before + inc2;
                 }
                 return;
@@ -954,20 +1080,30 @@ __global__ void __launch_bounds__(128) jpeg_huffman_kernel(const int16_t *__rest
         }
 }
 
-// ---- K3: exclusive scan of the per-CTA totals (second level; a frame has a few hundred of them) --------------------------------
+// ---- K3: exclusive scan of the per-CTA totals (second level; a frame has 8 100 - 36 450 of them) ------------------------------------
+// One CTA of 1024 threads, eight consecutive totals per thread and round (two 128-bit loads, thread-local prefix, one block scan of the
+// thread sums): an 8K UYVY frame is ONE round.  (Round 1 took 1024 totals per round with three barriers each - 12.4 us for 8 100 totals.)
 __global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *__restrict__ cta_total, int n, jpeg_geom g, uint32_t *__restrict__ total)
 {
         __shared__ uint32_t s_warp[32];
         __shared__ uint32_t s_carry;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (threadIdx.x == 0) {
-                s_carry = 0;
-        }
-        __syncthreads();
-        for (int base = 0; base < n; base += 1024) {
-                const int i = base + threadIdx.x;
-                const uint32_t v = i < n ? cta_total[i] : 0;
-                uint32_t incl = v;
+        uint32_t carry = 0;
+        for (int base = 0; base < n; base += 8192) {  // the buffer is padded to a multiple of 8 entries (configure)
+                const int i = base + threadIdx.x * 8;
+                uint4 a = make_uint4(0, 0, 0, 0), b = a;
+                if (i < n) {
+                        a = *(const uint4 *) (cta_total + i), b = *(const uint4 *) (cta_total + i + 4);
+                }
+                uint32_t v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+                uint32_t sum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                        const uint32_t x = i + k < n ? v[k] : 0u;
+                        v[k] = sum;  // exclusive within the thread
+                        sum += x;
+                }
+                uint32_t incl = sum;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                         const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -989,21 +1125,22 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *__restrict__ 
                                 }
                         }
                         s_warp[lane] = w;  // inclusive over warps
+                        if (lane == 31) {
+                                s_carry = w;
+                        }
                 }
                 __syncthreads();
-                const uint32_t before = s_carry + (warp ? s_warp[warp - 1] : 0);
-                if (i < n) {
-                        cta_total[i] = before + incl - v;  // exclusive prefix in place
+                const uint32_t before = carry + (warp ? s_warp[warp - 1] : 0) + incl - sum;
+                if (i < n) {  // exclusive prefixes in place (entries beyond n are padding)
+                        *(uint4 *) (cta_total + i) = make_uint4(before + v[0], before + v[1], before + v[2], before + v[3]);
+                        *(uint4 *) (cta_total + i + 4) = make_uint4(before + v[4], before + v[5], before + v[6], before + v[7]);
                 }
-                __syncthreads();
-                if (threadIdx.x == 1023) {
-                        s_carry = before + incl;
-                }
+                carry += s_carry;
                 __syncthreads();
         }
         if (threadIdx.x == 0) {
                 const int nscans = g.nseg / g.seg_per_scan;
-                *total = g.header_len + s_carry + g.sos_len * (nscans - 1) + 2;  // + later SOS headers + EOI
+                *total = g.header_len + carry + g.sos_len * (nscans - 1) + 2;  // + later SOS headers + EOI
         }
 }
 
@@ -1323,7 +1460,8 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                 return rc;
         }
         const jpeg_geom &g = e->g;
-        const bool vec_ok = fmt == FMT_UYVY_422 && !(15 & (size_t) src) && !(pitch & 15);
+        // UYVY: 128-bit loads and 16-byte cp.async; RGB: 8-byte cp.async pieces of the staged tile
+        const bool vec_ok = fmt == FMT_UYVY_422 ? !(15 & (size_t) src) && !(pitch & 15) : !(7 & (size_t) src) && !(pitch & 7);
         e->last_src = src, e->last_pitch = pitch, e->last_vec_ok = vec_ok;
         if (e->stats_pending && cudaEventQuery(e->stats_ev) == cudaSuccess) {
                 adapt_cap(e);  // the previous frame has finished although nobody fetched its result yet
@@ -1368,7 +1506,7 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                         }
                         e->attr_set[fmt == FMT_UYVY_422 ? 0 : 1] = true;
                 }
-                const dim3 grid = fmt == FMT_UYVY_422 || single_pass ? dim3(nctas) : dim3(ctas_per_scan, 3);  // single pass: tickets run over the three scans
+                const dim3 grid(nctas);  // RGB: component fastest (two-pass) or tickets running over the three scans (single pass)
 #define UGB_FUSED(FMT, MINB)                                                                                                                              \
         jpeg_fused_kernel<FMT, MINB><<<grid, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, vec_ok, cap, \
                                                                      e->total + 1, lb, e->qt, e->d_huff)
