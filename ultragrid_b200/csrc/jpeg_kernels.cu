@@ -503,6 +503,38 @@ struct jpeg_lookback {
         int ctas_per_scan;
 };
 
+// ---- TMA (bulk async copy) staging of the input tile: one thread arms an mbarrier with the byte count and issues one cp.async.bulk per tile
+//      row; the copy engine moves the rows while the CTA fetches its Huffman tables, and every thread waits on the mbarrier itself - no
+//      per-thread LDGSTS, no commit / wait group (SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t) __cvta_generic_to_shared(bar)), "r"(count) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t) __cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t) __cvta_generic_to_shared(dst)),
+                     "l"(src), "r"(bytes), "r"((uint32_t) __cvta_generic_to_shared(bar))
+                     : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+        asm volatile("{\n\t"
+                     ".reg .pred p;\n\t"
+                     "WAIT_%=:\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                     "@p bra DONE_%=;\n\t"
+                     "bra WAIT_%=;\n\t"
+                     "DONE_%=:\n\t"
+                     "}" ::"r"((uint32_t) __cvta_generic_to_shared(bar)),
+                     "r"(parity)
+                     : "memory");
+}
+
 /// MINB = resident CTAs per SM the register allocation aims at: 6 (80 registers) for any cap, 7 (72 registers) when the bit buffers are
 /// capped at 12 words or fewer (28 KB of dynamic shared memory per CTA)
 template <int FMT, int MINB>
@@ -511,14 +543,16 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                                                          uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats,
                                                          jpeg_lookback lb, const __grid_constant__ jpeg_qtab qt, const uint32_t *__restrict__ huff)
 {
-        extern __shared__ uint32_t smem[];
+        extern __shared__ __align__(128) uint32_t smem[];
         uint32_t *s_coef = smem;                // [32][128] zig-zag coefficients, two int16 per word
         uint32_t *s_bits = s_coef + 32 * 128;   // [cap][128]
         uint32_t *s_seg = s_bits + cap * 128;   // [segments of the CTA][bps * cap]
         __shared__ uint32_t s_dctab[2][16], s_ac[2][256], s_len[128], s_warp[4], s_max[4];
         __shared__ int s_dc[128];
         __shared__ uint32_t s_ticket, s_tot, s_base;
+        __shared__ __align__(8) unsigned long long s_bar;  // mbarrier of the input tile
         const int tid = threadIdx.x;
+        asm volatile("griddepcontrol.launch_dependents;");  // the one-CTA offset scan behind this kernel may be set up now (it waits for this grid to finish)
         int cta_x = blockIdx.x, cta_y = blockIdx.y, ticket = 0;
         if (lb.state != nullptr) {
                 if (tid == 0) {
@@ -571,7 +605,29 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 // instead of 64 single-byte loads per thread.  24 KB: the tile lies over the coefficient array, the bit strings and the segment images,
                 // all of which are written only after the last sample has been read (barrier below).
                 staged = vec_ok && cap >= 8 && first_mcu + 128 <= g.mcu_per_scan && (g.w & 7) == 0 && (g.h & 7) == 0;
-                if (staged) {
+                // 16-byte aligned rows and an even number of blocks per row: the (at most two) runs of a tile row start and end on 48-byte
+                // boundaries, so whole runs go through the copy engine
+                // (a frame less than 128 blocks wide wraps more than once inside a tile: that goes the cp.async way below)
+                const bool bulk = staged && g.bw >= 128 && !(g.bw & 1) && !(15 & (size_t) src) && !(pitch & 15);
+                if (bulk) {
+                        if (tid == 0) {
+                                mbar_init(&s_bar, 1);
+                        }
+                        __syncthreads();
+                        if (tid == 0) {
+                                const int bx0 = first_mcu % g.bw, by0 = first_mcu / g.bw;
+                                const int in_row = min(128, g.bw - bx0);  // blocks of the tile that lie in block row by0; the rest starts block row by0 + 1
+                                mbar_expect_tx(&s_bar, 8 * 3072);
+                                const uint8_t *ga = src + (long) (by0 * 8) * pitch + (long) bx0 * 24, *gb = src + (long) (by0 * 8 + 8) * pitch;
+                                for (int r = 0; r < 8; ++r, ga += pitch, gb += pitch) {
+                                        bulk_g2s((void *) (tile + r * 3072), ga, (uint32_t) in_row * 24, &s_bar);
+                                        if (in_row < 128) {
+                                                bulk_g2s((void *) (tile + r * 3072 + in_row * 24), gb, (uint32_t) (128 - in_row) * 24, &s_bar);
+                                        }
+                                }
+                        }
+                        mbar_wait(&s_bar, 0);
+                } else if (staged) {
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
                                 const int c = tid + 128 * j;            // 8-byte piece c of a 3072-byte tile row
@@ -592,15 +648,19 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         if (FMT == FMT_UYVY_422) {
                 const int mx0 = first_mcu % g.bw, my0 = first_mcu / g.bw;
                 staged = vec_ok && cap >= 8 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h;
-                if (staged) {
+                if (staged) {  // vec_ok: 16-byte aligned frame and pitch - one bulk copy per 1024-byte tile row
                         const uint8_t *gsrc = src + (long) (my0 * 8) * pitch + (long) mx0 * 32;
-                        for (int i = tid; i < 512; i += 128) {
-                                const int row = i >> 6, col = i & 63;
-                                const uint32_t dst = (uint32_t) __cvta_generic_to_shared(tile + row * 1024 + col * 16);
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc + (long) row * pitch + col * 16) : "memory");
+                        if (tid == 0) {
+                                mbar_init(&s_bar, 1);
                         }
-                        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
                         __syncthreads();
+                        if (tid == 0) {
+                                mbar_expect_tx(&s_bar, 8 * 1024);
+                                for (int r = 0; r < 8; ++r) {
+                                        bulk_g2s((void *) (tile + r * 1024), gsrc + (long) r * pitch, 1024, &s_bar);
+                                }
+                        }
+                        mbar_wait(&s_bar, 0);
                 }
         }
         // ---- 1. DCT + quantise, packed: lanes (x, y) of a float2 = rows (2r, 2r + 1) in the row pass, columns (2c, 2c + 1) in the column pass ----
@@ -1089,6 +1149,10 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *__restrict__ 
         __shared__ uint32_t s_carry;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint32_t carry = 0;
+        // programmatic dependent launch: this CTA may have been set up while the entropy kernel was still running; its totals are complete (and
+        // visible) behind the wait.  The compaction kernel may be set up in turn.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
         for (int base = 0; base < n; base += 8192) {  // the buffer is padded to a multiple of 8 entries (configure)
                 const int i = base + threadIdx.x * 8;
                 uint4 a = make_uint4(0, 0, 0, 0), b = a;
@@ -1157,6 +1221,7 @@ __global__ void __launch_bounds__(256) jpeg_compact_kernel(const uint8_t *__rest
 {
         const int t = blockIdx.x * blockDim.x + threadIdx.x;
         const int s = t / kCompactLanes, lane = t % kCompactLanes;
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // offsets of the scan kernel (programmatic dependent launch)
         if (s >= g.nseg || *total > out_cap) {  // a stream larger than the output buffer is reported by the host, never written
                 return;
         }
@@ -1534,12 +1599,23 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                 cudaEventRecord(e->stage_ev[1], e->stream);
         }
         if (!single_pass) {
-                jpeg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->cta_total, nctas, g, e->total);
+                // programmatic dependent launch: the scan and the compaction are set up while their predecessor drains (they wait for its results
+                // with griddepcontrol.wait), which takes the launch latencies of two tiny kernels out of the frame time.  Stage timing records
+                // events between the kernels, which serialises them again: timing mode launches the plain way.
+                cudaLaunchAttribute pdl[1];
+                pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                pdl[0].val.programmaticStreamSerializationAllowed = 1;
+                cudaLaunchConfig_t cfg{};
+                cfg.stream = e->stream;
+                cfg.attrs = pdl, cfg.numAttrs = e->stage_timing ? 0 : 1;
+                cfg.gridDim = dim3(1), cfg.blockDim = dim3(1024);
+                cudaLaunchKernelEx(&cfg, jpeg_scan_kernel, e->cta_total, nctas, g, e->total);
                 if (e->stage_timing) {
                         cudaEventRecord(e->stage_ev[2], e->stream);
                 }
-                jpeg_compact_kernel<<<(int) (((long) g.nseg * kCompactLanes + 255) / 256), 256, 0, e->stream>>>(e->slots, e->sizes, e->offsets, e->cta_total, g,
-                                                                                                   segs_per_cta, ctas_per_scan, e->out, e->total, (uint32_t) e->out_cap);
+                cfg.gridDim = dim3((unsigned) (((long) g.nseg * kCompactLanes + 255) / 256)), cfg.blockDim = dim3(256);
+                cudaLaunchKernelEx(&cfg, jpeg_compact_kernel, (const uint8_t *) e->slots, (const uint32_t *) e->sizes, (const uint32_t *) e->offsets,
+                                   (const uint32_t *) e->cta_total, g, segs_per_cta, ctas_per_scan, e->out, (const uint32_t *) e->total, (uint32_t) e->out_cap);
         }
         if (e->stage_timing) {
                 if (single_pass) {
