@@ -8,6 +8,7 @@
 
 #include "color_space.h"
 #include "pixfmt_conv.h"
+#include "from_planar.h"
 #include "to_planar.h"
 #include "utils/parallel_conv.h"
 #include "video_codec.h"
@@ -78,6 +79,18 @@ API void ref_v210_to_p010le_parallel(int width, int height, unsigned char *out_y
         d.out_linesize[0] = ls_y, d.out_linesize[1] = ls_c;
         d.in_data = in;
         decode_to_planar_parallel(v210_to_p010le, d, vc_get_linesize(width, v210), threads);
+}
+
+/* yuv422p10le_to_v210 (src/from_planar.c:295-333): the inverse the v210 <-> planar identity tests of the lavc bridge run through */
+API void ref_yuv422p10le_to_v210(int width, int height, unsigned char *out, unsigned out_pitch, const unsigned char *y, const unsigned char *cb,
+                                 const unsigned char *cr, unsigned ls_y, unsigned ls_c)
+{
+        struct from_planar_data d = { 0 };
+        d.width = width, d.height = height, d.out_data = out, d.out_pitch = out_pitch;
+        d.in_data[0] = y, d.in_data[1] = cb, d.in_data[2] = cr;
+        d.in_linesize[0] = ls_y, d.in_linesize[1] = ls_c, d.in_linesize[2] = ls_c;
+        d.in_depth = 10;
+        yuv422p10le_to_v210(d);
 }
 
 API int ref_get_best_decoder_from(int in_codec, const int *candidates, int count)

@@ -103,6 +103,15 @@ SIGNATURES = {
     "ugb200_jpeg_decoder_expect": (_i, [_vp, _i, _i]),
     "ugb200_jpeg_decode": (_i, [_vp, _vp, _sz, _vp, _i, _l, _i, _i, _i, _i]),
     "ugb200_jpeg_debug_coefficients": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    # include/ugb200_lavc.h
+    "ugb200_to_lavc_supported": (_i, [_i, _i]),
+    "ugb200_to_lavc_convert": (_i, [_i, _i, _vp, _vp, _i, _i, _vp]),
+    "ugb200_to_lavc_vid_conv_init": (_vp, [_i, _i, _i, _i]),
+    "ugb200_to_lavc_vid_conv": (_vp, [_vp, _vp, _i]),
+    "ugb200_to_lavc_vid_conv_destroy": (None, [_vp]),
+    "ugb200_get_av_to_uv_conversion": (_vp, [_i, _i]),
+    "ugb200_av_to_uv_convert": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ugb200_av_to_uv_conversion_destroy": (None, [_vp]),
     # include/ugb200_vcompress.h
     "ugb200_set_cuda_devices": (_i, [ctypes.POINTER(_i), _i]),
     "ugb200_compress_init": (_vp, [ctypes.c_char_p]),

@@ -144,6 +144,57 @@ def from_planar(name, planes, linesizes, width, height, out, out_pitch, in_depth
     return out
 
 
+class AvPlanes(ctypes.Structure):
+    """struct ugb200_av_planes (include/ugb200_lavc.h): AVFrame::data / AVFrame::linesize"""
+    _fields_ = [("data", ctypes.c_void_p * 4), ("linesize", ctypes.c_int * 4)]
+
+
+AV_PIXFMT = {n: i for i, n in enumerate(["NONE", "YUV420P", "YUV422P", "YUV444P", "NV12", "P010LE", "YUV420P10LE", "YUV422P10LE", "YUV444P10LE", "YUV422P12LE",
+                                          "YUV444P12LE", "YUV422P16LE", "YUV444P16LE", "GBRP"])}
+
+
+def av_plane_shapes(av_pixfmt, width, height, pad=0):
+    """[(linesize bytes, rows)] of the planes of a frame of `av_pixfmt` (name), rows padded by `pad` bytes"""
+    f = av_pixfmt
+    bps = 1 if f in ("YUV420P", "YUV422P", "YUV444P", "NV12", "GBRP") else 2
+    hs = 0 if "444" in f or f == "GBRP" else 1
+    vs = 1 if "420" in f or f in ("NV12", "P010LE") else 0
+    cw, ch = (width + (1 << hs) - 1) >> hs, (height + (1 << vs) - 1) >> vs
+    if f in ("NV12", "P010LE"):
+        return [(width * bps + pad, height), (cw * 2 * bps + pad, ch)]
+    return [(width * bps + pad, height), (cw * bps + pad, ch), (cw * bps + pad, ch)]
+
+
+def to_lavc(in_codec, av_pixfmt, src, width, height, planes=None, pad=0, stream=None):
+    """ugb200_to_lavc_convert: device frame of `in_codec` -> list of device plane tensors of `av_pixfmt` (a name of AV_PIXFMT)"""
+    shapes = av_plane_shapes(av_pixfmt, width, height, pad)
+    if planes is None:
+        planes = [torch.zeros(ls * rows, dtype=torch.uint8, device=src.device) for ls, rows in shapes]
+    p = AvPlanes()
+    for i, (t, (ls, _)) in enumerate(zip(planes, shapes)):
+        p.data[i], p.linesize[i] = t.data_ptr(), ls
+    _check(_L.ugb200_to_lavc_convert(int(in_codec), AV_PIXFMT[av_pixfmt], ctypes.byref(p), _ptr(src), width, height, _stream(stream)), "ugb200_to_lavc_convert")
+    return planes
+
+
+def from_lavc(av_pixfmt, out_codec, planes, linesizes, width, height, dst, pitch, rgb_shift=(0, 8, 16), stream=None):
+    """get_av_to_uv_cuda_conversion + av_to_uv_convert_cuda shape: device planes -> device frame of `out_codec`"""
+    st = _L.ugb200_get_av_to_uv_conversion(AV_PIXFMT[av_pixfmt], int(out_codec))
+    if not st:
+        raise RuntimeError(f"no av -> uv conversion {av_pixfmt} -> {out_codec}")
+    p = AvPlanes()
+    for i, (t, ls) in enumerate(zip(planes, linesizes)):
+        p.data[i], p.linesize[i] = t.data_ptr(), ls
+    shifts = (ctypes.c_int * 3)(*rgb_shift)
+    try:
+        _check(_L.ugb200_av_to_uv_convert(st, _ptr(dst), ctypes.byref(p), width, height, pitch, shifts, _stream(stream)), "ugb200_av_to_uv_convert")
+        torch.cuda.current_stream().synchronize()
+    finally:
+        h = ctypes.c_void_p(st)
+        _L.ugb200_av_to_uv_conversion_destroy(ctypes.byref(h))
+    return dst
+
+
 def bind_host_to_device(device):
     """cuda_wrapper_bind_thread_to_device: CPU affinity + preferred memory node of the calling thread := the GPU's NUMA node; returns the node or -1"""
     return _L.cuda_wrapper_bind_thread_to_device(int(device))
