@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/ugb200.h"
 
 namespace ugb {
@@ -101,6 +103,48 @@ __global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__re
         }
 }
 
+// ---- DXT1 palette tables ---------------------------------------------------------------------------------------------------------------
+// The four palette colours of a block are a function of its two 5:6:5 endpoints only, channel by channel.  Round 1 evaluated them per block in
+// FP64 (24 software divisions + 12 double -> int conversions per block: 0.31 of the HBM roofline).  The same FP64 expressions are now evaluated
+// ONCE per device for every endpoint pair by dxt1_tables_kernel - identical operations, so identical bytes - and a block reads the four bytes of
+// a channel with one 32-bit load: [mode][q0][q1] -> entries 0..3, mode 0 = four-colour (c0 > c1), 1 = three-colour + black.
+__device__ uint32_t g_dxt1_pal5[2][32][32], g_dxt1_pal6[2][64][64];
+
+__global__ void dxt1_tables_kernel()
+{
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= 2 * 64 * 64) {
+                return;
+        }
+        const int mode = i >> 12, q0 = (i >> 6) & 63, q1 = i & 63;
+#pragma unroll
+        for (int six = 0; six < 2; ++six) {
+                if (!six && (q0 >= 32 || q1 >= 32)) {
+                        continue;
+                }
+                const double den = six ? 63.0 : 31.0;
+                double v[4];
+                v[0] = __ddiv_rn((double) q0, den), v[1] = __ddiv_rn((double) q1, den);
+                if (mode == 0) {
+                        v[2] = third(v[0], v[1]);
+                        v[3] = __ddiv_rn(__dadd_rn(v[0], __dmul_rn(2.0, v[1])), 3.0);
+                } else {
+                        v[2] = __dmul_rn(__dadd_rn(v[0], v[1]), 0.5);
+                        v[3] = 0.0;
+                }
+                uint32_t w = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                        w |= to_byte(__dmul_rn(v[k], 255.0)) << (8 * k);
+                }
+                if (six) {
+                        g_dxt1_pal6[mode][q0][q1] = w;
+                } else {
+                        g_dxt1_pal5[mode][q0][q1] = w;
+                }
+        }
+}
+
 template <int BGR>
 __global__ void __launch_bounds__(128) dxt1_decode_kernel(const uint2 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch, bool aligned)
 {
@@ -110,21 +154,12 @@ __global__ void __launch_bounds__(128) dxt1_decode_kernel(const uint2 *__restric
         }
         const uint2 blk = __ldg(in + (long) by * bw + bx);
         const uint32_t c0 = blk.x & 0xffff, c1 = blk.x >> 16;
-        double r[4], g[4], b[4];
-        r[0] = __ddiv_rn((double) (c0 >> 11), 31.0), g[0] = __ddiv_rn((double) ((c0 >> 5) & 63), 63.0), b[0] = __ddiv_rn((double) (c0 & 31), 31.0);
-        r[1] = __ddiv_rn((double) (c1 >> 11), 31.0), g[1] = __ddiv_rn((double) ((c1 >> 5) & 63), 63.0), b[1] = __ddiv_rn((double) (c1 & 31), 31.0);
-        if (c0 > c1) {
-                r[2] = third(r[0], r[1]), g[2] = third(g[0], g[1]), b[2] = third(b[0], b[1]);
-                r[3] = __ddiv_rn(__dadd_rn(r[0], __dmul_rn(2.0, r[1])), 3.0), g[3] = __ddiv_rn(__dadd_rn(g[0], __dmul_rn(2.0, g[1])), 3.0),
-                b[3] = __ddiv_rn(__dadd_rn(b[0], __dmul_rn(2.0, b[1])), 3.0);
-        } else {
-                r[2] = __dmul_rn(__dadd_rn(r[0], r[1]), 0.5), g[2] = __dmul_rn(__dadd_rn(g[0], g[1]), 0.5), b[2] = __dmul_rn(__dadd_rn(b[0], b[1]), 0.5);
-                r[3] = g[3] = b[3] = 0.0;
-        }
+        const int mode = c0 > c1 ? 0 : 1;
+        const uint32_t pr = g_dxt1_pal5[mode][c0 >> 11][c1 >> 11], pg = g_dxt1_pal6[mode][(c0 >> 5) & 63][(c1 >> 5) & 63], pb = g_dxt1_pal5[mode][c0 & 31][c1 & 31];
         uint32_t pal[4];  // the four colours as 24-bit pixels, selected per pixel with two predicated moves
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-                pal[k] = pack_px<BGR>(to_byte(__dmul_rn(r[k], 255.0)), to_byte(__dmul_rn(g[k], 255.0)), to_byte(__dmul_rn(b[k], 255.0)));
+                pal[k] = pack_px<BGR>((pr >> (8 * k)) & 0xff, (pg >> (8 * k)) & 0xff, (pb >> (8 * k)) & 0xff);
         }
         uint32_t idx = blk.y;
         uint8_t *o = out + (long) by * 4 * pitch + (long) bx * 12;
@@ -154,6 +189,7 @@ using namespace ugb;
                 if (out_pitch == 0) {                                                                                                      \
                         out_pitch = (long) w * 3;                                                                                          \
                 }                                                                                                                          \
+                UGB_DECODE_PRE_##KERNEL(stream)                                                                                              \
                 dim3 grid((w / 4 + 127) / 128, h / 4);                                                                                     \
                 const bool aligned = !(3 & (size_t) out) && !(out_pitch & 3);                                                              \
                 if (bgr) {                                                                                                                 \
@@ -163,5 +199,36 @@ using namespace ugb;
                 }                                                                                                                          \
                 return cudaGetLastError() == cudaSuccess ? 0 : -2;                                                                         \
         }
+namespace ugb {
+/// the DXT1 palette tables exist once per device; the first decode call on a device builds them (host-synchronised, a one-off of a few
+/// microseconds - not inside a stream capture)
+static int ensure_dxt1_tables(cudaStream_t stream)
+{
+        static std::mutex m;
+        static bool ready[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+                return -2;
+        }
+        std::lock_guard<std::mutex> lk(m);
+        if (!ready[dev]) {
+                (void) stream;
+                cudaStream_t own;  // a stream of its own: the tables are complete (host-synchronised) before any decode kernel is queued anywhere
+                if (cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) != cudaSuccess) {
+                        return -2;
+                }
+                dxt1_tables_kernel<<<(2 * 64 * 64 + 255) / 256, 256, 0, own>>>();
+                const bool ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(own) == cudaSuccess;
+                cudaStreamDestroy(own);
+                if (!ok) {
+                        return -2;
+                }
+                ready[dev] = true;
+        }
+        return 0;
+}
+}  // namespace ugb
+#define UGB_DECODE_PRE_dxt1_decode_kernel(stream) if (ensure_dxt1_tables((cudaStream_t) (stream)) != 0) return -2;
+#define UGB_DECODE_PRE_dxt5ycocg_decode_kernel(stream)
 UGB_DECODE(ugb200_dxt1_to_rgb, dxt1_decode_kernel, uint2)
 UGB_DECODE(ugb200_dxt5ycocg_to_rgb, dxt5ycocg_decode_kernel, uint4)

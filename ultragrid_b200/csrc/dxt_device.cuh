@@ -229,25 +229,10 @@ __device__ __forceinline__ void load_row_uyvy_packed(uint32_t w0, uint32_t w1, f
 __device__ __forceinline__ float px(const float2 (&v)[8], int i) { return ((i & 3) >> 1) ? v[2 * (i >> 2) + (i & 1)].y : v[2 * (i >> 2) + (i & 1)].x; }
 
 /// BRANCH = false computes the indices of a flat block (max_code == min_code) too and discards them: straight-line code, so that
-/// the scheduler may interleave the two blocks of a thread
+/// the scheduler may interleave the two blocks of a thread.  Colour values come packed: element [2y + (x&1)].{x,y}[x>>1] = pixel (x, y).
 template <bool BRANCH = true>
-__device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][2])
+__device__ __forceinline__ uint2 dxt1_encode_packed_core(const float2 (&R)[8], const float2 (&G)[8], const float2 (&B)[8])
 {
-        float2 R[8], G[8], B[8];
-        const float2 c2 = dup(kInv255), ky2 = dup(kBiasY), kc2 = dup(kBiasC);
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-                const uint32_t w0 = w[y][0], w1 = w[y][1];
-                const float2 u = __ffma2_rn(f2(magic_byte(w0, 0), magic_byte(w1, 0)), c2, kc2);
-                const float2 v = __ffma2_rn(f2(magic_byte(w0, 2), magic_byte(w1, 2)), c2, kc2);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {  // k = 0: pixels x = 0, 2;  k = 1: pixels x = 1, 3
-                        const float2 yy = __fmul2_rn(__ffma2_rn(f2(magic_byte(w0, 1 + 2 * k), magic_byte(w1, 1 + 2 * k)), c2, ky2), dup(1.1643f));
-                        R[2 * y + k] = __ffma2_rn(v, dup(1.7926f), yy);
-                        G[2 * y + k] = __ffma2_rn(v, dup(-0.5328f), __ffma2_rn(u, dup(-0.2132f), yy));
-                        B[2 * y + k] = __ffma2_rn(u, dup(2.1124f), yy);
-                }
-        }
         // bounding box
         float mnr = R[0].x, mng = G[0].x, mnb = B[0].x, mxr = mnr, mxg = mng, mxb = mnb;
 #pragma unroll
@@ -321,6 +306,59 @@ __device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][
         indices = msbs ^ (2 * lsbs + (msbs >> 1));
         const uint32_t palette = swap_end ? min_code + (max_code << 16) : max_code + (min_code << 16);
         return make_uint2(palette, indices);
+}
+
+/// fused UYVY loader (chroma shared by a pixel pair) + the packed core
+template <bool BRANCH = true>
+__device__ __forceinline__ uint2 dxt1_encode_uyvy_packed(const uint32_t (&w)[4][2])
+{
+        float2 R[8], G[8], B[8];
+        const float2 c2 = dup(kInv255), ky2 = dup(kBiasY), kc2 = dup(kBiasC);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+                const uint32_t w0 = w[y][0], w1 = w[y][1];
+                const float2 u = __ffma2_rn(f2(magic_byte(w0, 0), magic_byte(w1, 0)), c2, kc2);
+                const float2 v = __ffma2_rn(f2(magic_byte(w0, 2), magic_byte(w1, 2)), c2, kc2);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {  // k = 0: pixels x = 0, 2;  k = 1: pixels x = 1, 3
+                        const float2 yy = __fmul2_rn(__ffma2_rn(f2(magic_byte(w0, 1 + 2 * k), magic_byte(w1, 1 + 2 * k)), c2, ky2), dup(1.1643f));
+                        R[2 * y + k] = __ffma2_rn(v, dup(1.7926f), yy);
+                        G[2 * y + k] = __ffma2_rn(v, dup(-0.5328f), __ffma2_rn(u, dup(-0.2132f), yy));
+                        B[2 * y + k] = __ffma2_rn(u, dup(2.1124f), yy);
+                }
+        }
+        return dxt1_encode_packed_core<BRANCH>(R, G, B);
+}
+
+/// packed 3-byte source (cuda_rgb_to_dxt1 / cuda_yuv_to_dxt1, cuda_dxt.cu:661-683 + :444-451): w[y] = the three words (4 pixels) of row y.  Same
+/// per-sample operations as load_row_packed3(), pixels x and x + 2 paired in one f32x2 instruction.
+template <bool YUV>
+__device__ __forceinline__ uint2 dxt1_encode_packed3(const uint32_t (&w)[4][3])
+{
+        float2 R[8], G[8], B[8];
+        const float2 c2 = dup(kInv255);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+                const uint32_t p0 = w[y][0], p1 = w[y][1], p2 = w[y][2];
+                // pixel 0 = p0.b0 p0.b1 p0.b2, pixel 1 = p0.b3 p1.b0 p1.b1, pixel 2 = p1.b2 p1.b3 p2.b0, pixel 3 = p2.b1 p2.b2 p2.b3
+                const float2 a0 = f2(magic_byte(p0, 0), magic_byte(p1, 2)), a1 = f2(magic_byte(p0, 1), magic_byte(p1, 3)), a2 = f2(magic_byte(p0, 2), magic_byte(p2, 0));
+                const float2 b0 = f2(magic_byte(p0, 3), magic_byte(p2, 1)), b1 = f2(magic_byte(p1, 0), magic_byte(p2, 2)), b2 = f2(magic_byte(p1, 1), magic_byte(p2, 3));
+                if (YUV) {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                                const float2 my = k ? b0 : a0, mu = k ? b1 : a1, mv = k ? b2 : a2;
+                                const float2 yy = __fmul2_rn(__ffma2_rn(my, c2, dup(kBiasY)), dup(1.1643f));
+                                const float2 u = __ffma2_rn(mu, c2, dup(kBiasC)), v = __ffma2_rn(mv, c2, dup(kBiasC));
+                                R[2 * y + k] = __ffma2_rn(v, dup(1.7926f), yy);
+                                G[2 * y + k] = __ffma2_rn(v, dup(-0.5328f), __ffma2_rn(u, dup(-0.2132f), yy));
+                                B[2 * y + k] = __ffma2_rn(u, dup(2.1124f), yy);
+                        }
+                } else {
+                        R[2 * y] = __ffma2_rn(a0, c2, dup(kBiasRGB)), G[2 * y] = __ffma2_rn(a1, c2, dup(kBiasRGB)), B[2 * y] = __ffma2_rn(a2, c2, dup(kBiasRGB));
+                        R[2 * y + 1] = __ffma2_rn(b0, c2, dup(kBiasRGB)), G[2 * y + 1] = __ffma2_rn(b1, c2, dup(kBiasRGB)), B[2 * y + 1] = __ffma2_rn(b2, c2, dup(kBiasRGB));
+                }
+        }
+        return dxt1_encode_packed_core<true>(R, G, B);
 }
 
 }  // namespace ugb
