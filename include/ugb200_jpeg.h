@@ -26,6 +26,8 @@ typedef struct ugb200_jpeg_encoder ugb200_jpeg_encoder;
 struct ugb200_jpeg_params {
         int quality;          /* 1..100; gpujpeg_set_default_parameters() gives 75 */
         int restart_interval; /* MCUs per restart segment; 0 = default for the input format */
+        int interleaved;      /* RGB input only: one scan of R G B MCUs instead of one scan per component (the `interleaved` option of the
+                               * reference module, gpujpeg.cpp:303,397-398); UYVY input is a single interleaved scan either way */
 };
 
 /* gpujpeg_set_default_parameters */

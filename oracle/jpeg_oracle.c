@@ -234,8 +234,16 @@ static void gather(const uint8_t *src, long pitch, int w, int h, int fmt, int co
 
 API int orc_jpeg_default_restart_interval(int fmt) { return fmt == FMT_RGB_444 ? 8 : 4; } /* gpujpeg.cpp:351 */
 
+API size_t orc_jpeg_encode_ex(const uint8_t *src, long pitch, int w, int h, int fmt, int quality, int ri, int interleaved, uint8_t *out, size_t cap);
 /* @returns number of bytes written (0 on error) */
 API size_t orc_jpeg_encode(const uint8_t *src, long pitch, int w, int h, int fmt, int quality, int ri, uint8_t *out, size_t cap)
+{
+        return orc_jpeg_encode_ex(src, pitch, w, h, fmt, quality, ri, 0, out, cap);
+}
+
+/* interleaved (RGB input only): one scan whose MCU is the R, G and B block of an 8x8 area - what the reference module asks of GPUJPEG with its
+ * `interleaved` option (gpujpeg.cpp:303,397-398); the default for RGB is one scan per component */
+API size_t orc_jpeg_encode_ex(const uint8_t *src, long pitch, int w, int h, int fmt, int quality, int ri, int interleaved, uint8_t *out, size_t cap)
 {
         /* worst case: 1658 bits per block, every byte stuffed (416 B), + RSTn per segment + headers */
         const size_t nblk = fmt == FMT_UYVY_422 ? (size_t) ((w + 15) / 16) * ((h + 7) / 8) * 4 : (size_t) ((w + 7) / 8) * ((h + 7) / 8) * 3;
@@ -275,6 +283,25 @@ API size_t orc_jpeg_encode(const uint8_t *src, long pitch, int w, int h, int fmt
                         for (int k = 0; k < 4; ++k) {
                                 const int comp = k < 2 ? 0 : k - 1;
                                 gather(src, pitch, w, h, fmt, comp, comp == 0 ? mx * 2 + k : mx, my, px);
+                                block_to_coeffs(px, comp == 0 ? ml : mc, zz);
+                                encode_block(&bw, zz, &pred[comp], comp == 0 ? &dcl : &dcc, comp == 0 ? &acl : &acc);
+                        }
+                }
+                flush_bits(&bw);
+                p = bw.p;
+        } else if (interleaved) { /* one scan; MCU = R, G, B block of the same 8x8 area */
+                p = write_sos(p, 0, 3);
+                const int bwid = (w + 7) / 8, bh = (h + 7) / 8, nm = bwid * bh;
+                struct bitw bw = { p, 0, 0 };
+                int pred[3] = { 0, 0, 0 };
+                for (int m = 0; m < nm; ++m) {
+                        if (m > 0 && m % ri == 0) {
+                                flush_bits(&bw);
+                                *bw.p++ = 0xFF, *bw.p++ = (uint8_t) (0xD0 + ((m / ri - 1) & 7));
+                                pred[0] = pred[1] = pred[2] = 0;
+                        }
+                        for (int comp = 0; comp < 3; ++comp) {
+                                gather(src, pitch, w, h, fmt, comp, m % bwid, m / bwid, px);
                                 block_to_coeffs(px, comp == 0 ? ml : mc, zz);
                                 encode_block(&bw, zz, &pred[comp], comp == 0 ? &dcl : &dcc, comp == 0 ? &acl : &acc);
                         }

@@ -154,3 +154,22 @@ API int ref_copyline_named(int func, unsigned char *dst, long dst_pitch, const u
         }
         return 0;
 }
+
+/* The RECEIVER side of RFC 2435 in UltraGrid: rtpdec_jpeg.c:150-200 (create_jpeg_frame) rebuilds a decodable JPEG around the scan data of the
+ * RTP payload with the reference's own jpeg_writer.c (:215-382): headers from (type, width, height, restart interval), the two quantisation tables
+ * of the payload, the scan data, EOI.  @returns the length of the rebuilt stream */
+#include "utils/jpeg_writer.h"
+API long ref_jpeg_writer_rebuild(int type, int width, int height, int restart_interval, unsigned char qt[2][64], const unsigned char *scan, long scan_len,
+                                 unsigned char *out)
+{
+        struct jpeg_writer_data info = { 0 };
+        info.subsampling = (enum gpujpeg_writer_subsasmpling) (type & 1);
+        info.width = (unsigned) width, info.height = (unsigned) height, info.restart_interval = (unsigned) restart_interval;
+        char *p = (char *) out;
+        jpeg_writer_write_headers(&p, &info);
+        jpeg_writer_fill_dqt(info.dqt_marker_start, qt);
+        memcpy(p, scan, (size_t) scan_len);
+        p += scan_len;
+        jpeg_writer_write_eoi(&p);
+        return (long) (p - (char *) out);
+}

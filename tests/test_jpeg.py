@@ -25,6 +25,17 @@ def orc_encode(orc, src, w, h, codec, quality, ri=0, pitch=0):
     return out[:n].tobytes()
 
 
+def orc_encode_interleaved_rgb(orc, src, w, h, quality, ri=0):
+    """RGB stored as one interleaved scan (the `interleaved` option of the GPUJPEG module, gpujpeg.cpp:303,397-398)"""
+    orc.orc_jpeg_encode_ex.restype = ctypes.c_size_t
+    orc.orc_jpeg_encode_ex.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_size_t]
+    out = np.zeros(((w + 15) // 16 * 16) * ((h + 7) // 8 * 8) * 3 // 64 * 418 + 4096, dtype=np.uint8)
+    n = orc.orc_jpeg_encode_ex(src.ctypes.data, w * 3, w, h, 1, quality, ri, 1, out.ctypes.data, out.size)
+    assert n > 0
+    return out[:n].tobytes()
+
+
 def orc_encode_parallel(orc, src, w, h, codec, quality, ri=0, pitch=0):
     """the all-threads CPU port (bench.py's cpu_baseline for the JPEG workloads)"""
     orc.orc_jpeg_encode_parallel.restype = ctypes.c_size_t
@@ -85,6 +96,19 @@ def test_oracle_rgb_stream_is_rgb_and_close(orc, w, h):
     im.load()
     assert im.mode == "RGB" and im.size == (w, h)  # Adobe APP14 transform 0: no YCbCr->RGB applied by the decoder
     assert psnr(np.asarray(im), rgb) > 33
+
+
+@pytest.mark.parametrize("w,h,ri", [(16, 8, 0), (100, 52, 0), (130, 37, 3), (640, 360, 8)])
+def test_oracle_interleaved_rgb_stream(orc, w, h, ri):
+    """one scan with three components, 1x1 sampling: an independent decoder reads it as RGB, and it carries the same pixels as the three-scan form"""
+    rgb = natural_rgb(w, h, 8)
+    a = orc_encode_interleaved_rgb(orc, rgb.reshape(-1), w, h, 90, ri)
+    b = orc_encode(orc, rgb.reshape(-1), w, h, RGB, 90, ri)
+    assert a.count(b"\xff\xda") == 1 and b.count(b"\xff\xda") >= 3
+    ia, ib = PIL.open(io.BytesIO(a)), PIL.open(io.BytesIO(b))
+    ia.load(), ib.load()
+    assert ia.mode == "RGB" and ia.size == (w, h)
+    assert np.array_equal(np.asarray(ia), np.asarray(ib))  # same coefficients, another scan order
 
 
 def test_flat_grey_roundtrip_like_reference_test(orc):
@@ -189,6 +213,22 @@ def test_gpu_encoder_equals_oracle_bytes(orc, codec, w, h, q, ri):
     # device-resident input path gives the same bytes
     enc.encode_device(torch.from_numpy(src).cuda(), w, h, codec, quality=q, restart_interval=ri)
     assert enc.result() == want
+    enc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,q,ri", [(16, 8, 90, 0), (130, 37, 50, 3), (640, 360, 90, 0), (1920, 1080, 90, 8), (200, 120, 100, 1)])
+def test_gpu_interleaved_rgb_equals_oracle_bytes(orc, w, h, q, ri):
+    import torch
+    from ultragrid_b200 import api
+    src = natural_rgb(w, h, 21).reshape(-1).copy()
+    src[: w * 3 * min(h, 8)] = util.rng_bytes(w * 3 * min(h, 8), 3)
+    want = orc_encode_interleaved_rgb(orc, src, w, h, q, ri)
+    enc = api.JpegEncoder()
+    assert enc.encode(src, w, h, RGB, quality=q, restart_interval=ri, interleaved=True) == want
+    enc.encode_device(torch.from_numpy(src).cuda(), w, h, RGB, quality=q, restart_interval=ri, interleaved=True)
+    assert enc.result() == want
+    assert enc.encode(src, w, h, RGB, quality=q, restart_interval=ri) == orc_encode(orc, src, w, h, RGB, q, ri)  # and back to three scans
     enc.close()
 
 

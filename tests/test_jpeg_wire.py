@@ -50,3 +50,58 @@ def test_reference_reader_and_adobe_rgb(orc, ref):
     s = np.frombuffer(orc_encode(orc, natural_rgb(w, h, 5).reshape(-1).copy(), w, h, RGB, 90), np.uint8).copy()
     out, qt, hf = (ctypes.c_int * 16)(), np.zeros(128, np.uint8), np.zeros(1088, np.uint8)
     assert ref.ref_jpeg_read_info(s.ctypes.data, len(s), out, qt.ctypes.data, hf.ctypes.data) == -1
+
+
+@pytest.mark.parametrize("w,h,q,ri", [(200, 120, 90, 0), (1920, 1080, 75, 8), (96, 48, 50, 2)])
+def test_rtp_round_trip_through_reference_reader_and_writer(orc, ref, w, h, q, ri):
+    """Sender side (jpeg_get_rtp_hdr_data, src/utils/jpeg_reader.c:1092-1160) strips our stream to the RFC 2435 payload - type, Q = 255 with both
+    quantisation tables in-band, restart interval, scan data; receiver side (create_jpeg_frame, src/rtp/rtpdec_jpeg.c:150-200) rebuilds a JPEG around
+    that payload with the reference's own src/utils/jpeg_writer.c:215-382.  The rebuilt stream must decode to exactly the pixels of the original:
+    the encoder's tables and scan layout are what an unmodified UltraGrid receiver assumes (Annex K Huffman tables, component 0 -> table 0, 2x1 luma)."""
+    from test_jpeg import decode_ycc
+    if not hasattr(ref, "ref_jpeg_writer_rebuild"):
+        pytest.skip("oracle/_ref built before the jpeg_writer shim")
+    src = util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h, 15).reshape(-1), w, h)
+    s = np.frombuffer(orc_encode(orc, src, w, h, UYVY, q, ri), np.uint8).copy()
+    rtp = (ctypes.c_int * 6)()
+    assert ref.ref_jpeg_get_rtp_hdr_data(s.ctypes.data, len(s), rtp) == 1
+    rw, rh, rtype, rq, rri, off = list(rtp)
+    assert rw % 8 == 0 and rh % 8 == 0 and rw // 8 < 256 and rh // 8 < 256  # what the 8-bit size fields of the RTP header can carry
+    out, qt, hf = (ctypes.c_int * 16)(), np.zeros(128, np.uint8), np.zeros(1088, np.uint8)
+    assert ref.ref_jpeg_read_info(s.ctypes.data, len(s), out, qt.ctypes.data, hf.ctypes.data) == 0
+    scan = s[off:len(s) - 2]  # the payload: entropy-coded data without the EOI
+    assert s[-2:].tolist() == [0xFF, 0xD9]
+    rebuilt = np.zeros(len(scan) + 2048, np.uint8)
+    ref.ref_jpeg_writer_rebuild.restype = ctypes.c_long
+    ref.ref_jpeg_writer_rebuild.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+    n = ref.ref_jpeg_writer_rebuild(rtype, rw, rh, rri, qt.ctypes.data, scan.ctypes.data, len(scan), rebuilt.ctypes.data)
+    assert 0 < n <= len(rebuilt)
+    a, b = decode_ycc(s.tobytes(), w, h), decode_ycc(rebuilt[:n].tobytes(), w, h)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_gpu_decoder_reads_the_stream_rebuilt_by_the_reference_writer(orc, ref):
+    """the same round trip with the CUDA encoder at the sender and the CUDA decoder at the receiver"""
+    from ultragrid_b200 import api
+    if not hasattr(ref, "ref_jpeg_writer_rebuild"):
+        pytest.skip("oracle/_ref built before the jpeg_writer shim")
+    w, h = 1920, 1080
+    src = util.convert_cpu(orc, "orc_convert", RGB, UYVY, natural_rgb(w, h, 16).reshape(-1), w, h)
+    enc = api.JpegEncoder()
+    s = np.frombuffer(enc.encode(src, w, h, UYVY, quality=85), np.uint8).copy()
+    enc.close()
+    rtp = (ctypes.c_int * 6)()
+    assert ref.ref_jpeg_get_rtp_hdr_data(s.ctypes.data, len(s), rtp) == 1
+    out, qt, hf = (ctypes.c_int * 16)(), np.zeros(128, np.uint8), np.zeros(1088, np.uint8)
+    assert ref.ref_jpeg_read_info(s.ctypes.data, len(s), out, qt.ctypes.data, hf.ctypes.data) == 0
+    scan = s[rtp[5]:len(s) - 2]
+    rebuilt = np.zeros(len(scan) + 2048, np.uint8)
+    ref.ref_jpeg_writer_rebuild.restype = ctypes.c_long
+    ref.ref_jpeg_writer_rebuild.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+    n = ref.ref_jpeg_writer_rebuild(rtp[2], rtp[0], rtp[1], rtp[4], qt.ctypes.data, scan.ctypes.data, len(scan), rebuilt.ctypes.data)
+    dec = api.JpegDecoder()
+    a = dec.decode(s.tobytes(), UYVY)
+    b = dec.decode(rebuilt[:n].tobytes(), UYVY)
+    dec.close()
+    assert np.array_equal(a, b)

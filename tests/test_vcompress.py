@@ -20,6 +20,21 @@ def test_registry_and_option_parsing_fail_cleanly():
         compress.Compress("GPUJPEG:bogus=1")
     with pytest.raises(RuntimeError):
         compress.Compress("GPUJPEG:lanes=0")
+    for bad in ("GPUJPEG:0", "GPUJPEG:101", "GPUJPEG:quality=0", "GPUJPEG:subsampling=411", "GPUJPEG:restart=-1"):
+        with pytest.raises(RuntimeError):
+            compress.Compress(bad)
+
+
+@pytest.mark.parametrize("cfg", ["GPUJPEG:90", "GPUJPEG:90:8", "GPUJPEG:quality=80:restart=4", "GPUJPEG:q=75:interleaved", "GPUJPEG:Y709", "GPUJPEG:RGB:subsampling=444",
+                                 "GPUJPEG:Y601full:alpha:lanes=2"])
+def test_gpujpeg_option_grammar_of_the_reference(cfg):
+    """state_video_compress_gpujpeg::parse_fmt (gpujpeg.cpp:371-424): positional quality / restart interval and every keyword parse; whether a colour
+    space or subsampling can be honoured is decided against the first frame's format"""
+    from ultragrid_b200 import compress
+    c = compress.Compress(cfg)
+    c.push(None, 0, 0, 0)
+    assert c.pop(16) is None
+    c.close()
 
 
 @pytest.mark.parametrize("cfg", ["GPUJPEG", "GPUJPEG:q=90:lanes=1", "GPUJPEG:lanes=4", "cuda_dxt:DXT5", "cuda_dxt_sync"])
@@ -126,6 +141,33 @@ def test_gpujpeg_module_keeps_order_and_matches_oracle(orc, devices, cfg):
         c.close()
     finally:
         compress.set_cuda_devices([0])
+
+
+@pytest.mark.gpu
+def test_gpujpeg_module_options_against_the_input_format(orc):
+    """interleaved RGB through the module == the oracle's single-scan stream; an internal colour space / subsampling that would need a transform
+    inside the codec drops the frame with a message (no silently different stream); the native ones pass"""
+    from test_jpeg import orc_encode_interleaved_rgb
+    from ultragrid_b200 import compress
+    w, h = 320, 184
+    rgb = natural_rgb(w, h, 4).reshape(-1)
+    uyvy = util.convert_cpu(orc, "orc_convert", RGB, UYVY, rgb, w, h)
+    c = compress.Compress("GPUJPEG:75:interleaved:RGB:subsampling=444")
+    c.push(rgb, w, h, RGB)
+    got, _, _ = c.pop(w * h * 3 + 4096)
+    assert got.tobytes() == orc_encode_interleaved_rgb(orc, rgb, w, h, 75)
+    c.close()
+    c = compress.Compress("GPUJPEG:75:Y709:subsampling=422:lanes=1")
+    c.push(uyvy, w, h, UYVY)
+    got, _, _ = c.pop(w * h * 3 + 4096)
+    assert got.tobytes() == orc_encode(orc, uyvy, w, h, UYVY, 75)
+    c.close()
+    for cfg, frame, codec in (("GPUJPEG:Y601:lanes=1", uyvy, UYVY), ("GPUJPEG:Y709:lanes=1", rgb, RGB), ("GPUJPEG:subsampling=420:lanes=1", uyvy, UYVY)):
+        c = compress.Compress(cfg)
+        c.push(frame, w, h, codec)
+        c.push(None, 0, 0, 0)
+        assert c.pop(w * h * 3 + 4096) is None  # the failed frame is skipped (gpujpeg.cpp:194-198), then end of stream
+        c.close()
 
 
 @pytest.mark.gpu

@@ -209,7 +209,7 @@ def pinned_near(nbytes, device):
 
 
 class JpegParams(ctypes.Structure):
-    _fields_ = [("quality", ctypes.c_int), ("restart_interval", ctypes.c_int)]
+    _fields_ = [("quality", ctypes.c_int), ("restart_interval", ctypes.c_int), ("interleaved", ctypes.c_int)]
 
 
 class JpegEncoder:
@@ -229,17 +229,18 @@ class JpegEncoder:
     def __del__(self):
         self.close()
 
-    def _params(self, quality, restart_interval):
+    def _params(self, quality, restart_interval, interleaved=False):
         p = JpegParams()
         _L.ugb200_jpeg_default_params(ctypes.byref(p))
         if quality is not None:
             p.quality = quality
         p.restart_interval = restart_interval
+        p.interleaved = 1 if interleaved else 0
         return p
 
-    def encode_device(self, src, width, height, codec, quality=None, restart_interval=0, pitch=0):
+    def encode_device(self, src, width, height, codec, quality=None, restart_interval=0, pitch=0, interleaved=False):
         """asynchronous; returns nothing — call result() for the bytes"""
-        p = self._params(quality, restart_interval)
+        p = self._params(quality, restart_interval, interleaved)
         _check(_L.ugb200_jpeg_encode_device(self._h, _ptr(src), pitch, width, height, int(codec), ctypes.byref(p)), "ugb200_jpeg_encode_device")
 
     def result(self):
@@ -250,9 +251,9 @@ class JpegEncoder:
         _check(_L.cuda_wrapper_memcpy(host, ptr, n.value, 1), "cuda_wrapper_memcpy")
         return bytes(host)
 
-    def encode(self, src, width, height, codec, quality=None, restart_interval=0, pitch=0):
+    def encode(self, src, width, height, codec, quality=None, restart_interval=0, pitch=0, interleaved=False):
         """gpujpeg_encoder_encode: src is a host numpy array or a CUDA tensor; returns the JPEG bytes"""
-        p = self._params(quality, restart_interval)
+        p = self._params(quality, restart_interval, interleaved)
         out, n = ctypes.c_void_p(), ctypes.c_size_t()
         if isinstance(src, torch.Tensor):
             sp, is_dev = _ptr(src), 1

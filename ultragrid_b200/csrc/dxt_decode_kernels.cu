@@ -46,69 +46,16 @@ __device__ __forceinline__ uint32_t pack_px(uint32_t r, uint32_t g, uint32_t b)
         return BGR ? b | g << 8 | r << 16 : r | g << 8 | b << 16;
 }
 
-template <int BGR>
-__global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch, bool aligned)
-{
-        // per-thread palettes live in shared memory ([entry][thread]: conflict-free, dynamically indexable without local memory)
-        __shared__ double s_ap[8][128], s_co[4][128], s_cg[4][128];
-        const int tid = threadIdx.x, bx = blockIdx.x * blockDim.x + tid, by = blockIdx.y;
-        if (bx >= bw) {
-                return;
-        }
-        const uint4 blk = __ldg(in + (long) by * bw + bx);
-        uint64_t alpha_code = (uint64_t) blk.x | (uint64_t) blk.y << 32, rgb_code = (uint64_t) blk.z | (uint64_t) blk.w << 32;
-        // alpha palette (dxt62tga.c:38-62): 8 luma levels
-        const double a0 = __ddiv_rn((double) (alpha_code & 0xFF), 255.0), a1 = __ddiv_rn((double) ((alpha_code >> 8) & 0xFF), 255.0);
-        s_ap[0][tid] = a0, s_ap[1][tid] = a1;
-        if (a0 > a1) {
-#pragma unroll
-                for (int k = 2; k < 8; ++k) {
-                        s_ap[k][tid] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (8 - k), a0), __dmul_rn((double) (k - 1), a1)), 7.0);
-                }
-        } else {
-#pragma unroll
-                for (int k = 2; k < 6; ++k) {
-                        s_ap[k][tid] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (6 - k), a0), __dmul_rn((double) (k - 1), a1)), 5.0);
-                }
-                s_ap[6][tid] = 0.0, s_ap[7][tid] = 1.0;
-        }
-        // colour palette (:68-81) and, per entry, the scaled Co / Cg (:24-27 depend on the entry only)
-        double r[4], g[4], b[4];
-        b[0] = __ddiv_rn((double) (rgb_code & 0x1F), 31.0), g[0] = __ddiv_rn((double) ((rgb_code >> 5) & 0x3F), 63.0), r[0] = __ddiv_rn((double) ((rgb_code >> 11) & 0x1F), 31.0);
-        b[1] = __ddiv_rn((double) ((rgb_code >> 16) & 0x1F), 31.0), g[1] = __ddiv_rn((double) ((rgb_code >> 21) & 0x3F), 63.0), r[1] = __ddiv_rn((double) ((rgb_code >> 27) & 0x1F), 31.0);
-        b[2] = third(b[0], b[1]), g[2] = third(g[0], g[1]), r[2] = third(r[0], r[1]);
-        b[3] = __ddiv_rn(__dadd_rn(b[0], __dmul_rn(2.0, b[1])), 3.0), g[3] = __ddiv_rn(__dadd_rn(g[0], __dmul_rn(2.0, g[1])), 3.0),
-        r[3] = __ddiv_rn(__dadd_rn(r[0], __dmul_rn(2.0, r[1])), 3.0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-                const double scale = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(31.875, b[k]), 1.0));
-                s_co[k][tid] = __dmul_rn(__dadd_rn(r[k], -5.01960814E-01), scale);
-                s_cg[k][tid] = __dmul_rn(__dadd_rn(g[k], -5.01960814E-01), scale);
-        }
-        alpha_code >>= 16, rgb_code >>= 32;
-        uint8_t *o = out + (long) by * 4 * pitch + (long) bx * 12;
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-                uint32_t px[4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                        const double a = s_ap[alpha_code & 7][tid];
-                        const int k = (int) (rgb_code & 3);
-                        alpha_code >>= 3, rgb_code >>= 2;
-                        const double co = s_co[k][tid], cg = s_cg[k][tid];
-                        const double R = __dadd_rn(__dadd_rn(a, co), -cg), G = __dadd_rn(a, cg), B = __dadd_rn(__dadd_rn(a, -co), -cg);
-                        px[x] = pack_px<BGR>(to_byte(__dmul_rn(R, 255.0)), to_byte(__dmul_rn(G, 255.0)), to_byte(__dmul_rn(B, 255.0)));
-                }
-                store_row(o + y * pitch, px[0], px[1], px[2], px[3], aligned);
-        }
-}
-
 // ---- DXT1 palette tables ---------------------------------------------------------------------------------------------------------------
 // The four palette colours of a block are a function of its two 5:6:5 endpoints only, channel by channel.  Round 1 evaluated them per block in
 // FP64 (24 software divisions + 12 double -> int conversions per block: 0.31 of the HBM roofline).  The same FP64 expressions are now evaluated
 // ONCE per device for every endpoint pair by dxt1_tables_kernel - identical operations, so identical bytes - and a block reads the four bytes of
 // a channel with one 32-bit load: [mode][q0][q1] -> entries 0..3, mode 0 = four-colour (c0 > c1), 1 = three-colour + black.
 __device__ uint32_t g_dxt1_pal5[2][32][32], g_dxt1_pal6[2][64][64];
+// DXT5-YCoCg: the FP64 quotients that depend on 5/6/8-bit codes only (dxt62tga.c:38-81), same expressions evaluated once per device:
+//   g_q31[q] = q / 31.0, g_q63[q] = q / 63.0, g_q255[q] = q / 255.0;  g_t5[q0][q1] = (2 q0/31 + q1/31) / 3 (entry 2; entry 3 = [q1][q0]), g_t6 likewise;
+//   g_s1[q] = 1 / (31.875 * q/31 + 1), g_s3[q0][q1] = 1 / (31.875 * g_t5[q0][q1] + 1)   (the scale of :24-27 per palette entry)
+__device__ double g_q31[32], g_q63[64], g_q255[256], g_t5[32][32], g_t6[64][64], g_s1[32], g_s3[32][32];
 
 __global__ void dxt1_tables_kernel()
 {
@@ -117,6 +64,26 @@ __global__ void dxt1_tables_kernel()
                 return;
         }
         const int mode = i >> 12, q0 = (i >> 6) & 63, q1 = i & 63;
+        if (mode == 0) {  // the double tables (one thread per pair)
+                const double a6 = __ddiv_rn((double) q0, 63.0), b6 = __ddiv_rn((double) q1, 63.0);
+                g_t6[q0][q1] = third(a6, b6);
+                if (q1 == 0) {
+                        g_q63[q0] = a6;
+                }
+                if (q0 < 32 && q1 < 32) {
+                        const double a5 = __ddiv_rn((double) q0, 31.0), b5 = __ddiv_rn((double) q1, 31.0), t = third(a5, b5);
+                        g_t5[q0][q1] = t;
+                        g_s3[q0][q1] = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(31.875, t), 1.0));
+                        if (q1 == 0) {
+                                g_q31[q0] = a5;
+                                g_s1[q0] = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(31.875, a5), 1.0));
+                        }
+                }
+                if (q0 < 4) {
+                        const int c = q0 * 64 + q1;
+                        g_q255[c] = __ddiv_rn((double) c, 255.0);
+                }
+        }
 #pragma unroll
         for (int six = 0; six < 2; ++six) {
                 if (!six && (q0 >= 32 || q1 >= 32)) {
@@ -142,6 +109,61 @@ __global__ void dxt1_tables_kernel()
                 } else {
                         g_dxt1_pal5[mode][q0][q1] = w;
                 }
+        }
+}
+
+template <int BGR>
+__global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch, bool aligned)
+{
+        // per-thread palettes live in shared memory ([entry][thread]: conflict-free, dynamically indexable without local memory)
+        __shared__ double s_ap[8][128], s_co[4][128], s_cg[4][128];
+        const int tid = threadIdx.x, bx = blockIdx.x * blockDim.x + tid, by = blockIdx.y;
+        if (bx >= bw) {
+                return;
+        }
+        const uint4 blk = __ldg(in + (long) by * bw + bx);
+        uint64_t alpha_code = (uint64_t) blk.x | (uint64_t) blk.y << 32, rgb_code = (uint64_t) blk.z | (uint64_t) blk.w << 32;
+        // alpha palette (dxt62tga.c:38-62): 8 luma levels
+        const double a0 = g_q255[alpha_code & 0xFF], a1 = g_q255[(alpha_code >> 8) & 0xFF];
+        s_ap[0][tid] = a0, s_ap[1][tid] = a1;
+        if (a0 > a1) {
+#pragma unroll
+                for (int k = 2; k < 8; ++k) {
+                        s_ap[k][tid] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (8 - k), a0), __dmul_rn((double) (k - 1), a1)), 7.0);
+                }
+        } else {
+#pragma unroll
+                for (int k = 2; k < 6; ++k) {
+                        s_ap[k][tid] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (6 - k), a0), __dmul_rn((double) (k - 1), a1)), 5.0);
+                }
+                s_ap[6][tid] = 0.0, s_ap[7][tid] = 1.0;
+        }
+        // colour palette (:68-81) and, per entry, the scaled Co / Cg (:24-27 depend on the entry only): every quotient is a function of the
+        // 5 / 6-bit endpoint codes and comes from the per-device tables (the same FP64 expressions, evaluated by dxt1_tables_kernel)
+        const int b0 = (int) (rgb_code & 0x1F), g0 = (int) ((rgb_code >> 5) & 0x3F), r0 = (int) ((rgb_code >> 11) & 0x1F);
+        const int b1 = (int) ((rgb_code >> 16) & 0x1F), g1 = (int) ((rgb_code >> 21) & 0x3F), r1 = (int) ((rgb_code >> 27) & 0x1F);
+        const double r[4] = { g_q31[r0], g_q31[r1], g_t5[r0][r1], g_t5[r1][r0] }, g[4] = { g_q63[g0], g_q63[g1], g_t6[g0][g1], g_t6[g1][g0] };
+        const double scale[4] = { g_s1[b0], g_s1[b1], g_s3[b0][b1], g_s3[b1][b0] };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+                s_co[k][tid] = __dmul_rn(__dadd_rn(r[k], -5.01960814E-01), scale[k]);
+                s_cg[k][tid] = __dmul_rn(__dadd_rn(g[k], -5.01960814E-01), scale[k]);
+        }
+        alpha_code >>= 16, rgb_code >>= 32;
+        uint8_t *o = out + (long) by * 4 * pitch + (long) bx * 12;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+                uint32_t px[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                        const double a = s_ap[alpha_code & 7][tid];
+                        const int k = (int) (rgb_code & 3);
+                        alpha_code >>= 3, rgb_code >>= 2;
+                        const double co = s_co[k][tid], cg = s_cg[k][tid];
+                        const double R = __dadd_rn(__dadd_rn(a, co), -cg), G = __dadd_rn(a, cg), B = __dadd_rn(__dadd_rn(a, -co), -cg);
+                        px[x] = pack_px<BGR>(to_byte(__dmul_rn(R, 255.0)), to_byte(__dmul_rn(G, 255.0)), to_byte(__dmul_rn(B, 255.0)));
+                }
+                store_row(o + y * pitch, px[0], px[1], px[2], px[3], aligned);
         }
 }
 
@@ -229,6 +251,6 @@ static int ensure_dxt1_tables(cudaStream_t stream)
 }
 }  // namespace ugb
 #define UGB_DECODE_PRE_dxt1_decode_kernel(stream) if (ensure_dxt1_tables((cudaStream_t) (stream)) != 0) return -2;
-#define UGB_DECODE_PRE_dxt5ycocg_decode_kernel(stream)
+#define UGB_DECODE_PRE_dxt5ycocg_decode_kernel(stream) if (ensure_dxt1_tables((cudaStream_t) (stream)) != 0) return -2;
 UGB_DECODE(ugb200_dxt1_to_rgb, dxt1_decode_kernel, uint2)
 UGB_DECODE(ugb200_dxt5ycocg_to_rgb, dxt5ycocg_decode_kernel, uint4)

@@ -23,6 +23,7 @@
 #include "../../../include/cuda_dxt.h"
 #include "../../../include/ugb200_jpeg.h"
 #include "../../../include/ugb200_vcompress.h"
+#include "gpujpeg_opts.h"
 #include "video_codec.h"
 
 unsigned int cuda_devices[MAX_CUDA_DEVICES] = { 0 };
@@ -442,7 +443,7 @@ struct encoder_state {  // one per CUDA device, gpujpeg.cpp:103-252
 };
 
 struct state_video_compress_gpujpeg {
-        int quality = -1, restart_interval = 0;
+        gpujpeg_opts opts;  // quality, restart interval, interleaved, ... (gpujpeg.cpp:371-424)
         int lanes = 3;  // workers (encoder + stream + thread) per CUDA device: the H2D of one frame overlaps kernel + D2H of the previous ones
         std::vector<encoder_state *> workers;
         bool uses_worker_threads = false;
@@ -488,6 +489,9 @@ std::shared_ptr<video_frame> encoder_state::compress_step(std::shared_ptr<video_
                         fprintf(stderr, "[GPUJPEG] Unsupported codec: %s\n", get_codec_name(desc.color_spec));
                         return {};
                 }
+                if (!parent->opts.check_against_input(enc_input_codec == RGB)) {
+                        return {};
+                }
                 saved_desc = desc;
         }
         const unsigned w = desc.width, h = desc.height;
@@ -530,10 +534,11 @@ std::shared_ptr<video_frame> encoder_state::compress_step(std::shared_ptr<video_
         }
         struct ugb200_jpeg_params p;
         ugb200_jpeg_default_params(&p);
-        if (parent->quality != -1) {
-                p.quality = parent->quality;
+        if (parent->opts.quality != -1) {
+                p.quality = parent->opts.quality;
         }
-        p.restart_interval = parent->restart_interval;
+        p.restart_interval = parent->opts.restart_interval;
+        p.interleaved = parent->opts.interleaved ? 1 : 0;
         // the stream goes straight into the pooled (pinned) output frame: no encoder-owned buffer + memcpy as at :629-630
         const size_t out_cap = (size_t) w * h * 3 + 4096;  // :355 plus the header allowance of the encoder's own buffer (ugb200_jpeg.h): tiny or
                                                            // noisy frames at high quality exceed the raw size by their ~600-byte header
@@ -595,34 +600,14 @@ void encoder_state::worker()
 void *gpujpeg_compress_init(struct module *, const char *opts)
 {
         auto *s = new state_video_compress_gpujpeg();
-        std::string o = opts ? opts : "";
-        size_t pos = 0;
-        while (pos < o.size()) {  // option parser of gpujpeg.cpp:371-424 (subset)
-                size_t end = o.find(':', pos);
-                if (end == std::string::npos) {
-                        end = o.size();
+        if (!s->opts.parse(opts) || s->opts.help) {  // gpujpeg.cpp:371-424
+                if (s->opts.help) {
+                        gpujpeg_opts::usage();
                 }
-                const std::string item = o.substr(pos, end - pos);
-                pos = end + 1;
-                if (item.rfind("q=", 0) == 0) {
-                        s->quality = atoi(item.c_str() + 2);
-                } else if (item.rfind("restart=", 0) == 0) {
-                        s->restart_interval = atoi(item.c_str() + 8);
-                } else if (item.rfind("lanes=", 0) == 0) {  // B200 addition; lanes=1 on one device = the reference's synchronous push
-                        s->lanes = atoi(item.c_str() + 6);
-                        if (s->lanes < 1 || s->lanes > 8) {
-                                fprintf(stderr, "[GPUJPEG] lanes must be 1..8\n");
-                                delete s;
-                                return nullptr;
-                        }
-                } else if (!item.empty() && isdigit((unsigned char) item[0])) {
-                        s->quality = atoi(item.c_str());  // legacy "GPUJPEG:<quality>"
-                } else if (!item.empty()) {
-                        fprintf(stderr, "[GPUJPEG] unknown option: %s\nusage:\n\t-c GPUJPEG[:q=<quality>][:restart=<interval>][:lanes=<frames in flight per device>]\n", item.c_str());
-                        delete s;
-                        return nullptr;
-                }
+                delete s;
+                return nullptr;
         }
+        s->lanes = s->opts.lanes;
         for (int l = 0; l < s->lanes; ++l) {  // one encoder per device (:446-466), times `lanes`; lane-major so that the first idle
                 for (unsigned i = 0; i < cuda_devices_count; ++i) {  // workers found by push() spread over the devices first
                         s->workers.push_back(new encoder_state(s, (int) cuda_devices[i]));

@@ -417,6 +417,9 @@ struct ugb200_jpeg_decoder {
         } hs[2];
         unsigned frame_no = 0;
         int expect_w = 0, expect_h = 0;  // ugb200_jpeg_decoder_expect: the destination was sized for these; 0 = unchecked
+        // host scratch that keeps its capacity from frame to frame
+        std::vector<uint64_t> scan_part[8], markers;
+        std::vector<uint32_t> seg_begin, seg_end;
 };
 
 namespace {
@@ -705,14 +708,21 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
 }
 
 /// all marker candidates of the stream, in order; large streams are split over the pool (piece 0 on the calling thread)
-void collect_markers(const uint8_t *stream, size_t len, scan_pool *pool, uint8_t *copy_to, std::vector<uint64_t> &markers)
+constexpr int kMaxScanThreads = 8;
+/// `scratch`: kMaxScanThreads vectors that keep their capacity between frames (a decoder's frames have the same ~65 000 markers each time:
+/// growing eight fresh vectors and the merged list per frame was a visible share of the host time), or nullptr
+void collect_markers(const uint8_t *stream, size_t len, scan_pool *pool, uint8_t *copy_to, std::vector<uint64_t> &markers, std::vector<uint64_t> *scratch = nullptr)
 {
-        constexpr int kMaxThreads = 8;
+        constexpr int kMaxThreads = kMaxScanThreads;
         int nt = len > (4u << 20) ? kMaxThreads : len > (1u << 20) ? 4 : 1;
         if (pool == nullptr || pool->size() + 1 < nt) {
                 nt = pool ? pool->size() + 1 : 1;
         }
-        std::vector<uint64_t> part[kMaxThreads];
+        std::vector<uint64_t> own[kMaxThreads];
+        std::vector<uint64_t> *part = scratch ? scratch : own;
+        for (int i = 0; i < kMaxThreads; ++i) {
+                part[i].clear();
+        }
         const size_t chunk = (len / nt + 15) & ~(size_t) 15;
         auto range = [&](int i) {
                 const size_t lo = std::min(len, chunk * i), hi = i == nt - 1 ? len : std::min(len, chunk * (i + 1));
@@ -858,6 +868,8 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 H.pending = false;
         }
         parsed P;
+        P.seg_begin.swap(d->seg_begin), P.seg_end.swap(d->seg_end);  // last frame's capacity
+        P.seg_begin.clear(), P.seg_end.clear();
         memset(H.tables, 0, sizeof(dec_tables));
         memcpy(H.tables->zz, kZigzag, 64);
         if (!hgrow(H.stream, H.stream_cap, len)) {
@@ -865,10 +877,16 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         }
         // one pass over the caller's (pageable) buffer: copy it to the pinned staging buffer and collect the marker candidates, split over a
         // few threads when the stream is large (an 8K frame is 5-50 MB)
-        std::vector<uint64_t> markers;
-        collect_markers(stream, len, &d->pool, H.stream, markers);
+        std::vector<uint64_t> &markers = d->markers;
+        markers.clear();
+        collect_markers(stream, len, &d->pool, H.stream, markers, d->scan_part);
         lap("scan+stage");
         int rc = parse_stream(stream, len, P, H.tables, true, &markers);
+        struct give_back {  // the segment vectors return to the decoder on every path out of this function
+                parsed &p;
+                ugb200_jpeg_decoder *dec;
+                ~give_back() { p.seg_begin.swap(dec->seg_begin), p.seg_end.swap(dec->seg_end); }
+        } give_back_guard{ P, d };
         if (rc != 0) {
                 return rc;
         }

@@ -54,6 +54,7 @@ struct jpeg_geom {
         int slot;          // bytes reserved per segment
         int header_len;    // bytes before the first entropy-coded byte (including the first SOS)
         int sos_len;       // length of one later SOS header (RGB)
+        int interleaved;   // RGB only: one scan, MCU = the R, G and B block of an 8x8 area (GPUJPEG's `interleaved` option, gpujpeg.cpp:303)
 };
 
 // ---- K1 -------------------------------------------------------------------------------------------------------------
@@ -149,10 +150,16 @@ __global__ void __launch_bounds__(128) jpeg_dct_kernel(const uint8_t *__restrict
                 if (b >= g.nblocks) {
                         return;
                 }
-                const int per = g.bw * g.bh;
-                comp = b / per;
-                const int r = b - comp * per;
-                bx = r % g.bw, by = r / g.bw;
+                if (g.interleaved) {  // scan order: block b = component b % 3 of MCU b / 3
+                        const int m = b / 3;
+                        comp = b - 3 * m;
+                        bx = m % g.bw, by = m / g.bw;
+                } else {
+                        const int per = g.bw * g.bh;
+                        comp = b / per;
+                        const int r = b - comp * per;
+                        bx = r % g.bw, by = r / g.bw;
+                }
         }
         // interior: the whole block lies inside the image (and vector loads are aligned)
         const int px_w = (g.fmt == FMT_UYVY_422 && comp != 0) ? 16 : 8;
@@ -1053,6 +1060,9 @@ __global__ void __launch_bounds__(128) jpeg_huffman_kernel(const int16_t *__rest
                                 if (g.fmt == FMT_UYVY_422) {
                                         comp = k < 2 ? 0 : k - 1;
                                         blk = (long) m * 4 + k;
+                                } else if (g.interleaved) {
+                                        comp = k;
+                                        blk = (long) m * 3 + k;
                                 } else {
                                         comp = scan;
                                         blk = (long) scan * g.mcu_per_scan + m;
@@ -1252,7 +1262,7 @@ using namespace ugb;
 struct ugb200_jpeg_encoder {
         cudaStream_t stream = nullptr;
         // cached configuration
-        int fmt = -1, w = 0, h = 0, quality = -1, ri = -1;
+        int fmt = -1, w = 0, h = 0, quality = -1, ri = -1, interleaved = -1;
         jpeg_geom g{};
         std::vector<uint8_t> header;
         // device buffers
@@ -1361,7 +1371,7 @@ void build_header(ugb200_jpeg_encoder *e, const uint8_t ql[64], const uint8_t qc
         put_dht(v, 0x11, ugb_jpeg_ac_chroma_bits, ugb_jpeg_ac_chroma_vals, 162);
         v.push_back(0xFF), v.push_back(0xDD);
         put16(v, 4), put16(v, e->ri);
-        const int ncomp = e->fmt == FMT_UYVY_422 ? 3 : 1;
+        const int ncomp = e->fmt == FMT_UYVY_422 || e->g.interleaved ? 3 : 1;
         v.push_back(0xFF), v.push_back(0xDA);
         put16(v, 6 + 2 * ncomp);
         v.push_back((uint8_t) ncomp);
@@ -1372,8 +1382,9 @@ void build_header(ugb200_jpeg_encoder *e, const uint8_t ql[64], const uint8_t qc
         v.push_back(0), v.push_back(63), v.push_back(0);
 }
 
-int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri)
+int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri, int interleaved)
 {
+        interleaved = fmt == FMT_RGB_444 && interleaved ? 1 : 0;  // a UYVY stream is one interleaved scan anyway
         if (ri <= 0) {
                 ri = fmt == FMT_RGB_444 ? 8 : 4;  // src/video_compress/gpujpeg.cpp:351
         }
@@ -1381,13 +1392,13 @@ int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri
                 return -1;
         }
         quality = quality < 1 ? 1 : quality > 100 ? 100 : quality;
-        const bool same = e->fmt == fmt && e->w == w && e->h == h && e->quality == quality && e->ri == ri;
+        const bool same = e->fmt == fmt && e->w == w && e->h == h && e->quality == quality && e->ri == ri && e->interleaved == interleaved;
         if (same) {
                 return 0;
         }
-        e->fmt = fmt, e->w = w, e->h = h, e->quality = quality, e->ri = ri;
+        e->fmt = fmt, e->w = w, e->h = h, e->quality = quality, e->ri = ri, e->interleaved = interleaved;
         jpeg_geom &g = e->g;
-        g.fmt = fmt, g.w = w, g.h = h, g.ri = ri;
+        g.fmt = fmt, g.w = w, g.h = h, g.ri = ri, g.interleaved = interleaved;
         if (fmt == FMT_UYVY_422) {
                 g.bw = (w + 15) / 16, g.bh = (h + 7) / 8;
                 g.mcu_per_scan = g.bw * g.bh, g.blocks_per_mcu = 4;
@@ -1402,6 +1413,10 @@ int configure(ugb200_jpeg_encoder *e, int fmt, int w, int h, int quality, int ri
                 g.seg_per_scan = (g.mcu_per_scan + ri - 1) / ri;
                 g.nseg = g.seg_per_scan * 3;
                 g.sos_len = 10;
+                if (interleaved) {  // one scan of R G B MCUs
+                        g.blocks_per_mcu = 3;
+                        g.nseg = g.seg_per_scan, g.sos_len = 0;
+                }
         }
         g.slot = ri * g.blocks_per_mcu * kSlotBytesPerBlock + kSlotExtra;
 
@@ -1462,6 +1477,7 @@ void ugb200_jpeg_default_params(struct ugb200_jpeg_params *p)
 {
         p->quality = 75;  // gpujpeg_set_default_parameters
         p->restart_interval = 0;
+        p->interleaved = 0;
 }
 
 ugb200_jpeg_encoder *ugb200_jpeg_encoder_create(cuda_wrapper_stream_t stream)
@@ -1520,7 +1536,7 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         if (pitch == 0) {
                 pitch = (long) width * (fmt == FMT_UYVY_422 ? 2 : 3);
         }
-        const int rc = configure(e, fmt, width, height, params->quality, params->restart_interval);
+        const int rc = configure(e, fmt, width, height, params->quality, params->restart_interval, params->interleaved);
         if (rc != 0) {
                 return rc;
         }
@@ -1533,7 +1549,7 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
         }
         const int bps = g.ri * g.blocks_per_mcu;
         static const bool force_split = getenv("UGB200_JPEG_SPLIT") != nullptr;
-        const bool fused = !force_split && (bps == 4 || bps == 8 || bps == 16 || bps == 32);
+        const bool fused = !force_split && !g.interleaved && (bps == 4 || bps == 8 || bps == 16 || bps == 32);
         e->last_fused = fused;
         int nctas, segs_per_cta, ctas_per_scan;
         bool single_pass = false;

@@ -30,6 +30,7 @@
 #include "video_compress.h"          // video_compress_info, VIDEO_COMPRESS_ABI_VERSION
 #include "video_frame.h"             // video_desc_from_frame, video_desc_eq
 
+#include "../host/gpujpeg_opts.h"
 #include "../../../include/cuda_dxt.h"
 #include "../../../include/ugb200.h"
 #include "../../../include/ugb200_jpeg.h"
@@ -232,7 +233,8 @@ struct jpeg_worker {
 };
 
 struct state_gpujpeg {
-        int quality = -1, restart_interval = 0, lanes = 3;
+        gpujpeg_opts opts;
+        int lanes = 3;
         std::vector<jpeg_worker *> workers;
         bool threaded = false;
         synchronized_queue<shared_ptr<video_frame>, -1> out_queue;
@@ -275,6 +277,9 @@ shared_ptr<video_frame> jpeg_worker::compress_step(shared_ptr<video_frame> tx)  
                         fprintf(stderr, "[GPUJPEG] Unsupported codec: %s\n", get_codec_name(desc.color_spec));
                         return {};
                 }
+                if (!parent->opts.check_against_input(enc_input_codec == RGB)) {
+                        return {};
+                }
                 struct video_desc compressed = desc;
                 compressed.color_spec = JPEG;
                 compressed.tile_count = 1;
@@ -299,10 +304,11 @@ shared_ptr<video_frame> jpeg_worker::compress_step(shared_ptr<video_frame> tx)  
         }
         struct ugb200_jpeg_params p;
         ugb200_jpeg_default_params(&p);
-        if (parent->quality != -1) {
-                p.quality = parent->quality;
+        if (parent->opts.quality != -1) {
+                p.quality = parent->opts.quality;
         }
-        p.restart_interval = parent->restart_interval;
+        p.restart_interval = parent->opts.restart_interval;
+        p.interleaved = parent->opts.interleaved ? 1 : 0;
         shared_ptr<video_frame> out = pool.get_frame();
         size_t size = 0;
         if (!out || ugb200_jpeg_encode_into(encoder, in, 1, 0, (int) w, (int) h, (int) enc_input_codec, &p, (uint8_t *) out->tiles[0].data, (size_t) w * h * 3 + 4096, &size) != 0) {
@@ -369,36 +375,16 @@ void gpujpeg_done(void *state)
 void *gpujpeg_init(struct module *, const char *opts)
 {
         auto *s = new state_gpujpeg();
-        std::string o = opts ? opts : "";
-        size_t pos = 0;
-        while (pos < o.size()) {  // gpujpeg.cpp:371-424
-                size_t end = o.find(':', pos);
-                end = end == std::string::npos ? o.size() : end;
-                const std::string item = o.substr(pos, end - pos);
-                pos = end + 1;
-                if (item == "help") {
-                        printf("usage:\n\t-c GPUJPEG[:q=<quality>][:restart=<interval>][:lanes=<frames in flight per device>]\n");
-                        delete s;
-                        return INIT_NOERR;
-                } else if (item.rfind("q=", 0) == 0) {
-                        s->quality = atoi(item.c_str() + 2);
-                } else if (item.rfind("restart=", 0) == 0) {
-                        s->restart_interval = atoi(item.c_str() + 8);
-                } else if (item.rfind("lanes=", 0) == 0) {
-                        s->lanes = atoi(item.c_str() + 6);
-                } else if (!item.empty() && item[0] >= '0' && item[0] <= '9') {
-                        s->quality = atoi(item.c_str());  // legacy "GPUJPEG:<quality>"
-                } else if (!item.empty()) {
-                        fprintf(stderr, "[GPUJPEG] unknown option: %s\n", item.c_str());
-                        delete s;
-                        return nullptr;
-                }
-        }
-        if (s->lanes < 1 || s->lanes > 8) {
-                fprintf(stderr, "[GPUJPEG] lanes must be 1..8\n");
+        if (!s->opts.parse(opts)) {  // gpujpeg.cpp:371-424
                 delete s;
                 return nullptr;
         }
+        if (s->opts.help) {
+                gpujpeg_opts::usage();
+                delete s;
+                return INIT_NOERR;
+        }
+        s->lanes = s->opts.lanes;
         for (int l = 0; l < s->lanes; ++l) {
                 for (unsigned i = 0; i < cuda_devices_count; ++i) {
                         s->workers.push_back(new jpeg_worker(s, (int) cuda_devices[i]));
