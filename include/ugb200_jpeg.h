@@ -60,9 +60,10 @@ UGB_API int ugb200_jpeg_encode_into(ugb200_jpeg_encoder *enc, const void *src, i
 
 /* Measurement: with stage timing on, every encode records CUDA events between its kernels on the encoder's stream;
  * ugb200_jpeg_encoder_stage_times waits for the last encode and returns the device time in microseconds of
- * us[0] the fused DCT + entropy kernel (or the DCT + Huffman pair of the split path), us[1] the offset scan, us[2] the compaction. */
+ * us[0] the DCT + entropy kernel (one-kernel form: the whole fused kernel; split path: the DCT + Huffman pair), us[1] the restart-segment
+ * assembly kernel of the two-kernel form (0 otherwise), us[2] the offset scan, us[3] the compaction. */
 UGB_API int ugb200_jpeg_encoder_stage_timing(ugb200_jpeg_encoder *enc, int enable);
-UGB_API int ugb200_jpeg_encoder_stage_times(ugb200_jpeg_encoder *enc, float us[3]);
+UGB_API int ugb200_jpeg_encoder_stage_times(ugb200_jpeg_encoder *enc, float us[4]);
 
 /* Stage access for tests: quantised zig-zag coefficients (int16[blocks][64], scan order) of the last encode, device ptr. */
 UGB_API int ugb200_jpeg_debug_coefficients(ugb200_jpeg_encoder *enc, const int16_t **dev_ptr, size_t *count);
