@@ -1081,7 +1081,7 @@ __global__ void __launch_bounds__(128) jpeg_assemble_kernel(jpeg_geom g, const u
                                                             uint32_t *__restrict__ local_off, uint32_t *__restrict__ cta_total, int cap, int ctas_per_scan,
                                                             const uint32_t *__restrict__ huff)
 {
-        extern __shared__ __align__(16) uint32_t smem[];
+        extern __shared__ __align__(128) uint32_t smem[];
         uint32_t *s_seg = smem;                 // [segments of the CTA][bps * cap]
         uint32_t *s_stage = smem + cap * 128;   // stuffing area, same partition
         __shared__ uint32_t s_warp[4];
