@@ -86,6 +86,11 @@ UGB_API int ugb200_jpeg_get_image_info(const uint8_t *stream, size_t len, struct
 /* host only, for tests: the restart segments the stream parser found ([begin, end) byte offsets of their entropy-coded data);
  * returns their number (may exceed cap) or a negative error */
 UGB_API long ugb200_jpeg_debug_segments(const uint8_t *stream, size_t len, uint32_t *begin, uint32_t *end, long cap);
+/* Where the restart segments are found: a stream of at least 1 MB with ONE scan that holds all components (UltraGrid's UYVY streams) has its RSTn
+ * markers located on the device (the host only reads the header segments and copies the stream to pinned memory); other streams are scanned by a
+ * few host threads.  UGB200_JPEG_MARKER_SCAN=host|device at decoder creation forces one way (device: whenever the stream has one scan).
+ * ugb200_jpeg_decoder_last_segments returns the segment table of the last decode as the device holds it (waits for the decoder's stream). */
+UGB_API long ugb200_jpeg_decoder_last_segments(ugb200_jpeg_decoder *dec, uint32_t *begin, uint32_t *end, long cap);
 UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t stream);   /* gpujpeg_decoder_create, gpujpeg.c:93 */
 UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *dec);                      /* gpujpeg_decoder_destroy */
 /* The destination of ugb200_jpeg_decode is sized by the CALLER (video_desc of reconfigure(), gpujpeg.c:176-203) while the stream's SOF0

@@ -291,3 +291,70 @@ def test_decoder_refuses_stream_of_another_size(orc):
     st, out, _ = d.frame(small)
     assert st == d.GOT_FRAME
     d.close()
+
+
+def _segments(lib, dec, cap=1 << 17):
+    begin, end = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    n = lib.ugb200_jpeg_decoder_last_segments(dec._h, begin.ctypes.data, end.ctypes.data, cap)
+    return n, begin[:max(n, 0)].tolist(), end[:max(n, 0)].tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,w,h,q,ri,damage", [
+    ("ours-uyvy", 1920, 1080, 90, 0, None), ("ours-uyvy", 200, 120, 90, 0, None), ("ours-uyvy", 322, 50, 75, 3, None), ("pil-422", 640, 480, 85, 5, None),
+    ("pil-444", 333, 211, 90, 2, None), ("pil-420", 640, 480, 85, 0, None),                         # the last one: no DRI, one segment
+    ("ours-uyvy", 1920, 1080, 90, 0, "truncate"), ("ours-uyvy", 1920, 1080, 90, 0, "drop-rst"), ("ours-uyvy", 1920, 1080, 90, 0, "extra-rst"),
+    ("ours-uyvy", 1920, 1080, 90, 0, "foreign-marker"), ("ours-uyvy", 7680, 4320, 90, 0, None)])
+def test_gpu_device_marker_scan_equals_host_scan(orc, monkeypatch, kind, w, h, q, ri, damage):
+    """single-scan streams: the restart segments found by the device kernels are the host parser's, intact or damaged; the decoded frame is the same.
+    (8K: the automatic choice - device scan for streams of 1 MB and more; the others force it.)"""
+    from ultragrid_b200 import _lib, api
+    lib = _lib.load()
+    s, _ = make_stream(orc, kind, w, h, q, ri)
+    a = np.frombuffer(s, np.uint8).copy()
+    ff = np.flatnonzero((a[:-1] == 0xFF) & (a[1:] >= 0xD0) & (a[1:] <= 0xD7))
+    if damage == "truncate":
+        a = a[:len(a) * 6 // 10]
+    elif damage == "drop-rst":      # two restart markers turned into entropy-coded bytes: their segments merge, the table's tail is empty
+        a[ff[5]:ff[5] + 2] = (0x12, 0x34)
+        a[ff[40]:ff[40] + 2] = (0x12, 0x34)
+    elif damage == "extra-rst":     # more restart markers than the frame has segments
+        a = np.concatenate([a[:-2], np.tile(np.array([0x55, 0xFF, 0xD3], np.uint8), 50), a[-2:]])
+    elif damage == "foreign-marker":  # a non-RSTn marker in the middle of the scan ends it (an early EOI; the host parser goes on reading
+        a[ff[len(ff) // 2] + 1] = 0xD9  # segments behind any other marker and may reject the stream, the device path never looks behind the scan)
+    a = np.ascontiguousarray(a)
+    data = a.tobytes()
+    monkeypatch.setenv("UGB200_JPEG_MARKER_SCAN", "host")
+    host = api.JpegDecoder()
+    if w < 7680:
+        monkeypatch.setenv("UGB200_JPEG_MARKER_SCAN", "device")
+    else:
+        monkeypatch.delenv("UGB200_JPEG_MARKER_SCAN")
+    dev = api.JpegDecoder()
+    monkeypatch.delenv("UGB200_JPEG_MARKER_SCAN", raising=False)
+    codec = UYVY if kind in ("ours-uyvy", "pil-422", "pil-420") else VUYA
+    for _ in range(2):  # second turn: the decoders' scratch of the first one is reused
+        want = host.decode(data, codec, device=True)
+        n_h, b_h, e_h = _segments(lib, host)
+        got = dev.decode(data, codec, device=True)
+        n_d, b_d, e_d = _segments(lib, dev)
+        assert n_h == n_d > 0
+        assert b_h == b_d and e_h == e_d
+        assert bool((want == got).all())
+    cap = 1 << 17
+    begin, end = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    assert lib.ugb200_jpeg_debug_segments(a.ctypes.data, len(a), begin.ctypes.data, end.ctypes.data, cap) == n_h
+    assert begin[:n_h].tolist() == b_h and end[:n_h].tolist() == e_h
+    host.close(), dev.close()
+
+
+@pytest.mark.gpu
+def test_gpu_device_marker_scan_leaves_multi_scan_streams_to_the_host(orc, monkeypatch):
+    """three scans (RGB as GPUJPEG stores it): later SOS headers lie behind entropy-coded data, the host scan takes the stream even when the device scan is forced"""
+    from ultragrid_b200 import api
+    s, _ = make_stream(orc, "ours-rgb", 640, 360, 90, 0)
+    want = api.JpegDecoder().decode(s, RGB)
+    monkeypatch.setenv("UGB200_JPEG_MARKER_SCAN", "device")
+    dec = api.JpegDecoder()
+    assert (dec.decode(s, RGB) == want).all()
+    dec.close()

@@ -31,6 +31,7 @@
 
 #include "../../include/ugb200.h"
 #include "../../include/ugb200_jpeg.h"
+#include "../../include/cuda_wrapper.h"
 
 namespace ugb {
 
@@ -328,6 +329,160 @@ __global__ void __launch_bounds__(128) jpeg_idct_uyvy_kernel(const int16_t *__re
         }
 }
 
+// ---- marker scan on the device (streams with one interleaved scan: what UltraGrid sends) ------------------------------------------------------
+// The host's part shrinks to the header segments in front of the SOS and a plain copy of the stream into pinned memory; the RSTn markers that
+// split the entropy-coded data are found here: K-a counts the marker candidates of every 4 KB piece, K-b is a one-CTA exclusive scan, K-c writes
+// their positions in stream order and notes the first one that is not an RSTn (it ends the scan), K-d turns the list into the segment table the
+// Huffman kernel reads - the same rules as parse_stream (excess RSTn are ignored, missing segments decode as nothing).
+constexpr int kMarkThreads = 256;  // x 16 bytes
+
+/// bit k: byte base + k is 0xFF, its follower neither a stuffed 0x00 nor a fill 0xFF, and the pair lies inside [from, len)
+__device__ __forceinline__ unsigned marker_mask16(const uint8_t *__restrict__ s, size_t len, size_t base, size_t from)
+{
+        if (base + 1 >= len) {
+                return 0;
+        }
+        const uint4 v = *(const uint4 *) (s + base);       // the buffer is 16 bytes longer than the stream
+        const uint32_t nxt = s[base + 16];
+        const uint32_t w[5] = { v.x, v.y, v.z, v.w, nxt };
+        unsigned mask = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+                const uint32_t follower = __funnelshift_r(w[i], w[i + 1], 8);
+                const uint32_t cand = __vcmpeq4(w[i], 0xffffffffu) & ~(__vcmpeq4(follower, 0u) | __vcmpeq4(follower, 0xffffffffu));
+                mask |= (((cand & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+        }
+        const size_t last = len - 1;  // candidates need p + 1 < len
+        if (base + 16 > last) {
+                mask &= (1u << (unsigned) (last - base)) - 1u;
+        }
+        if (from > base) {
+                mask &= from - base >= 16 ? 0u : ~((1u << (unsigned) (from - base)) - 1u);
+        }
+        return mask;
+}
+
+__global__ void __launch_bounds__(kMarkThreads) jpeg_marker_count_kernel(const uint8_t *__restrict__ s, size_t len, size_t from, uint32_t *__restrict__ cnt)
+{
+        __shared__ uint32_t s_w[kMarkThreads / 32];
+        const size_t base = ((size_t) blockIdx.x * kMarkThreads + threadIdx.x) * 16;
+        uint32_t n = __popc(marker_mask16(s, len, base, from));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+                n += __shfl_xor_sync(0xffffffffu, n, d);
+        }
+        if ((threadIdx.x & 31) == 0) {
+                s_w[threadIdx.x >> 5] = n;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+                uint32_t t = 0;
+                for (int i = 0; i < kMarkThreads / 32; ++i) {
+                        t += s_w[i];
+                }
+                cnt[blockIdx.x] = t;
+        }
+}
+
+/// exclusive scan of cnt[0..n) in place; meta[0] = total, meta[1] = 0xFFFFFFFF (index of the first non-RSTn candidate, filled by K-c)
+__global__ void __launch_bounds__(1024) jpeg_marker_scan_kernel(uint32_t *__restrict__ cnt, int n, uint32_t *__restrict__ meta)
+{
+        __shared__ uint32_t s_w[32];
+        __shared__ uint32_t s_carry;
+        if (threadIdx.x == 0) {
+                s_carry = 0;
+        }
+        __syncthreads();
+        for (int base = 0; base < n; base += 1024) {
+                const int i = base + (int) threadIdx.x;
+                const uint32_t v = i < n ? cnt[i] : 0;
+                uint32_t incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if ((threadIdx.x & 31) >= (unsigned) d) {
+                                incl += o;
+                        }
+                }
+                if ((threadIdx.x & 31) == 31) {
+                        s_w[threadIdx.x >> 5] = incl;
+                }
+                __syncthreads();
+                uint32_t before = s_carry;
+                for (int w = 0; w < (int) (threadIdx.x >> 5); ++w) {
+                        before += s_w[w];
+                }
+                if (i < n) {
+                        cnt[i] = before + incl - v;
+                }
+                __syncthreads();
+                if (threadIdx.x == 1023) {
+                        s_carry = before + incl;
+                }
+                __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+                meta[0] = s_carry, meta[1] = 0xffffffffu;
+        }
+}
+
+__global__ void __launch_bounds__(kMarkThreads) jpeg_marker_write_kernel(const uint8_t *__restrict__ s, size_t len, size_t from, const uint32_t *__restrict__ off,
+                                                                         uint32_t *__restrict__ list, uint32_t *__restrict__ meta)
+{
+        __shared__ uint32_t s_w[kMarkThreads / 32];
+        const size_t base = ((size_t) blockIdx.x * kMarkThreads + threadIdx.x) * 16;
+        unsigned mask = marker_mask16(s, len, base, from);
+        const uint32_t n = __popc(mask);
+        uint32_t incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((threadIdx.x & 31) >= (unsigned) d) {
+                        incl += o;
+                }
+        }
+        if ((threadIdx.x & 31) == 31) {
+                s_w[threadIdx.x >> 5] = incl;
+        }
+        __syncthreads();
+        uint32_t idx = off[blockIdx.x] + incl - n;
+        for (int w = 0; w < (int) (threadIdx.x >> 5); ++w) {
+                idx += s_w[w];
+        }
+        while (mask) {
+                const size_t p = base + (size_t) (__ffs((int) mask) - 1);
+                mask &= mask - 1;
+                list[idx] = (uint32_t) p;
+                const int code = s[p + 1];
+                if (code < 0xD0 || code > 0xD7) {
+                        atomicMin(meta + 1, idx);
+                }
+                ++idx;
+        }
+}
+
+/// segment table of ONE scan that starts at `begin0`: the rules of parse_stream's SOS branch
+__global__ void __launch_bounds__(256) jpeg_marker_segments_kernel(const uint32_t *__restrict__ list, const uint32_t *__restrict__ meta, uint32_t begin0, uint32_t len,
+                                                                   int nseg, uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ seg_end)
+{
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= nseg) {
+                return;
+        }
+        const uint32_t total = meta[0], stop = min(meta[1], total);  // `stop` RSTn candidates precede the marker that ends the scan
+        const uint32_t term = stop < total ? list[stop] : len;
+        const uint32_t pushed = min(stop, (uint32_t) (nseg - 1));
+        uint32_t b, e;
+        if ((uint32_t) i < pushed) {
+                b = i == 0 ? begin0 : list[i - 1] + 2, e = list[i];
+        } else if ((uint32_t) i == pushed) {
+                b = stop == 0 ? begin0 : list[stop - 1] + 2, e = term;
+        } else {
+                b = e = term;
+        }
+        seg_begin[i] = b, seg_end[i] = e;
+}
+
 }  // namespace ugb
 
 using namespace ugb;
@@ -402,9 +557,11 @@ struct ugb200_jpeg_decoder {
         scan_pool pool{ 7 };
         uint8_t *d_stream = nullptr, *planes = nullptr, *native = nullptr, *staging = nullptr;
         int16_t *coef = nullptr;
-        uint32_t *d_seg = nullptr;
+        uint32_t *d_seg = nullptr, *d_marks = nullptr, *d_mark_cnt = nullptr;  // d_mark_cnt: per-piece counts / offsets, then meta[2]
         dec_tables *d_tables = nullptr;
-        size_t stream_cap = 0, planes_cap = 0, native_cap = 0, staging_cap = 0, coef_cap = 0, seg_cap = 0;
+        size_t stream_cap = 0, planes_cap = 0, native_cap = 0, staging_cap = 0, coef_cap = 0, seg_cap = 0, marks_cap = 0, mark_cnt_cap = 0;
+        int scan_mode = 0;      // 0: device scan for large single-scan streams, 1: always the host scan, 2: device scan whenever the stream has one scan
+        size_t last_nseg = 0;   // segments of the last decode (ugb200_jpeg_decoder_last_segments)
         // pinned staging (the caller's stream buffer is pageable and freed right after the call), two slots: the host side of frame
         // i + 1 (scan, parse, staging copy) runs while the device still works on frame i
         struct host_slot {
@@ -499,6 +656,11 @@ bool build_table(dec_tables &t, int tab, const uint8_t *bits, const uint8_t *val
         return true;
 }
 
+const bool g_stream_stores = [] {
+        const char *e = getenv("UGB200_JPEG_STAGE");  // "plain": ordinary stores into the pinned staging buffer (A/B timing)
+        return !(e && e[0] == 'p');
+}();
+
 const float kAan[8] = { 1.0f, 1.387039845f, 1.306562965f, 1.175875602f, 1.0f, 0.785694958f, 0.541196100f, 0.275899379f };
 
 /// marker candidates of [lo, hi): positions p with s[p] == 0xFF and s[p + 1] neither a stuffed 0x00 nor a fill 0xFF.  One SSE2 compare per
@@ -507,11 +669,18 @@ void scan_markers(const uint8_t *s, size_t lo, size_t hi, size_t len, std::vecto
 {
         const __m128i ff16 = _mm_set1_epi8((char) 0xFF), zero = _mm_setzero_si128();
         size_t i = lo;
+        // the staging buffer is read next by the copy engine, not by a CPU: non-temporal stores keep it out of the caches (measured: the upload of a
+        // 6 MB stream that eight cores had just written through their caches ran at 5.5 GB/s, see profiles/r02_h_jpeg_decode.md)
+        const bool stream_stores = copy_to != nullptr && g_stream_stores && ((uintptr_t) (copy_to + lo) & 15) == 0;
         // 0xFF is frequent in Huffman-coded data (runs of 1-bits), a marker is not: the follower byte is tested in the vector domain too
         for (; i + 17 <= len && i + 16 <= hi; i += 16) {
                 const __m128i v = _mm_loadu_si128((const __m128i *) (s + i)), nx = _mm_loadu_si128((const __m128i *) (s + i + 1));
                 if (copy_to) {
-                        _mm_storeu_si128((__m128i *) (copy_to + i), v);
+                        if (stream_stores) {
+                                _mm_stream_si128((__m128i *) (copy_to + i), v);
+                        } else {
+                                _mm_storeu_si128((__m128i *) (copy_to + i), v);
+                        }
                 }
                 const __m128i stuffed = _mm_or_si128(_mm_cmpeq_epi8(nx, zero), _mm_cmpeq_epi8(nx, ff16));
                 unsigned mask = (unsigned) _mm_movemask_epi8(_mm_andnot_si128(stuffed, _mm_cmpeq_epi8(v, ff16)));
@@ -529,11 +698,33 @@ void scan_markers(const uint8_t *s, size_t lo, size_t hi, size_t len, std::vecto
                         out.push_back((uint64_t) s[i + 1] << 32 | i);
                 }
         }
+        if (stream_stores) {
+                _mm_sfence();
+        }
+}
+
+/// plain staging copy (device marker scan): non-temporal stores when the destination allows it
+void stage_copy(uint8_t *dst, const uint8_t *src, size_t n)
+{
+        if (!g_stream_stores || ((uintptr_t) dst & 15) != 0) {
+                memcpy(dst, src, n);
+                return;
+        }
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+                const __m128i a = _mm_loadu_si128((const __m128i *) (src + i)), b = _mm_loadu_si128((const __m128i *) (src + i + 16));
+                const __m128i c = _mm_loadu_si128((const __m128i *) (src + i + 32)), e = _mm_loadu_si128((const __m128i *) (src + i + 48));
+                _mm_stream_si128((__m128i *) (dst + i), a), _mm_stream_si128((__m128i *) (dst + i + 16), b);
+                _mm_stream_si128((__m128i *) (dst + i + 32), c), _mm_stream_si128((__m128i *) (dst + i + 48), e);
+        }
+        memcpy(dst + i, src + i, n - i);
+        _mm_sfence();
 }
 
 /// header markers up to and including every SOS; `full` also finds the restart segments of the entropy-coded data, from the marker
 /// candidates in `markers` (sorted; scanned here when the caller has none)
-int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool full, const std::vector<uint64_t> *markers = nullptr)
+int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool full, const std::vector<uint64_t> *markers = nullptr,
+                 size_t *first_scan_data = nullptr)
 {
         std::vector<uint64_t> own;
         if (full && markers == nullptr) {
@@ -674,6 +865,9 @@ int parse_stream(const uint8_t *s, size_t len, parsed &P, dec_tables *T, bool fu
                         ++g.nscans;
                         p = dend;
                         if (!full) {
+                                if (first_scan_data) {
+                                        *first_scan_data = (size_t) (p - s);
+                                }
                                 return 0;  // enough for the image info
                         }
                         // entropy-coded segment(s): RSTn candidates split it, the first other marker ends it
@@ -808,6 +1002,8 @@ UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t st
                 ugb200_jpeg_decoder_destroy(d);
                 return nullptr;
         }
+        const char *m = getenv("UGB200_JPEG_MARKER_SCAN");  // "host" / "device": force one of the two marker scans (tests, A/B timing)
+        d->scan_mode = !m ? 0 : m[0] == 'h' ? 1 : m[0] == 'd' ? 2 : 0;
         return d;
 }
 
@@ -818,13 +1014,35 @@ UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *d)
         }
         cudaStreamSynchronize(d->stream);
         cudaFree(d->d_stream), cudaFree(d->planes), cudaFree(d->native), cudaFree(d->staging), cudaFree(d->coef), cudaFree(d->d_seg), cudaFree(d->d_tables);
+        cudaFree(d->d_marks), cudaFree(d->d_mark_cnt);
         for (auto &h : d->hs) {
-                cudaFreeHost(h.stream), cudaFreeHost(h.seg), cudaFreeHost(h.tables);
+                if (h.stream) {
+                        cuda_wrapper_free_host(h.stream);
+                }
+                cudaFreeHost(h.seg), cudaFreeHost(h.tables);
                 if (h.uploaded) {
                         cudaEventDestroy(h.uploaded);
                 }
         }
         delete d;
+}
+
+/// the segment table of the last decode as the device holds it (tests: the device marker scan against the host's)
+UGB_API long ugb200_jpeg_decoder_last_segments(ugb200_jpeg_decoder *d, uint32_t *begin, uint32_t *end, long cap)
+{
+        if (!d || !begin || !end) {
+                return -1;
+        }
+        const long n = (long) d->last_nseg;
+        if (cudaStreamSynchronize(d->stream) != cudaSuccess) {
+                return -2;
+        }
+        const long m = n < cap ? n : cap;
+        if (m > 0 && (cudaMemcpy(begin, d->d_seg, (size_t) m * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                      cudaMemcpy(end, d->d_seg + n, (size_t) m * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) {
+                return -2;
+        }
+        return n;
 }
 
 UGB_API int ugb200_jpeg_decoder_expect(ugb200_jpeg_decoder *d, int width, int height)
@@ -845,10 +1063,16 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         if (out_codec != UGB_UYVY && out_codec != UGB_RGB && out_codec != UGB_RGBA && out_codec != UGB_VUYA && out_codec != UGB_I420) {
                 return -4;
         }
-        static const bool timing = getenv("UGB200_JPEG_TIMING") != nullptr;  // stage times of the host side on stderr
+        static const int timing = getenv("UGB200_JPEG_TIMING") ? atoi(getenv("UGB200_JPEG_TIMING")) : 0;  // 1: stage times of the host side on stderr; 2: + device stages
         const auto t_start = std::chrono::steady_clock::now();
         auto lap = [&](const char *what) {
                 if (timing) {
+                        if (what[0] == '+') {  // device stages: wait for the stream, so that the lap is the stage's own time (serialises the pipeline)
+                                if (timing < 2) {
+                                        return;
+                                }
+                                cudaStreamSynchronize(d->stream);
+                        }
                         fprintf(stderr, "[jpeg decode] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
                 }
         };
@@ -867,21 +1091,63 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 cudaEventSynchronize(H.uploaded);  // the uploads of the frame before last left this slot long ago
                 H.pending = false;
         }
+        lap("slot free");
         parsed P;
         P.seg_begin.swap(d->seg_begin), P.seg_end.swap(d->seg_end);  // last frame's capacity
         P.seg_begin.clear(), P.seg_end.clear();
         memset(H.tables, 0, sizeof(dec_tables));
         memcpy(H.tables->zz, kZigzag, 64);
-        if (!hgrow(H.stream, H.stream_cap, len)) {
-                return -2;
+        if (len > H.stream_cap) {  // pinned pages on the GPU's NUMA node (cuda_wrapper_malloc_host_near falls back to cudaMallocHost)
+                if (H.stream) {
+                        cuda_wrapper_free_host(H.stream);
+                }
+                H.stream = nullptr, H.stream_cap = 0;
+                int device = 0;
+                cudaGetDevice(&device);
+                const size_t want = len + len / 4 + 4096;
+                if (cuda_wrapper_malloc_host_near((void **) &H.stream, want, device) != 0) {
+                        return -2;
+                }
+                H.stream_cap = want;
         }
-        // one pass over the caller's (pageable) buffer: copy it to the pinned staging buffer and collect the marker candidates, split over a
-        // few threads when the stream is large (an 8K frame is 5-50 MB)
+        // Streams with ONE scan holding all components (UltraGrid's UYVY streams, interleaved RGB): the host reads the headers in front of the SOS and
+        // copies the stream to pinned memory; the restart markers are found on the device (jpeg_marker_*_kernel).  Everything else - several scans,
+        // whose later SOS headers lie behind entropy-coded data - takes the host scan below.
+        size_t scan_data = 0;
+        bool device_scan = false;
+        int rc = 0;
+        if (d->scan_mode != 1 && (d->scan_mode == 2 || len >= (1u << 20))) {
+                rc = parse_stream(stream, len, P, H.tables, false, nullptr, &scan_data);
+                device_scan = rc == 0 && P.g.nscans == 1 && P.g.s[0].ns == P.g.ncomp && scan_data > 0;
+                if (!device_scan) {  // start over on the host path (tables and geometry are rebuilt there)
+                        P.g = dec_geom{}, P.adobe = -1, P.have_sof = false;
+                        memset(P.have_q, 0, sizeof P.have_q);
+                        memset(H.tables, 0, sizeof(dec_tables));
+                        memcpy(H.tables->zz, kZigzag, 64);
+                }
+        }
         std::vector<uint64_t> &markers = d->markers;
-        markers.clear();
-        collect_markers(stream, len, &d->pool, H.stream, markers, d->scan_part);
-        lap("scan+stage");
-        int rc = parse_stream(stream, len, P, H.tables, true, &markers);
+        if (device_scan) {
+                const int nt = len > (4u << 20) ? kMaxScanThreads : len > (1u << 20) ? 4 : 1;
+                if (nt == 1) {
+                        stage_copy(H.stream, stream, len);
+                } else {
+                        const size_t chunk = (len / nt + 63) & ~(size_t) 63;
+                        auto piece = [&](int i) {
+                                const size_t lo = std::min(len, chunk * i), hi = i == nt - 1 ? len : std::min(len, chunk * (i + 1));
+                                stage_copy(H.stream + lo, stream + lo, hi - lo);
+                        };
+                        d->pool.parallel(nt - 1, [&](int w) { piece(w + 1); }, [&] { piece(0); });
+                }
+                lap("stage");
+        } else {
+                // one pass over the caller's (pageable) buffer: copy it to the pinned staging buffer and collect the marker candidates, split over a
+                // few threads when the stream is large (an 8K frame is 5-50 MB)
+                markers.clear();
+                collect_markers(stream, len, &d->pool, H.stream, markers, d->scan_part);
+                lap("scan+stage");
+                rc = parse_stream(stream, len, P, H.tables, true, &markers);
+        }
         struct give_back {  // the segment vectors return to the decoder on every path out of this function
                 parsed &p;
                 ugb200_jpeg_decoder *dec;
@@ -892,7 +1158,8 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         }
         lap("parse");
         const dec_geom &g = P.g;
-        const size_t nseg = P.seg_begin.size();
+        const size_t nseg = device_scan ? (size_t) g.s[0].nseg : P.seg_begin.size();
+        d->last_nseg = nseg;
         const long plane_bytes = (long) g.nblocks * 64;
         const int native = native_codec(P);
         const long npitch = native == UGB_UYVY ? (long) ((g.w + 1) / 2) * 4 : native == UGB_RGB ? (long) g.w * 3 : (long) g.w * 4;
@@ -906,13 +1173,29 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         }
         cudaStream_t s = d->stream;
         cudaMemcpyAsync(d->d_stream, H.stream, len, cudaMemcpyHostToDevice, s);
-        memcpy(H.seg, P.seg_begin.data(), nseg * 4), memcpy(H.seg + nseg, P.seg_end.data(), nseg * 4);
-        cudaMemcpyAsync(d->d_seg, H.seg, 2 * nseg * 4, cudaMemcpyHostToDevice, s);
+        lap("+stream on the device");
+        if (device_scan) {
+                const unsigned pieces = (unsigned) ((len + kMarkThreads * 16 - 1) / (kMarkThreads * 16));
+                if (!dgrow(d->d_marks, d->marks_cap, len / 2 + 2) || !dgrow(d->d_mark_cnt, d->mark_cnt_cap, (size_t) pieces + 2)) {
+                        return -2;
+                }
+                uint32_t *meta = d->d_mark_cnt + pieces;
+                jpeg_marker_count_kernel<<<pieces, kMarkThreads, 0, s>>>(d->d_stream, len, scan_data, d->d_mark_cnt);
+                jpeg_marker_scan_kernel<<<1, 1024, 0, s>>>(d->d_mark_cnt, (int) pieces, meta);
+                jpeg_marker_write_kernel<<<pieces, kMarkThreads, 0, s>>>(d->d_stream, len, scan_data, d->d_mark_cnt, d->d_marks, meta);
+                jpeg_marker_segments_kernel<<<(unsigned) ((nseg + 255) / 256), 256, 0, s>>>(d->d_marks, meta, (uint32_t) scan_data, (uint32_t) len, (int) nseg, d->d_seg,
+                                                                                             d->d_seg + nseg);
+        } else {
+                memcpy(H.seg, P.seg_begin.data(), nseg * 4), memcpy(H.seg + nseg, P.seg_end.data(), nseg * 4);
+                cudaMemcpyAsync(d->d_seg, H.seg, 2 * nseg * 4, cudaMemcpyHostToDevice, s);
+        }
         cudaMemcpyAsync(d->d_tables, H.tables, sizeof(dec_tables), cudaMemcpyHostToDevice, s);
         cudaEventRecord(H.uploaded, s);
         H.pending = true;
         lap("uploads queued");
+        lap("+segments on the device");
         cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
+        lap("+coefficients cleared");
         jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d->d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef);
         const bool direct = native == out_codec && dst_is_device;
         uint8_t *nat = direct ? (uint8_t *) dst : d->native;
@@ -927,6 +1210,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 return -2;
         }
         lap("kernels queued");
+        lap("+huffman + idct");
         // component planes -> the stream's native packed format
         struct ugb200_from_planar_data fp;
         memset(&fp, 0, sizeof fp);
