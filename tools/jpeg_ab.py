@@ -3,7 +3,7 @@ variables read once per process (UGB200_JPEG_TWO_KERNELS), so each variant runs 
 usage: python tools/jpeg_ab.py            (parent: runs every variant)"""
 import os, subprocess, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-VARIANTS = [("balanced (default)", {}), ("block per thread", {"UGB200_JPEG_BALANCED": "0"}), ("two_kernels", {"UGB200_JPEG_TWO_KERNELS": "1"})]
+VARIANTS = [("one kernel (default)", {}), ("two_kernels", {"UGB200_JPEG_TWO_KERNELS": "1"}), ("two_kernels_a8", {"UGB200_JPEG_TWO_KERNELS": "8"})]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     VARIANTS = VARIANTS[:2]
 

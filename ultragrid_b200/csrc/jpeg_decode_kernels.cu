@@ -1116,7 +1116,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         size_t scan_data = 0;
         bool device_scan = false;
         int rc = 0;
-        if (d->scan_mode != 1 && (d->scan_mode == 2 || len >= (1u << 20))) {
+        if (d->scan_mode != 1 && len <= (1u << 30) && (d->scan_mode == 2 || len >= (1u << 20))) {
                 rc = parse_stream(stream, len, P, H.tables, false, nullptr, &scan_data);
                 device_scan = rc == 0 && P.g.nscans == 1 && P.g.s[0].ns == P.g.ncomp && scan_data > 0;
                 if (!device_scan) {  // start over on the host path (tables and geometry are rebuilt there)

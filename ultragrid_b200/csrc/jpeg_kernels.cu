@@ -550,7 +550,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 /// warps finish their entropy coding long before its luma warps: 11 % of all warp samples of the one-kernel form sit at that barrier), needs 16 KB of
 /// shared memory instead of 28, and the assembly runs as a light kernel of its own at full occupancy.  A block longer than `cap` words (noise) also
 /// leaves its coefficients in `gcoef` (DC slot = the DC DIFFERENCE), from which the assembly kernel codes it again inside a serial segment.
-template <int FMT, int MINB, bool BLOCKS_ONLY = false, bool BAL = false>
+template <int FMT, int MINB, bool BLOCKS_ONLY = false>
 __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
                                                          uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
                                                          uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats,
@@ -762,115 +762,9 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         }
         // linear index of this CTA (the order of cta_total / gbits / glen) and of my block in the frame's scan order
         const int cta_lin = FMT == FMT_UYVY_422 ? cta_x : cta_y * lb.ctas_per_scan + cta_x;
-        // ---- 2. entropy coding ---------------------------------------------------------------------------------------------------
+        // ---- 2. entropy-code my block --------------------------------------------------------------------------------------------
         uint32_t bits = 0;
-        if constexpr (BAL) {
-                // Balanced form.  A block's code is a list of ITEMS: the DC code, one item per non-zero AC coefficient (ZRLs ride with the coefficient
-                // behind them) and the EOB.  The items of a restart segment are dealt out evenly to the segment's bps threads, thread gl coding items
-                // [gl q, gl q + q): a warp then runs ceil(items of its busiest segment / bps) turns instead of the item count of its busiest BLOCK
-                // (measured 2.5-3 x the average, profiles/r02_g_jpeg_two_kernels.md).  A thread's output is one bit string per thread - exactly what
-                // phase 3 expects, with "block" read as "chunk": the chunks of a segment concatenate to the same bits as its blocks.
-                __shared__ uint32_t s_nzlo[128], s_nzhi[128], s_dcw[128];
-                __shared__ uint16_t s_lin[128];
-                {  // A. the owner of a block publishes its non-zero map and its finished DC item (length << 26 | code; 0 = no such block)
-                        const int t = comp == 0 ? 0 : 1;
-                        int pred;
-                        if (FMT == FMT_UYVY_422) {
-                                const int k = tid >> 5;
-                                const bool first = (p % bps) < 4;
-                                pred = k == 1 ? s_dc[blk_col(p - 1)] : first ? 0 : k == 0 ? s_dc[blk_col(p - 3)] : s_dc[blk_col(p - 4)];
-                        } else {
-                                pred = (p % bps) == 0 ? 0 : s_dc[blk_col(p - 1)];
-                        }
-                        const int diff = dcv - pred;
-                        const int sz = category(diff);
-                        const uint32_t e = s_dctab[t][sz];
-                        const uint32_t code = ((e & 0xffffu) << sz) | ((uint32_t) (diff < 0 ? diff - 1 : diff) & ((1u << sz) - 1u));
-                        s_dcw[pc] = valid ? (((e >> 16) + (uint32_t) sz) << 26) | code : 0u;
-                        s_nzlo[pc] = valid ? (uint32_t) nz : 0u, s_nzhi[pc] = valid ? (uint32_t) (nz >> 32) : 0u;
-                }
-                __syncthreads();
-                // B. thread tid, as the scan-order owner of block tid: item prefix inside the segment
-                const int sgb = tid / bps, glb = tid % bps;
-                const unsigned gm = bps == 32 ? 0xffffffffu : (((1u << bps) - 1u) << ((tid & 31) - glb));
-                auto items_of = [&](int col) -> uint32_t {  // DC + non-zero ACs + EOB unless coefficient 63 is coded
-                        const uint32_t hi = s_nzhi[col];
-                        return s_dcw[col] ? 1u + __popc(s_nzlo[col]) + __popc(hi) + (hi >> 31 ? 0u : 1u) : 0u;
-                };
-                const uint32_t mine_items = items_of(blk_col(tid));
-                uint32_t incl_items = mine_items;
-                for (int d = 1; d < bps; d <<= 1) {
-                        const uint32_t o = __shfl_up_sync(gm, incl_items, d, bps);
-                        if (glb >= d) {
-                                incl_items += o;
-                        }
-                }
-                const uint32_t seg_items = __shfl_sync(gm, incl_items, bps - 1, bps);
-                s_lin[tid] = (uint16_t) (incl_items - mine_items);
-                __syncwarp(gm);
-                // C. my share of the segment's items
-                const uint32_t q = (seg_items + (uint32_t) bps - 1u) >> (31 - __clz(bps));
-                const uint32_t j0 = (uint32_t) glb * q, j1 = min(j0 + q, seg_items);
-                if (j0 < j1) {
-                        int pb = sgb * bps;  // the block that holds item j0: the last one whose prefix is <= j0 (blocks without items only trail)
-                        for (int step = bps >> 1; step > 0; step >>= 1) {
-                                if (s_lin[pb + step] <= j0) {
-                                        pb += step;
-                                }
-                        }
-                        const uint32_t r = j0 - s_lin[pb];
-                        int colw = blk_col(pb);
-                        uint64_t m = (uint64_t) s_nzhi[colw] << 32 | s_nzlo[colw];
-                        uint32_t rem = items_of(colw) - r;
-                        bool dc_next = r == 0;
-                        int prev = 0;
-                        for (uint32_t k = 1; k < r && m; ++k) {  // items 1 .. r - 1 of the block are its first r - 1 non-zero coefficients
-                                prev = __ffsll((long long) m) - 1;
-                                m &= m - 1;
-                        }
-                        const uint32_t *cw = s_coef + colw;
-                        const uint32_t *act = s_ac[FMT == FMT_UYVY_422 ? ((pb & 3) >= 2 ? 1 : 0) : (cta_y != 0 ? 1 : 0)];
-                        block_bits bw = { s_bits + blk_col(tid), 0, 0, 0, cap };
-                        for (uint32_t j = j0; j < j1; ++j) {
-                                uint32_t code;
-                                int len;
-                                if (dc_next) {
-                                        const uint32_t w = s_dcw[colw];
-                                        code = w & 0x3ffffffu, len = (int) (w >> 26);
-                                        dc_next = false;
-                                } else if (m) {
-                                        const int i = __ffsll((long long) m) - 1;
-                                        m &= m - 1;
-                                        int run = i - prev - 1;
-                                        prev = i;
-                                        while (run > 15) {
-                                                bw.put(act[0xF0] & 0xffff, act[0xF0] >> 16);  // ZRL
-                                                run -= 16;
-                                        }
-                                        const uint32_t w = cw[(i & 31) * 128];
-                                        const int v = (i & 32) ? (int) w >> 16 : (int) (short) (w & 0xffffu);
-                                        const int sz = category(v);
-                                        const uint32_t e = act[(run << 4) | sz];
-                                        code = ((e & 0xffffu) << sz) | ((uint32_t) (v < 0 ? v - 1 : v) & ((1u << sz) - 1u)), len = (int) (e >> 16) + sz;
-                                } else {
-                                        code = act[0] & 0xffffu, len = (int) (act[0] >> 16);  // EOB
-                                }
-                                bw.put(code, len);
-                                if (--rem == 0 && j + 1 < j1) {  // next block of the segment
-                                        ++pb;
-                                        colw = blk_col(pb);
-                                        m = (uint64_t) s_nzhi[colw] << 32 | s_nzlo[colw];
-                                        rem = items_of(colw);
-                                        dc_next = true, prev = 0;
-                                        cw = s_coef + colw;
-                                        if (FMT == FMT_UYVY_422) {
-                                                act = s_ac[(pb & 3) >= 2 ? 1 : 0];
-                                        }
-                                }
-                        }
-                        bits = bw.finish();
-                }
-        } else if (valid) {
+        if (valid) {
                 const int t = comp == 0 ? 0 : 1;
                 int pred;
                 if (FMT == FMT_UYVY_422) {  // MCU = Y0 Y1 Cb Cr; a segment starts every ri MCUs (ri divides the CTA's 32 MCUs)
@@ -944,7 +838,7 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 }
                 return;
         }
-        s_len[BAL ? blk_col(tid) : pc] = bits;  // BAL: the bit string of thread tid is chunk tid of the scan order
+        s_len[pc] = bits;
         const bool overflow = __syncthreads_or(bits > (uint32_t) cap * 32u) != 0;
         {  // largest block of the CTA (reported at the end: the host sizes the next frame's cap from the frame maximum)
                 uint32_t mx = bits;
@@ -1600,8 +1494,7 @@ struct ugb200_jpeg_encoder {
         cudaEvent_t stats_ev = nullptr;  // recorded behind the copy of h_total: lets an asynchronous caller adapt the cap too
         bool stats_pending = false;
         int form = 0;  // 0: one fused kernel (default), 1 / 2: block kernel + assembly kernel
-        bool balanced = false;  // UGB200_JPEG_BALANCED=1: entropy coding dealt out per restart segment (measured slower than one thread per block)
-        bool attr_set[4] = { false, false, false, false };  // cudaFuncSetAttribute done for the fused / assembly kernels on this encoder's device
+        bool attr_set[3] = { false, false, false };  // cudaFuncSetAttribute done for the fused / assembly kernels on this encoder's device
         bool stage_timing = false;       // ugb200_jpeg_encoder_stage_timing: events between the kernels of an encode
         cudaEvent_t stage_ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -1801,8 +1694,6 @@ ugb200_jpeg_encoder *ugb200_jpeg_encoder_create(cuda_wrapper_stream_t stream)
         ugb200_jpeg_encoder *e = new (std::nothrow) ugb200_jpeg_encoder;
         if (e) {
                 e->stream = (cudaStream_t) stream;
-                const char *b = getenv("UGB200_JPEG_BALANCED");
-                e->balanced = b && b[0] == '1';
                 const char *f = getenv("UGB200_JPEG_TWO_KERNELS");  // "1": two-kernel form, "8": the same with the 64-register block kernel
                 e->form = !f ? 0 : f[0] == '8' ? 2 : 1;
         }
@@ -1835,9 +1726,7 @@ static void adapt_cap(ugb200_jpeg_encoder *e)
 {
         if (e->last_fused && e->stats_pending) {
                 const int want = (int) ((e->h_total[1] + e->h_total[1] / 4 + 31) / 32);
-                // (the balanced coder's unit is a thread's share of a segment, far smaller than the largest block: an 8-word tier for it; 8 words is
-                // also the least the staged input tile needs)
-                e->cap_words = want <= 8 && e->balanced && e->form == 0 ? 8 : want <= 12 ? 12 : want <= 16 ? 16 : want <= 24 ? 24 : want <= 32 ? 32 : kBlkWords;
+                e->cap_words = want <= 12 ? 12 : want <= 16 ? 16 : want <= 24 ? 24 : want <= 32 ? 32 : kBlkWords;
         }
         e->stats_pending = false;
 }
@@ -1900,8 +1789,7 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                         cudaMemsetAsync(e->lb_state, 0, ((size_t) nctas + 1) * sizeof(unsigned long long), e->stream);
                         lb.state = e->lb_state + 1, lb.ticket = (uint32_t *) e->lb_state;  // word 0 of the array = the ticket counter
                 }
-                // seven CTAs (28 warps) per SM: 28 KB of dynamic shared memory per CTA (the balanced coder has 2 KB more of static arrays: 24 KB)
-                const bool seven = cap <= (e->balanced ? 8 : 12);
+                const bool seven = cap <= 12;  // 28 KB per CTA: seven CTAs (28 warps) fit an SM
                 const int max_smem = (int) ((32 * 128 + 2 * kBlkWords * 128) * sizeof(uint32_t));
                 if (!e->attr_set[fmt == FMT_UYVY_422 ? 0 : 1]) {  // per encoder = per device context: the attribute does not carry over to another GPU
                         if (fmt == FMT_UYVY_422) {
@@ -1960,39 +1848,20 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                                                    e->slots, e->sizes, e->offsets, e->cta_total, cap, ctas_per_scan, (const uint32_t *) e->d_huff);
                         }
                 } else {
-#define UGB_FUSED(FMT, MINB, BAL)                                                                                                                         \
-        jpeg_fused_kernel<FMT, MINB, false, BAL><<<grid, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, \
-                                                                                 vec_ok, cap, e->total + 1, lb, e->qt, e->d_huff)
-                if (e->balanced) {
-                        if (!e->attr_set[3]) {
-                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_UYVY_422, 6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-                                cudaFuncSetAttribute(jpeg_fused_kernel<FMT_RGB_444, 6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-                                e->attr_set[3] = true;
-                        }
-                        if (fmt == FMT_UYVY_422) {
-                                if (seven) {
-                                        UGB_FUSED(FMT_UYVY_422, 7, true);
-                                } else {
-                                        UGB_FUSED(FMT_UYVY_422, 6, true);
-                                }
-                        } else {
-                                if (seven) {
-                                        UGB_FUSED(FMT_RGB_444, 7, true);
-                                } else {
-                                        UGB_FUSED(FMT_RGB_444, 6, true);
-                                }
-                        }
-                } else if (fmt == FMT_UYVY_422) {
+#define UGB_FUSED(FMT, MINB)                                                                                                                              \
+        jpeg_fused_kernel<FMT, MINB><<<grid, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, vec_ok, cap, \
+                                                                     e->total + 1, lb, e->qt, e->d_huff)
+                if (fmt == FMT_UYVY_422) {
                         if (seven) {
-                                UGB_FUSED(FMT_UYVY_422, 7, false);
+                                UGB_FUSED(FMT_UYVY_422, 7);
                         } else {
-                                UGB_FUSED(FMT_UYVY_422, 6, false);
+                                UGB_FUSED(FMT_UYVY_422, 6);
                         }
                 } else {
                         if (seven) {
-                                UGB_FUSED(FMT_RGB_444, 7, false);
+                                UGB_FUSED(FMT_RGB_444, 7);
                         } else {
-                                UGB_FUSED(FMT_RGB_444, 6, false);
+                                UGB_FUSED(FMT_RGB_444, 6);
                         }
                 }
 #undef UGB_FUSED
