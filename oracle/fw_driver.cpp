@@ -3,7 +3,8 @@
  * open_all() does (lib_common.cpp:186-204), looked up by name through load_library(), and fed real struct video_frame's through
  * compress_init / compress_frame / compress_pop (src/video_compress.h:84-96).  Compiled against the reference's own headers; supplies the few
  * globals that live in src/host.cpp.  Used by tests/test_real_module.py to show that ultragrid_b200/modules/ultragrid_vcompress_*.so load into an
- * unmodified UltraGrid.  Never part of the product. */
+ * unmodified UltraGrid.  The decompress side (fwd_dec_*) does the same with src/video_decompress.c: decompress_init_multi picks the module by the
+ * priorities the modules report, decompress_reconfigure / decompress_frame / decompress_done drive it.  Never part of the product. */
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -15,6 +16,7 @@
 #include "module.h"
 #include "video_codec.h"
 #include "video_compress.h"
+#include "video_decompress.h"
 #include "video_frame.h"
 
 /* src/host.cpp:177-179 */
@@ -43,6 +45,11 @@ API int fwd_load_module(const char *path)
 API int fwd_has_module(const char *name)
 {
         return load_library(name, LIBRARY_CLASS_VIDEO_COMPRESS, VIDEO_COMPRESS_ABI_VERSION) != nullptr;
+}
+
+API int fwd_has_decompress_module(const char *name)
+{
+        return load_library(name, LIBRARY_CLASS_VIDEO_DECOMPRESS, VIDEO_DECOMPRESS_ABI_VERSION) != nullptr;
 }
 
 API void fwd_set_device(int dev) { cuda_devices[0] = (unsigned) dev, cuda_devices_count = 1; }
@@ -101,4 +108,40 @@ API void fwd_done(void *st)
         module_done(&s->root);
         delete s;
 }
+
+/* ---- decompress side: the receiver's calls (src/rtp/video_decoders.cpp: decompress_init_multi -> reconfigure -> frame) ---- */
+API void *fwd_dec_init(int compression, int out_codec)
+{
+        struct state_decompress *st = nullptr;
+        struct pixfmt_desc internal {};
+        if (!decompress_init_multi((codec_t) compression, internal, (codec_t) out_codec, &st, 1)) {
+                return nullptr;
+        }
+        return st;
+}
+
+API int fwd_dec_reconfigure(void *st, int width, int height, int compression, int rshift, int gshift, int bshift, int pitch, int out_codec)
+{
+        struct video_desc d {};
+        d.width = (unsigned) width, d.height = (unsigned) height, d.color_spec = (codec_t) compression, d.fps = 30.0, d.interlacing = PROGRESSIVE, d.tile_count = 1;
+        return decompress_reconfigure((struct state_decompress *) st, d, rshift, gshift, bshift, pitch, (codec_t) out_codec);
+}
+
+/* returns the decompress_status; props = { depth, subsampling, rgb } as filled for DECODER_GOT_CODEC */
+API int fwd_dec_frame(void *st, void *dst, void *src, unsigned src_len, int frame_seq, int *props)
+{
+        struct pixfmt_desc p {};
+        const decompress_status rc = decompress_frame((struct state_decompress *) st, (unsigned char *) dst, (unsigned char *) src, src_len, frame_seq, nullptr, &p);
+        props[0] = p.depth, props[1] = (int) p.subsampling, props[2] = p.rgb;
+        return (int) rc;
+}
+
+API int fwd_dec_accepts_corrupted(void *st)
+{
+        int v = -1;
+        size_t len = sizeof v;
+        return decompress_get_property((struct state_decompress *) st, DECOMPRESS_PROPERTY_ACCEPTS_CORRUPTED_FRAME, &v, &len) ? v : -1;
+}
+
+API void fwd_dec_done(void *st) { decompress_done((struct state_decompress *) st); }
 }

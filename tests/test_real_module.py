@@ -13,6 +13,7 @@ import util
 RGBA, UYVY, RGB, DXT1, DXT5, JPEG = 1, 2, 12, 9, 11, 13
 FW = os.path.join(util.ROOT, "oracle", "_ref", "libugframework.so")
 MODS = [os.path.join(util.ROOT, "ultragrid_b200", "modules", f"ultragrid_vcompress_{m}.so") for m in ("cuda_dxt", "gpujpeg")]
+DEC_MODS = [os.path.join(util.ROOT, "ultragrid_b200", "modules", f"ultragrid_vdecompress_{m}.so") for m in ("gpujpeg", "gpujpeg_to_dxt", "dxt_cuda")]
 _fw = None
 
 
@@ -20,7 +21,7 @@ def framework():
     global _fw
     if _fw is not None:
         return _fw
-    if not os.path.exists(FW) or not all(os.path.exists(m) for m in MODS):
+    if not os.path.exists(FW) or not all(os.path.exists(m) for m in MODS + DEC_MODS):
         pytest.skip("reference framework / real-ABI modules not built (reference tree absent)")
     fw = ctypes.CDLL(FW, mode=ctypes.RTLD_GLOBAL)  # the module libraries resolve register_library, vf_*, video_frame_pool, cuda_devices ... here
     fw.fwd_load_module.argtypes = [ctypes.c_char_p]
@@ -30,8 +31,15 @@ def framework():
     fw.fwd_pop.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int),
                            ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint)]
     fw.fwd_done.argtypes = [ctypes.c_void_p]
+    fw.fwd_has_decompress_module.argtypes = [ctypes.c_char_p]
+    fw.fwd_dec_init.argtypes, fw.fwd_dec_init.restype = [ctypes.c_int, ctypes.c_int], ctypes.c_void_p
+    fw.fwd_dec_reconfigure.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 8
+    fw.fwd_dec_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    fw.fwd_dec_accepts_corrupted.argtypes = [ctypes.c_void_p]
+    fw.fwd_dec_done.argtypes = [ctypes.c_void_p]
     assert not fw.fwd_has_module(b"cuda_dxt") and not fw.fwd_has_module(b"gpujpeg")  # the framework alone knows neither
-    for m in MODS:
+    assert not fw.fwd_has_decompress_module(b"gpujpeg") and not fw.fwd_has_decompress_module(b"dxt_cuda")
+    for m in MODS + DEC_MODS:
         assert fw.fwd_load_module(m.encode()) == 0, m
     _fw = fw
     return fw
@@ -118,3 +126,94 @@ def test_gpujpeg_through_reference_framework(orc, cfg):
         assert got.tobytes() == want[i], i
     assert pop(fw, st, 16) is None
     fw.fwd_done(st)
+
+
+# ---- decompress side: ultragrid_vdecompress_{gpujpeg,gpujpeg_to_dxt,dxt_cuda}.so in the unmodified src/video_decompress.c -------------------------
+def dec_frame(fw, st, data, out_bytes, seq=0):
+    src = np.frombuffer(data, dtype=np.uint8)
+    dst = np.zeros(max(out_bytes, 1), np.uint8)
+    props = (ctypes.c_int * 3)()
+    rc = fw.fwd_dec_frame(st, dst.ctypes.data, src.ctypes.data, len(src), seq, props)
+    return rc, dst, list(props)
+
+
+def test_decompress_modules_register_with_the_reference_registry():
+    fw = framework()
+    for name in (b"gpujpeg", b"gpujpeg_to_dxt", b"dxt_cuda"):
+        assert fw.fwd_has_decompress_module(name), name
+    assert not fw.fwd_has_decompress_module(b"libavcodec")
+    assert not fw.fwd_dec_init(UYVY, RGB)  # not a compression: every module answers VDEC_PRIO_NA, decompress_init_multi fails
+
+
+@pytest.mark.gpu
+def test_gpujpeg_decompress_through_reference_framework(orc):
+    """decompress_init_multi of the unmodified video_decompress.c picks our module by its priority; probe + decode == the decoder called by hand"""
+    from test_jpeg import natural_rgb, orc_encode
+    from ultragrid_b200 import api
+    fw = framework()
+    w, h = 640, 360
+    rgb = natural_rgb(w, h, 31)
+    uyvy = util.convert_cpu(orc, "orc_convert", RGB, UYVY, rgb.reshape(-1), w, h)
+    s_yuv, s_rgb = orc_encode(orc, uyvy, w, h, UYVY, 90), orc_encode(orc, rgb.reshape(-1).copy(), w, h, RGB, 90)
+    probe = fw.fwd_dec_init(JPEG, 0)  # out_codec VIDEO_CODEC_NONE: VDEC_PRIO_PROBE_HI
+    assert probe and fw.fwd_dec_accepts_corrupted(probe) == 0
+    assert fw.fwd_dec_reconfigure(probe, w, h, JPEG, 0, 8, 16, 0, 0)
+    rc, _, props = dec_frame(fw, probe, s_yuv, 0)
+    assert rc == 2 and props == [8, 4220, 0]  # DECODER_GOT_CODEC
+    rc, _, props = dec_frame(fw, probe, s_rgb, 0)
+    assert rc == 2 and props == [8, 4440, 1]
+    fw.fwd_dec_done(probe)
+    dec = api.JpegDecoder()
+    for out_c, bpp, shifts in ((UYVY, 2, (0, 8, 16)), (RGB, 3, (0, 8, 16)), (RGBA, 4, (16, 8, 0))):
+        st = fw.fwd_dec_init(JPEG, out_c)
+        assert st
+        pitch = w * bpp
+        assert fw.fwd_dec_reconfigure(st, w, h, JPEG, *shifts, pitch, out_c)
+        for stream in (s_yuv, s_rgb):
+            rc, out, _ = dec_frame(fw, st, stream, pitch * h)
+            assert rc == 1  # DECODER_GOT_FRAME
+            assert np.array_equal(out, dec.decode(stream, out_c, shifts=shifts))
+        assert dec_frame(fw, st, b"not a jpeg at all", pitch * h)[0] == 0  # DECODER_NO_FRAME
+        assert not fw.fwd_dec_reconfigure(st, w, h, JPEG, *shifts, pitch, DXT1)  # not an output of this module
+        fw.fwd_dec_done(st)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out_c", [DXT1, DXT5])
+def test_gpujpeg_to_dxt_through_reference_framework(orc, out_c):
+    from test_jpeg import natural_rgb, orc_encode
+    from ultragrid_b200 import api
+    fw = framework()
+    w, h = 256, 128
+    stream = orc_encode(orc, natural_rgb(w, h, 8).reshape(-1).copy(), w, h, RGB, 90)
+    st = fw.fwd_dec_init(JPEG, out_c)  # only gpujpeg_to_dxt answers for JPEG -> DXT
+    assert st
+    pitch = w // (2 if out_c == DXT1 else 1)  # vc_get_linesize(width, DXT1 / DXT5)
+    assert fw.fwd_dec_reconfigure(st, w, h, JPEG, 0, 8, 16, pitch, out_c)
+    n = w * h // (2 if out_c == DXT1 else 1)
+    rc, out, _ = dec_frame(fw, st, stream, n)
+    assert rc == 1
+    rgb = api.JpegDecoder().decode(stream, RGB, device=True)
+    want = api.compat_to_dxt("cuda_rgb_to_dxt1" if out_c == DXT1 else "cuda_rgb_to_dxt6", rgb, w, -h).cpu().numpy()
+    assert np.array_equal(out[:want.size], want)
+    fw.fwd_dec_done(st)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("comp", [DXT1, DXT5])
+def test_dxt_cuda_through_reference_framework(orc, comp):
+    import torch
+    from ultragrid_b200 import api
+    fw = framework()
+    w, h = 256, 128
+    blocks = util.rng_bytes(w * h // (2 if comp == DXT1 else 1), 4)
+    rgb = api.dxt_to_rgb(torch.from_numpy(blocks).cuda(), w, h, 1 if comp == DXT1 else 6).cpu().numpy()
+    for out_c, bpp, shifts in ((RGB, 3, (0, 8, 16)), (RGBA, 4, (8, 16, 24)), (UYVY, 2, (0, 8, 16))):
+        st = fw.fwd_dec_init(comp, out_c)
+        assert st
+        assert fw.fwd_dec_reconfigure(st, w, h, comp, *shifts, w * bpp, out_c)
+        rc, out, _ = dec_frame(fw, st, blocks.tobytes(), w * h * bpp)
+        assert rc == 1
+        want = rgb if out_c == RGB else util.convert_cpu(orc, "orc_convert", RGB, out_c, rgb, w, h, shifts=shifts)
+        assert np.array_equal(out, want)
+        fw.fwd_dec_done(st)
