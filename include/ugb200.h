@@ -53,6 +53,12 @@ UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *dst, long d
                           int dst_len, int height, long src_size, int rshift, int gshift, int bshift,
                           cuda_wrapper_stream_t stream);
 
+/* Launch form of the line converters: -1 (default) = per converter, whichever measured faster at 8K (staged through shared memory with coalesced 16-byte
+ * accesses, or one chunk per thread straight from / to global memory); 0 = never staged, 1 = always staged when pointers and pitches are 16-byte aligned.
+ * The results are identical; the knob exists for the sweep (tools/pixfmt_sweep.py) and the tests.  Env UGB200_LINE_STAGED sets the initial value.
+ * Returns the previous mode. */
+UGB_API int ugb200_pixfmt_staged_mode(int mode);
+
 /* The line converters pixfmt_conv.h exports OUTSIDE the decoders[] table (pixfmt_conv.h:93-101; callers: screen capture, DeckLink): same
  * whole-buffer form and return codes as ugb200_pixfmt_convert.  rshift/gshift/bshift are used by UGB_LINE_TO_RGBA_INPLACE only (SOURCE shifts). */
 enum ugb200_line_func {

@@ -38,6 +38,29 @@ def test_line_converters_vs_oracle(api, orc, inc, outc):
             assert np.array_equal(got, want), (w, h, dl)
 
 
+@pytest.mark.parametrize("inc,outc", PAIRS)
+def test_staged_and_direct_launch_forms_agree(api, orc, inc, outc):
+    """every converter through both kernels (line_conv_kernel / line_conv_staged_kernel) on 16-byte aligned pitches: identical and == oracle"""
+    try:
+        for i, (w, h) in enumerate([(64, 2), (192, 3), (1920, 5), (2048 + 64, 2), (7680, 2)]):
+            si, so = orc.orc_vc_get_linesize(w, inc), orc.orc_vc_get_linesize(w, outc)
+            sp, dp = (si + 15) // 16 * 16 + 32, (so + 15) // 16 * 16 + 16
+            src = util.rng_bytes(sp * h, 2100 + i)
+            want = util.convert_cpu(orc, "orc_convert", inc, outc, src, w, h, src_pitch=sp, dst_pitch=dp)
+            got = []
+            for mode in (0, 1):
+                api.pixfmt_staged_mode(mode)
+                got.append(api.pixfmt_convert(inc, outc, dev(src), w, h, src_pitch=sp, dst_pitch=dp).cpu().numpy())
+            assert np.array_equal(got[0], want) and np.array_equal(got[1], want), (w, h)
+            for dl in (so, max(so - 20, 0) // 4 * 4):  # a dst_len that ends inside a 16-byte unit
+                want = util.convert_cpu(orc, "orc_convert", inc, outc, src, w, h, src_pitch=sp, dst_pitch=dp, dst_len=dl)
+                api.pixfmt_staged_mode(1)
+                g1 = api.pixfmt_convert(inc, outc, dev(src), w, h, src_pitch=sp, dst_pitch=dp, dst_len=dl).cpu().numpy()
+                assert np.array_equal(g1, want), (w, h, dl)
+    finally:
+        api.pixfmt_staged_mode(-1)
+
+
 def test_unaligned_pitches_take_the_guarded_path(api, orc):
     w, h = 100, 5
     for inc, outc in ((UYVY, RGB), (RGB, UYVY), (V210, UYVY)):

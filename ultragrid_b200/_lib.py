@@ -47,6 +47,7 @@ SIGNATURES = {
     "ugb200_dxt5ycocg_to_rgb": (_i, [_vp, _vp, _i, _i, _l, _i, _vp]),
     "ugb200_vc_copyline": (_i, [_i, _vp, _l, _vp, _l, _i, _i, _l, _i, _i, _i, _vp]),
     "ugb200_pixfmt_supported": (_i, [_i, _i]),
+    "ugb200_pixfmt_staged_mode": (_i, [_i]),
     "ugb200_pixfmt_convert": (_i, [_i, _i, _vp, _l, _vp, _l, _i, _i, _l, _i, _i, _i, _vp]),
     "ugb200_v210_to_p010le": (_i, [_vp, _l, _vp]),
     # the other to_planar.h / from_planar.h functions: (struct *, stream)

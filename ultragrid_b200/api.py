@@ -75,6 +75,11 @@ def pixfmt_convert(in_codec, out_codec, src, width, height, dst=None, dst_len=No
     return dst
 
 
+def pixfmt_staged_mode(mode):
+    """-1 default (per converter), 0 never, 1 always staged through shared memory; returns the previous mode"""
+    return _L.ugb200_pixfmt_staged_mode(int(mode))
+
+
 LINE_FUNCS = {"ABGRtoRGB": 1, "BGRAtoRGB": 2, "ToRGBA_inplace": 3, "UYVYtoGrayscale": 4}
 
 

@@ -8,6 +8,7 @@
 // dst_len each reference loop really writes) are preserved exactly.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/ugb200.h"
 #include "color_space.h"
@@ -1172,6 +1173,99 @@ __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ ds
         }
 }
 
+// ---- staged kernel: the same converter structs behind coalesced global accesses --------------------------------------------
+// A thread of line_conv_kernel owns C::IN input bytes and C::OUT output bytes; with chunks of 64 bytes and more, the lanes of a warp sit 64-256 bytes
+// apart and every 16-byte access of a warp touches 32 different cache lines (each line several times over the unrolled accesses): the L1 tag stage, one
+// line per clock, becomes the limiter (R12L family, v210 -> RG48: 0.44-0.68 of the copy bandwidth in round 1).  Here a CTA of T threads moves the T chunks
+// of a row span as ONE contiguous byte run - 16 bytes per lane, 512 contiguous bytes per warp access - through shared memory: global -> shared
+// (chunk c at 16-byte unit c * SI, SI = units per chunk made odd so that the per-thread 128-bit shared accesses of a quarter warp fall into distinct
+// banks), C::run on registers exactly as in line_conv_kernel, registers -> shared (stride SO) -> global.  Used when pointers and pitches are 16-byte
+// aligned (vec_ok) and the converter is marked staged (measured per converter, profiles/r02_i_pixfmt_sweep_8k.md); results are identical by construction.
+template <class C, int T>
+__global__ void __launch_bounds__(T) line_conv_staged_kernel(uint8_t *__restrict__ dst, long dst_pitch, const uint8_t *__restrict__ src, long src_pitch,
+                                                             int wlen_last, int height, long src_total, conv_params p)
+{
+        constexpr int NI = C::IN / 4, NO = C::OUT / 4, UI = C::IN / 16, UO = C::OUT / 16, SI = UI | 1, SO = UO | 1;
+        static_assert(C::IN % 16 == 0 && C::OUT % 16 == 0, "chunks are whole 16-byte units");
+        __shared__ uint4 sm[T * (SI > SO ? SI : SO)];
+        const int tid = threadIdx.x, chunk0 = blockIdx.x * T;
+        const long out_base = (long) chunk0 * C::OUT, in_base_row = (long) chunk0 * C::IN;
+        for (int row = blockIdx.y; row < height; row += gridDim.y) {
+                const int wlen = (row == height - 1 || wlen_last <= dst_pitch) ? wlen_last : (int) dst_pitch;  // see line_conv_kernel
+                if (out_base >= wlen) {
+                        continue;  // uniform for the CTA
+                }
+                const long left = wlen - out_base;
+                const int nchunks = left >= (long) T * C::OUT ? T : (int) ((left + C::OUT - 1) / C::OUT);
+                const long in_abs0 = row * src_pitch + in_base_row;
+                // global -> shared, linear in the byte run
+                for (int j = tid; j < nchunks * UI; j += T) {
+                        const int c = j / UI, k = j - c * UI;
+                        const long a = in_abs0 + 16l * j;
+                        uint4 v;
+                        if (a + 16 <= src_total) {
+                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + a));
+                        } else {  // reads past src_size give 0 (include/ugb200.h)
+                                uint32_t w[4] = { 0, 0, 0, 0 };
+                                for (int b = 0; b < 16; ++b) {
+                                        if (a + b < src_total) {
+                                                w[b >> 2] |= (uint32_t) src[a + b] << (8 * (b & 3));
+                                        }
+                                }
+                                v = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                        sm[c * SI + k] = v;
+                }
+                __syncthreads();
+                uint32_t in[NI], out[NO];
+                if (tid < nchunks) {
+#pragma unroll
+                        for (int i = 0; i < UI; ++i) {
+                                const uint4 v = sm[tid * SI + i];
+                                in[4 * i] = v.x, in[4 * i + 1] = v.y, in[4 * i + 2] = v.z, in[4 * i + 3] = v.w;
+                        }
+                }
+                __syncthreads();  // the output image reuses the staging buffer
+                if (tid < nchunks) {
+                        const row_ctx rc = { src, row * src_pitch, src_total, chunk0 + tid };
+                        C::run(in, out, p, rc);
+#pragma unroll
+                        for (int i = 0; i < UO; ++i) {
+                                sm[tid * SO + i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                        }
+                }
+                __syncthreads();
+                // shared -> global: whole 16-byte units, then the bytes of a last partial unit (wlen need not be a multiple of 16)
+                const long nbytes = left < (long) nchunks * C::OUT ? left : (long) nchunks * C::OUT;
+                uint8_t *d = dst + row * dst_pitch + out_base;
+                const int nfull = (int) (nbytes >> 4);
+                for (int j = tid; j < nfull; j += T) {
+                        const int c = j / UO, k = j - c * UO;
+                        ((uint4 *) d)[j] = sm[c * SO + k];
+                }
+                if (tid < (int) (nbytes & 15)) {
+                        const int j = nfull, c = j / UO, k = j - c * UO;
+                        d[16l * j + tid] = ((const uint8_t *) &sm[c * SO + k])[tid];
+                }
+                __syncthreads();  // before the next row's fill
+        }
+}
+
+/// which converters take the staged kernel by default (the ones it measured faster for at 8K); UGB200_LINE_STAGED=0 / 1 forces none / all (experiments)
+template <class C>
+struct staged_default {
+        static constexpr bool value = false;
+};
+static int &staged_mode()
+{
+        static int v = [] {
+                const char *e = getenv("UGB200_LINE_STAGED");
+                return e == nullptr || e[0] == '\0' ? -1 : atoi(e);
+        }();
+        return v;
+}
+static int staged_override() { return staged_mode(); }
+
 template <class C>
 static int launch_line(void *dst, long dst_pitch, const void *src, long src_pitch, int dst_len, int height, long src_size,
                        conv_params p, cudaStream_t s)
@@ -1187,6 +1281,13 @@ static int launch_line(void *dst, long dst_pitch, const void *src, long src_pitc
         const int chunks = (wlen + C::OUT - 1) / C::OUT;
         const int threads = 128;
         dim3 grid((chunks + threads - 1) / threads, height > 65535 ? 65535 : height);
+        if constexpr (C::IN % 16 == 0 && C::OUT % 16 == 0) {
+                const int ov = staged_override();
+                if (vec_ok && (ov < 0 ? staged_default<C>::value : ov != 0)) {
+                        line_conv_staged_kernel<C, threads><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height, src_size, p);
+                        return cudaGetLastError() == cudaSuccess ? 0 : -2;
+                }
+        }
         line_conv_kernel<C><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height,
                                                      src_size, vec_ok, p);
         return cudaGetLastError() == cudaSuccess ? 0 : -2;
@@ -1226,6 +1327,13 @@ extern "C" UGB_API int ugb200_vc_copyline(int func, void *dst, long dst_pitch, c
         default:
                 return -4;
         }
+}
+
+extern "C" UGB_API int ugb200_pixfmt_staged_mode(int mode)
+{
+        const int prev = staged_mode();
+        staged_mode() = mode < 0 ? -1 : mode != 0;
+        return prev;
 }
 
 extern "C" UGB_API int ugb200_pixfmt_supported(int in_codec, int out_codec)
@@ -1408,4 +1516,34 @@ extern "C" UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *
         }
         }
         return -4;  // no decoder (get_decoder_from_to() == NULL, pixfmt_conv.c:3122-3124)
+}
+
+// ---- src/cuda_wrapper/kernels.cu under its own names (include/cuda_wrapper_kernels.hpp) ------------------------------------------------
+// The reference's two callbacks are vc_copylineRG48toR12L / vc_copylineR12LtoRG48 run over tightly packed rows (kernels.cu:72-74,312 say so):
+// the same converter structs, launched with the reference's row geometry.
+#include "../../include/cuda_wrapper_kernels.hpp"
+
+int postprocess_rg48_to_r12l(void *, void *, size_t, int size_x, int size_y, struct cmpto_j2k_dec_comp_format *, int, void *input_samples, size_t, void *, size_t,
+                             void *output_buffer, size_t, void *stream)
+{
+        if (size_x <= 0 || size_y <= 0) {
+                return (int) cudaSuccess;  // the reference launches an empty grid
+        }
+        const long r12_pitch = (long) ((size_x + 7) / 8) * 36, rg48_pitch = (long) size_x * 6;
+        // dst_len = the whole R12L row: the last (partial) group is written too, as kernel_rg48_to_r12l does (kernels.cu:238-257)
+        launch_line<conv_x_r12l<2>>(output_buffer, r12_pitch, input_samples, rg48_pitch, (int) r12_pitch, size_y, rg48_pitch * size_y, conv_params{ 0, 8, 16, 0 },
+                                    (cudaStream_t) stream);
+        return (int) cudaGetLastError();
+}
+
+int preprocess_r12l_to_rg48(void *, void *, size_t, int size_x, int size_y, struct cmpto_j2k_enc_comp_format *, int, void *input_samples, size_t, void *output_samples,
+                            size_t, void *stream)
+{
+        if (size_x <= 0 || size_y <= 0) {
+                return (int) cudaSuccess;
+        }
+        const long r12_pitch = (long) ((size_x + 7) / 8) * 36, rg48_pitch = (long) size_x * 6;
+        launch_line<conv_r12l_rgbx<2>>(output_samples, rg48_pitch, input_samples, r12_pitch, (int) rg48_pitch, size_y, r12_pitch * size_y, conv_params{ 0, 8, 16, 0 },
+                                       (cudaStream_t) stream);
+        return (int) cudaGetLastError();
 }
