@@ -54,7 +54,7 @@ UGB_API int ugb200_pixfmt_convert(int in_codec, int out_codec, void *dst, long d
                           cuda_wrapper_stream_t stream);
 
 /* Launch form of the line converters: -1 (default) = per converter, whichever measured faster at 8K (staged through shared memory with coalesced 16-byte
- * accesses, or one chunk per thread straight from / to global memory); 0 = never staged, 1 = always staged when pointers and pitches are 16-byte aligned.
+ * accesses, or one chunk per thread straight from / to global memory); 0 = never staged; 1 / 2 / 3 = input and output / output only / input only staged whenever pointers and pitches are 16-byte aligned.
  * The results are identical; the knob exists for the sweep (tools/pixfmt_sweep.py) and the tests.  Env UGB200_LINE_STAGED sets the initial value.
  * Returns the previous mode. */
 UGB_API int ugb200_pixfmt_staged_mode(int mode);

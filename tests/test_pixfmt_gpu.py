@@ -40,7 +40,7 @@ def test_line_converters_vs_oracle(api, orc, inc, outc):
 
 @pytest.mark.parametrize("inc,outc", PAIRS)
 def test_staged_and_direct_launch_forms_agree(api, orc, inc, outc):
-    """every converter through both kernels (line_conv_kernel / line_conv_staged_kernel) on 16-byte aligned pitches: identical and == oracle"""
+    """every converter through all four launch forms (line_conv_kernel / line_conv_staged_kernel<in, out>) on 16-byte aligned pitches: identical and == oracle"""
     try:
         for i, (w, h) in enumerate([(64, 2), (192, 3), (1920, 5), (2048 + 64, 2), (7680, 2)]):
             si, so = orc.orc_vc_get_linesize(w, inc), orc.orc_vc_get_linesize(w, outc)
@@ -48,15 +48,16 @@ def test_staged_and_direct_launch_forms_agree(api, orc, inc, outc):
             src = util.rng_bytes(sp * h, 2100 + i)
             want = util.convert_cpu(orc, "orc_convert", inc, outc, src, w, h, src_pitch=sp, dst_pitch=dp)
             got = []
-            for mode in (0, 1):
+            for mode in (0, 1, 2, 3):  # direct, input + output staged, output only, input only
                 api.pixfmt_staged_mode(mode)
                 got.append(api.pixfmt_convert(inc, outc, dev(src), w, h, src_pitch=sp, dst_pitch=dp).cpu().numpy())
-            assert np.array_equal(got[0], want) and np.array_equal(got[1], want), (w, h)
+            assert all(np.array_equal(g, want) for g in got), (w, h, [np.array_equal(g, want) for g in got])
             for dl in (so, max(so - 20, 0) // 4 * 4):  # a dst_len that ends inside a 16-byte unit
                 want = util.convert_cpu(orc, "orc_convert", inc, outc, src, w, h, src_pitch=sp, dst_pitch=dp, dst_len=dl)
-                api.pixfmt_staged_mode(1)
-                g1 = api.pixfmt_convert(inc, outc, dev(src), w, h, src_pitch=sp, dst_pitch=dp, dst_len=dl).cpu().numpy()
-                assert np.array_equal(g1, want), (w, h, dl)
+                for mode in (1, 2, 3):
+                    api.pixfmt_staged_mode(mode)
+                    g1 = api.pixfmt_convert(inc, outc, dev(src), w, h, src_pitch=sp, dst_pitch=dp, dst_len=dl).cpu().numpy()
+                    assert np.array_equal(g1, want), (w, h, dl, mode)
     finally:
         api.pixfmt_staged_mode(-1)
 

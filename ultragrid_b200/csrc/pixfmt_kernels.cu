@@ -1181,13 +1181,14 @@ __global__ void __launch_bounds__(256) line_conv_kernel(uint8_t *__restrict__ ds
 // (chunk c at 16-byte unit c * SI, SI = units per chunk made odd so that the per-thread 128-bit shared accesses of a quarter warp fall into distinct
 // banks), C::run on registers exactly as in line_conv_kernel, registers -> shared (stride SO) -> global.  Used when pointers and pitches are 16-byte
 // aligned (vec_ok) and the converter is marked staged (measured per converter, profiles/r02_i_pixfmt_sweep_8k.md); results are identical by construction.
-template <class C, int T>
+template <class C, int T, bool SIN, bool SOUT>
 __global__ void __launch_bounds__(T) line_conv_staged_kernel(uint8_t *__restrict__ dst, long dst_pitch, const uint8_t *__restrict__ src, long src_pitch,
                                                              int wlen_last, int height, long src_total, conv_params p)
 {
         constexpr int NI = C::IN / 4, NO = C::OUT / 4, UI = C::IN / 16, UO = C::OUT / 16, SI = UI | 1, SO = UO | 1;
         static_assert(C::IN % 16 == 0 && C::OUT % 16 == 0, "chunks are whole 16-byte units");
-        __shared__ uint4 sm[T * (SI > SO ? SI : SO)];
+        static_assert(SIN || SOUT, "the unstaged form is line_conv_kernel");
+        __shared__ uint4 sm[T * ((SIN ? SI : 0) > (SOUT ? SO : 0) ? SI : SO)];
         const int tid = threadIdx.x, chunk0 = blockIdx.x * T;
         const long out_base = (long) chunk0 * C::OUT, in_base_row = (long) chunk0 * C::IN;
         for (int row = blockIdx.y; row < height; row += gridDim.y) {
@@ -1196,66 +1197,172 @@ __global__ void __launch_bounds__(T) line_conv_staged_kernel(uint8_t *__restrict
                         continue;  // uniform for the CTA
                 }
                 const long left = wlen - out_base;
-                const int nchunks = left >= (long) T * C::OUT ? T : (int) ((left + C::OUT - 1) / C::OUT);
+                const bool whole = left >= (long) T * C::OUT;  // all T chunks of the CTA are whole
+                const int nchunks = whole ? T : (int) ((left + C::OUT - 1) / C::OUT);
                 const long in_abs0 = row * src_pitch + in_base_row;
-                // global -> shared, linear in the byte run
-                for (int j = tid; j < nchunks * UI; j += T) {
-                        const int c = j / UI, k = j - c * UI;
-                        const long a = in_abs0 + 16l * j;
-                        uint4 v;
-                        if (a + 16 <= src_total) {
-                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + a));
-                        } else {  // reads past src_size give 0 (include/ugb200.h)
-                                uint32_t w[4] = { 0, 0, 0, 0 };
-                                for (int b = 0; b < 16; ++b) {
-                                        if (a + b < src_total) {
-                                                w[b >> 2] |= (uint32_t) src[a + b] << (8 * (b & 3));
-                                        }
-                                }
-                                v = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                        sm[c * SI + k] = v;
-                }
-                __syncthreads();
                 uint32_t in[NI], out[NO];
-                if (tid < nchunks) {
+                if (SIN) {  // global -> shared, linear in the byte run
+                        if (whole && in_abs0 + (long) T * C::IN <= src_total) {
+                                uint4 v[UI];
 #pragma unroll
-                        for (int i = 0; i < UI; ++i) {
-                                const uint4 v = sm[tid * SI + i];
-                                in[4 * i] = v.x, in[4 * i + 1] = v.y, in[4 * i + 2] = v.z, in[4 * i + 3] = v.w;
+                                for (int i = 0; i < UI; ++i) {  // all loads of the thread in flight before the first shared store
+                                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                                     : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                                                     : "l"(src + in_abs0 + 16l * (tid + i * T)));
+                                }
+#pragma unroll
+                                for (int i = 0; i < UI; ++i) {
+                                        const int j = tid + i * T, c = j / UI, k = j - c * UI;
+                                        sm[c * SI + k] = v[i];
+                                }
+                        } else {
+                                for (int j = tid; j < nchunks * UI; j += T) {
+                                        const int c = j / UI, k = j - c * UI;
+                                        const long a = in_abs0 + 16l * j;
+                                        uint32_t w[4] = { 0, 0, 0, 0 };
+                                        for (int b = 0; b < 16; ++b) {  // reads past src_size give 0 (include/ugb200.h)
+                                                if (a + b < src_total) {
+                                                        w[b >> 2] |= (uint32_t) src[a + b] << (8 * (b & 3));
+                                                }
+                                        }
+                                        sm[c * SI + k] = make_uint4(w[0], w[1], w[2], w[3]);
+                                }
+                        }
+                        __syncthreads();
+                        if (tid < nchunks) {
+#pragma unroll
+                                for (int i = 0; i < UI; ++i) {
+                                        const uint4 v = sm[tid * SI + i];
+                                        in[4 * i] = v.x, in[4 * i + 1] = v.y, in[4 * i + 2] = v.z, in[4 * i + 3] = v.w;
+                                }
+                        }
+                        if (SOUT) {
+                                __syncthreads();  // the output image reuses the staging buffer
+                        }
+                } else if (tid < nchunks) {  // own chunk straight from global memory, as line_conv_kernel
+                        const long in_abs = in_abs0 + (long) tid * C::IN;
+                        if (in_abs + C::IN <= src_total) {
+                                const uint4 *s4 = (const uint4 *) (src + in_abs);
+#pragma unroll
+                                for (int i = 0; i < UI; ++i) {
+                                        uint4 v;
+                                        if (NI >= 16) {
+                                                v = __ldg(s4 + i);
+                                        } else {
+                                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(s4 + i));
+                                        }
+                                        in[4 * i] = v.x, in[4 * i + 1] = v.y, in[4 * i + 2] = v.z, in[4 * i + 3] = v.w;
+                                }
+                        } else {
+#pragma unroll
+                                for (int i = 0; i < NI; ++i) {
+                                        uint32_t w = 0;
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                                const long a = in_abs + 4 * i + k;
+                                                if (a < src_total) {
+                                                        w |= (uint32_t) src[a] << (8 * k);
+                                                }
+                                        }
+                                        in[i] = w;
+                                }
                         }
                 }
-                __syncthreads();  // the output image reuses the staging buffer
                 if (tid < nchunks) {
                         const row_ctx rc = { src, row * src_pitch, src_total, chunk0 + tid };
                         C::run(in, out, p, rc);
+                }
+                uint8_t *d = dst + row * dst_pitch + out_base;
+                if (SOUT) {
+                        if (tid < nchunks) {
 #pragma unroll
-                        for (int i = 0; i < UO; ++i) {
-                                sm[tid * SO + i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                                for (int i = 0; i < UO; ++i) {
+                                        sm[tid * SO + i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                                }
+                        }
+                        __syncthreads();
+                        // shared -> global: whole 16-byte units, then the bytes of a last partial unit (wlen need not be a multiple of 16)
+                        if (whole) {
+#pragma unroll
+                                for (int i = 0; i < UO; ++i) {
+                                        const int j = tid + i * T, c = j / UO, k = j - c * UO;
+                                        ((uint4 *) d)[j] = sm[c * SO + k];
+                                }
+                        } else {
+                                const long nbytes = left < (long) nchunks * C::OUT ? left : (long) nchunks * C::OUT;
+                                const int nfull = (int) (nbytes >> 4);
+                                for (int j = tid; j < nfull; j += T) {
+                                        const int c = j / UO, k = j - c * UO;
+                                        ((uint4 *) d)[j] = sm[c * SO + k];
+                                }
+                                if (tid < (int) (nbytes & 15)) {
+                                        const int j = nfull, c = j / UO, k = j - c * UO;
+                                        d[16l * j + tid] = ((const uint8_t *) &sm[c * SO + k])[tid];
+                                }
+                        }
+                        __syncthreads();  // before the next row touches the buffer
+                } else if (tid < nchunks) {  // own chunk straight to global memory
+                        const long out_off = (long) tid * C::OUT;
+                        if (out_base + out_off + C::OUT <= wlen) {
+#pragma unroll
+                                for (int i = 0; i < UO; ++i) {
+                                        ((uint4 *) (d + out_off))[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                                }
+                        } else {
+#pragma unroll
+                                for (int i = 0; i < NO; ++i) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                                if (out_base + out_off + 4 * i + k < wlen) {
+                                                        d[out_off + 4 * i + k] = (uint8_t) (out[i] >> (8 * k));
+                                                }
+                                        }
+                                }
                         }
                 }
-                __syncthreads();
-                // shared -> global: whole 16-byte units, then the bytes of a last partial unit (wlen need not be a multiple of 16)
-                const long nbytes = left < (long) nchunks * C::OUT ? left : (long) nchunks * C::OUT;
-                uint8_t *d = dst + row * dst_pitch + out_base;
-                const int nfull = (int) (nbytes >> 4);
-                for (int j = tid; j < nfull; j += T) {
-                        const int c = j / UO, k = j - c * UO;
-                        ((uint4 *) d)[j] = sm[c * SO + k];
+                if (SIN && !SOUT) {
+                        __syncthreads();  // the next row's fill must not overtake this row's reads (the row loop only repeats for height > 65535)
                 }
-                if (tid < (int) (nbytes & 15)) {
-                        const int j = nfull, c = j / UO, k = j - c * UO;
-                        d[16l * j + tid] = ((const uint8_t *) &sm[c * SO + k])[tid];
-                }
-                __syncthreads();  // before the next row's fill
         }
 }
 
 /// which converters take the staged kernel by default (the ones it measured faster for at 8K); UGB200_LINE_STAGED=0 / 1 forces none / all (experiments)
 template <class C>
 struct staged_default {
-        static constexpr bool value = false;
+        static constexpr int value = 0;  // 0 direct, 1 input and output staged, 2 output only, 3 input only
 };
+// measured at 7680x4320 (profiles/r02_i_pixfmt_sweep_8k.md: all four forms of every converter); only gains of 5 % and more are taken.  The pattern: staging
+// the OUTPUT pays wherever a thread's output chunk is large or oddly sized (36-byte R12L groups, 48-byte RG48 / Y416 runs): the direct form stores 16 bytes
+// per lane at a stride of the whole chunk.  Staging the input almost never pays - strided 16-byte loads of a warp hit L1 lines the previous load brought in.
+#define UGB_STAGED(CONV, MODE)                                                                                                                \
+        template <>                                                                                                                           \
+        struct staged_default<CONV> {                                                                                                         \
+                static constexpr int value = MODE;                                                                                            \
+        };
+UGB_STAGED(conv_v210_rg48, 2)        // 101.2 -> 54.1 us
+UGB_STAGED(conv_r12l_rgbx<0>, 2)     // R12L -> RGB    48.0 -> 43.9
+UGB_STAGED(conv_r12l_rgbx<1>, 2)     // R12L -> RGBA   64.3 -> 49.7
+UGB_STAGED(conv_r12l_rgbx<2>, 2)     // R12L -> RG48   88.9 -> 57.5
+UGB_STAGED(conv_r12l_rgbx<3>, 2)     // R12L -> R10k   81.5 -> 49.0
+UGB_STAGED(conv_r12l_y416, 2)        // 117.6 -> 68.4
+UGB_STAGED(conv_x_r12l<0>, 2)        // RGB  -> R12L   62.9 -> 41.5
+UGB_STAGED(conv_x_r12l<1>, 2)        // RGBA -> R12L   64.4 -> 52.1
+UGB_STAGED(conv_x_r12l<2>, 2)        // RG48 -> R12L   70.2 -> 60.2
+UGB_STAGED(conv_x_r12l<3>, 2)        // Y416 -> R12L  105.3 -> 81.4
+UGB_STAGED(conv_rgb_rgba, 2)         // 53.9 -> 41.9
+UGB_STAGED(conv_bytemap<map_uyvy_y416>, 1)  // 76.7 -> 57.9
+UGB_STAGED(conv_r10k_y416, 2)        // 90.9 -> 71.6
+UGB_STAGED(conv_uyvy_v210, 2)        // 35.2 -> 28.4
+UGB_STAGED(conv_vuya_rgb, 2)         // 52.2 -> 48.2
+UGB_STAGED(conv_rg48_y416, 2)        // 91.0 -> 72.7
+UGB_STAGED(conv_r10k_rg48, 2)        // 64.3 -> 56.1
+UGB_STAGED(conv_v210_y416, 2)        // 68.6 -> 56.9
+UGB_STAGED(conv_rg48_v210, 2)        // 55.0 -> 51.9
+UGB_STAGED(conv_rg48_y216, 3)        // 60.2 -> 54.0
+UGB_STAGED(conv_v210_uyvy, 2)        // 28.0 -> 25.6
+UGB_STAGED(conv_rg48_r10k, 2)        // 58.1 -> 55.2
+#undef UGB_STAGED
+
 static int &staged_mode()
 {
         static int v = [] {
@@ -1283,8 +1390,15 @@ static int launch_line(void *dst, long dst_pitch, const void *src, long src_pitc
         dim3 grid((chunks + threads - 1) / threads, height > 65535 ? 65535 : height);
         if constexpr (C::IN % 16 == 0 && C::OUT % 16 == 0) {
                 const int ov = staged_override();
-                if (vec_ok && (ov < 0 ? staged_default<C>::value : ov != 0)) {
-                        line_conv_staged_kernel<C, threads><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height, src_size, p);
+                const int mode = !vec_ok ? 0 : ov < 0 ? staged_default<C>::value : ov;
+                if (mode == 1) {
+                        line_conv_staged_kernel<C, threads, true, true><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height, src_size, p);
+                } else if (mode == 2) {
+                        line_conv_staged_kernel<C, threads, false, true><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height, src_size, p);
+                } else if (mode == 3) {
+                        line_conv_staged_kernel<C, threads, true, false><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height, src_size, p);
+                }
+                if (mode != 0) {
                         return cudaGetLastError() == cudaSuccess ? 0 : -2;
                 }
         }
@@ -1332,7 +1446,7 @@ extern "C" UGB_API int ugb200_vc_copyline(int func, void *dst, long dst_pitch, c
 extern "C" UGB_API int ugb200_pixfmt_staged_mode(int mode)
 {
         const int prev = staged_mode();
-        staged_mode() = mode < 0 ? -1 : mode != 0;
+        staged_mode() = mode < 0 || mode > 3 ? -1 : mode;
         return prev;
 }
 
