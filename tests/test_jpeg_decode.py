@@ -349,12 +349,63 @@ def test_gpu_device_marker_scan_equals_host_scan(orc, monkeypatch, kind, w, h, q
 
 
 @pytest.mark.gpu
-def test_gpu_device_marker_scan_leaves_multi_scan_streams_to_the_host(orc, monkeypatch):
-    """three scans (RGB as GPUJPEG stores it): later SOS headers lie behind entropy-coded data, the host scan takes the stream even when the device scan is forced"""
-    from ultragrid_b200 import api
-    s, _ = make_stream(orc, "ours-rgb", 640, 360, 90, 0)
-    want = api.JpegDecoder().decode(s, RGB)
-    monkeypatch.setenv("UGB200_JPEG_MARKER_SCAN", "device")
-    dec = api.JpegDecoder()
-    assert (dec.decode(s, RGB) == want).all()
-    dec.close()
+@pytest.mark.parametrize("w,h,q,ri,damage", [
+    (640, 360, 90, 0, None), (200, 120, 75, 3, None), (1920, 1080, 90, 0, None), (7680, 4320, 90, 0, None),
+    (1920, 1080, 90, 0, "truncate"), (1920, 1080, 90, 0, "truncate-scan1"), (1920, 1080, 90, 0, "drop-rst"), (1920, 1080, 90, 0, "extra-rst"),
+    (1920, 1080, 90, 0, "foreign-marker"), (1920, 1080, 90, 0, "swap-tables"), (1920, 1080, 90, 0, "other-component"), (1920, 1080, 90, 0, "dht-between")])
+def test_gpu_device_marker_scan_of_multi_scan_streams(orc, monkeypatch, w, h, q, ri, damage):
+    """three scans (RGB as GPUJPEG stores it, one per component): the device finds the later SOS headers behind the entropy-coded data, checks that they
+    are what the first one promises and builds the segment table of all three scans; a stream that breaks the promise (damaged, tables redefined between the
+    scans, another component order) is handed back to the host parser - either way segments and pixels are the host path's."""
+    from ultragrid_b200 import _lib, api
+    lib = _lib.load()
+    s, _ = make_stream(orc, "ours-rgb", w, h, q, ri)
+    a = np.frombuffer(s, np.uint8).copy()
+    rst = np.flatnonzero((a[:-1] == 0xFF) & (a[1:] >= 0xD0) & (a[1:] <= 0xD7))
+    sos = np.flatnonzero((a[:-1] == 0xFF) & (a[1:] == 0xDA))
+    assert len(sos) == 3
+    if damage == "truncate":            # inside the last scan
+        a = a[:(sos[2] + len(a)) // 2]
+    elif damage == "truncate-scan1":    # the later scans are missing altogether
+        a = a[:(sos[0] + sos[1]) // 2]
+    elif damage == "drop-rst":
+        a[rst[5]:rst[5] + 2] = (0x12, 0x34)
+        k = int(np.searchsorted(rst, sos[1])) + 7
+        a[rst[k]:rst[k] + 2] = (0x12, 0x34)
+    elif damage == "extra-rst":
+        a = np.concatenate([a[:sos[1]], np.tile(np.array([0x55, 0xFF, 0xD3], np.uint8), 50), a[sos[1]:]])
+    elif damage == "foreign-marker":    # an EOI in the middle of the second scan
+        k = int(np.searchsorted(rst, (sos[1] + sos[2]) // 2))
+        a[rst[k] + 1] = 0xD9
+    elif damage == "swap-tables":       # legal: the second scan codes with the luminance tables selectors (the data was coded with the others: garbage, equally on both paths)
+        a[sos[1] + 6] = 0x00
+    elif damage == "other-component":   # legal: the second scan names the third component
+        a[sos[1] + 5] = a[sos[2] + 5]
+    elif damage == "dht-between":       # legal: a (repeated) DHT segment between the scans
+        dht = int(np.flatnonzero((a[:-1] == 0xFF) & (a[1:] == 0xC4))[0])
+        L = int(a[dht + 2]) << 8 | int(a[dht + 3])
+        a = np.concatenate([a[:sos[1]], a[dht:dht + 2 + L], a[sos[1]:]])
+    a = np.ascontiguousarray(a)
+    data = a.tobytes()
+    monkeypatch.setenv("UGB200_JPEG_MARKER_SCAN", "host")
+    host = api.JpegDecoder()
+    if w < 7680:
+        monkeypatch.setenv("UGB200_JPEG_MARKER_SCAN", "device")
+    else:
+        monkeypatch.delenv("UGB200_JPEG_MARKER_SCAN")
+    dev = api.JpegDecoder()
+    monkeypatch.delenv("UGB200_JPEG_MARKER_SCAN", raising=False)
+    for _ in range(2):
+        try:
+            want = host.decode(data, RGB, device=True)
+        except RuntimeError:
+            with pytest.raises(RuntimeError):  # what the host parser refuses, the device path refuses too (it hands the frame back)
+                dev.decode(data, RGB, device=True)
+            continue
+        n_h, b_h, e_h = _segments(lib, host, 1 << 18)
+        got = dev.decode(data, RGB, device=True)
+        n_d, b_d, e_d = _segments(lib, dev, 1 << 18)
+        assert n_h == n_d > 0
+        assert b_h == b_d and e_h == e_d
+        assert bool((want == got).all())
+    host.close(), dev.close()

@@ -17,19 +17,20 @@ def child():
     g.manual_seed(1)
     rgb = (base + torch.randint(-6, 7, base.shape, dtype=torch.int32, device=dev, generator=g)).clamp_(0, 255).to(torch.uint8).reshape(-1)
     enc = api.JpegEncoder()
-    enc.encode_device(api.pixfmt_convert(12, 2, rgb, W, H), W, H, 2, quality=90)
+    codec = 12 if os.environ.get("JPEGDEC_AB_RGB") else 2  # RGB: three scans, as GPUJPEG stores RGB (config 3 of BASELINE.json on the receiving side)
+    enc.encode_device(rgb if codec == 12 else api.pixfmt_convert(12, 2, rgb, W, H), W, H, codec, quality=90)
     stream = enc.result()
     dec = api.JpegDecoder()
-    out = dec.decode(stream, 2, device=True)
+    out = dec.decode(stream, codec, device=True)
     for _ in range(4):
-        dec.decode(stream, 2, device=True, out=out, sync=False)
+        dec.decode(stream, codec, device=True, out=out, sync=False)
     torch.cuda.synchronize()
     n = 64
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(n):
-        dec.decode(stream, 2, device=True, out=out, sync=False)
+        dec.decode(stream, codec, device=True, out=out, sync=False)
     t_host = time.perf_counter() - t0
     e1.record()
     torch.cuda.synchronize()
@@ -37,7 +38,7 @@ def child():
     lat = []
     for _ in range(8):
         t0 = time.perf_counter()
-        dec.decode(stream, 2, device=True, out=out, sync=True)
+        dec.decode(stream, codec, device=True, out=out, sync=True)
         lat.append(time.perf_counter() - t0)
     print("stream %d B: pipelined wall %.3f ms/frame, host side %.3f ms/frame, device span %.3f ms/frame, synchronous latency %.3f ms (median of 8)"
           % (len(stream), wall / n * 1e3, t_host / n * 1e3, e0.elapsed_time(e1) / n, sorted(lat)[4] * 1e3), flush=True)
@@ -48,8 +49,12 @@ if __name__ == "__main__":
         child()
     else:
         out = os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out")
-        for name, env in (("host scan", {"UGB200_JPEG_MARKER_SCAN": "host"}), ("host scan, plain stores", {"UGB200_JPEG_MARKER_SCAN": "host", "UGB200_JPEG_STAGE": "plain"}),
-                          ("device scan (default for this stream)", {}), ("device scan, plain stores", {"UGB200_JPEG_STAGE": "plain"})):
+        variants = (("host scan", {"UGB200_JPEG_MARKER_SCAN": "host"}), ("host scan, plain stores", {"UGB200_JPEG_MARKER_SCAN": "host", "UGB200_JPEG_STAGE": "plain"}),
+                    ("device scan (default for this stream)", {}), ("device scan, plain stores", {"UGB200_JPEG_STAGE": "plain"}))
+        if len(sys.argv) > 1 and sys.argv[1] == "short":  # the two scans only, UYVY and RGB streams
+            variants = (("host scan", {"UGB200_JPEG_MARKER_SCAN": "host"}), ("device scan (default for this stream)", {}),
+                        ("RGB host scan", {"UGB200_JPEG_MARKER_SCAN": "host", "JPEGDEC_AB_RGB": "1"}), ("RGB device scan (default for this stream)", {"JPEGDEC_AB_RGB": "1"}))
+        for name, env in variants:
             print("==", name, flush=True)
             subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env={**os.environ, **env}, timeout=400)
             tag = name.replace(" ", "_").replace(",", "").replace("(", "").replace(")", "")

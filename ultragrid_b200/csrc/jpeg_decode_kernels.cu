@@ -67,12 +67,31 @@ struct dec_geom {
         dec_scan s[3];
 };
 
+// layout of the marker scan's `meta` words on the device (jpeg_marker_*_kernel)
+constexpr int kMetaTotal = 0, kMetaFirstOther = 1, kMetaOtherCount = 2, kMetaOther = 3, kMaxOther = 8, kMetaError = 11, kMetaBounds = 12, kMetaWords = 32;
+
 struct bit_reader {  // MSB-first, removes stuffed zero bytes, feeds zeros beyond `end`
         const uint8_t *p, *end;
         uint64_t acc;
         int nbits;
+        /// after the call at least 33 bits are valid (code of up to 16 bits + up to 15 value bits), zeros beyond `end`.
+        /// Fast path: four stream bytes at once when none of them is 0xFF (entropy-coded data holds one 0xFF in ~256 bytes): two aligned word
+        /// loads + a funnel shift instead of four byte loads with a stuffing test each.  The stream buffer is 16 bytes longer than the stream, so
+        /// the aligned loads of bytes p .. p + 3 never leave the allocation.
         __device__ __forceinline__ void refill()
         {
+                if (nbits > 32) {
+                        return;
+                }
+                if (p + 4 <= end) {
+                        const uint32_t *a = (const uint32_t *) ((size_t) p & ~(size_t) 3);
+                        const uint32_t le = __funnelshift_r(__ldg(a), __ldg(a + 1), 8 * (unsigned) ((size_t) p & 3));  // bytes p[0..3], p[0] lowest
+                        if (__vcmpeq4(le, 0xffffffffu) == 0) {
+                                acc |= (uint64_t) __byte_perm(le, 0, 0x0123) << (32 - nbits);
+                                nbits += 32, p += 4;
+                                return;
+                        }
+                }
                 while (nbits <= 56) {
                         uint32_t b = 0;
                         if (p < end) {
@@ -116,7 +135,7 @@ __device__ __forceinline__ int receive_extend(bit_reader &r, int n)  // F.2.2.1,
 
 __global__ void __launch_bounds__(128) jpeg_decode_huffman_kernel(const uint8_t *__restrict__ stream, const uint32_t *__restrict__ seg_begin,
                                                                   const uint32_t *__restrict__ seg_end, const dec_tables *__restrict__ tables,
-                                                                  dec_geom g, int16_t *__restrict__ coef)
+                                                                  dec_geom g, int16_t *__restrict__ coef, const uint32_t *__restrict__ dev_scans)
 {
         extern __shared__ uint8_t smem_raw[];
         dec_tables *t = (dec_tables *) smem_raw;
@@ -132,7 +151,10 @@ __global__ void __launch_bounds__(128) jpeg_decode_huffman_kernel(const uint8_t 
         if (sc >= g.nscans) {
                 return;
         }
-        const dec_scan &S = g.s[sc];
+        dec_scan S = g.s[sc];
+        if (dev_scans != nullptr && sc > 0) {  // multi-scan stream with the marker scan on the device: the SOS headers of the later scans were read there
+                S.td[0] = (int) dev_scans[kMetaBounds + 6 * sc + 4], S.ta[0] = (int) dev_scans[kMetaBounds + 6 * sc + 5];
+        }
         const int ls = s - S.seg0;
         const int m0 = g.ri ? ls * g.ri : 0, m1 = g.ri ? min(m0 + g.ri, S.nmcu) : S.nmcu;
         bit_reader r = { stream + seg_begin[s], stream + seg_end[s], 0, 0 };
@@ -167,7 +189,7 @@ __global__ void __launch_bounds__(128) jpeg_decode_huffman_kernel(const uint8_t 
                                                         continue;
                                                 }
                                                 i += run;
-                                                const int v = receive_extend(r, sz);  // refill guarantees >= 57 bits: 16 + 15 fit
+                                                const int v = receive_extend(r, sz);  // refill guarantees >= 33 bits: 16 + 15 fit
                                                 if (i < 64 && inside) {
                                                         blk[t->zz[i]] = (int16_t) v;
                                                 }
@@ -422,7 +444,7 @@ __global__ void __launch_bounds__(1024) jpeg_marker_scan_kernel(uint32_t *__rest
                 __syncthreads();
         }
         if (threadIdx.x == 0) {
-                meta[0] = s_carry, meta[1] = 0xffffffffu;
+                meta[kMetaTotal] = s_carry, meta[kMetaFirstOther] = 0xffffffffu, meta[kMetaOtherCount] = 0, meta[kMetaError] = 0;
         }
 }
 
@@ -455,7 +477,11 @@ __global__ void __launch_bounds__(kMarkThreads) jpeg_marker_write_kernel(const u
                 list[idx] = (uint32_t) p;
                 const int code = s[p + 1];
                 if (code < 0xD0 || code > 0xD7) {
-                        atomicMin(meta + 1, idx);
+                        atomicMin(meta + kMetaFirstOther, idx);
+                        const uint32_t k = atomicAdd(meta + kMetaOtherCount, 1u);  // the handful of markers that are not RSTn: SOS of later scans, EOI
+                        if (k < (uint32_t) kMaxOther) {
+                                meta[kMetaOther + k] = idx;
+                        }
                 }
                 ++idx;
         }
@@ -481,6 +507,92 @@ __global__ void __launch_bounds__(256) jpeg_marker_segments_kernel(const uint32_
                 b = e = term;
         }
         seg_begin[i] = b, seg_end[i] = e;
+}
+
+/// Streams with one scan PER COMPONENT (RGB as GPUJPEG stores it, gpujpeg.cpp:303-305): the SOS headers of scans 2 and 3 lie behind entropy-coded data, where
+/// the host does not look any more.  One thread walks the few candidates that are not RSTn: each scan's data runs from behind its SOS header to the next such
+/// marker; that marker must be the next scan's SOS (one component, the expected component id, baseline table selectors), the last scan must end in EOI or with
+/// the stream.  bounds[j] = { first list index, RSTn count, data begin, terminator position, Td, Ta }.  Anything else - tables redefined between the scans,
+/// another component order, more markers than expected - sets meta[kMetaError]: the host then repeats the frame with its own parser, which defines what
+/// happens to irregular and damaged streams.
+__global__ void jpeg_marker_bounds_kernel(const uint8_t *__restrict__ s, uint32_t len, const uint32_t *__restrict__ list, uint32_t *__restrict__ meta, uint32_t begin0,
+                                          int nscans, uint32_t comp_ids)
+{
+        if (threadIdx.x != 0 || blockIdx.x != 0) {
+                return;
+        }
+        const uint32_t total = meta[kMetaTotal];
+        uint32_t n = meta[kMetaOtherCount];
+        if (n > (uint32_t) kMaxOther) {
+                meta[kMetaError] = 1;
+                return;
+        }
+        uint32_t idx[kMaxOther];
+        for (uint32_t i = 0; i < n; ++i) {  // the atomics hand them out in any order
+                uint32_t v = meta[kMetaOther + i], j = i;
+                for (; j > 0 && idx[j - 1] > v; --j) {
+                        idx[j] = idx[j - 1];
+                }
+                idx[j] = v;
+        }
+        uint32_t begin = begin0, k = 0, err = 0;
+        for (int j = 0; j < nscans; ++j) {
+                uint32_t lo = 0, hi = total;  // first candidate at or behind `begin`
+                while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (list[mid] < begin) {
+                                lo = mid + 1;
+                        } else {
+                                hi = mid;
+                        }
+                }
+                while (k < n && idx[k] < lo) {
+                        ++k;
+                }
+                const uint32_t term_idx = k < n ? idx[k] : total, term = k < n ? list[term_idx] : len;
+                uint32_t *b = meta + kMetaBounds + 6 * j;
+                b[0] = lo, b[1] = term_idx - lo, b[2] = begin, b[3] = term;
+                if (j == nscans - 1) {
+                        if (k < n && s[term + 1] != 0xD9) {
+                                err = 1;  // something follows the last scan that is not EOI
+                        }
+                        break;
+                }
+                if (k >= n || term + 10 > len || s[term + 1] != 0xDA || s[term + 2] != 0 || s[term + 3] != 8 || s[term + 4] != 1 ||
+                    s[term + 5] != ((comp_ids >> (8 * (j + 1))) & 0xff) || (s[term + 6] >> 4) > 1 || (s[term + 6] & 15) > 1) {
+                        err = 1;
+                        break;
+                }
+                b[6 + 4] = s[term + 6] >> 4, b[6 + 5] = s[term + 6] & 15;  // Td, Ta of scan j + 1
+                begin = term + 10;
+                ++k;
+        }
+        meta[kMetaError] = err;
+}
+
+/// segment table of a multi-scan stream from the bounds above: the rules of jpeg_marker_segments_kernel per scan
+__global__ void __launch_bounds__(256) jpeg_marker_segments_multi_kernel(const uint32_t *__restrict__ list, const uint32_t *__restrict__ meta, int nscans, int seg1, int seg2,
+                                                                         int nseg, uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ seg_end)
+{
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= nseg) {
+                return;
+        }
+        const int j = nscans > 2 && i >= seg2 ? 2 : nscans > 1 && i >= seg1 ? 1 : 0;
+        const int first = j == 2 ? seg2 : j == 1 ? seg1 : 0, last = j == 0 ? (nscans > 1 ? seg1 : nseg) : j == 1 ? (nscans > 2 ? seg2 : nseg) : nseg;
+        const int li = i - first, n = last - first;
+        const uint32_t *b = meta + kMetaBounds + 6 * j;
+        const uint32_t lo = b[0], stop = b[1], begin0 = b[2], term = b[3];
+        const uint32_t pushed = min(stop, (uint32_t) (n - 1));
+        uint32_t bb, e;
+        if ((uint32_t) li < pushed) {
+                bb = li == 0 ? begin0 : list[lo + li - 1] + 2, e = list[lo + li];
+        } else if ((uint32_t) li == pushed) {
+                bb = stop == 0 ? begin0 : list[lo + stop - 1] + 2, e = term;
+        } else {
+                bb = e = term;
+        }
+        seg_begin[i] = bb, seg_end[i] = e;
 }
 
 }  // namespace ugb
@@ -557,10 +669,12 @@ struct ugb200_jpeg_decoder {
         scan_pool pool{ 7 };
         uint8_t *d_stream = nullptr, *planes = nullptr, *native = nullptr, *staging = nullptr;
         int16_t *coef = nullptr;
-        uint32_t *d_seg = nullptr, *d_marks = nullptr, *d_mark_cnt = nullptr;  // d_mark_cnt: per-piece counts / offsets, then meta[2]
+        uint32_t *d_seg = nullptr, *d_marks = nullptr, *d_mark_cnt = nullptr;  // d_mark_cnt: per-piece counts / offsets, then meta[kMetaWords]
         dec_tables *d_tables = nullptr;
         size_t stream_cap = 0, planes_cap = 0, native_cap = 0, staging_cap = 0, coef_cap = 0, seg_cap = 0, marks_cap = 0, mark_cnt_cap = 0;
-        int scan_mode = 0;      // 0: device scan for large single-scan streams, 1: always the host scan, 2: device scan whenever the stream has one scan
+        int scan_mode = 0;      // 0: device scan for large streams (one interleaved scan, or one scan per component), 1: always the host scan, 2: device scan at any size
+        bool host_once = false; // the device found a multi-scan stream irregular: this frame is repeated with the host parser
+        uint32_t *h_flag = nullptr;  // pinned: the device's verdict on a multi-scan stream
         size_t last_nseg = 0;   // segments of the last decode (ugb200_jpeg_decoder_last_segments)
         // pinned staging (the caller's stream buffer is pageable and freed right after the call), two slots: the host side of frame
         // i + 1 (scan, parse, staging copy) runs while the device still works on frame i
@@ -996,7 +1110,7 @@ UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t st
         }
         d->stream = (cudaStream_t) stream;
         if (cudaMalloc((void **) &d->d_tables, sizeof(dec_tables)) != cudaSuccess || cudaMallocHost((void **) &d->hs[0].tables, sizeof(dec_tables)) != cudaSuccess ||
-            cudaMallocHost((void **) &d->hs[1].tables, sizeof(dec_tables)) != cudaSuccess ||
+            cudaMallocHost((void **) &d->hs[1].tables, sizeof(dec_tables)) != cudaSuccess || cudaMallocHost((void **) &d->h_flag, 64) != cudaSuccess ||
             cudaEventCreateWithFlags(&d->hs[0].uploaded, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&d->hs[1].uploaded, cudaEventDisableTiming) != cudaSuccess) {
                 ugb200_jpeg_decoder_destroy(d);
@@ -1015,6 +1129,7 @@ UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *d)
         cudaStreamSynchronize(d->stream);
         cudaFree(d->d_stream), cudaFree(d->planes), cudaFree(d->native), cudaFree(d->staging), cudaFree(d->coef), cudaFree(d->d_seg), cudaFree(d->d_tables);
         cudaFree(d->d_marks), cudaFree(d->d_mark_cnt);
+        cudaFreeHost(d->h_flag);
         for (auto &h : d->hs) {
                 if (h.stream) {
                         cuda_wrapper_free_host(h.stream);
@@ -1057,6 +1172,7 @@ UGB_API int ugb200_jpeg_decoder_expect(ugb200_jpeg_decoder *d, int width, int he
 UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, size_t len, void *dst, int dst_is_device, long dst_pitch, int out_codec,
                                int rshift, int gshift, int bshift)
 {
+        const long dst_pitch_arg = dst_pitch;
         if (!d || !stream || !dst || len > 0xFFFFFFF0u) {
                 return -1;
         }
@@ -1114,11 +1230,30 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         // copies the stream to pinned memory; the restart markers are found on the device (jpeg_marker_*_kernel).  Everything else - several scans,
         // whose later SOS headers lie behind entropy-coded data - takes the host scan below.
         size_t scan_data = 0;
-        bool device_scan = false;
+        bool device_scan = false, multi = false;
         int rc = 0;
-        if (d->scan_mode != 1 && len <= (1u << 30) && (d->scan_mode == 2 || len >= (1u << 20))) {
+        const bool host_only = d->host_once;
+        d->host_once = false;
+        if (d->scan_mode != 1 && !host_only && len <= (1u << 30) && (d->scan_mode == 2 || len >= (1u << 20))) {
                 rc = parse_stream(stream, len, P, H.tables, false, nullptr, &scan_data);
                 device_scan = rc == 0 && P.g.nscans == 1 && P.g.s[0].ns == P.g.ncomp && scan_data > 0;
+                if (rc == 0 && !device_scan && P.g.nscans == 1 && P.g.s[0].ns == 1 && P.g.s[0].comp[0] == 0 && P.g.ncomp == 3 && scan_data > 0 && P.have_q[P.g.c[1].tq] &&
+                    P.have_q[P.g.c[2].tq]) {
+                        // one scan per component, in component order, is what the first SOS promises (GPUJPEG's RGB streams): scans 2 and 3 are laid out as the
+                        // host parser would lay them out, their table selectors come from the device, and the device checks the promise
+                        dec_geom &g = P.g;
+                        for (int j = 1; j < 3; ++j) {
+                                dec_scan &S = g.s[j];
+                                const dec_comp &c = g.c[j];
+                                S.ns = 1, S.comp[0] = j, S.td[0] = S.ta[0] = 0;
+                                S.mcux = ((g.w * c.h + g.hmax - 1) / g.hmax + 7) / 8;
+                                S.nmcu = S.mcux * (((g.h * c.v + g.vmax - 1) / g.vmax + 7) / 8);
+                                S.seg0 = g.s[j - 1].seg0 + g.s[j - 1].nseg;
+                                S.nseg = g.ri ? (S.nmcu + g.ri - 1) / g.ri : 1;
+                        }
+                        g.nscans = 3;
+                        device_scan = multi = true;
+                }
                 if (!device_scan) {  // start over on the host path (tables and geometry are rebuilt there)
                         P.g = dec_geom{}, P.adobe = -1, P.have_sof = false;
                         memset(P.have_q, 0, sizeof P.have_q);
@@ -1158,7 +1293,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         }
         lap("parse");
         const dec_geom &g = P.g;
-        const size_t nseg = device_scan ? (size_t) g.s[0].nseg : P.seg_begin.size();
+        const size_t nseg = multi ? (size_t) (g.s[2].seg0 + g.s[2].nseg) : device_scan ? (size_t) g.s[0].nseg : P.seg_begin.size();
         d->last_nseg = nseg;
         const long plane_bytes = (long) g.nblocks * 64;
         const int native = native_codec(P);
@@ -1172,19 +1307,39 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 return -2;
         }
         cudaStream_t s = d->stream;
+        const uint32_t *dev_scans = nullptr;
         cudaMemcpyAsync(d->d_stream, H.stream, len, cudaMemcpyHostToDevice, s);
         lap("+stream on the device");
         if (device_scan) {
                 const unsigned pieces = (unsigned) ((len + kMarkThreads * 16 - 1) / (kMarkThreads * 16));
-                if (!dgrow(d->d_marks, d->marks_cap, len / 2 + 2) || !dgrow(d->d_mark_cnt, d->mark_cnt_cap, (size_t) pieces + 2)) {
+                if (!dgrow(d->d_marks, d->marks_cap, len / 2 + 2) || !dgrow(d->d_mark_cnt, d->mark_cnt_cap, (size_t) pieces + kMetaWords)) {
                         return -2;
                 }
                 uint32_t *meta = d->d_mark_cnt + pieces;
+                dev_scans = multi ? meta : nullptr;
                 jpeg_marker_count_kernel<<<pieces, kMarkThreads, 0, s>>>(d->d_stream, len, scan_data, d->d_mark_cnt);
                 jpeg_marker_scan_kernel<<<1, 1024, 0, s>>>(d->d_mark_cnt, (int) pieces, meta);
                 jpeg_marker_write_kernel<<<pieces, kMarkThreads, 0, s>>>(d->d_stream, len, scan_data, d->d_mark_cnt, d->d_marks, meta);
-                jpeg_marker_segments_kernel<<<(unsigned) ((nseg + 255) / 256), 256, 0, s>>>(d->d_marks, meta, (uint32_t) scan_data, (uint32_t) len, (int) nseg, d->d_seg,
-                                                                                             d->d_seg + nseg);
+                if (multi) {
+                        jpeg_marker_bounds_kernel<<<1, 32, 0, s>>>(d->d_stream, (uint32_t) len, d->d_marks, meta, (uint32_t) scan_data, g.nscans,
+                                                                   (uint32_t) P.comp_id[0] | (uint32_t) P.comp_id[1] << 8 | (uint32_t) P.comp_id[2] << 16);
+                        jpeg_marker_segments_multi_kernel<<<(unsigned) ((nseg + 255) / 256), 256, 0, s>>>(d->d_marks, meta, g.nscans, g.s[1].seg0, g.s[2].seg0, (int) nseg, d->d_seg,
+                                                                                                           d->d_seg + nseg);
+                        // The verdict must be known before the Huffman kernel is queued (an irregular stream is decoded by the host parser's rules instead).
+                        // The wait covers the upload and four small kernels of THIS frame - and whatever the stream still holds of the frame before, which
+                        // the device works on anyway; the host side of the next frame still overlaps this frame's Huffman and IDCT kernels.
+                        if (cudaMemcpyAsync(d->h_flag, meta + kMetaError, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+                                return -2;
+                        }
+                        lap("verdict");
+                        if (*d->h_flag != 0) {
+                                d->host_once = true;
+                                return ugb200_jpeg_decode(d, stream, len, dst, dst_is_device, dst_pitch_arg, out_codec, rshift, gshift, bshift);
+                        }
+                } else {
+                        jpeg_marker_segments_kernel<<<(unsigned) ((nseg + 255) / 256), 256, 0, s>>>(d->d_marks, meta, (uint32_t) scan_data, (uint32_t) len, (int) nseg, d->d_seg,
+                                                                                                     d->d_seg + nseg);
+                }
         } else {
                 memcpy(H.seg, P.seg_begin.data(), nseg * 4), memcpy(H.seg + nseg, P.seg_end.data(), nseg * 4);
                 cudaMemcpyAsync(d->d_seg, H.seg, 2 * nseg * 4, cudaMemcpyHostToDevice, s);
@@ -1196,7 +1351,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         lap("+segments on the device");
         cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
         lap("+coefficients cleared");
-        jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d->d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef);
+        jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d->d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef, dev_scans);
         const bool direct = native == out_codec && dst_is_device;
         uint8_t *nat = direct ? (uint8_t *) dst : d->native;
         const bool fused_uyvy = native == UGB_UYVY && g.c[0].v == 1;  // 4:2:2: IDCT and packing in one kernel, no component planes
