@@ -79,11 +79,3 @@ def test_gpu_encode_decode_roundtrip_8k(orc):
         back = api.dxt_to_rgb(api.uyvy_to_dxt(uyvy, w, h, dxt_type=t), w, h, t).cpu().numpy()
         assert psnr(back, rgb) > floor
 
-
-def test_alpha_palette_division_identity(orc):
-    """the decode kernel divides by 7 and 5 with a reciprocal multiplication + one FMA correction (dxt_decode_kernels.cu div_small): equal to the IEEE
-    division for every value the alpha palette can take (oracle/dxt_div_identity.c)"""
-    import ctypes
-    orc.orc_dxt_div_identity.argtypes, orc.orc_dxt_div_identity.restype = [ctypes.POINTER(ctypes.c_long)], ctypes.c_long
-    n = ctypes.c_long()
-    assert orc.orc_dxt_div_identity(ctypes.byref(n)) == 0 and n.value == 327424

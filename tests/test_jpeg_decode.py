@@ -379,8 +379,8 @@ def test_gpu_device_marker_scan_of_multi_scan_streams(orc, monkeypatch, w, h, q,
         a[rst[k] + 1] = 0xD9
     elif damage == "swap-tables":       # legal: the second scan codes with the luminance tables selectors (the data was coded with the others: garbage, equally on both paths)
         a[sos[1] + 6] = 0x00
-    elif damage == "other-component":   # legal: the second scan names the third component
-        a[sos[1] + 5] = a[sos[2] + 5]
+    elif damage == "other-component":   # legal: the second scan carries the third component and the third scan the second
+        a[sos[1] + 5], a[sos[2] + 5] = a[sos[2] + 5], a[sos[1] + 5]
     elif damage == "dht-between":       # legal: a (repeated) DHT segment between the scans
         dht = int(np.flatnonzero((a[:-1] == 0xFF) & (a[1:] == 0xC4))[0])
         L = int(a[dht + 2]) << 8 | int(a[dht + 3])

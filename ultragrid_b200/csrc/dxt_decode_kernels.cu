@@ -10,7 +10,6 @@
 // (DADD/DMUL run at half the FP32 rate on this part; the double -> int conversion is the slow instruction).
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include <mutex>
 
@@ -22,23 +21,6 @@ __device__ __forceinline__ uint32_t to_byte(double s)  // dxt62tga.c:14-21
 {
         const int is = __double2int_rz(__dadd_rn(s, 0.5));
         return (uint32_t) min(max(is, 0), 255);
-}
-/// to_byte() on the pixel path without the slow double -> int conversion (16 lanes/clk/SM on this part, against 64 for DADD): t = RN(s + 0.5) as in the
-/// reference, then t + 1.5 * 2^52 rounded DOWN leaves floor(t) in the low word (|t| < 2^51).  floor = the reference's truncation for t >= 0; below
-/// zero both end at 0 after the clamp.
-__device__ __forceinline__ uint32_t to_byte_fast(double s)
-{
-        const int is = __double2loint(__dadd_rd(__dadd_rn(s, 0.5), 6755399441055744.0));
-        return (uint32_t) min(max(is, 0), 255);
-}
-/// x / 7.0 and x / 5.0 (the alpha palette, dxt62tga.c:44-58) as a multiplication by the rounded reciprocal plus one FMA correction step:
-/// q = RN(x * r), q' = fma(fma(-d, q, x), r, q).  For the 327 424 values x that the palette can take (every endpoint pair, every entry) q' is the
-/// correctly rounded quotient - compared one by one with the division on the CPU (oracle/dxt_div_identity.c, tests/test_oracle_pinning.py);
-/// 3 FP64 instructions instead of the ~30 of the division routine.
-__device__ __forceinline__ double div_small(double x, double d, double r)
-{
-        const double q = __dmul_rn(x, r);
-        return __fma_rn(__fma_rn(-d, q, x), r, q);
 }
 __device__ __forceinline__ double third(double a, double b)  // (2.0 * a + 1.0 * b) / 3.0, dxt62tga.c:76-81
 {
@@ -130,7 +112,7 @@ __global__ void dxt1_tables_kernel()
         }
 }
 
-template <int BGR, int VAR>  // VAR (experiment, UGB200_DXT5DEC): bit 0 = to_byte without F2I, bit 1 = palette divisions by reciprocal + FMA correction
+template <int BGR>
 __global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__restrict__ in, uint8_t *__restrict__ out, int bw, int bh, long pitch, bool aligned)
 {
         // per-thread palettes live in shared memory ([entry][thread]: conflict-free, dynamically indexable without local memory)
@@ -147,14 +129,12 @@ __global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__re
         if (a0 > a1) {
 #pragma unroll
                 for (int k = 2; k < 8; ++k) {
-                        const double x = __dadd_rn(__dmul_rn((double) (8 - k), a0), __dmul_rn((double) (k - 1), a1));
-                        s_ap[k][tid] = (VAR & 2) ? div_small(x, 7.0, 1.0 / 7.0) : __ddiv_rn(x, 7.0);
+                        s_ap[k][tid] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (8 - k), a0), __dmul_rn((double) (k - 1), a1)), 7.0);
                 }
         } else {
 #pragma unroll
                 for (int k = 2; k < 6; ++k) {
-                        const double x = __dadd_rn(__dmul_rn((double) (6 - k), a0), __dmul_rn((double) (k - 1), a1));
-                        s_ap[k][tid] = (VAR & 2) ? div_small(x, 5.0, 1.0 / 5.0) : __ddiv_rn(x, 5.0);
+                        s_ap[k][tid] = __ddiv_rn(__dadd_rn(__dmul_rn((double) (6 - k), a0), __dmul_rn((double) (k - 1), a1)), 5.0);
                 }
                 s_ap[6][tid] = 0.0, s_ap[7][tid] = 1.0;
         }
@@ -181,8 +161,7 @@ __global__ void __launch_bounds__(128) dxt5ycocg_decode_kernel(const uint4 *__re
                         alpha_code >>= 3, rgb_code >>= 2;
                         const double co = s_co[k][tid], cg = s_cg[k][tid];
                         const double R = __dadd_rn(__dadd_rn(a, co), -cg), G = __dadd_rn(a, cg), B = __dadd_rn(__dadd_rn(a, -co), -cg);
-                        px[x] = (VAR & 1) ? pack_px<BGR>(to_byte_fast(__dmul_rn(R, 255.0)), to_byte_fast(__dmul_rn(G, 255.0)), to_byte_fast(__dmul_rn(B, 255.0)))
-                                          : pack_px<BGR>(to_byte(__dmul_rn(R, 255.0)), to_byte(__dmul_rn(G, 255.0)), to_byte(__dmul_rn(B, 255.0)));
+                        px[x] = pack_px<BGR>(to_byte(__dmul_rn(R, 255.0)), to_byte(__dmul_rn(G, 255.0)), to_byte(__dmul_rn(B, 255.0)));
                 }
                 store_row(o + y * pitch, px[0], px[1], px[2], px[3], aligned);
         }
@@ -274,28 +253,4 @@ static int ensure_dxt1_tables(cudaStream_t stream)
 #define UGB_DECODE_PRE_dxt1_decode_kernel(stream) if (ensure_dxt1_tables((cudaStream_t) (stream)) != 0) return -2;
 #define UGB_DECODE_PRE_dxt5ycocg_decode_kernel(stream) if (ensure_dxt1_tables((cudaStream_t) (stream)) != 0) return -2;
 UGB_DECODE(ugb200_dxt1_to_rgb, dxt1_decode_kernel, uint2)
-extern "C" UGB_API int ugb200_dxt5ycocg_to_rgb(const void *src, void *out, int w, int h, long out_pitch, int bgr, cuda_wrapper_stream_t stream)
-{
-        if (src == nullptr || out == nullptr || w <= 0 || h <= 0 || (w & 3) || (h & 3) || (15 & (size_t) src)) {
-                return -1;
-        }
-        if (out_pitch == 0) {
-                out_pitch = (long) w * 3;
-        }
-        if (ensure_dxt1_tables((cudaStream_t) stream) != 0) {
-                return -2;
-        }
-        static const int var = getenv("UGB200_DXT5DEC") ? atoi(getenv("UGB200_DXT5DEC")) & 3 : 2;
-        dim3 grid((w / 4 + 127) / 128, h / 4);
-        const bool aligned = !(3 & (size_t) out) && !(out_pitch & 3);
-        const uint4 *s4 = (const uint4 *) src;
-        cudaStream_t st = (cudaStream_t) stream;
-#define UGB_L(B, V) dxt5ycocg_decode_kernel<B, V><<<grid, 128, 0, st>>>(s4, (uint8_t *) out, w / 4, h / 4, out_pitch, aligned)
-        if (bgr) {
-                var == 0 ? UGB_L(1, 0) : var == 1 ? UGB_L(1, 1) : var == 2 ? UGB_L(1, 2) : UGB_L(1, 3);
-        } else {
-                var == 0 ? UGB_L(0, 0) : var == 1 ? UGB_L(0, 1) : var == 2 ? UGB_L(0, 2) : UGB_L(0, 3);
-        }
-#undef UGB_L
-        return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
+UGB_DECODE(ugb200_dxt5ycocg_to_rgb, dxt5ycocg_decode_kernel, uint4)

@@ -667,11 +667,12 @@ private:
 struct ugb200_jpeg_decoder {
         cudaStream_t stream = nullptr;
         scan_pool pool{ 7 };
-        uint8_t *d_stream = nullptr, *planes = nullptr, *native = nullptr, *staging = nullptr;
+        cudaStream_t copy = nullptr;  // the stream upload of frame n + 1 runs here, under the kernels of frame n (its device copy is double-buffered with the host slots)
+        uint8_t *planes = nullptr, *native = nullptr, *staging = nullptr;
         int16_t *coef = nullptr;
         uint32_t *d_seg = nullptr, *d_marks = nullptr, *d_mark_cnt = nullptr;  // d_mark_cnt: per-piece counts / offsets, then meta[kMetaWords]
         dec_tables *d_tables = nullptr;
-        size_t stream_cap = 0, planes_cap = 0, native_cap = 0, staging_cap = 0, coef_cap = 0, seg_cap = 0, marks_cap = 0, mark_cnt_cap = 0;
+        size_t planes_cap = 0, native_cap = 0, staging_cap = 0, coef_cap = 0, seg_cap = 0, marks_cap = 0, mark_cnt_cap = 0;
         int scan_mode = 0;      // 0: device scan for large streams (one interleaved scan, or one scan per component), 1: always the host scan, 2: device scan at any size
         bool host_once = false; // the device found a multi-scan stream irregular: this frame is repeated with the host parser
         uint32_t *h_flag = nullptr;  // pinned: the device's verdict on a multi-scan stream
@@ -682,9 +683,12 @@ struct ugb200_jpeg_decoder {
                 uint8_t *stream = nullptr;
                 uint32_t *seg = nullptr;
                 dec_tables *tables = nullptr;
-                size_t stream_cap = 0, seg_cap = 0;
-                cudaEvent_t uploaded = nullptr;
-                bool pending = false;
+                uint8_t *d_stream = nullptr;  // this slot's copy of the stream on the device (16 bytes longer than the stream)
+                size_t stream_cap = 0, seg_cap = 0, d_stream_cap = 0;
+                cudaEvent_t uploaded = nullptr;   // segment table + Huffman / quantisation tables left the pinned slot (decoder's stream)
+                cudaEvent_t stream_up = nullptr;  // the stream left the pinned slot and is on the device (copy stream)
+                cudaEvent_t consumed = nullptr;   // the last kernel that reads d_stream is done (decoder's stream)
+                bool pending = false, consumed_pending = false;
         } hs[2];
         unsigned frame_no = 0;
         int expect_w = 0, expect_h = 0;  // ugb200_jpeg_decoder_expect: the destination was sized for these; 0 = unchecked
@@ -1112,7 +1116,12 @@ UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t st
         if (cudaMalloc((void **) &d->d_tables, sizeof(dec_tables)) != cudaSuccess || cudaMallocHost((void **) &d->hs[0].tables, sizeof(dec_tables)) != cudaSuccess ||
             cudaMallocHost((void **) &d->hs[1].tables, sizeof(dec_tables)) != cudaSuccess || cudaMallocHost((void **) &d->h_flag, 64) != cudaSuccess ||
             cudaEventCreateWithFlags(&d->hs[0].uploaded, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&d->hs[1].uploaded, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&d->hs[1].uploaded, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d->hs[0].stream_up, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d->hs[1].stream_up, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d->hs[0].consumed, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d->hs[1].consumed, cudaEventDisableTiming) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking) != cudaSuccess) {
                 ugb200_jpeg_decoder_destroy(d);
                 return nullptr;
         }
@@ -1127,7 +1136,11 @@ UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *d)
                 return;
         }
         cudaStreamSynchronize(d->stream);
-        cudaFree(d->d_stream), cudaFree(d->planes), cudaFree(d->native), cudaFree(d->staging), cudaFree(d->coef), cudaFree(d->d_seg), cudaFree(d->d_tables);
+        if (d->copy) {
+                cudaStreamSynchronize(d->copy);
+                cudaStreamDestroy(d->copy);
+        }
+        cudaFree(d->planes), cudaFree(d->native), cudaFree(d->staging), cudaFree(d->coef), cudaFree(d->d_seg), cudaFree(d->d_tables);
         cudaFree(d->d_marks), cudaFree(d->d_mark_cnt);
         cudaFreeHost(d->h_flag);
         for (auto &h : d->hs) {
@@ -1135,6 +1148,12 @@ UGB_API void ugb200_jpeg_decoder_destroy(ugb200_jpeg_decoder *d)
                         cuda_wrapper_free_host(h.stream);
                 }
                 cudaFreeHost(h.seg), cudaFreeHost(h.tables);
+                cudaFree(h.d_stream);
+                for (cudaEvent_t e : { h.stream_up, h.consumed }) {
+                        if (e) {
+                                cudaEventDestroy(e);
+                        }
+                }
                 if (h.uploaded) {
                         cudaEventDestroy(h.uploaded);
                 }
@@ -1205,6 +1224,7 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         ugb200_jpeg_decoder::host_slot &H = d->hs[d->frame_no++ & 1];
         if (H.pending) {
                 cudaEventSynchronize(H.uploaded);  // the uploads of the frame before last left this slot long ago
+                cudaEventSynchronize(H.stream_up);
                 H.pending = false;
         }
         lap("slot free");
@@ -1302,13 +1322,21 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         if (dst_pitch == 0) {
                 dst_pitch = opitch;
         }
-        if (!dgrow(d->d_stream, d->stream_cap, len + 16) || !dgrow(d->planes, d->planes_cap, (size_t) plane_bytes) || !dgrow(d->coef, d->coef_cap, (size_t) g.nblocks * 64) ||
+        if (!dgrow(H.d_stream, H.d_stream_cap, len + 16) || !dgrow(d->planes, d->planes_cap, (size_t) plane_bytes) || !dgrow(d->coef, d->coef_cap, (size_t) g.nblocks * 64) ||
             !dgrow(d->d_seg, d->seg_cap, 2 * nseg) || !dgrow(d->native, d->native_cap, (size_t) npitch * g.h + 64) || !hgrow(H.seg, H.seg_cap, 2 * nseg)) {
                 return -2;
         }
         cudaStream_t s = d->stream;
         const uint32_t *dev_scans = nullptr;
-        cudaMemcpyAsync(d->d_stream, H.stream, len, cudaMemcpyHostToDevice, s);
+        // the upload goes over the copy stream: it may start as soon as the kernels of the frame before last have read this slot's device copy, i.e. it
+        // runs under the kernels of the previous frame; this frame's kernels wait for it
+        uint8_t *const d_stream = H.d_stream;
+        if (H.consumed_pending) {
+                cudaStreamWaitEvent(d->copy, H.consumed, 0);
+        }
+        cudaMemcpyAsync(d_stream, H.stream, len, cudaMemcpyHostToDevice, d->copy);
+        cudaEventRecord(H.stream_up, d->copy);
+        cudaStreamWaitEvent(s, H.stream_up, 0);
         lap("+stream on the device");
         if (device_scan) {
                 const unsigned pieces = (unsigned) ((len + kMarkThreads * 16 - 1) / (kMarkThreads * 16));
@@ -1317,11 +1345,11 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
                 }
                 uint32_t *meta = d->d_mark_cnt + pieces;
                 dev_scans = multi ? meta : nullptr;
-                jpeg_marker_count_kernel<<<pieces, kMarkThreads, 0, s>>>(d->d_stream, len, scan_data, d->d_mark_cnt);
+                jpeg_marker_count_kernel<<<pieces, kMarkThreads, 0, s>>>(d_stream, len, scan_data, d->d_mark_cnt);
                 jpeg_marker_scan_kernel<<<1, 1024, 0, s>>>(d->d_mark_cnt, (int) pieces, meta);
-                jpeg_marker_write_kernel<<<pieces, kMarkThreads, 0, s>>>(d->d_stream, len, scan_data, d->d_mark_cnt, d->d_marks, meta);
+                jpeg_marker_write_kernel<<<pieces, kMarkThreads, 0, s>>>(d_stream, len, scan_data, d->d_mark_cnt, d->d_marks, meta);
                 if (multi) {
-                        jpeg_marker_bounds_kernel<<<1, 32, 0, s>>>(d->d_stream, (uint32_t) len, d->d_marks, meta, (uint32_t) scan_data, g.nscans,
+                        jpeg_marker_bounds_kernel<<<1, 32, 0, s>>>(d_stream, (uint32_t) len, d->d_marks, meta, (uint32_t) scan_data, g.nscans,
                                                                    (uint32_t) P.comp_id[0] | (uint32_t) P.comp_id[1] << 8 | (uint32_t) P.comp_id[2] << 16);
                         jpeg_marker_segments_multi_kernel<<<(unsigned) ((nseg + 255) / 256), 256, 0, s>>>(d->d_marks, meta, g.nscans, g.s[1].seg0, g.s[2].seg0, (int) nseg, d->d_seg,
                                                                                                            d->d_seg + nseg);
@@ -1351,7 +1379,9 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         lap("+segments on the device");
         cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
         lap("+coefficients cleared");
-        jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d->d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef, dev_scans);
+        jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef, dev_scans);
+        cudaEventRecord(H.consumed, s);  // nothing behind this kernel reads the stream
+        H.consumed_pending = true;
         const bool direct = native == out_codec && dst_is_device;
         uint8_t *nat = direct ? (uint8_t *) dst : d->native;
         const bool fused_uyvy = native == UGB_UYVY && g.c[0].v == 1;  // 4:2:2: IDCT and packing in one kernel, no component planes
