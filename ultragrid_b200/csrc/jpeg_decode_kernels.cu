@@ -74,21 +74,29 @@ struct bit_reader {  // MSB-first, removes stuffed zero bytes, feeds zeros beyon
         const uint8_t *p, *end;
         uint64_t acc;
         int nbits;
+        // the two aligned words that hold bytes p .. p + 3, fetched one refill AHEAD of their use: the thread's next four bytes are already in registers when
+        // it needs them (ncu of the byte-wise reader: `long_scoreboard` on top of the stall list - every refill waited for its own loads with ~13 warps per SM)
+        const uint32_t *wa;
+        uint32_t w0, w1;
+        /// the stream buffer is 16 bytes longer than the stream: the aligned loads around any p <= end stay inside the allocation
+        __device__ __forceinline__ void prime()
+        {
+                wa = (const uint32_t *) ((size_t) p & ~(size_t) 3);
+                w0 = __ldg(wa), w1 = __ldg(wa + 1);
+        }
         /// after the call at least 33 bits are valid (code of up to 16 bits + up to 15 value bits), zeros beyond `end`.
-        /// Fast path: four stream bytes at once when none of them is 0xFF (entropy-coded data holds one 0xFF in ~256 bytes): two aligned word
-        /// loads + a funnel shift instead of four byte loads with a stuffing test each.  The stream buffer is 16 bytes longer than the stream, so
-        /// the aligned loads of bytes p .. p + 3 never leave the allocation.
+        /// Fast path: four stream bytes at once when none of them is 0xFF (entropy-coded data holds one 0xFF in ~256 bytes).
         __device__ __forceinline__ void refill()
         {
                 if (nbits > 32) {
                         return;
                 }
                 if (p + 4 <= end) {
-                        const uint32_t *a = (const uint32_t *) ((size_t) p & ~(size_t) 3);
-                        const uint32_t le = __funnelshift_r(__ldg(a), __ldg(a + 1), 8 * (unsigned) ((size_t) p & 3));  // bytes p[0..3], p[0] lowest
+                        const uint32_t le = __funnelshift_r(w0, w1, 8 * (unsigned) ((size_t) p & 3));  // bytes p[0..3], p[0] lowest
                         if (__vcmpeq4(le, 0xffffffffu) == 0) {
                                 acc |= (uint64_t) __byte_perm(le, 0, 0x0123) << (32 - nbits);
                                 nbits += 32, p += 4;
+                                ++wa, w0 = w1, w1 = __ldg(wa + 1);  // for the next refill
                                 return;
                         }
                 }
@@ -103,6 +111,7 @@ struct bit_reader {  // MSB-first, removes stuffed zero bytes, feeds zeros beyon
                         acc |= (uint64_t) b << (56 - nbits);
                         nbits += 8;
                 }
+                prime();
         }
         __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t) (acc >> (64 - n)); }
         __device__ __forceinline__ void skip(int n) { acc <<= n, nbits -= n; }
@@ -157,7 +166,8 @@ __global__ void __launch_bounds__(128) jpeg_decode_huffman_kernel(const uint8_t 
         }
         const int ls = s - S.seg0;
         const int m0 = g.ri ? ls * g.ri : 0, m1 = g.ri ? min(m0 + g.ri, S.nmcu) : S.nmcu;
-        bit_reader r = { stream + seg_begin[s], stream + seg_end[s], 0, 0 };
+        bit_reader r = { stream + seg_begin[s], stream + seg_end[s], 0, 0, nullptr, 0, 0 };
+        r.prime();
         int pred[3] = { 0, 0, 0 };
         for (int m = m0; m < m1; ++m) {
                 const int mx = m % S.mcux, my = m / S.mcux;
