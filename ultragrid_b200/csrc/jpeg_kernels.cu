@@ -562,7 +562,10 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         uint32_t *s_coef = smem;                // [32][128] zig-zag coefficients, two int16 per word
         uint32_t *s_bits = s_coef + 32 * 128;   // [cap][128]   (BLOCKS_ONLY: not allocated - the bit strings live in gbits)
         uint32_t *s_seg = s_bits + cap * 128;   // [segments of the CTA][bps * cap]
-        __shared__ uint32_t s_dctab[2][16], s_ac[2][256], s_len[128], s_warp[4], s_max[4];
+        __shared__ __align__(16) uint32_t s_huff[32 + 512];  // jpeg_hufftab as it lies in global memory: dc[2][16], ac[2][256]
+        uint32_t(*const s_dctab)[16] = (uint32_t(*)[16]) s_huff;
+        uint32_t(*const s_ac)[256] = (uint32_t(*)[256]) (s_huff + 32);
+        __shared__ uint32_t s_len[128], s_warp[4], s_max[4];
         __shared__ int s_dc[128];
         __shared__ uint32_t s_ticket, s_tot, s_base;
         __shared__ __align__(8) unsigned long long s_bar;  // mbarrier of the input tile
@@ -581,11 +584,47 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 // instead of three passes over the frame)
                 cta_x = blockIdx.x / 3, cta_y = blockIdx.x - 3 * cta_x;
         }
-        for (int i = tid; i < 32; i += 128) {
-                s_dctab[i >> 4][i & 15] = __ldg(huff + i);
+        // UYVY: the tile copy is issued before anything else - the copy engine moves the 8 KB while the CTA fetches its Huffman tables and works out its
+        // block mapping (round 2, state i: the tables used to be fetched first and the copy waited behind their barrier: two global latencies in a row)
+        bool early_tile = false;
+        if (FMT == FMT_UYVY_422) {
+                const int fm = cta_x * 32, mx0 = fm % g.bw, my0 = fm / g.bw;
+                early_tile = vec_ok && cap >= 8 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h;
+                if (early_tile && tid == 0) {
+                        uint8_t *tile0 = (uint8_t *) (BLOCKS_ONLY ? s_coef : s_bits);
+                        const uint8_t *gsrc = src + (long) (my0 * 8) * pitch + (long) mx0 * 32;
+                        mbar_init(&s_bar, 1);
+                        mbar_expect_tx(&s_bar, 8 * 1024 + (uint32_t) sizeof s_huff);
+                        for (int r = 0; r < 8; ++r) {
+                                bulk_g2s((void *) (tile0 + r * 1024), gsrc + (long) r * pitch, 1024, &s_bar);
+                        }
+                        bulk_g2s((void *) s_huff, huff, (uint32_t) sizeof s_huff, &s_bar);  // the Huffman tables ride the same barrier (cudaMalloc'ed: 256-byte aligned)
+                }
         }
-        for (int i = tid; i < 512; i += 128) {
-                s_ac[i >> 8][i & 255] = __ldg(huff + 32 + i);
+        if (FMT == FMT_RGB_444) {  // the same for the packed-RGB tile (8 rows x 3072 bytes, at most two runs per row) when whole runs can go through the copy engine
+                const int fm = cta_x * 128;
+                early_tile = vec_ok && cap >= 8 && fm + 128 <= g.mcu_per_scan && (g.w & 7) == 0 && (g.h & 7) == 0 && g.bw >= 128 && !(g.bw & 1) && !(15 & (size_t) src) &&
+                             !(pitch & 15);
+                if (early_tile && tid == 0) {
+                        uint8_t *tile0 = (uint8_t *) s_coef;
+                        const int bx0 = fm % g.bw, by0 = fm / g.bw;
+                        const int in_row = min(128, g.bw - bx0);  // blocks of the tile that lie in block row by0; the rest starts block row by0 + 1
+                        mbar_init(&s_bar, 1);
+                        mbar_expect_tx(&s_bar, 8 * 3072 + (uint32_t) sizeof s_huff);
+                        const uint8_t *ga = src + (long) (by0 * 8) * pitch + (long) bx0 * 24, *gb = src + (long) (by0 * 8 + 8) * pitch;
+                        for (int r = 0; r < 8; ++r, ga += pitch, gb += pitch) {
+                                bulk_g2s((void *) (tile0 + r * 3072), ga, (uint32_t) in_row * 24, &s_bar);
+                                if (in_row < 128) {
+                                        bulk_g2s((void *) (tile0 + r * 3072 + in_row * 24), gb, (uint32_t) (128 - in_row) * 24, &s_bar);
+                                }
+                        }
+                        bulk_g2s((void *) s_huff, huff, (uint32_t) sizeof s_huff, &s_bar);
+                }
+        }
+        if (!early_tile) {
+                for (int i = tid; i < 32 + 512; i += 128) {
+                        s_huff[i] = __ldg(huff + i);
+                }
         }
         // ---- which block is mine -------------------------------------------------------------------------------------------
         const int bps = g.ri * g.blocks_per_mcu;  // blocks per restart segment: 4, 8, 16 or 32 (checked by the host)
@@ -623,24 +662,9 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 // 16-byte aligned rows and an even number of blocks per row: the (at most two) runs of a tile row start and end on 48-byte
                 // boundaries, so whole runs go through the copy engine
                 // (a frame less than 128 blocks wide wraps more than once inside a tile: that goes the cp.async way below)
-                const bool bulk = staged && g.bw >= 128 && !(g.bw & 1) && !(15 & (size_t) src) && !(pitch & 15);
+                const bool bulk = early_tile;  // issued at the top of the kernel
                 if (bulk) {
-                        if (tid == 0) {
-                                mbar_init(&s_bar, 1);
-                        }
-                        __syncthreads();
-                        if (tid == 0) {
-                                const int bx0 = first_mcu % g.bw, by0 = first_mcu / g.bw;
-                                const int in_row = min(128, g.bw - bx0);  // blocks of the tile that lie in block row by0; the rest starts block row by0 + 1
-                                mbar_expect_tx(&s_bar, 8 * 3072);
-                                const uint8_t *ga = src + (long) (by0 * 8) * pitch + (long) bx0 * 24, *gb = src + (long) (by0 * 8 + 8) * pitch;
-                                for (int r = 0; r < 8; ++r, ga += pitch, gb += pitch) {
-                                        bulk_g2s((void *) (tile + r * 3072), ga, (uint32_t) in_row * 24, &s_bar);
-                                        if (in_row < 128) {
-                                                bulk_g2s((void *) (tile + r * 3072 + in_row * 24), gb, (uint32_t) (128 - in_row) * 24, &s_bar);
-                                        }
-                                }
-                        }
+                        __syncthreads();  // the mbarrier's initialisation (thread 0) is visible to the waiting threads
                         mbar_wait(&s_bar, 0);
                 } else if (staged) {
 #pragma unroll
@@ -662,19 +686,10 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         }
         if (FMT == FMT_UYVY_422) {
                 const int mx0 = first_mcu % g.bw, my0 = first_mcu / g.bw;
-                staged = vec_ok && cap >= 8 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h;
-                if (staged) {  // vec_ok: 16-byte aligned frame and pitch - one bulk copy per 1024-byte tile row
-                        const uint8_t *gsrc = src + (long) (my0 * 8) * pitch + (long) mx0 * 32;
-                        if (tid == 0) {
-                                mbar_init(&s_bar, 1);
-                        }
-                        __syncthreads();
-                        if (tid == 0) {
-                                mbar_expect_tx(&s_bar, 8 * 1024);
-                                for (int r = 0; r < 8; ++r) {
-                                        bulk_g2s((void *) (tile + r * 1024), gsrc + (long) r * pitch, 1024, &s_bar);
-                                }
-                        }
+                staged = early_tile;
+                (void) mx0, (void) my0;
+                if (staged) {  // vec_ok: 16-byte aligned frame and pitch - one bulk copy per 1024-byte tile row, issued at the top of the kernel
+                        __syncthreads();  // the mbarrier's initialisation (thread 0) is visible to the waiting threads
                         mbar_wait(&s_bar, 0);
                 }
         }
