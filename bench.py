@@ -796,24 +796,27 @@ def extra_decode(ctx):
         res[name] = {"us": secs * 1e6, "fps": 1 / secs, "GBps": (nb + w * h * 3) / secs / 1e9, "frac_of_peak": (nb + w * h * 3) / secs / 1e9 / ctx.peak}
         del blocks
     orc = util.oracle()
-    uyvy, _ = _natural_uyvy_cpu(orc)
-    enc = api.JpegEncoder()
-    enc.encode_device(torch.from_numpy(uyvy).cuda(), w, h, UYVY, quality=90)
-    stream = enc.result()
-    enc.close()
-    dec = api.JpegDecoder()
-    out = dec.decode(stream, UYVY, device=True)
-    for _ in range(3):  # both host slots have their pinned staging, the scratch vectors their capacity
-        dec.decode(stream, UYVY, device=True, out=out, sync=False)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    n = 16
-    for _ in range(n):
-        dec.decode(stream, UYVY, device=True, out=out, sync=False)
-    torch.cuda.synchronize()
-    res["jpeg_decode_natural_8k"] = {"ms_wall_per_frame": (time.perf_counter() - t0) / n * 1e3, "stream_bytes": len(stream),
-                                     "output": "UYVY on the device; host stream in"}
-    dec.close()
+    uyvy, rgb = _natural_uyvy_cpu(orc)
+    # UYVY: one interleaved scan (what UltraGrid sends for UYVY input); RGB: one scan per component, as GPUJPEG stores RGB (config 3 on the receiving side)
+    for name, codec, frame in (("jpeg_decode_natural_8k", UYVY, uyvy), ("jpeg_decode_rgb_natural_8k", RGB, rgb)):
+        enc = api.JpegEncoder()
+        enc.encode_device(torch.from_numpy(frame).cuda(), w, h, codec, quality=90)
+        stream = enc.result()
+        enc.close()
+        dec = api.JpegDecoder()
+        out = dec.decode(stream, codec, device=True)
+        for _ in range(3):  # both host slots have their pinned staging, the scratch vectors their capacity
+            dec.decode(stream, codec, device=True, out=out, sync=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 16
+        for _ in range(n):
+            dec.decode(stream, codec, device=True, out=out, sync=False)
+        torch.cuda.synchronize()
+        res[name] = {"ms_wall_per_frame": (time.perf_counter() - t0) / n * 1e3, "stream_bytes": len(stream),
+                     "output": ("UYVY" if codec == UYVY else "RGB") + " on the device; host stream in (marker scan on the device, upload on a copy stream)"}
+        dec.close()
+        del out
     return res
 
 
