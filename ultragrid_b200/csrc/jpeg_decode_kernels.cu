@@ -142,12 +142,20 @@ __device__ __forceinline__ int receive_extend(bit_reader &r, int n)  // F.2.2.1,
         return v < (1 << (n - 1)) ? v - (1 << n) + 1 : v;
 }
 
-__global__ void __launch_bounds__(128) jpeg_decode_huffman_kernel(const uint8_t *__restrict__ stream, const uint32_t *__restrict__ seg_begin,
+/// FULL: every block of the coefficient array is decoded by exactly one thread (the host checks: every component in a scan, the scans' MCU grids equal to the
+/// padded planes) - the thread then builds its block in shared memory ([word][thread]: conflict-free, dynamically indexable) and writes all 128 bytes of it,
+/// so the array needs no clearing beforehand (133 MB at 8K) and the scattered 2-byte stores become whole-line stores.  !FULL: sparse stores into a cleared array.
+/// kHuffThreads: an 8K UYVY frame has 64 800 restart segments = threads, all resident at once; with 128-thread CTAs that is 3.4 CTAs per SM (some SMs run four, the
+/// kernel lasts as long as those), with 64-thread CTAs 6.8 (seven against six)
+constexpr int kHuffThreads = 64;
+template <bool FULL>
+__global__ void __launch_bounds__(kHuffThreads) jpeg_decode_huffman_kernel(const uint8_t *__restrict__ stream, const uint32_t *__restrict__ seg_begin,
                                                                   const uint32_t *__restrict__ seg_end, const dec_tables *__restrict__ tables,
                                                                   dec_geom g, int16_t *__restrict__ coef, const uint32_t *__restrict__ dev_scans)
 {
         extern __shared__ uint8_t smem_raw[];
         dec_tables *t = (dec_tables *) smem_raw;
+        uint32_t *const col = (uint32_t *) (smem_raw + ((sizeof(dec_tables) + 15) & ~(size_t) 15)) + threadIdx.x;  // FULL: word w of my block at col[w * kHuffThreads]
         for (int i = threadIdx.x; i < (int) (sizeof(dec_tables) / 4); i += blockDim.x) {
                 ((uint32_t *) t)[i] = ((const uint32_t *) tables)[i];
         }
@@ -179,13 +187,21 @@ __global__ void __launch_bounds__(128) jpeg_decode_huffman_kernel(const uint8_t 
                                         const int X = mx * nh + bx, Y = my * nv + by;
                                         const bool inside = X < c.bw && Y < c.bh;
                                         int16_t *blk = coef + ((long) c.blk_off + (long) Y * c.bw + X) * 64;
+                                        if (FULL) {
+#pragma unroll
+                                                for (int w = 0; w < 32; ++w) {
+                                                        col[w * kHuffThreads] = 0;
+                                                }
+                                        }
                                         r.refill();
                                         const int tt = decode_symbol(r, t, S.td[k]);
                                         r.refill();
                                         if (tt) {
                                                 pred[k] += receive_extend(r, tt & 15);
                                         }
-                                        if (inside && pred[k] != 0) {
+                                        if (FULL) {
+                                                col[0] = (uint32_t) pred[k] & 0xffffu;
+                                        } else if (inside && pred[k] != 0) {
                                                 blk[0] = (int16_t) pred[k];
                                         }
                                         for (int i = 1; i < 64;) {
@@ -200,10 +216,21 @@ __global__ void __launch_bounds__(128) jpeg_decode_huffman_kernel(const uint8_t 
                                                 }
                                                 i += run;
                                                 const int v = receive_extend(r, sz);  // refill guarantees >= 33 bits: 16 + 15 fit
-                                                if (i < 64 && inside) {
+                                                if (FULL) {
+                                                        if (i < 64) {
+                                                                const int n = t->zz[i];
+                                                                ((int16_t *) (col + (n >> 1) * kHuffThreads))[n & 1] = (int16_t) v;
+                                                        }
+                                                } else if (i < 64 && inside) {
                                                         blk[t->zz[i]] = (int16_t) v;
                                                 }
                                                 ++i;
+                                        }
+                                        if (FULL && inside) {
+#pragma unroll
+                                                for (int q = 0; q < 8; ++q) {
+                                                        ((uint4 *) blk)[q] = make_uint4(col[(4 * q) * kHuffThreads], col[(4 * q + 1) * kHuffThreads], col[(4 * q + 2) * kHuffThreads], col[(4 * q + 3) * kHuffThreads]);
+                                                }
                                         }
                                 }
                         }
@@ -1387,9 +1414,33 @@ UGB_API int ugb200_jpeg_decode(ugb200_jpeg_decoder *d, const uint8_t *stream, si
         H.pending = true;
         lap("uploads queued");
         lap("+segments on the device");
-        cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
-        lap("+coefficients cleared");
-        jpeg_decode_huffman_kernel<<<(unsigned) ((nseg + 127) / 128), 128, sizeof(dec_tables), s>>>(d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef, dev_scans);
+        // Does every block of the coefficient array belong to exactly one scan's MCU grid?  (Interleaved scans cover the padded planes by construction; a
+        // one-component scan covers ceil(w_c / 8) x ceil(h_c / 8) blocks, which is the whole plane only without MCU padding; a component no scan names - a
+        // truncated multi-scan stream - is covered by nobody.)  Then the Huffman kernel writes whole blocks and the array is not cleared.
+        bool full = true;
+        {
+                int seen[3] = { 0, 0, 0 };
+                for (int j = 0; j < g.nscans; ++j) {
+                        const dec_scan &S = g.s[j];
+                        for (int k = 0; k < S.ns; ++k) {
+                                ++seen[S.comp[k]];
+                        }
+                        if (S.ns == 1) {
+                                const dec_comp &c = g.c[S.comp[0]];
+                                full = full && S.mcux == c.bw && S.nmcu == c.bw * c.bh;
+                        }
+                }
+                full = full && seen[0] == 1 && seen[1] == 1 && seen[2] == 1;
+        }
+        const unsigned hgrid = (unsigned) ((nseg + kHuffThreads - 1) / kHuffThreads);
+        const size_t hsmem = ((sizeof(dec_tables) + 15) & ~(size_t) 15) + (size_t) kHuffThreads * 128;
+        if (full) {
+                jpeg_decode_huffman_kernel<true><<<hgrid, kHuffThreads, hsmem, s>>>(d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef, dev_scans);
+        } else {
+                cudaMemsetAsync(d->coef, 0, (size_t) g.nblocks * 128, s);
+                lap("+coefficients cleared");
+                jpeg_decode_huffman_kernel<false><<<hgrid, kHuffThreads, hsmem, s>>>(d_stream, d->d_seg, d->d_seg + nseg, d->d_tables, g, d->coef, dev_scans);
+        }
         cudaEventRecord(H.consumed, s);  // nothing behind this kernel reads the stream
         H.consumed_pending = true;
         const bool direct = native == out_codec && dst_is_device;
