@@ -11,14 +11,14 @@ from ultragrid_b200 import api, _lib, vc_get_linesize
 lib = _lib.load()
 n = 0
 ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
-for inc, outc in ([] if ONLY == "jpeg" else PAIRS):  # line converters: tight buffers, ragged widths
+for inc, outc in ([] if ONLY in ("jpeg", "staged") else PAIRS):  # line converters: tight buffers, ragged widths
     for w, h in ((50, 3), (17, 2), (256, 2)):
         ls_i, ls_o = vc_get_linesize(w, inc), vc_get_linesize(w, outc)
         src = torch.randint(0, 256, (ls_i * h + 64,), dtype=torch.uint8, device="cuda")  # MAX_PADDING of over-read slack, video_codec.h:61
         dst = torch.zeros(ls_o * h + 64, dtype=torch.uint8, device="cuda")
         api.pixfmt_convert(inc, outc, src, w, h, dst=dst)
         n += 1
-for name, depth in ([] if ONLY == "jpeg" else pc.all_cases()):  # planar converters
+for name, depth in ([] if ONLY in ("jpeg", "staged") else pc.all_cases()):  # planar converters
     for w, h in ((50, 5), (17, 3), (64, 4)):
         if name == "yuv420_to_i420" and (w % 2 or h % 2):
             continue
@@ -26,7 +26,7 @@ for name, depth in ([] if ONLY == "jpeg" else pc.all_cases()):  # planar convert
             c = pc.Case(name, w, h, seed=3, mode=mode, depth=depth)
             c.run_gpu(lib, torch, 0)
             n += 1
-for w, h in ((8, 4), (260, 36)):  # DXT encode / decode
+for w, h in ([] if ONLY == "staged" else ((8, 4), (260, 36))):  # DXT encode / decode
     uy = torch.randint(0, 256, (w * h * 2,), dtype=torch.uint8, device="cuda")
     rgb = torch.randint(0, 256, (w * h * 3,), dtype=torch.uint8, device="cuda")
     for t in (1, 6):
@@ -35,7 +35,7 @@ for w, h in ((8, 4), (260, 36)):  # DXT encode / decode
         api.compat_to_dxt("cuda_rgb_to_dxt1" if t == 1 else "cuda_rgb_to_dxt6", rgb, w, -h)
         n += 3
 enc, dec = api.JpegEncoder(), api.JpegDecoder()
-for codec, w, h, q, ri in ((2, 100, 52, 90, 0), (2, 98, 50, 100, 1), (12, 77, 33, 85, 8), (12, 64, 64, 100, 5)):  # JPEG encode (fused, serial route, split) / decode
+for codec, w, h, q, ri in ([] if ONLY == "staged" else ((2, 100, 52, 90, 0), (2, 98, 50, 100, 1), (12, 77, 33, 85, 8), (12, 64, 64, 100, 5))):  # JPEG encode (fused, serial route, split) / decode
     bpp = 2 if codec == 2 else 3
     src = torch.randint(0, 256, (((w + 1) // 2 * 2) * bpp * h,), dtype=torch.uint8, device="cuda")
     for _ in range(2):
@@ -78,7 +78,7 @@ for w, h in ((64, 3), (30, 2), (1921, 2)):
 # JPEG decoder with the marker scan forced onto the device: one interleaved scan (UYVY) and one scan per component (RGB), intact and truncated
 os.environ["UGB200_JPEG_MARKER_SCAN"] = "device"
 dec2 = api.JpegDecoder()
-for codec, w, h in ((2, 320, 200), (12, 200, 120), (12, 1920, 1080)):
+for codec, w, h in ([] if ONLY == "staged" else ((2, 320, 200), (12, 200, 120), (12, 1920, 1080))):
     bpp = 2 if codec == 2 else 3
     src = torch.randint(96, 160, (w * bpp * h,), dtype=torch.uint8, device="cuda")
     enc.encode_device(src, w, h, codec, quality=90)
