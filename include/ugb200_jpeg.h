@@ -86,9 +86,11 @@ UGB_API int ugb200_jpeg_get_image_info(const uint8_t *stream, size_t len, struct
 /* host only, for tests: the restart segments the stream parser found ([begin, end) byte offsets of their entropy-coded data);
  * returns their number (may exceed cap) or a negative error */
 UGB_API long ugb200_jpeg_debug_segments(const uint8_t *stream, size_t len, uint32_t *begin, uint32_t *end, long cap);
-/* Where the restart segments are found: a stream of at least 1 MB with ONE scan that holds all components (UltraGrid's UYVY streams) has its RSTn
- * markers located on the device (the host only reads the header segments and copies the stream to pinned memory); other streams are scanned by a
- * few host threads.  UGB200_JPEG_MARKER_SCAN=host|device at decoder creation forces one way (device: whenever the stream has one scan).
+/* Where the restart segments are found: a stream of at least 1 MB with ONE scan that holds all components (UltraGrid's UYVY streams) or with one scan
+ * per component in component order (RGB as GPUJPEG stores it, gpujpeg.cpp:303-305) has its RSTn markers located on the device (the host only reads the
+ * header segments in front of the first SOS and copies the stream to pinned memory; for the second form the device also checks the later SOS headers
+ * and hands an irregular stream back to the host parser); other streams are scanned by a few host threads.  UGB200_JPEG_MARKER_SCAN=host|device at
+ * decoder creation forces one way (device: at any size).  The stream is uploaded on a copy stream of the decoder, under the kernels of the frame before.
  * ugb200_jpeg_decoder_last_segments returns the segment table of the last decode as the device holds it (waits for the decoder's stream). */
 UGB_API long ugb200_jpeg_decoder_last_segments(ugb200_jpeg_decoder *dec, uint32_t *begin, uint32_t *end, long cap);
 UGB_API ugb200_jpeg_decoder *ugb200_jpeg_decoder_create(cuda_wrapper_stream_t stream);   /* gpujpeg_decoder_create, gpujpeg.c:93 */

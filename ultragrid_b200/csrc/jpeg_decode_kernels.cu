@@ -3,9 +3,12 @@
 //
 //   host   parse_stream     markers up to each SOS (tables, frame, scans) and ONE pass over the entropy-coded bytes that records
 //                           where every restart segment starts (what GPUJPEG's reader does when the stream carries no segment info)
+//   K0     jpeg_marker_*_kernel   the same segment table built on the device for the two regular stream shapes (one interleaved scan, or one scan
+//                           per component): the host then only reads the headers in front of the first SOS
 //   K1     jpeg_decode_huffman_kernel   one thread per restart segment: T.81 F.2.2 Huffman decoding with a 9-bit look-ahead
-//                           table per Huffman table in shared memory (longer codes: min/max-code walk), DC prediction,
-//                           coefficients scattered in natural order into a zeroed int16 [block][64] buffer
+//                           table per Huffman table in shared memory (longer codes: min/max-code walk), DC prediction; every block is
+//                           built in shared memory and written as 128 bytes into the int16 [block][64] buffer (or, when the scans do
+//                           not cover every block, scattered into a cleared buffer)
 //   K2     jpeg_idct_kernel one thread per 8x8 block: dequantise, float AAN inverse DCT (fixed operation order = bit-exact with
 //                           oracle/jpeg_decode_oracle.c), level shift, clamp, 8 x 8-byte stores into the component plane
 //   pack   the component planes go through the from_planar kernels that already exist (planar_conv_kernels.cu):
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(128) jpeg_idct_uyvy_kernel(const int16_t *__re
         }
 }
 
-// ---- marker scan on the device (streams with one interleaved scan: what UltraGrid sends) ------------------------------------------------------
+// ---- marker scan on the device (streams with one interleaved scan: what UltraGrid sends for UYVY; or one scan per component: RGB) ---------------
 // The host's part shrinks to the header segments in front of the SOS and a plain copy of the stream into pinned memory; the RSTn markers that
 // split the entropy-coded data are found here: K-a counts the marker candidates of every 4 KB piece, K-b is a one-CTA exclusive scan, K-c writes
 // their positions in stream order and notes the first one that is not an RSTn (it ends the scan), K-d turns the list into the segment table the
