@@ -423,10 +423,9 @@ def test_gpu_rgb_jpeg_config3_sizes(orc, w, h):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("knob,value", [("UGB200_JPEG_SINGLE_PASS", "1"), ("UGB200_JPEG_SPLIT", "1"), ("UGB200_JPEG_CAP", "12"),
-                                        ("UGB200_JPEG_CAP", "8"), ("UGB200_JPEG_CAP", "24"), ("UGB200_JPEG_CLUSTER", "1")])
+                                        ("UGB200_JPEG_CAP", "8"), ("UGB200_JPEG_CAP", "24")])
 def test_gpu_alternative_routes_give_the_same_bytes(knob, value):
-    """the single-pass compaction (decoupled look-back), the forced split path, the RGB kernel launched as clusters of three with the tile's bulk copies
-    multicast (measured slower, off by default) and the bit-buffer cap (12 words and fewer = the instantiation
+    """the single-pass compaction (decoupled look-back), the forced split path and the bit-buffer cap (12 words and fewer = the instantiation
     for seven CTAs per SM, with the input tile reaching into the segment images; 24 = a larger cap) are process-wide switches: the
     byte-exactness tests run once more in a child process with the switch set"""
     import subprocess

@@ -528,30 +528,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                      "l"(src), "r"(bytes), "r"((uint32_t) __cvta_generic_to_shared(bar))
                      : "memory");
 }
-/// the same copy delivered to the same shared-memory offset of every CTA of the cluster named in `mask`; each of their mbarriers (same offset) gets the bytes
-__device__ __forceinline__ void bulk_g2s_multicast(void *dst, const void *src, uint32_t bytes, unsigned long long *bar, uint16_t mask)
-{
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-                             (uint32_t) __cvta_generic_to_shared(dst)),
-                     "l"(src), "r"(bytes), "r"((uint32_t) __cvta_generic_to_shared(bar)), "h"(mask)
-                     : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_nctas()
-{
-        uint32_t n;
-        asm("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(n));
-        return n;
-}
-__device__ __forceinline__ uint32_t cluster_rank()
-{
-        uint32_t r;
-        asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-        return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
         asm volatile("{\n\t"
@@ -629,32 +605,13 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 const int fm = cta_x * 128;
                 early_tile = vec_ok && cap >= 8 && fm + 128 <= g.mcu_per_scan && (g.w & 7) == 0 && (g.h & 7) == 0 && g.bw >= 128 && !(g.bw & 1) && !(15 & (size_t) src) &&
                              !(pitch & 15);
-                // Launched as clusters of three (the three component CTAs of one tile, host: UGB200_JPEG_CLUSTER): every CTA fetches a third of the tile's rows and
-                // the copy engine MULTICASTS each run into all three CTAs' shared memory - the 24 KB leave L2 once instead of three times (DRAM traffic of the
-                // RGB encode was 1.43 x the algorithmic bytes because the three CTAs do not always meet in L2).  Each CTA's own mbarrier counts the whole tile.
-                const bool clustered = lb.state == nullptr && cluster_nctas() == 3;
-                uint8_t *tile0 = (uint8_t *) s_coef;
-                const int bx0 = fm % g.bw, by0 = fm / g.bw;
-                const int in_row = min(128, g.bw - bx0);  // blocks of the tile that lie in block row by0; the rest starts block row by0 + 1
-                const uint8_t *ga = src + (long) (by0 * 8) * pitch + (long) bx0 * 24, *gb = src + (long) (by0 * 8 + 8) * pitch;
-                if (clustered) {
-                        if (early_tile && tid == 0) {
-                                mbar_init(&s_bar, 1);
-                                mbar_expect_tx(&s_bar, 8 * 3072 + (uint32_t) sizeof s_huff);
-                        }
-                        cluster_sync_all();  // every CTA's mbarrier is armed before a peer's copy can signal it (early_tile is the same in all three)
-                        if (early_tile && tid == 0) {
-                                for (int r = (int) cluster_rank(); r < 8; r += 3) {
-                                        bulk_g2s_multicast((void *) (tile0 + r * 3072), ga + (long) r * pitch, (uint32_t) in_row * 24, &s_bar, 7);
-                                        if (in_row < 128) {
-                                                bulk_g2s_multicast((void *) (tile0 + r * 3072 + in_row * 24), gb + (long) r * pitch, (uint32_t) (128 - in_row) * 24, &s_bar, 7);
-                                        }
-                                }
-                                bulk_g2s((void *) s_huff, huff, (uint32_t) sizeof s_huff, &s_bar);
-                        }
-                } else if (early_tile && tid == 0) {
+                if (early_tile && tid == 0) {
+                        uint8_t *tile0 = (uint8_t *) s_coef;
+                        const int bx0 = fm % g.bw, by0 = fm / g.bw;
+                        const int in_row = min(128, g.bw - bx0);  // blocks of the tile that lie in block row by0; the rest starts block row by0 + 1
                         mbar_init(&s_bar, 1);
                         mbar_expect_tx(&s_bar, 8 * 3072 + (uint32_t) sizeof s_huff);
+                        const uint8_t *ga = src + (long) (by0 * 8) * pitch + (long) bx0 * 24, *gb = src + (long) (by0 * 8 + 8) * pitch;
                         for (int r = 0; r < 8; ++r, ga += pitch, gb += pitch) {
                                 bulk_g2s((void *) (tile0 + r * 3072), ga, (uint32_t) in_row * 24, &s_bar);
                                 if (in_row < 128) {
@@ -1909,29 +1866,11 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
 #define UGB_FUSED(FMT, MINB)                                                                                                                              \
         jpeg_fused_kernel<FMT, MINB><<<grid, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, vec_ok, cap, \
                                                                      e->total + 1, lb, e->qt, e->d_huff)
-                // Off by default: byte-exact, and the tile leaves L2 once instead of three times, but clusters of three CTAs schedule worse and pay a cluster barrier
-                // per CTA: 193.6 -> 217.2 us for the 8K RGB frame (profiles/r02_experiments.md).  UGB200_JPEG_CLUSTER=1 turns it on.
-                static const bool use_cluster = getenv("UGB200_JPEG_CLUSTER") != nullptr && atoi(getenv("UGB200_JPEG_CLUSTER")) != 0;
                 if (fmt == FMT_UYVY_422) {
                         if (seven) {
                                 UGB_FUSED(FMT_UYVY_422, 7);
                         } else {
                                 UGB_FUSED(FMT_UYVY_422, 6);
-                        }
-                } else if (use_cluster && !single_pass && grid.y == 1 && grid.x % 3 == 0) {
-                        // the three component CTAs of a tile (adjacent in the 1-D grid) as one cluster: the tile's bulk copies are multicast
-                        cudaLaunchAttribute at[1];
-                        at[0].id = cudaLaunchAttributeClusterDimension;
-                        at[0].val.clusterDim.x = 3, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-                        cudaLaunchConfig_t cfg{};
-                        cfg.stream = e->stream, cfg.attrs = at, cfg.numAttrs = 1;
-                        cfg.gridDim = grid, cfg.blockDim = dim3(128), cfg.dynamicSmemBytes = smem;
-                        if (seven) {
-                                cudaLaunchKernelEx(&cfg, jpeg_fused_kernel<FMT_RGB_444, 7>, (const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, vec_ok, cap,
-                                                   e->total + 1, lb, e->qt, (const uint32_t *) e->d_huff, (uint32_t *) nullptr, (uint16_t *) nullptr, (int16_t *) nullptr);
-                        } else {
-                                cudaLaunchKernelEx(&cfg, jpeg_fused_kernel<FMT_RGB_444, 6>, (const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, vec_ok, cap,
-                                                   e->total + 1, lb, e->qt, (const uint32_t *) e->d_huff, (uint32_t *) nullptr, (uint16_t *) nullptr, (int16_t *) nullptr);
                         }
                 } else {
                         if (seven) {
