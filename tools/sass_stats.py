@@ -37,7 +37,7 @@ def main():
             continue
         ops, seq, stall, n = collections.Counter(), [], 0, 0
         for i, line in enumerate(lines):
-            m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_.]+).*?/\* (0x[0-9a-f]{16}) \*/", line)
+            m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_.]+).*?/\* (0x[0-9a-f]{16}) \*/", line)
             if not m:
                 continue
             op = m.group(1).rstrip(";")
