@@ -6,6 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 VARIANTS = [("one kernel (default)", {}), ("two_kernels", {"UGB200_JPEG_TWO_KERNELS": "1"}), ("two_kernels_a8", {"UGB200_JPEG_TWO_KERNELS": "8"})]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     VARIANTS = VARIANTS[:2]
+if len(sys.argv) > 1 and sys.argv[1] == "lean":  # the instantiation without fall-back paths (default where the frame geometry allows) against the general kernel
+    VARIANTS = [("lean kernel (default)", {}), ("general kernel", {"UGB200_JPEG_LEAN": "0"}), ("lean kernel again", {})]
 
 
 def child():

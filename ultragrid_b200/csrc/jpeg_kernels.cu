@@ -227,11 +227,12 @@ __device__ __forceinline__ void fdct8_2(float2 &d0, float2 &d1, float2 &d2, floa
         d7 = __fadd2_rn(z11, neg2(z4));
 }
 /// the 8 samples of one row of a block as 2^23 + sample (level shift and conversion happen in one packed add later)
+/// TILE_ONLY: the caller guarantees the staged tile (the global-memory forms below are not instantiated: LEAN kernels)
+template <bool TILE_ONLY = false>
 __device__ __forceinline__ void load_row_magic(const uint8_t *__restrict__ src, long pitch, const jpeg_geom &g, int comp, int bx, int y, bool interior,
                                                float *m, const uint8_t *tile_row = nullptr, int tile_x = 0)
 {
-        const uint8_t *row = src + (long) clampi(y, g.h - 1) * pitch;
-        if (tile_row != nullptr) {  // the CTA's 8 x 1024-byte input tile is in shared memory (UYVY only): tile_x = my MCU within the tile
+        if (TILE_ONLY || tile_row != nullptr) {  // the CTA's 8 x 1024-byte input tile is in shared memory (UYVY only): tile_x = my MCU within the tile
                 if (comp == 0) {
                         const uint4 v = *(const uint4 *) (tile_row + tile_x * 32 + (bx & 1) * 16);
                         const uint32_t w[4] = { v.x, v.y, v.z, v.w };
@@ -251,6 +252,10 @@ __device__ __forceinline__ void load_row_magic(const uint8_t *__restrict__ src, 
                 }
                 return;
         }
+        if (TILE_ONLY) {
+                return;
+        }
+        const uint8_t *row = src + (long) clampi(y, g.h - 1) * pitch;
         if (g.fmt == FMT_UYVY_422) {
                 if (interior && comp == 0) {
                         const uint4 v = __ldg((const uint4 *) (row + (long) bx * 16));
@@ -550,7 +555,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 /// warps finish their entropy coding long before its luma warps: 11 % of all warp samples of the one-kernel form sit at that barrier), needs 16 KB of
 /// shared memory instead of 28, and the assembly runs as a light kernel of its own at full occupancy.  A block longer than `cap` words (noise) also
 /// leaves its coefficients in `gcoef` (DC slot = the DC DIFFERENCE), from which the assembly kernel codes it again inside a serial segment.
-template <int FMT, int MINB, bool BLOCKS_ONLY = false>
+/// LEAN (state j): an instantiation for frames in which EVERY CTA's tile is whole and goes through the copy engine (the host checks the geometry: 8K and other sizes whose
+/// MCU rows are multiples of the tile) - the global-memory fall-back loads, the cp.async staging and the edge handling are not compiled in: about a fifth less code in
+/// a kernel whose instruction fetch shows up in the stall list (`no_instruction`, profiles/r02_i_jpeg_fused_uyvy.md).  Same arithmetic, same bytes.
+template <int FMT, int MINB, bool BLOCKS_ONLY = false, bool LEAN = false>
 __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__restrict__ src, long pitch, jpeg_geom g, uint8_t *__restrict__ slots,
                                                          uint32_t *__restrict__ sizes, uint32_t *__restrict__ local_off,
                                                          uint32_t *__restrict__ cta_total, bool vec_ok, int cap, uint32_t *__restrict__ stats,
@@ -589,7 +597,7 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         bool early_tile = false;
         if (FMT == FMT_UYVY_422) {
                 const int fm = cta_x * 32, mx0 = fm % g.bw, my0 = fm / g.bw;
-                early_tile = vec_ok && cap >= 8 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h;
+                early_tile = LEAN || (vec_ok && cap >= 8 && mx0 + 32 <= g.bw && (mx0 + 32) * 16 <= g.w && (my0 + 1) * 8 <= g.h);
                 if (early_tile && tid == 0) {
                         uint8_t *tile0 = (uint8_t *) (BLOCKS_ONLY ? s_coef : s_bits);
                         const uint8_t *gsrc = src + (long) (my0 * 8) * pitch + (long) mx0 * 32;
@@ -603,8 +611,8 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         }
         if (FMT == FMT_RGB_444) {  // the same for the packed-RGB tile (8 rows x 3072 bytes, at most two runs per row) when whole runs can go through the copy engine
                 const int fm = cta_x * 128;
-                early_tile = vec_ok && cap >= 8 && fm + 128 <= g.mcu_per_scan && (g.w & 7) == 0 && (g.h & 7) == 0 && g.bw >= 128 && !(g.bw & 1) && !(15 & (size_t) src) &&
-                             !(pitch & 15);
+                early_tile = LEAN || (vec_ok && cap >= 8 && fm + 128 <= g.mcu_per_scan && (g.w & 7) == 0 && (g.h & 7) == 0 && g.bw >= 128 && !(g.bw & 1) &&
+                                      !(15 & (size_t) src) && !(pitch & 15));
                 if (early_tile && tid == 0) {
                         uint8_t *tile0 = (uint8_t *) s_coef;
                         const int bx0 = fm % g.bw, by0 = fm / g.bw;
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 const int k = tid >> 5, lane = tid & 31;
                 first_mcu = cta_x * 32;
                 const int m = first_mcu + lane;
-                valid = m < g.mcu_per_scan;
+                valid = LEAN || m < g.mcu_per_scan;
                 comp = k < 2 ? 0 : k - 1;
                 const int mx = m % g.bw;
                 bx = comp == 0 ? mx * 2 + k : mx, by = m / g.bw;
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         } else {
                 first_mcu = cta_x * 128;
                 const int b = first_mcu + tid;
-                valid = b < g.mcu_per_scan;
+                valid = LEAN || b < g.mcu_per_scan;
                 comp = cta_y;
                 bx = b % g.bw, by = b / g.bw;
                 p = tid;
@@ -658,7 +666,7 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                 // next block row; the tile keeps block order, not image order).  cp.async in 8-byte pieces - a block starts at a multiple of 24 bytes -
                 // instead of 64 single-byte loads per thread.  24 KB: the tile lies over the coefficient array, the bit strings and the segment images,
                 // all of which are written only after the last sample has been read (barrier below).
-                staged = vec_ok && cap >= 8 && first_mcu + 128 <= g.mcu_per_scan && (g.w & 7) == 0 && (g.h & 7) == 0;
+                staged = LEAN || (vec_ok && cap >= 8 && first_mcu + 128 <= g.mcu_per_scan && (g.w & 7) == 0 && (g.h & 7) == 0);
                 // 16-byte aligned rows and an even number of blocks per row: the (at most two) runs of a tile row start and end on 48-byte
                 // boundaries, so whole runs go through the copy engine
                 // (a frame less than 128 blocks wide wraps more than once inside a tile: that goes the cp.async way below)
@@ -697,7 +705,7 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
         float2 g2[8][4];  // after the column pass: g2[r][cp] = coefficients (r, 2cp) and (r, 2cp + 1), still as 1.5 * 2^23 + q
         {
                 const int px_w = (FMT == FMT_UYVY_422 && comp != 0) ? 16 : 8;
-                const bool interior = vec_ok && valid && (bx + 1) * px_w <= g.w && (by + 1) * 8 <= g.h;
+                const bool interior = LEAN || (vec_ok && valid && (bx + 1) * px_w <= g.w && (by + 1) * 8 <= g.h);
                 float2 f2[4][8];
 #pragma unroll
                 for (int rp = 0; rp < 4; ++rp) {
@@ -706,10 +714,10 @@ __global__ void __launch_bounds__(128, MINB) jpeg_fused_kernel(const uint8_t *__
                                 load_row_rgb_tile(tile + (2 * rp) * 3072 + tid * 24, comp, ma);
                                 load_row_rgb_tile(tile + (2 * rp + 1) * 3072 + tid * 24, comp, mb);
                         } else {
-                                load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp : 0, interior, ma,
-                                               staged ? tile + (2 * rp) * 1024 : nullptr, tid & 31);
-                                load_row_magic(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp + 1 : 0, interior, mb,
-                                               staged ? tile + (2 * rp + 1) * 1024 : nullptr, tid & 31);
+                                load_row_magic<LEAN>(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp : 0, interior, ma,
+                                                     staged ? tile + (2 * rp) * 1024 : nullptr, tid & 31);
+                                load_row_magic<LEAN>(src, pitch, g, comp, valid ? bx : 0, valid ? by * 8 + 2 * rp + 1 : 0, interior, mb,
+                                                     staged ? tile + (2 * rp + 1) * 1024 : nullptr, tid & 31);
                         }
 #pragma unroll
                         for (int x = 0; x < 8; ++x) {  // (2^23 + s) - (2^23 + 128): level shift, exact
@@ -1863,20 +1871,25 @@ int ugb200_jpeg_encode_device(ugb200_jpeg_encoder *e, const void *src, long pitc
                                                    e->slots, e->sizes, e->offsets, e->cta_total, cap, ctas_per_scan, (const uint32_t *) e->d_huff);
                         }
                 } else {
-#define UGB_FUSED(FMT, MINB)                                                                                                                              \
-        jpeg_fused_kernel<FMT, MINB><<<grid, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, vec_ok, cap, \
-                                                                     e->total + 1, lb, e->qt, e->d_huff)
+#define UGB_FUSED(FMT, MINB, LEAN)                                                                                                                        \
+        jpeg_fused_kernel<FMT, MINB, false, LEAN><<<grid, 128, smem, e->stream>>>((const uint8_t *) src, pitch, g, e->slots, e->sizes, e->offsets, e->cta_total, vec_ok, \
+                                                                                  cap, e->total + 1, lb, e->qt, e->d_huff)
+                // every CTA's tile whole and bulk-copyable?  (the conditions of the kernel's `early_tile`, for all CTAs at once; UGB200_JPEG_LEAN=0 keeps the general kernel)
+                static const bool allow_lean = getenv("UGB200_JPEG_LEAN") == nullptr || atoi(getenv("UGB200_JPEG_LEAN")) != 0;
+                const bool lean = allow_lean && vec_ok && cap >= 8 && (g.h & 7) == 0 &&
+                                  (fmt == FMT_UYVY_422 ? g.bw % 32 == 0 && g.bw * 16 == g.w
+                                                       : g.mcu_per_scan % 128 == 0 && (g.w & 7) == 0 && g.bw >= 128 && !(g.bw & 1) && !(15 & (size_t) src) && !(pitch & 15));
                 if (fmt == FMT_UYVY_422) {
                         if (seven) {
-                                UGB_FUSED(FMT_UYVY_422, 7);
+                                lean ? UGB_FUSED(FMT_UYVY_422, 7, true) : UGB_FUSED(FMT_UYVY_422, 7, false);
                         } else {
-                                UGB_FUSED(FMT_UYVY_422, 6);
+                                lean ? UGB_FUSED(FMT_UYVY_422, 6, true) : UGB_FUSED(FMT_UYVY_422, 6, false);
                         }
                 } else {
                         if (seven) {
-                                UGB_FUSED(FMT_RGB_444, 7);
+                                lean ? UGB_FUSED(FMT_RGB_444, 7, true) : UGB_FUSED(FMT_RGB_444, 7, false);
                         } else {
-                                UGB_FUSED(FMT_RGB_444, 6);
+                                lean ? UGB_FUSED(FMT_RGB_444, 6, true) : UGB_FUSED(FMT_RGB_444, 6, false);
                         }
                 }
 #undef UGB_FUSED
