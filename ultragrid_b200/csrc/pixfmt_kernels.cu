@@ -1373,6 +1373,66 @@ static int &staged_mode()
 }
 static int staged_override() { return staged_mode(); }
 
+/// LEAN form of line_conv_kernel for the common case the host can guarantee up front: 16-byte aligned pointers and pitches, every chunk of every row whole, inside the
+/// readable source and inside the destination pitch.  Nothing but the vector loads, C::run and the vector stores is compiled in - the byte-wise paths of the general
+/// kernel cost registers (v210 -> RG48: 170) and instruction-cache footprint even when they never run (the lesson of the JPEG encoder's lean instantiation).
+template <class C>
+__global__ void __launch_bounds__(256) line_conv_lean_kernel(uint8_t *__restrict__ dst, long dst_pitch, const uint8_t *__restrict__ src, long src_pitch, int wlen, int height,
+                                                             long src_total, conv_params p)
+{
+        constexpr int NI = C::IN / 4, NO = C::OUT / 4;
+        const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+        const long out_off = (long) cx * C::OUT;
+        if (out_off >= wlen) {
+                return;
+        }
+        const long in_off = (long) cx * C::IN;
+        for (int row = blockIdx.y; row < height; row += gridDim.y) {
+                uint32_t in[NI], out[NO];
+                const uint4 *s4 = (const uint4 *) (src + row * src_pitch + in_off);
+#pragma unroll
+                for (int i = 0; i < NI / 4; ++i) {
+                        uint4 v;
+                        if (NI >= 16) {
+                                v = __ldg(s4 + i);
+                        } else {
+                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(s4 + i));
+                        }
+                        in[4 * i] = v.x, in[4 * i + 1] = v.y, in[4 * i + 2] = v.z, in[4 * i + 3] = v.w;
+                }
+                const row_ctx rc = { src, row * src_pitch, src_total, cx };
+                C::run(in, out, p, rc);
+                uint4 *d4 = (uint4 *) (dst + row * dst_pitch + out_off);
+#pragma unroll
+                for (int i = 0; i < NO / 4; ++i) {
+                        d4[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                }
+        }
+}
+
+/// which converters take the lean kernel by default: the ones it measured at least 5 % faster for at 8K (last GPU call of round 2, profiles/r02_k_line_lean.md; it is
+/// slower for a few - v210 -> RGB by half: with 46 instead of 90 registers ptxas schedules its long arithmetic chains with less overlap).  UGB200_LINE_LEAN=0 / 1: none / all.
+template <class C>
+struct lean_default {
+        static constexpr bool value = false;
+};
+#define UGB_LEAN(...)                                                                                                                         \
+        template <>                                                                                                                           \
+        struct lean_default<__VA_ARGS__> {                                                                                                    \
+                static constexpr bool value = true;                                                                                           \
+        };
+UGB_LEAN(conv_uyvy_rgba)               // 50.1 -> 44.4 us
+UGB_LEAN(conv_r10k_rgba)               // 57.0 -> 47.9
+UGB_LEAN(conv_uyvy_rg48)               // 54.0 -> 49.9
+UGB_LEAN(conv_rgba_vuya)               // 54.0 -> 48.0
+UGB_LEAN(conv_to_uyvy<2, 1, 0, 3>)     // BGR  -> UYVY  33.7 -> 31.5
+UGB_LEAN(conv_to_uyvy<0, 1, 2, 4>)     // RGBA -> UYVY  39.7 -> 34.1
+UGB_LEAN(conv_rgba_r10k)               // 47.9 -> 44.7
+UGB_LEAN(conv_y416_rgbx<3>)            // Y416 -> R10k  70.5 -> 62.2
+UGB_LEAN(conv_y416_rgbx<2>)            // Y416 -> RGBA  66.1 -> 62.4
+UGB_LEAN(conv_vuya_uyvy)               // 31.8 -> 30.0
+#undef UGB_LEAN
+
 template <class C>
 static int launch_line(void *dst, long dst_pitch, const void *src, long src_pitch, int dst_len, int height, long src_size,
                        conv_params p, cudaStream_t s)
@@ -1399,6 +1459,14 @@ static int launch_line(void *dst, long dst_pitch, const void *src, long src_pitc
                         line_conv_staged_kernel<C, threads, true, false><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height, src_size, p);
                 }
                 if (mode != 0) {
+                        return cudaGetLastError() == cudaSuccess ? 0 : -2;
+                }
+        }
+        if constexpr (C::IN % 16 == 0 && C::OUT % 16 == 0) {
+                static const int lean_env = getenv("UGB200_LINE_LEAN") == nullptr ? -1 : atoi(getenv("UGB200_LINE_LEAN"));
+                const bool allow_lean = lean_env < 0 ? lean_default<C>::value : lean_env != 0;
+                if (allow_lean && vec_ok && wlen % C::OUT == 0 && wlen <= dst_pitch && (long) (height - 1) * src_pitch + (long) chunks * C::IN <= src_size) {
+                        line_conv_lean_kernel<C><<<grid, threads, 0, s>>>((uint8_t *) dst, dst_pitch, (const uint8_t *) src, src_pitch, wlen, height, src_size, p);
                         return cudaGetLastError() == cudaSuccess ? 0 : -2;
                 }
         }
